@@ -1,0 +1,66 @@
+"""Build ``libcrb200.so`` (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+Equivalent of the reference's ``cellular_raza-core/build.rs:9-19`` (``cc`` + nvcc for the ``cara``
+backend), with the architecture flags that file lacks.  ``python -m cellular_raza_b200.build``.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB_DIR = PKG / "lib"
+LIB = LIB_DIR / "libcrb200.so"
+SOURCES = [CSRC / "crb_api.cu"]
+HEADERS = [CSRC / "crb_internal.cuh", CSRC / "crb_kernels.cuh", PKG.parent / "include" / "crb.h"]
+
+NVCC_FLAGS = [
+    "-O3",
+    "-std=c++17",
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "--shared",
+    "-Xcompiler",
+    "-fPIC",
+]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found; cannot build libcrb200.so")
+    return p
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(f.stat().st_mtime > t for f in SOURCES + HEADERS + [Path(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> Path:
+    if not force and not needs_build():
+        return LIB
+    LIB_DIR.mkdir(exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), "-o", str(LIB), *map(str, SOURCES)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libcrb200.so")
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,912 @@
+// crb_api.cu — host side of the C ABI declared in include/crb.h.
+//
+// Owns all device memory behind the opaque handle, sequences the kernels of one step on the
+// handle's stream and latches device-side errors (SimulationError variants of
+// cellular_raza-core/src/backend/chili/errors.rs:73-121).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "crb_kernels.cuh"
+
+using namespace crb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct StageTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    double ms = 0;
+    u64 launches = 0;
+};
+constexpr int kNumStages = 5;
+
+}  // namespace
+
+struct crb_sim {
+    crb_config cfg;
+    Grid g;
+    int D = 3, V = 1;
+    int n_mp = 0, n_ip = 0;
+    bool uniform = true;
+    Uniform uni;
+    u64 cap = 0, n = 0;
+    u64 nvox = 0;
+    cudaStream_t stream = nullptr;
+    State X, T, Y;  // X: sorted state read by the force pass, T: integrated, Y: reorder target
+    u32 *key = nullptr, *key_alt = nullptr;
+    u32 *start = nullptr, *start_alt = nullptr;
+    u32* count_new = nullptr;
+    u32 *newkey = nullptr, *rank_arb = nullptr, *tmp_idx = nullptr, *slot_of_src = nullptr;
+    u64* sortkey = nullptr;
+    u32* tile_sums = nullptr;
+    u32 n_tiles = 0;
+    double* stage = nullptr;  // cap * 8 doubles staging for agent-major host rows
+    double* force_out = nullptr;
+    double* noise = nullptr;
+    u64 noise_steps = 0, noise_ids = 0, noise_cursor = 0;
+    int* err = nullptr;       // device latch
+    int* err_host = nullptr;  // pinned
+    u64* scratch_u64 = nullptr;  // small device scratch (counters)
+    u64 iteration = 0;
+    u64 launches = 0;
+    bool have_agents = false;
+    bool aux_settable = false;
+    u64 last_step_n = 0;  // agents that took part in the last step (migration tap)
+    bool timers_on = false;
+    StageTimer timers[kNumStages];
+    std::vector<void*> allocs;
+    std::string error;
+};
+
+namespace {
+
+int fail(crb_sim* s, int code, const std::string& msg) {
+    if (s)
+        s->error = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+#define CU(s, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(s, CRB_ERR_CUDA,                                                   \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+template <class T>
+int dalloc(crb_sim* s, T** p, u64 count) {
+    void* q = nullptr;
+    CU(s, cudaMalloc(&q, std::max<u64>(count, 1) * sizeof(T)));
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
+    std::memset(&st, 0, sizeof(st));
+    const u64 c = s->cap * s->V;
+    int rc;
+    if (dynamic) {
+        for (int d = 0; d < s->D; ++d) {
+            if ((rc = dalloc(s, &st.pos[d], c))) return rc;
+            if ((rc = dalloc(s, &st.vel[d], c))) return rc;
+            if ((rc = dalloc(s, &st.h1x[d], c))) return rc;
+            if ((rc = dalloc(s, &st.h1v[d], c))) return rc;
+            if ((rc = dalloc(s, &st.h0x[d], c))) return rc;
+            if ((rc = dalloc(s, &st.h0v[d], c))) return rc;
+        }
+        if ((rc = dalloc(s, &st.hlen, s->cap))) return rc;
+    }
+    if (stat) {
+        if ((rc = dalloc(s, &st.id, s->cap))) return rc;
+        if ((rc = dalloc(s, &st.species, s->cap))) return rc;
+        for (int k = 0; k < s->n_mp; ++k)
+            if ((rc = dalloc(s, &st.mp[k], s->cap))) return rc;
+        for (int k = 0; k < s->n_ip; ++k)
+            if ((rc = dalloc(s, &st.ip[k], s->cap))) return rc;
+    }
+    return 0;
+}
+
+inline u32 blocks_for(u64 n, u32 threads) { return (u32)((n + threads - 1) / threads); }
+
+void stage_begin(crb_sim* s, int stage) {
+    if (!s->timers_on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s->stream);
+    s->timers[stage].ev.emplace_back(a, b);
+}
+void stage_end(crb_sim* s, int stage, int n_launches) {
+    s->launches += n_launches;
+    if (!s->timers_on) return;
+    cudaEventRecord(s->timers[stage].ev.back().second, s->stream);
+    s->timers[stage].launches += n_launches;
+}
+void timers_resolve(crb_sim* s) {
+    for (auto& t : s->timers) {
+        for (auto& e : t.ev) {
+            float ms = 0;
+            cudaEventSynchronize(e.second);
+            cudaEventElapsedTime(&ms, e.first, e.second);
+            t.ms += ms;
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        t.ev.clear();
+    }
+}
+
+KParams make_params(crb_sim* s) {
+    KParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.g = s->g;
+    P.A = s->X;
+    P.B = s->T;
+    P.u = s->uni;
+    P.n = s->n;
+    P.cap = s->cap;
+    P.key = s->key;
+    P.start = s->start;
+    P.newkey = s->newkey;
+    P.rank_arb = s->rank_arb;
+    P.sortkey = s->sortkey;
+    P.count_new = s->count_new;
+    P.force_out = s->force_out;
+    P.noise = s->noise;
+    P.noise_ids = s->noise_ids;
+    P.noise_cursor = s->noise_cursor;
+    P.iteration = s->iteration;
+    P.seed = s->cfg.rng_seed;
+    P.err = s->err;
+    P.dt = s->cfg.dt;
+    P.mech = (int)s->cfg.mechanics_kind;
+    P.inter = (int)s->cfg.interaction_kind;
+    P.order = (int)s->cfg.solver_order;
+    P.weight_mode = (int)s->cfg.pair_weight_mode;
+    P.noise_mode = (int)s->cfg.noise_mode;
+    P.save_prev = 0;
+    return P;
+}
+
+template <int D, int INTER, bool UNIFORM>
+void launch_force_t(crb_sim* s, const KParams& P, bool force_only) {
+    const u32 grid = blocks_for(P.n, kForceThreads);
+    if (!grid) return;
+    if (force_only)
+        k_force_integrate<D, INTER, UNIFORM, true><<<grid, kForceThreads, 0, s->stream>>>(P, 0, P.n);
+    else
+        k_force_integrate<D, INTER, UNIFORM, false><<<grid, kForceThreads, 0, s->stream>>>(P, 0, P.n);
+}
+
+template <int D, int INTER>
+void launch_force_u(crb_sim* s, const KParams& P, bool force_only) {
+    if (s->uniform)
+        launch_force_t<D, INTER, true>(s, P, force_only);
+    else
+        launch_force_t<D, INTER, false>(s, P, force_only);
+}
+
+template <int D>
+void launch_force_d(crb_sim* s, const KParams& P, bool force_only) {
+    switch (s->cfg.interaction_kind) {
+        case CRB_INT_CELL_SORTING: launch_force_u<D, CRB_INT_CELL_SORTING>(s, P, force_only); break;
+        case CRB_INT_CELL_SORTING_BENCH:
+            launch_force_u<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only);
+            break;
+        case CRB_INT_MORSE: launch_force_u<D, CRB_INT_MORSE>(s, P, force_only); break;
+        case CRB_INT_BOUND_LJ: launch_force_u<D, CRB_INT_BOUND_LJ>(s, P, force_only); break;
+        case CRB_INT_MIE: launch_force_u<D, CRB_INT_MIE>(s, P, force_only); break;
+    }
+}
+
+void launch_force(crb_sim* s, const KParams& P, bool force_only) {
+    if (s->D == 3)
+        launch_force_d<3>(s, P, force_only);
+    else
+        launch_force_d<2>(s, P, force_only);
+}
+
+// scan count_new -> start_alt, fill, reorder T(+X static) -> Y, swap
+int sort_into_place(crb_sim* s, u64 n_src, bool save_prev, bool ingest) {
+    const u64 nv = s->nvox;
+    stage_begin(s, 1);
+    k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt,
+                                                            s->tile_sums, nv);
+    k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv);
+    k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
+    stage_end(s, 1, 3);
+    stage_begin(s, 2);
+    if (n_src) {
+        k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt,
+                                                             s->tmp_idx, n_src);
+        ReorderParams R;
+        std::memset(&R, 0, sizeof(R));
+        R.A = s->X;
+        R.B = s->T;
+        R.Y = s->Y;
+        R.newkey = s->newkey;
+        R.start_new = s->start_alt;
+        R.tmp_idx = s->tmp_idx;
+        R.sortkey = s->sortkey;
+        R.key_out = s->key_alt;
+        R.slot_of_src = ingest ? s->slot_of_src : nullptr;
+        R.n = n_src;
+        R.D = s->D;
+        R.V = s->V;
+        R.n_mp = s->uniform ? 0 : s->n_mp;
+        R.n_ip = s->uniform ? 0 : s->n_ip;
+        R.save_prev = save_prev ? 1 : 0;
+        R.has_species = 1;
+        k_reorder<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(R);
+    }
+    stage_end(s, 2, n_src ? 2 : 0);
+    std::swap(s->X, s->Y);
+    std::swap(s->key, s->key_alt);
+    std::swap(s->start, s->start_alt);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
+int check_latch(crb_sim* s) {
+    CU(s, cudaMemcpyAsync(s->err_host, s->err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (s->err_host[1]) {
+        const int code = s->err_host[0];
+        u64 id;
+        std::memcpy(&id, s->err_host + 2, sizeof(id));
+        CU(s, cudaMemsetAsync(s->err, 0, 4 * sizeof(int), s->stream));
+        switch (code) {
+            case CRB_ERR_CALC:
+                return fail(s, code,
+                            "CalcError: identical position for two objects. Cannot Calculate force "
+                            "in Mie potential (agent id " + std::to_string(id) + ")");
+            case CRB_ERR_BOUNDARY:
+                return fail(s, code, "BoundaryError: Particle is out of domain (agent id " +
+                                         std::to_string(id) + ")");
+            case CRB_ERR_INDEX:
+                return fail(s, code, "IndexError: could not find voxel index (agent " +
+                                         std::to_string(id) + ")");
+            default: return fail(s, code, "device error " + std::to_string(code));
+        }
+    }
+    return 0;
+}
+
+// host rows (agent-major, `width` doubles) -> device columns
+int upload_rows(crb_sim* s, const double* host, int width, double* const* cols, u64 n) {
+    if (!n) return 0;
+    if (width > 8) return fail(s, CRB_ERR_INVALID_ARG, "row width > 8");
+    CU(s, cudaMemcpyAsync(s->stage, host, n * width * sizeof(double), cudaMemcpyHostToDevice,
+                          s->stream));
+    double* c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < width; ++k) c[k] = cols[k];
+    k_unpack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, width, c[0], c[1], c[2], c[3],
+                                                            c[4], c[5], c[6], c[7], n);
+    s->launches++;
+    return 0;
+}
+
+int download_rows(crb_sim* s, double* host, int width, const double* const* cols, u64 n) {
+    if (!n) return 0;
+    const double* c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < width; ++k) c[k] = cols[k];
+    k_pack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, width, c[0], c[1], c[2], c[3],
+                                                          c[4], c[5], c[6], c[7], n);
+    s->launches++;
+    CU(s, cudaMemcpyAsync(host, s->stage, n * width * sizeof(double), cudaMemcpyDeviceToHost,
+                          s->stream));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+uint32_t crb_abi_version(void) { return CRB_ABI_VERSION; }
+
+uint32_t crb_n_mech_params(uint32_t kind) {
+    switch (kind) {
+        case CRB_MECH_NEWTON_DAMPED: return 2;
+        case CRB_MECH_BROWNIAN: return 2;
+        case CRB_MECH_LANGEVIN: return 3;
+        case CRB_MECH_ROD: return 7;
+    }
+    return 0;
+}
+
+uint32_t crb_n_inter_params(uint32_t kind) {
+    switch (kind) {
+        case CRB_INT_CELL_SORTING:
+        case CRB_INT_CELL_SORTING_BENCH: return 3;
+        case CRB_INT_MORSE: return 4;
+        case CRB_INT_BOUND_LJ: return 4;
+        case CRB_INT_MIE: return 6;
+    }
+    return 0;
+}
+
+const char* crb_last_error(const crb_sim* sim) {
+    return sim ? sim->error.c_str() : g_create_error.c_str();
+}
+
+// get_decomp_res (cartesian_cuboid_n.rs:19-59)
+int crb_decomp_res(uint64_t n_voxel, uint64_t n_regions, uint64_t* n_out, uint64_t* m_out,
+                   uint64_t* avg_out) {
+    if (!n_regions) return CRB_ERR_DECOMPOSE;
+    long long average_len = (long long)std::ceil((double)n_voxel / (double)n_regions);
+    long long n = (long long)n_regions, m = 0;
+    for (uint64_t it = 0; it < n_regions; ++it) {
+        const long long residue = (long long)n_voxel - average_len * n - (average_len - 1) * m;
+        if (residue == 0) {
+            *n_out = (uint64_t)n;
+            *m_out = (uint64_t)m;
+            *avg_out = (uint64_t)average_len;
+            return 0;
+        }
+        if (residue > 0) {
+            if (n == (long long)n_regions) {
+                average_len += 1;
+                m = 0;
+            }
+        } else {
+            n -= 1;
+            m += 1;
+        }
+    }
+    return CRB_ERR_DECOMPOSE;
+}
+
+// CartesianCuboid::from_boundaries_and_interaction_range (cartesian_cuboid_n.rs:183-222)
+int crb_domain_from_interaction_range(uint32_t dim, const double* min, const double* max,
+                                      double interaction_range, uint64_t* n_voxels, double* dx) {
+    for (uint32_t i = 0; i < dim; ++i) {
+        if (min[i] >= max[i]) return CRB_ERR_BOUNDARY;
+        const double n = std::floor((max[i] - min[i]) / interaction_range);
+        if (!(n > -1.0 && n < 18446744073709551616.0)) return CRB_ERR_BOUNDARY;
+        const uint64_t m = n <= 0.0 ? 0 : (uint64_t)n;
+        n_voxels[i] = m > 1 ? m : 1;
+        dx[i] = (max[i] - min[i]) / n;
+    }
+    return 0;
+}
+
+// CartesianCuboid::from_boundaries_and_n_voxels (cartesian_cuboid_n.rs:226-256)
+int crb_domain_from_n_voxels(uint32_t dim, const double* min, const double* max,
+                             const uint64_t* n_voxels, double* dx) {
+    for (uint32_t i = 0; i < dim; ++i) {
+        if (min[i] >= max[i]) return CRB_ERR_BOUNDARY;
+        dx[i] = (max[i] - min[i]) / (double)n_voxels[i];
+    }
+    return 0;
+}
+
+int crb_create(const crb_config* cfg, crb_sim** out) {
+    if (!cfg || !out) return fail(nullptr, CRB_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != CRB_ABI_VERSION)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "abi_version mismatch");
+    if (cfg->dim != 2 && cfg->dim != 3)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "dim must be 2 or 3");
+    if (cfg->mechanics_kind > CRB_MECH_LANGEVIN)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "unsupported mechanics_kind for point agents");
+    if (cfg->interaction_kind > CRB_INT_MIE)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
+    if (cfg->solver_order > 2)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "solver_order must be 0, 1 or 2");
+    if (cfg->world_size != 1 || cfg->rank != 0)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "use crb_create with world_size 1 (slabs: crb_mgpu.h)");
+    if (!(cfg->dt > 0.0)) return fail(nullptr, CRB_ERR_INVALID_ARG, "dt must be positive");
+    const int D = (int)cfg->dim;
+    u64 nv = 1;
+    for (int i = 0; i < D; ++i) {
+        if (cfg->n_voxels[i] == 0 || !(cfg->domain_min[i] < cfg->domain_max[i]))
+            return fail(nullptr, CRB_ERR_BOUNDARY, "Min must be smaller than Max for domain boundaries");
+        nv *= cfg->n_voxels[i];
+    }
+    if (nv >= (1ull << 31)) return fail(nullptr, CRB_ERR_INVALID_ARG, "more than 2^31 voxels");
+    if (cfg->capacity == 0 || cfg->capacity >= (1ull << 32) - 1)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "capacity must be in [1, 2^32-2]");
+
+    crb_sim* s = new crb_sim();
+    s->cfg = *cfg;
+    s->D = D;
+    s->V = 1;
+    s->n_mp = (int)crb_n_mech_params(cfg->mechanics_kind);
+    s->n_ip = (int)crb_n_inter_params(cfg->interaction_kind);
+    s->cap = cfg->capacity;
+    Grid& g = s->g;
+    std::memset(&g, 0, sizeof(g));
+    g.D = D;
+    g.ng[0] = (int)cfg->n_voxels[0];
+    g.ng[1] = D == 3 ? (int)cfg->n_voxels[1] : 1;
+    g.ng[2] = (int)cfg->n_voxels[D - 1];
+    g.cax[0] = 0;
+    g.cax[1] = D == 3 ? 1 : -1;
+    g.cax[2] = D - 1;
+    g.L0 = g.ng[0];
+    g.p0 = 0;
+    g.own_lo = 0;
+    g.own_hi = g.ng[0];
+    for (int i = 0; i < D; ++i) {
+        g.mn[i] = cfg->domain_min[i];
+        g.mx[i] = cfg->domain_max[i];
+        g.dx[i] = cfg->dx[i];
+    }
+    const u64 nsub = cfg->ref_n_subdomains ? cfg->ref_n_subdomains : 1;
+    uint64_t sn, sm, savg;
+    if (crb_decomp_res(nv, nsub, &sn, &sm, &savg) != 0) {
+        delete s;
+        return fail(nullptr, CRB_ERR_DECOMPOSE, "DecomposeError: Could not find a suiting decomposition");
+    }
+    g.sm_n = sn;
+    g.sm_avg = savg;
+    g.sm_switch = sn * savg;
+    g.sm_nsub = nsub;
+    s->nvox = g.nvox_local();
+
+    auto bail = [&](int rc) {
+        g_create_error = s->error;
+        crb_destroy(s);
+        return rc;
+    };
+    cudaError_t e = cudaSetDevice((int)cfg->device);
+    if (e != cudaSuccess) {
+        s->error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return bail(CRB_ERR_CUDA);
+    }
+    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        s->error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        return bail(CRB_ERR_CUDA);
+    }
+    int rc;
+    if ((rc = alloc_state(s, s->X, true, true))) return bail(rc);
+    if ((rc = alloc_state(s, s->Y, true, true))) return bail(rc);
+    if ((rc = alloc_state(s, s->T, true, false))) return bail(rc);
+    s->n_tiles = (u32)((s->nvox + kScanTile - 1) / kScanTile);
+    if ((rc = dalloc(s, &s->key, s->cap)) || (rc = dalloc(s, &s->key_alt, s->cap)) ||
+        (rc = dalloc(s, &s->start, s->nvox + 1)) || (rc = dalloc(s, &s->start_alt, s->nvox + 1)) ||
+        (rc = dalloc(s, &s->count_new, s->nvox + 1)) || (rc = dalloc(s, &s->newkey, s->cap)) ||
+        (rc = dalloc(s, &s->rank_arb, s->cap)) || (rc = dalloc(s, &s->tmp_idx, s->cap)) ||
+        (rc = dalloc(s, &s->slot_of_src, s->cap)) || (rc = dalloc(s, &s->sortkey, s->cap)) ||
+        (rc = dalloc(s, &s->tile_sums, s->n_tiles + 1)) || (rc = dalloc(s, &s->stage, s->cap * 8)) ||
+        (rc = dalloc(s, &s->err, 4)) || (rc = dalloc(s, &s->scratch_u64, 16)))
+        return bail(rc);
+    e = cudaMallocHost((void**)&s->err_host, 4 * sizeof(int));
+    if (e != cudaSuccess) {
+        s->error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        return bail(CRB_ERR_CUDA);
+    }
+    cudaMemsetAsync(s->err, 0, 4 * sizeof(int), s->stream);
+    cudaMemsetAsync(s->start, 0, (s->nvox + 1) * sizeof(u32), s->stream);
+    e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        s->error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+        return bail(CRB_ERR_CUDA);
+    }
+    *out = s;
+    return 0;
+}
+
+void crb_destroy(crb_sim* s) {
+    if (!s) return;
+    cudaSetDevice((int)s->cfg.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    timers_resolve(s);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->err_host) cudaFreeHost(s->err_host);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+uint64_t crb_n_agents(const crb_sim* s) { return s ? s->n : 0; }
+uint64_t crb_iteration(const crb_sim* s) { return s ? s->iteration : 0; }
+uint64_t crb_kernel_launches(const crb_sim* s) { return s ? s->launches : 0; }
+
+int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
+                   const double* mech_params, const double* inter_params, const uint8_t* species,
+                   const uint64_t* ids) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (n > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
+    if (n && (!pos || !mech_params || !inter_params))
+        return fail(s, CRB_ERR_INVALID_ARG, "pos, mech_params and inter_params are required");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const int D = s->D;
+    // uniform-parameter fast path: all agents share one parameter row
+    s->uniform = true;
+    for (int k = 0; k < s->n_mp; ++k) s->uni.mp[k] = n ? mech_params[k] : 0.0;
+    for (int k = 0; k < s->n_ip; ++k) s->uni.ip[k] = n ? inter_params[k] : 0.0;
+    for (u64 i = 1; i < n && s->uniform; ++i) {
+        for (int k = 0; k < s->n_mp; ++k)
+            if (mech_params[i * s->n_mp + k] != s->uni.mp[k]) s->uniform = false;
+        for (int k = 0; k < s->n_ip; ++k)
+            if (inter_params[i * s->n_ip + k] != s->uni.ip[k]) s->uniform = false;
+    }
+    int rc;
+    if ((rc = upload_rows(s, pos, D, s->T.pos, n))) return rc;
+    if (vel && s->cfg.mechanics_kind != CRB_MECH_BROWNIAN) {
+        if ((rc = upload_rows(s, vel, D, s->T.vel, n))) return rc;
+    } else {
+        for (int d = 0; d < D; ++d)
+            CU(s, cudaMemsetAsync(s->T.vel[d], 0, n * sizeof(double), s->stream));
+    }
+    for (int d = 0; d < D; ++d) {
+        CU(s, cudaMemsetAsync(s->T.h1x[d], 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h1v[d], 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h0x[d], 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h0v[d], 0, n * sizeof(double), s->stream));
+    }
+    CU(s, cudaMemsetAsync(s->T.hlen, 0, n, s->stream));
+    if (!s->uniform) {
+        if ((rc = upload_rows(s, mech_params, s->n_mp, s->X.mp, n))) return rc;
+        if ((rc = upload_rows(s, inter_params, s->n_ip, s->X.ip, n))) return rc;
+    }
+    if (species)
+        CU(s, cudaMemcpyAsync(s->X.species, species, n, cudaMemcpyHostToDevice, s->stream));
+    else
+        CU(s, cudaMemsetAsync(s->X.species, 0, n, s->stream));
+    if (ids)
+        CU(s, cudaMemcpyAsync(s->X.id, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    else if (n) {
+        k_iota_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X.id, n);
+        s->launches++;
+    }
+    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    s->n = n;
+    KParams P = make_params(s);
+    if (n) {
+        if (D == 3)
+            k_ingest_keys<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(P);
+        else
+            k_ingest_keys<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(P);
+        s->launches++;
+    }
+    if ((rc = check_latch(s))) {
+        s->n = 0;
+        s->have_agents = false;
+        return rc;
+    }
+    if ((rc = sort_into_place(s, n, true, true))) return rc;
+    CU(s, cudaStreamSynchronize(s->stream));
+    s->have_agents = true;
+    s->aux_settable = true;
+    s->last_step_n = 0;
+    s->noise_cursor = 0;
+    return 0;
+}
+
+int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t* ids,
+                   uint64_t* voxel) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    int rc;
+    const u64 n = s->n;
+    if (pos) {
+        if ((rc = download_rows(s, pos, s->D, s->X.pos, n))) return rc;
+        CU(s, cudaStreamSynchronize(s->stream));
+    }
+    if (vel) {
+        if (s->cfg.mechanics_kind == CRB_MECH_BROWNIAN) {
+            std::memset(vel, 0, n * s->D * sizeof(double));
+        } else {
+            if ((rc = download_rows(s, vel, s->D, s->X.vel, n))) return rc;
+            CU(s, cudaStreamSynchronize(s->stream));
+        }
+    }
+    if (ids) CU(s, cudaMemcpyAsync(ids, s->X.id, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    if (voxel && n) {
+        const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
+        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key, (u64*)s->stage, base, n);
+        s->launches++;
+        CU(s, cudaMemcpyAsync(voxel, s->stage, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_params,
+                   uint8_t* species) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const u64 n = s->n;
+    int rc;
+    if (mech_params) {
+        if (s->uniform) {
+            for (u64 i = 0; i < n; ++i)
+                for (int k = 0; k < s->n_mp; ++k) mech_params[i * s->n_mp + k] = s->uni.mp[k];
+        } else {
+            if ((rc = download_rows(s, mech_params, s->n_mp, s->X.mp, n))) return rc;
+            CU(s, cudaStreamSynchronize(s->stream));
+        }
+    }
+    if (inter_params) {
+        if (s->uniform) {
+            for (u64 i = 0; i < n; ++i)
+                for (int k = 0; k < s->n_ip; ++k) inter_params[i * s->n_ip + k] = s->uni.ip[k];
+        } else {
+            if ((rc = download_rows(s, inter_params, s->n_ip, s->X.ip, n))) return rc;
+            CU(s, cudaStreamSynchronize(s->stream));
+        }
+    }
+    if (species)
+        CU(s, cudaMemcpyAsync(species, s->X.species, n, cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int crb_get_aux(crb_sim* s, uint64_t cap, double* hist_dx, double* hist_dv, uint32_t* hist_len) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const u64 n = s->n;
+    const int D = s->D;
+    std::vector<u8> hl(n);
+    CU(s, cudaMemcpyAsync(hl.data(), s->X.hlen, n, cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    int rc;
+    // rows of [h0 (older), h1 (newest)], re-packed oldest-first per agent below
+    std::vector<double> tmp(n * 2 * D);
+    for (int which = 0; which < 2; ++which) {
+        double* outp = which == 0 ? hist_dx : hist_dv;
+        if (!outp) continue;
+        const double* cols[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int d = 0; d < D; ++d) {
+            cols[d] = which == 0 ? s->X.h0x[d] : s->X.h0v[d];
+            cols[D + d] = which == 0 ? s->X.h1x[d] : s->X.h1v[d];
+        }
+        if ((rc = download_rows(s, tmp.data(), 2 * D, cols, n))) return rc;
+        CU(s, cudaStreamSynchronize(s->stream));
+        for (u64 i = 0; i < n; ++i) {
+            double* o = outp + i * 2 * D;
+            const double* t = tmp.data() + i * 2 * D;
+            for (int k = 0; k < 2 * D; ++k) o[k] = 0.0;
+            if (hl[i] == 2) {
+                for (int k = 0; k < 2 * D; ++k) o[k] = t[k];
+            } else if (hl[i] == 1) {
+                for (int d = 0; d < D; ++d) o[d] = t[D + d];
+            }
+        }
+    }
+    if (hist_len)
+        for (u64 i = 0; i < n; ++i) hist_len[i] = hl[i];
+    return 0;
+}
+
+namespace {
+__global__ void k_scatter_aux(State X, State T, const u32* __restrict__ slot, int D, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 d = slot[i];
+    for (int c = 0; c < D; ++c) {
+        X.h0x[c][d] = T.h0x[c][i];
+        X.h1x[c][d] = T.h1x[c][i];
+        X.h0v[c][d] = T.h0v[c][i];
+        X.h1v[c][d] = T.h1v[c][i];
+    }
+    X.hlen[d] = T.hlen[i];
+}
+}  // namespace
+
+int crb_set_aux(crb_sim* s, uint64_t n, const double* hist_dx, const double* hist_dv,
+                const uint32_t* hist_len) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->aux_settable || n != s->n)
+        return fail(s, CRB_ERR_STATE, "crb_set_aux must directly follow crb_set_agents with the same n");
+    if (!hist_dx || !hist_dv || !hist_len) return fail(s, CRB_ERR_INVALID_ARG, "null argument");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const int D = s->D;
+    const u32 N = s->cfg.solver_order;
+    // host rows are oldest-first; device keeps h1 = newest, h0 = older
+    std::vector<double> rx(n * 2 * D), rv(n * 2 * D);
+    std::vector<u8> hl(n);
+    for (u64 i = 0; i < n; ++i) {
+        const u32 len = std::min<u32>(hist_len[i], N);
+        hl[i] = (u8)len;
+        for (int d = 0; d < D; ++d) {
+            double o_x = 0, n_x = 0, o_v = 0, n_v = 0;
+            if (len == 2) {
+                o_x = hist_dx[(i * 2 + 0) * D + d];
+                n_x = hist_dx[(i * 2 + 1) * D + d];
+                o_v = hist_dv[(i * 2 + 0) * D + d];
+                n_v = hist_dv[(i * 2 + 1) * D + d];
+            } else if (len == 1) {
+                n_x = hist_dx[(i * 2 + 0) * D + d];
+                n_v = hist_dv[(i * 2 + 0) * D + d];
+            }
+            rx[i * 2 * D + d] = o_x;
+            rx[i * 2 * D + D + d] = n_x;
+            rv[i * 2 * D + d] = o_v;
+            rv[i * 2 * D + D + d] = n_v;
+        }
+    }
+    double* cx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double* cv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int d = 0; d < D; ++d) {
+        cx[d] = s->T.h0x[d];
+        cx[D + d] = s->T.h1x[d];
+        cv[d] = s->T.h0v[d];
+        cv[D + d] = s->T.h1v[d];
+    }
+    int rc;
+    if ((rc = upload_rows(s, rx.data(), 2 * D, cx, n))) return rc;
+    CU(s, cudaStreamSynchronize(s->stream));
+    if ((rc = upload_rows(s, rv.data(), 2 * D, cv, n))) return rc;
+    CU(s, cudaMemcpyAsync(s->T.hlen, hl.data(), n, cudaMemcpyHostToDevice, s->stream));
+    if (n) {
+        k_scatter_aux<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X, s->T, s->slot_of_src, D, n);
+        s->launches++;
+    }
+    CU(s, cudaStreamSynchronize(s->stream));
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
+int crb_set_noise(crb_sim* s, const double* z, uint64_t n_steps, uint64_t n_ids) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->cfg.noise_mode != CRB_NOISE_TABLE)
+        return fail(s, CRB_ERR_STATE, "crb_set_noise needs noise_mode == CRB_NOISE_TABLE");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const u64 count = n_steps * n_ids * s->D;
+    if (s->noise) {
+        cudaFree(s->noise);
+        s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)s->noise));
+        s->noise = nullptr;
+    }
+    int rc;
+    if ((rc = dalloc(s, &s->noise, count))) return rc;
+    CU(s, cudaMemcpyAsync(s->noise, z, count * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    s->noise_steps = n_steps;
+    s->noise_ids = n_ids;
+    s->noise_cursor = 0;
+    return 0;
+}
+
+int crb_step(crb_sim* s, uint64_t n_steps) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "crb_step before crb_set_agents");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const bool stochastic = s->cfg.noise_mode == CRB_NOISE_TABLE &&
+                            s->cfg.mechanics_kind != CRB_MECH_NEWTON_DAMPED;
+    s->aux_settable = false;
+    for (u64 it = 0; it < n_steps; ++it) {
+        if (stochastic && s->noise_cursor >= s->noise_steps)
+            return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
+        const bool last = it + 1 == n_steps;
+        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+        KParams P = make_params(s);
+        P.save_prev = last ? 1 : 0;
+        stage_begin(s, 0);
+        launch_force(s, P, false);
+        stage_end(s, 0, s->n ? 1 : 0);
+        CU(s, cudaGetLastError());
+        int rc;
+        s->last_step_n = s->n;
+        if ((rc = sort_into_place(s, s->n, last, false))) return rc;
+        s->iteration++;
+        s->noise_cursor++;
+    }
+    return check_latch(s);
+}
+
+int crb_sync(crb_sim* s) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    return check_latch(s);
+}
+
+int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
+    if (!s || !force) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    int rc;
+    if (!s->force_out)
+        if ((rc = dalloc(s, &s->force_out, s->cap * 3))) return rc;
+    KParams P = make_params(s);
+    launch_force(s, P, true);
+    s->launches += s->n ? 1 : 0;
+    CU(s, cudaGetLastError());
+    const double* cols[8] = {s->force_out, s->force_out + s->cap, s->force_out + 2 * s->cap, 0, 0, 0, 0, 0};
+    if ((rc = download_rows(s, force, s->D, cols, s->n))) return rc;
+    return check_latch(s);
+}
+
+int crb_get_migrations(crb_sim* s, uint64_t cap, uint64_t* ids, uint64_t* old_voxel,
+                       uint64_t* new_voxel, uint64_t* n_out) {
+    if (!s || !n_out) return CRB_ERR_INVALID_ARG;
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    *n_out = 0;
+    const u64 n = s->last_step_n;
+    if (!n) return 0;
+    // after the step the pre-step static fields (ids by old slot) live in Y
+    u64 *d_ids, *d_old, *d_new;
+    CU(s, cudaMalloc((void**)&d_ids, std::max<u64>(cap, 1) * 3 * sizeof(u64)));
+    d_old = d_ids + std::max<u64>(cap, 1);
+    d_new = d_old + std::max<u64>(cap, 1);
+    cudaMemsetAsync(s->scratch_u64, 0, sizeof(u64), s->stream);
+    k_collect_migrations<<<blocks_for(n, 256), 256, 0, s->stream>>>(
+        s->sortkey, s->newkey, s->Y.id, s->g, n, cap, d_ids, d_old, d_new, s->scratch_u64);
+    s->launches++;
+    u64 cnt = 0;
+    cudaMemcpyAsync(&cnt, s->scratch_u64, sizeof(u64), cudaMemcpyDeviceToHost, s->stream);
+    cudaStreamSynchronize(s->stream);
+    const u64 m = std::min<u64>(cnt, cap);
+    if (ids) cudaMemcpy(ids, d_ids, m * sizeof(u64), cudaMemcpyDeviceToHost);
+    if (old_voxel) cudaMemcpy(old_voxel, d_old, m * sizeof(u64), cudaMemcpyDeviceToHost);
+    if (new_voxel) cudaMemcpy(new_voxel, d_new, m * sizeof(u64), cudaMemcpyDeviceToHost);
+    cudaFree(d_ids);
+    *n_out = cnt;
+    CU(s, cudaGetLastError());
+    if (cnt > cap) return fail(s, CRB_ERR_CAPACITY, "migration buffers too small");
+    return 0;
+}
+
+int crb_get_voxel_counts(crb_sim* s, uint64_t cap, uint32_t* counts) {
+    if (!s || !counts) return CRB_ERR_INVALID_ARG;
+    const u64 plane = (u64)s->g.ng[1] * s->g.ng[2];
+    const u64 first = (u64)s->g.own_lo * plane, last = (u64)s->g.own_hi * plane;
+    if (cap < last - first) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    std::vector<u32> st(last - first + 1);
+    CU(s, cudaMemcpyAsync(st.data(), s->start + first, st.size() * sizeof(u32),
+                          cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    for (u64 v = 0; v + 1 < st.size(); ++v) counts[v] = st[v + 1] - st[v];
+    return 0;
+}
+
+int crb_count_candidate_pairs(crb_sim* s, uint64_t* n_pairs) {
+    if (!s || !n_pairs) return CRB_ERR_INVALID_ARG;
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    *n_pairs = 0;
+    if (!s->n) return 0;
+    CU(s, cudaMemsetAsync(s->scratch_u64, 0, sizeof(u64), s->stream));
+    KParams P = make_params(s);
+    k_count_pairs<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(P, s->scratch_u64);
+    s->launches++;
+    CU(s, cudaMemcpyAsync(n_pairs, s->scratch_u64, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
+int crb_enable_timers(crb_sim* s, int on) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    s->timers_on = on != 0;
+    return 0;
+}
+
+int crb_reset_timers(crb_sim* s) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    timers_resolve(s);
+    for (auto& t : s->timers) {
+        t.ms = 0;
+        t.launches = 0;
+    }
+    return 0;
+}
+
+int crb_stage_time_ms(crb_sim* s, uint32_t stage, double* ms, uint64_t* launches) {
+    if (!s || stage >= (uint32_t)kNumStages) return CRB_ERR_INVALID_ARG;
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    timers_resolve(s);
+    if (ms) *ms = s->timers[stage].ms;
+    if (launches) *launches = s->timers[stage].launches;
+    return 0;
+}
+
+}  // extern "C"

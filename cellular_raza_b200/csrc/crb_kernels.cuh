@@ -1,0 +1,731 @@
+// crb_kernels.cuh — device code of the mechanics/interaction step (sm_100a).
+//
+// Stages of one step:
+//   k_force_integrate  pair forces over the 3^D voxel neighbourhood (A5/A6), increment +
+//                      Adams-Bashforth/Euler update (A7/A8), reflective boundary (A9), new voxel
+//                      key + per-voxel histogram (A1/A10)             -> FP64-pipe bound
+//   k_scan_*           exclusive prefix scan of the histogram          -> HBM bound (tiny)
+//   k_fill, k_reorder  stable counting-sort scatter of the full state  -> HBM bound
+// Row labels (A1..A10) refer to SURVEY.md §8a; reference file:line are cited per function.
+#pragma once
+#include "crb_internal.cuh"
+
+namespace crb {
+
+constexpr int kForceThreads = 128;
+
+__device__ __forceinline__ void latch_error(int* err, int code, u64 id) {
+    if (atomicCAS(&err[1], 0, 1) == 0) {
+        err[0] = code;
+        *reinterpret_cast<u64*>(err + 2) = id;
+        __threadfence();
+    }
+}
+
+// A1: CartesianSubDomain::get_index_of (cartesian_cuboid_n.rs:469-490) for one axis.
+// IEEE subtraction + IEEE division + truncation (num-traits to_usize: Some iff -1 < q < 2^64).
+// Never a multiply by a reciprocal: the result must be bit-exact.
+__device__ __forceinline__ bool voxel_axis_index(double p, double mn, double dx, u64* idx) {
+    const double q = __ddiv_rn(__dsub_rn(p, mn), dx);
+    if (q > -1.0 && q < 18446744073709551616.0) {
+        *idx = q <= 0.0 ? 0ull : (u64)q;
+        return true;
+    }
+    return false;
+}
+
+// global plain index of a position, or false when chili's lookup would fail (to_usize None or
+// index not a key of voxel_index_to_plain_index): the agent then stays where it is
+// (chili/update_mechanics.rs:430-455 collects these errors and drops them).
+template <int D>
+__device__ __forceinline__ bool voxel_of(const Grid& g, const double* p, int* i0, int* i1,
+                                         int* i2) {
+    u64 a0, a1 = 0, a2;
+    if (!voxel_axis_index(p[0], g.mn[0], g.dx[0], &a0)) return false;
+    if (D == 3) {
+        if (!voxel_axis_index(p[1], g.mn[1], g.dx[1], &a1)) return false;
+    }
+    if (!voxel_axis_index(p[D - 1], g.mn[D - 1], g.dx[D - 1], &a2)) return false;
+    if (a0 >= (u64)g.ng[0] || a1 >= (u64)g.ng[1] || a2 >= (u64)g.ng[2]) return false;
+    *i0 = (int)a0;
+    *i1 = (int)a1;
+    *i2 = (int)a2;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A6: pair potentials.  Every potential of the closed model set returns
+//   f_own = z * coef,  f_ext = -f_own,   z = own_pos - ext_pos,
+// so one scalar `coef` per (own parameters, ext information, r^2) describes the pair.
+// Tolerance contract: 1e-12 relative on the accumulated force (BASELINE.json north_star), which is
+// why reciprocal square roots and multiplication chains replace the reference's
+// norm/normalize/powf sequence (SURVEY.md "hard parts").
+// ------------------------------------------------------------------------------------------------
+template <int INTER>
+struct Pot;
+
+// cellular_raza-examples/cell_sorting/src/main.rs:43-97; benchmark copy with the opposite sign
+// cellular_raza-benchmarks/src/cell_sorting.rs:34-88.
+template <bool BENCH>
+struct PotCellSorting {
+    static constexpr int NI = 3;
+    static constexpr bool kUsesSpecies = true;
+    double R, strength, range, rmin, inv_rmin;
+    __device__ __forceinline__ void init(const double* ip) {
+        R = ip[0];
+        strength = ip[1];
+        range = ip[2];
+        rmin = R * 0.3162277660168379;
+        inv_rmin = 1.0 / rmin;
+    }
+    __device__ __forceinline__ double coef(double r2, double ext_radius, bool same_species,
+                                           int* flag) const {
+        if (r2 == 0.0) return 0.0;  // own_pos == ext_pos -> zero force (:60-63)
+        const double rinv = rsqrt(r2);
+        const double r_true = r2 * rinv;
+        const bool clamp = r_true < rmin;  // (:51-52, 67-68): r is clamped, dir is not
+        const double r = clamp ? rmin : r_true;
+        const double rcinv = clamp ? inv_rmin : rinv;
+        const double Rs = R + ext_radius;
+        const double sinv = Rs * rcinv;  // 1 / sigma
+        const double bound = 4.0 + sinv;
+        const double s2 = sinv * sinv;
+        double val = s2 - s2 * s2;  // (1/sigma)^2 - (1/sigma)^4
+        val = fmax(fmin(val, bound), -bound);
+        double st = strength * val;
+        if (!same_species) st = fmin(st, 0.0);  // only the repelling part acts between species
+        // spatial_cutoff = (1 + signum(range*(R1+R2) - r)) / 2 ; signum(+0) = 1
+        const double cut = (range * Rs - r >= 0.0) ? 1.0 : 0.0;
+        const double c = st * cut * rinv;
+        return BENCH ? c : -c;
+    }
+};
+template <>
+struct Pot<CRB_INT_CELL_SORTING> : PotCellSorting<false> {};
+template <>
+struct Pot<CRB_INT_CELL_SORTING_BENCH> : PotCellSorting<true> {};
+
+// calculate_morse_interaction (interaction.rs:151-182)
+template <>
+struct Pot<CRB_INT_MORSE> {
+    static constexpr int NI = 4;
+    static constexpr bool kUsesSpecies = false;
+    double radius, a, cutoff, m2sa;
+    __device__ __forceinline__ void init(const double* ip) {
+        radius = ip[0];
+        a = ip[1];
+        cutoff = ip[2];
+        m2sa = -2.0 * ip[3] * ip[1];
+    }
+    __device__ __forceinline__ double coef(double r2, double ext_radius, bool, int*) const {
+        if (r2 == 0.0) return 0.0;
+        const double rinv = rsqrt(r2);
+        const double dist = r2 * rinv;
+        if (dist > cutoff) return 0.0;
+        const double e = exp(-a * (dist - (radius + ext_radius)));
+        return m2sa * e * (1.0 - e) * rinv;
+    }
+};
+
+// BoundLennardJones (interaction.rs:122-138); no r == 0 guard in the reference -> NaN
+template <>
+struct Pot<CRB_INT_BOUND_LJ> {
+    static constexpr int NI = 4;
+    static constexpr bool kUsesSpecies = false;
+    double eps4, sigma, bound, cutoff;
+    __device__ __forceinline__ void init(const double* ip) {
+        eps4 = 4.0 * ip[0];
+        sigma = ip[1];
+        bound = ip[2];
+        cutoff = ip[3];
+    }
+    __device__ __forceinline__ double coef(double r2, double, bool, int*) const {
+        if (r2 == 0.0) return __longlong_as_double(0x7ff8000000000000ll);
+        const double rinv = rsqrt(r2);
+        const double r = r2 * rinv;
+        const double x = sigma * rinv;
+        const double x2 = x * x;
+        const double x5 = x2 * x2 * x;
+        const double x11 = x5 * x5 * x;
+        const double val = eps4 * rinv * (12.0 * x11 - 6.0 * x5);
+        const double mx = bound * rinv;
+        const double q = cutoff >= r ? 1.0 : 0.0;
+        return -(q * fmin(mx, val)) * rinv;
+    }
+};
+
+// MiePotential (interaction.rs:345-389)
+template <>
+struct Pot<CRB_INT_MIE> {
+    static constexpr int NI = 6;
+    static constexpr bool kUsesSpecies = false;
+    double radius, strength, bound, cutoff, en, em, sig_factor, mie_c;
+    __device__ __forceinline__ void init(const double* ip) {
+        radius = ip[0];
+        strength = ip[1];
+        bound = ip[2];
+        cutoff = ip[3];
+        en = ip[4];
+        em = ip[5];
+        sig_factor = pow(em / en, 1.0 / (en - em));              // radius_to_sigma_factor()
+        mie_c = en / (en - em) * pow(en / em, em / (en - em));  // mie_constant
+    }
+    __device__ __forceinline__ double coef(double r2, double ext_radius, bool, int* flag) const {
+        if (r2 == 0.0) {
+            *flag = 1;  // CalcError: identical position for two objects
+            return 0.0;
+        }
+        const double rinv = rsqrt(r2);
+        const double r = r2 * rinv;
+        if (r > cutoff) return 0.0;
+        const double sigma = sig_factor * (radius + ext_radius);
+        const double x = sigma * rinv;
+        const double pp = en / sigma * pow(x, en + 1.0) - em / sigma * pow(x, em + 1.0);
+        const double force = fmin(mie_c * strength * pp, bound);
+        return force * rinv;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// A8 helper formulas with the reference's operation order, no fma
+// (chili/solvers.rs:303-347; Xapy = self * a + y, concepts/src/reactions.rs:72-82)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xapy(double x, double a, double y) {
+    return __dadd_rn(__dmul_rn(x, a), y);
+}
+__device__ __forceinline__ double helper_euler(double x, double dx, double dt, double dr) {
+    return xapy(xapy(dx, dt, x), 1.0, __dmul_rn(dr, dt));
+}
+__device__ __forceinline__ double helper_ab2(double x, double dx0, double dx1, double dt,
+                                             double dr) {
+    return xapy(xapy(xapy(dx0, 1.5, __dmul_rn(dx1, -0.5)), dt, x), 1.0, __dmul_rn(dr, dt));
+}
+__device__ __forceinline__ double helper_ab3(double x, double dx0, double dx1, double dx2,
+                                             double dt, double dr) {
+    const double f0 = 23.0 / 12.0, f1 = -16.0 / 12.0, f2 = 5.0 / 12.0;
+    return xapy(xapy(xapy(dx0, f0, xapy(dx1, f1, __dmul_rn(dx2, f2))), dt, x), 1.0,
+                __dmul_rn(dr, dt));
+}
+
+// counter-based standard normal numbers for CRB_NOISE_PHILOX: Philox4x32-10 keyed by the seed,
+// counter = (agent id, iteration); Box-Muller on the four words.
+__device__ __forceinline__ void philox_round(u32& c0, u32& c1, u32& c2, u32& c3, u32 k0, u32 k1) {
+    const u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const u32 n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+}
+__device__ __forceinline__ void philox_normal4(u64 seed, u64 id, u64 iter, u32 stream,
+                                               double* z) {
+    u32 c0 = (u32)id, c1 = (u32)(id >> 32), c2 = (u32)iter, c3 = (u32)(iter >> 32) ^ (stream << 24);
+    u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    // two Box-Muller pairs from 4 x 32 random bits (32-bit uniforms in (0,1])
+    const double u0 = ((double)c0 + 1.0) * (1.0 / 4294967296.0);
+    const double u1 = ((double)c1 + 0.5) * (1.0 / 4294967296.0);
+    const double u2 = ((double)c2 + 1.0) * (1.0 / 4294967296.0);
+    const double u3 = ((double)c3 + 0.5) * (1.0 / 4294967296.0);
+    const double ra = sqrt(-2.0 * log(u0)), rb = sqrt(-2.0 * log(u2));
+    double s, c;
+    sincospi(2.0 * u1, &s, &c);
+    z[0] = ra * c;
+    z[1] = ra * s;
+    sincospi(2.0 * u3, &s, &c);
+    z[2] = rb * c;
+    z[3] = rb * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// force + integrate + boundary + new key, one thread per agent of A (sorted by voxel).
+//
+// Pair weights (SURVEY.md finding 2; chili/update_mechanics.rs:186-234, 285-382): agent i always
+// receives 1/2 f_own(own = i, ext = j).  The other half, f_ext(own = j, ext = i), reaches i when j
+// is in the same voxel, in another chili subdomain, or always in PHYSICAL mode.  Because chili's
+// subdomains are contiguous plain-index chunks and agents are sorted by plain index, "same
+// voxel" and "same subdomain" are index-range tests on j.
+// ------------------------------------------------------------------------------------------------
+template <int D, int INTER, bool UNIFORM, bool FORCE_ONLY>
+__global__ void __launch_bounds__(kForceThreads)
+    k_force_integrate(const KParams P, const u64 first, const u64 count) {
+    const u64 t = (u64)blockIdx.x * kForceThreads + threadIdx.x;
+    if (t >= count) return;
+    const u64 i = first + t;
+    const Grid& g = P.g;
+    const int n1 = g.ng[1], n2 = g.ng[2];
+
+    double xi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) xi[c] = P.A.pos[c][i];
+    double ipi[CRB_MAX_INTER_PARAMS];
+#pragma unroll
+    for (int k = 0; k < Pot<INTER>::NI; ++k) ipi[k] = UNIFORM ? P.u.ip[k] : P.A.ip[k][i];
+    Pot<INTER> own;
+    own.init(ipi);
+    const u8 spi = Pot<INTER>::kUsesSpecies ? P.A.species[i] : 0;
+
+    const u32 v = P.key[i];
+    const int i2 = (int)(v % (u32)n2);
+    const u32 tq = v / (u32)n2;
+    const int i1 = (int)(tq % (u32)n1);
+    const int i0 = (int)(tq / (u32)n1);  // local plane
+
+    const u32 own_lo = P.start[v], own_hi = P.start[v + 1];
+    u32 sub_lo = 0, sub_hi = 0;  // agents of i's chili subdomain (empty range => all weights 1)
+    if (P.weight_mode == CRB_WEIGHT_CHILI) {
+        const u64 plane = (u64)n1 * n2;
+        const u64 gp = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
+        const u64 s = g.sub_of(gp);
+        const u64 base = (u64)g.p0 * plane, nloc = g.nvox_local();
+        u64 f = g.sub_first_voxel(s), l = g.sub_first_voxel(s + 1);
+        f = f < base ? 0 : (f - base > nloc ? nloc : f - base);
+        l = l < base ? 0 : (l - base > nloc ? nloc : l - base);
+        sub_lo = P.start[f];
+        sub_hi = P.start[l];
+    }
+
+    double acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.0;
+    int calc_flag = 0;
+
+    const int z_lo = i2 > 0 ? i2 - 1 : 0;
+    const int z_hi = i2 + 1 < n2 ? i2 + 1 : n2 - 1;
+    for (int d0 = -1; d0 <= 1; ++d0) {
+        const int X = i0 + d0;
+        if (X < 0 || X >= g.L0) continue;
+        for (int d1 = -1; d1 <= 1; ++d1) {
+            const int Y = i1 + d1;
+            if (Y < 0 || Y >= n1) continue;
+            const u32 row = ((u32)X * (u32)n1 + (u32)Y) * (u32)n2;
+            const u32 jb = P.start[row + z_lo], je = P.start[row + z_hi + 1];
+            for (u32 j = jb; j < je; ++j) {
+                double z[D];
+                double r2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    z[c] = xi[c] - __ldg(&P.A.pos[c][j]);
+                    r2 = fma(z[c], z[c], r2);
+                }
+                if (j == (u32)i) continue;
+                const bool same_voxel = (j >= own_lo) & (j < own_hi);
+                const bool same_sub = (j >= sub_lo) & (j < sub_hi);
+                const bool keep = same_voxel | !same_sub;  // second half reaches i
+                const u8 spj = Pot<INTER>::kUsesSpecies ? __ldg(&P.A.species[j]) : 0;
+                double cf;
+                if (UNIFORM) {
+                    const double ext_radius = ipi[0];
+                    cf = own.coef(r2, ext_radius, spi == spj, &calc_flag);
+                    cf = keep ? cf : 0.5 * cf;
+                } else {
+                    double ipj[CRB_MAX_INTER_PARAMS];
+#pragma unroll
+                    for (int k = 0; k < Pot<INTER>::NI; ++k) ipj[k] = __ldg(&P.A.ip[k][j]);
+                    const double ci = own.coef(r2, ipj[0], spi == spj, &calc_flag);
+                    cf = 0.5 * ci;
+                    if (keep) {
+                        Pot<INTER> other;
+                        other.init(ipj);
+                        cf += 0.5 * other.coef(r2, ipi[0], spi == spj, &calc_flag);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[c] = fma(z[c], cf, acc[c]);
+            }
+        }
+    }
+    if (calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
+
+    if constexpr (FORCE_ONLY) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
+    } else {
+    // ---- A7: Mechanics::calculate_increment / get_random_contribution ---------------------------
+    double mp[CRB_MAX_MECH_PARAMS];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mp[k] = UNIFORM ? P.u.mp[k] : (P.A.mp[k] ? P.A.mp[k][i] : 0.0);
+    double vel[D], dxv[D], dvv[D], rx[D], rv[D];
+    const bool brownian = P.mech == CRB_MECH_BROWNIAN;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        vel[c] = brownian ? 0.0 : P.A.vel[c][i];  // Brownian::velocity() == 0 (mechanics.rs:371-378)
+        rx[c] = 0.0;
+        rv[c] = 0.0;
+    }
+    if (P.mech == CRB_MECH_NEWTON_DAMPED) {  // mechanics.rs:165-172
+        const double damping = mp[0], mass = mp[1];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            dxv[c] = vel[c];
+            dvv[c] = __dsub_rn(__ddiv_rn(acc[c], mass), __dmul_rn(damping, vel[c]));
+        }
+    } else if (brownian) {  // mechanics.rs:349-356
+        const double f = __ddiv_rn(mp[0], mp[1]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            dxv[c] = __dmul_rn(f, acc[c]);
+            dvv[c] = 0.0;
+        }
+    } else {  // Langevin, mechanics.rs:450-462
+        const double mass = mp[0], damping = mp[1];
+        const double minv = __ddiv_rn(1.0, mass);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            dxv[c] = vel[c];
+            dvv[c] = __dadd_rn(__dmul_rn(minv, acc[c]), __dmul_rn(-damping, vel[c]));
+        }
+    }
+    if (P.noise_mode != CRB_NOISE_NONE && P.mech != CRB_MECH_NEWTON_DAMPED) {
+        // wiener_process (mechanics.rs:211-226): (mean + std_dev * z) / dt with mean = 0
+        double zn[4];
+        const u64 id = P.A.id[i];
+        if (P.noise_mode == CRB_NOISE_TABLE) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) zn[c] = P.noise[(P.noise_cursor * P.noise_ids + id) * D + c];
+        } else {
+            philox_normal4(P.seed, id, P.iteration, 0, zn);
+        }
+        const double sd = sqrt(P.dt);
+        double scale;
+        if (brownian)
+            scale = sqrt(__dmul_rn(2.0, mp[0]));
+        else
+            scale = sqrt(__ddiv_rn(__dmul_rn(__dmul_rn(2.0, mp[1]), mp[2]), mp[0]));
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double w = __ddiv_rn(__dadd_rn(0.0, __dmul_rn(sd, zn[c])), P.dt);
+            if (brownian)
+                rx[c] = __dmul_rn(scale, w);
+            else
+                rv[c] = __dmul_rn(scale, w);
+        }
+    }
+
+    // ---- A8: local_mechanics_update (chili/solvers.rs:156-300) -----------------------------------
+    const int N = P.order;
+    const int hlen = P.A.hlen[i];
+    const int n_prev = N == 0 ? 0 : (hlen + 1 < N ? hlen + 1 : N);  // ring size AFTER the push
+    double p_new[D], v_new[D], oldx[D], oldv[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        oldx[c] = P.A.h1x[c][i];
+        oldv[c] = P.A.h1v[c][i];
+        if (N == 2 && n_prev == 2) {
+            // ring = [previous, current] oldest first; dx = [current, ring[0], ring[1]]
+            p_new[c] = helper_ab3(xi[c], dxv[c], oldx[c], dxv[c], P.dt, rx[c]);
+            v_new[c] = helper_ab3(vel[c], dvv[c], oldv[c], dvv[c], P.dt, rv[c]);
+        } else if (n_prev == 1) {
+            // ring = [current]; dx = [current, current]
+            p_new[c] = helper_ab2(xi[c], dxv[c], dxv[c], P.dt, rx[c]);
+            v_new[c] = helper_ab2(vel[c], dvv[c], dvv[c], P.dt, rv[c]);
+        } else {
+            p_new[c] = helper_euler(xi[c], dxv[c], P.dt, rx[c]);
+            v_new[c] = helper_euler(vel[c], dvv[c], P.dt, rv[c]);
+        }
+    }
+
+    // ---- A9: CartesianSubDomain::apply_boundary (cartesian_cuboid_n.rs:594-631) ------------------
+    bool outside = false;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        double p = p_new[c], w = brownian ? 0.0 : v_new[c];
+        if (p < g.mn[c]) {
+            p = __dsub_rn(__dmul_rn(2.0, g.mn[c]), p);
+            w = fabs(w);
+        }
+        if (p > g.mx[c]) {
+            p = __dsub_rn(__dmul_rn(2.0, g.mx[c]), p);
+            w = -fabs(w);
+        }
+        outside |= (p < g.mn[c]) | (p > g.mx[c]);
+        p_new[c] = p;
+        v_new[c] = w;
+    }
+    if (outside) latch_error(P.err, CRB_ERR_BOUNDARY, P.A.id[i]);
+
+    // ---- A1/A10: new voxel, migration flag, histogram --------------------------------------------
+    int q0, q1, q2;
+    u32 nk = v;
+    if (voxel_of<D>(g, p_new, &q0, &q1, &q2)) {
+        const int l0 = q0 - g.p0;
+        if (l0 >= 0 && l0 < g.L0) nk = ((u32)l0 * (u32)n1 + (u32)q1) * (u32)n2 + (u32)q2;
+        // (a target plane outside the local planes cannot happen on one device; the multi-GPU
+        //  path handles it before this point is reached)
+    }
+    const u64 gp_old = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
+    u64 rank_old = i - own_lo;
+    if (rank_old > CRB_SK_RANK_MASK) rank_old = CRB_SK_RANK_MASK;
+    P.sortkey[i] = (nk != v ? CRB_SK_MOVED : 0ull) | (gp_old << CRB_SK_RANK_BITS) | rank_old;
+    P.newkey[i] = nk;
+    P.rank_arb[i] = atomicAdd(&P.count_new[nk], 1u);
+
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        P.B.pos[c][i] = p_new[c];
+        P.B.vel[c][i] = v_new[c];
+        P.B.h1x[c][i] = N >= 1 ? dxv[c] : oldx[c];
+        P.B.h1v[c][i] = N >= 1 ? dvv[c] : oldv[c];
+        if (P.save_prev) {
+            P.B.h0x[c][i] = oldx[c];
+            P.B.h0v[c][i] = oldv[c];
+        }
+    }
+    P.B.hlen[i] = (u8)n_prev;
+    }  // !FORCE_ONLY
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of count_new[0..n) -> start_new[0..n], start_new[n] = total.
+// three passes: per-block scan (4096 items), scan of block sums (one block), add.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 x, u32* total) {
+    __shared__ u32 warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        u32 w = warp_sums[lane];
+        u32 wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        warp_sums[lane] = wi - w;  // exclusive warp offsets
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    const u32 r = incl - x + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_scan_tiles(const u32* __restrict__ in, u32* __restrict__ out, u32* __restrict__ tile_sums,
+                 u64 n) {
+    __shared__ u32 tot;
+    const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+    u32 v[kScanItems];
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        s += v[k];
+    }
+    u32 off = block_exclusive_scan(s, &tot);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_scan_sums(u32* __restrict__ tile_sums, u32 n_tiles, u32* __restrict__ grand_total) {
+    __shared__ u32 tot;
+    u32 carry = 0;
+    for (u32 base = 0; base < n_tiles; base += kScanThreads) {
+        const u32 idx = base + threadIdx.x;
+        const u32 x = idx < n_tiles ? tile_sums[idx] : 0u;
+        const u32 off = block_exclusive_scan(x, &tot);
+        if (idx < n_tiles) tile_sums[idx] = off + carry;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_scan_add(u32* __restrict__ out, const u32* __restrict__ tile_sums, u64 n) {
+    const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+    const u32 add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A10: stable counting-sort scatter.  k_fill places every agent at an arbitrary slot of its new
+// voxel's segment; k_reorder computes the stable rank inside the segment from the sortkeys and
+// moves the whole state B (dynamic fields) + A (static fields) -> Y.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill(const u32* __restrict__ newkey, const u32* __restrict__ rank_arb,
+                       const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tmp_idx[start_new[newkey[i]] + rank_arb[i]] = (u32)i;
+}
+
+struct ReorderParams {
+    State A, B, Y;
+    const u32* newkey;
+    const u32* start_new;
+    const u32* tmp_idx;
+    const u64* sortkey;
+    u32* key_out;
+    u32* slot_of_src;  // optional: destination slot of every source index (ingestion only)
+    u64 n;
+    int D, V;
+    int n_mp, n_ip;  // per-agent parameter columns to move (0 when uniform)
+    int save_prev;
+    int has_species;
+};
+
+__global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= R.n) return;
+    const u32 i = R.tmp_idx[p];
+    const u32 v = R.newkey[i];
+    const u32 sb = R.start_new[v], se = R.start_new[v + 1];
+    const u64 my = R.sortkey[i];
+    u32 rank = 0;
+    for (u32 q = sb; q < se; ++q) rank += (R.sortkey[R.tmp_idx[q]] < my) ? 1u : 0u;
+    const u64 d = (u64)sb + rank;
+    R.key_out[d] = v;
+    if (R.slot_of_src) R.slot_of_src[i] = (u32)d;
+    for (int c = 0; c < R.D; ++c) {
+        R.Y.pos[c][d] = R.B.pos[c][i];
+        R.Y.vel[c][d] = R.B.vel[c][i];
+        R.Y.h1x[c][d] = R.B.h1x[c][i];
+        R.Y.h1v[c][d] = R.B.h1v[c][i];
+        if (R.save_prev) {
+            R.Y.h0x[c][d] = R.B.h0x[c][i];
+            R.Y.h0v[c][d] = R.B.h0v[c][i];
+        }
+    }
+    R.Y.hlen[d] = R.B.hlen[i];
+    R.Y.id[d] = R.A.id[i];
+    if (R.has_species) R.Y.species[d] = R.A.species[i];
+    for (int k = 0; k < R.n_mp; ++k) R.Y.mp[k][d] = R.A.mp[k][i];
+    for (int k = 0; k < R.n_ip; ++k) R.Y.ip[k][d] = R.A.ip[k][i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingestion (crb_set_agents): agent-major host rows -> SoA columns, setup-time voxel index
+// (CartesianCuboid::get_voxel_index_of_raw, cartesian_cuboid_n.rs:320-337)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_unpack_rows(const double* __restrict__ rows, int width, double* c0, double* c1, double* c2, double* c3, double* c4,
+                              double* c5, double* c6, double* c7, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* cols[8] = {c0, c1, c2, c3, c4, c5, c6, c7};
+    for (int k = 0; k < width; ++k)
+        if (cols[k]) cols[k][i] = rows[i * width + k];
+}
+
+__global__ void k_pack_rows(double* __restrict__ rows, int width, const double* c0,
+                            const double* c1, const double* c2, const double* c3,
+                            const double* c4, const double* c5, const double* c6,
+                            const double* c7, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* cols[8] = {c0, c1, c2, c3, c4, c5, c6, c7};
+    for (int k = 0; k < width; ++k) rows[i * width + k] = cols[k] ? cols[k][i] : 0.0;
+}
+
+template <int D>
+__global__ void k_ingest_keys(const KParams P) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const Grid& g = P.g;
+    double p[D];
+    bool below = false;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        p[c] = P.B.pos[c][i];
+        below |= (g.mn[c] >= p[c]);  // check_min_max(min, pos) (:149-162, 321)
+    }
+    int q0 = 0, q1 = 0, q2 = 0;
+    u32 nk = 0;
+    if (below || !(p[0] == p[0])) {
+        latch_error(P.err, CRB_ERR_BOUNDARY, i);
+    } else if (!voxel_of<D>(g, p, &q0, &q1, &q2)) {
+        latch_error(P.err, CRB_ERR_INDEX, i);
+    } else {
+        const int l0 = q0 - g.p0;
+        if (l0 < g.own_lo || l0 >= g.own_hi)
+            latch_error(P.err, CRB_ERR_INDEX, i);  // not in this device's slab
+        else
+            nk = ((u32)l0 * (u32)g.ng[1] + (u32)q1) * (u32)g.ng[2] + (u32)q2;
+    }
+    P.newkey[i] = nk;
+    P.sortkey[i] = i;  // input order inside a voxel (chili/datastructures.rs:278-299)
+    P.rank_arb[i] = atomicAdd(&P.count_new[nk], 1u);
+}
+
+// ordered candidate pairs of the current state
+__global__ void k_count_pairs(const KParams P, u64* out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 c = 0;
+    if (i < P.n) {
+        const Grid& g = P.g;
+        const int n1 = g.ng[1], n2 = g.ng[2];
+        const u32 v = P.key[i];
+        const int i2 = (int)(v % (u32)n2);
+        const u32 tq = v / (u32)n2;
+        const int i1 = (int)(tq % (u32)n1), i0 = (int)(tq / (u32)n1);
+        const int z_lo = i2 > 0 ? i2 - 1 : 0, z_hi = i2 + 1 < n2 ? i2 + 1 : n2 - 1;
+        for (int d0 = -1; d0 <= 1; ++d0) {
+            const int X = i0 + d0;
+            if (X < 0 || X >= g.L0) continue;
+            for (int d1 = -1; d1 <= 1; ++d1) {
+                const int Y = i1 + d1;
+                if (Y < 0 || Y >= n1) continue;
+                const u32 row = ((u32)X * (u32)n1 + (u32)Y) * (u32)n2;
+                c += P.start[row + z_hi + 1] - P.start[row + z_lo];
+            }
+        }
+        c -= 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// migration tap: (id, old plain, new plain) of every agent flagged as moved in the last step
+__global__ void k_collect_migrations(const u64* __restrict__ sortkey, const u32* __restrict__ newkey,
+                                     const u64* __restrict__ id_old, Grid g, u64 n, u64 cap,
+                                     u64* ids, u64* oldv, u64* newv, u64* counter) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 sk = sortkey[i];
+    if (!(sk & CRB_SK_MOVED)) return;
+    const u64 slot = atomicAdd(counter, 1ull);
+    if (slot >= cap) return;
+    ids[slot] = id_old[i];
+    oldv[slot] = (sk & ~CRB_SK_MOVED) >> CRB_SK_RANK_BITS;
+    newv[slot] = (u64)newkey[i] + (u64)g.p0 * g.ng[1] * g.ng[2];
+}
+
+__global__ void k_iota_u64(u64* a, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+__global__ void k_fill_f64(double* a, double v, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+__global__ void k_global_keys(const u32* key, u64* out, u64 base, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u64)key[i] + base;
+}
+
+}  // namespace crb

@@ -1,0 +1,174 @@
+"""Synthetic populations of the BASELINE.json configurations.
+
+The reference seeds its examples with ChaCha8 (cellular_raza-examples/cell_sorting/src/main.rs:113-124),
+a stream that cannot be reproduced here; positions therefore come from numpy's PCG64 with a fixed
+seed and are handed to the oracle and to the device alike.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from .device import make_config
+
+
+@dataclass
+class Workload:
+    name: str
+    cfg_kwargs: dict
+    pos: np.ndarray
+    vel: np.ndarray
+    mech_params: np.ndarray
+    inter_params: np.ndarray
+    species: np.ndarray | None = None
+    noise_steps: int = 0
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def n(self) -> int:
+        return self.pos.shape[0]
+
+    def config(self, **overrides):
+        kw = dict(self.cfg_kwargs)
+        kw.update(overrides)
+        kw.setdefault("capacity", max(self.n, 1))
+        return make_config(**kw)
+
+
+def _domain_from_interaction_range(mn, mx, rng):
+    """CartesianCuboid::from_boundaries_and_interaction_range (cartesian_cuboid_n.rs:183-222)."""
+    mn = np.asarray(mn, dtype=np.float64)
+    mx = np.asarray(mx, dtype=np.float64)
+    n = np.floor((mx - mn) / rng)
+    nv = np.maximum(n.astype(np.uint64), 1)
+    with np.errstate(divide="ignore"):
+        dx = (mx - mn) / n
+    return nv, dx
+
+
+def _uniform_positions(rng, n, dim, lo, hi):
+    pos = rng.uniform(lo, hi, size=(n, dim))
+    # check_min_max(min, pos) rejects pos <= min at setup (cartesian_cuboid_n.rs:149-162, 321)
+    tiny = np.nextafter(lo, hi)
+    np.maximum(pos, tiny, out=pos)
+    return pos
+
+
+def cell_sorting(
+    n_cells: int = 1600,
+    domain_size: float = 110.0,
+    *,
+    seed: int = 1,
+    dim: int = 3,
+    dt: float = 0.2,
+    n_threads: int = 4,
+    bench_sign: bool = False,
+    pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI,
+    solver_order: int = 2,
+) -> Workload:
+    """cellular_raza-examples/cell_sorting as shipped (src/main.rs:9-24, 113-170): NewtonDamped3D
+    (damping 2, mass 1) + species potential (R 6, strength 2, range 1.5); voxels from
+    interaction range 18.  ``n <= N_CELLS_1`` are BlueCell => one more blue than red (:132)."""
+    rng = np.random.default_rng(seed)
+    pos = _uniform_positions(rng, n_cells, dim, 0.0, domain_size)
+    vel = np.zeros((n_cells, dim))
+    half = n_cells // 2
+    species = (np.arange(n_cells) <= half).astype(np.uint8)  # 1 = BlueCell, 0 = RedCell
+    mn = [0.0] * dim
+    mx = [domain_size] * dim
+    nv, dx = _domain_from_interaction_range(mn, mx, 1.5 * 6.0 * 2.0)
+    cfg = dict(
+        dim=dim,
+        mechanics_kind=_abi.CRB_MECH_NEWTON_DAMPED,
+        interaction_kind=_abi.CRB_INT_CELL_SORTING_BENCH if bench_sign else _abi.CRB_INT_CELL_SORTING,
+        domain_min=mn,
+        domain_max=mx,
+        n_voxels=nv,
+        dx=dx,
+        dt=dt,
+        solver_order=solver_order,
+        pair_weight_mode=pair_weight_mode,
+        ref_n_subdomains=n_threads,
+    )
+    return Workload(
+        name=f"cell_sorting_{dim}d_{n_cells}",
+        cfg_kwargs=cfg,
+        pos=pos,
+        vel=vel,
+        mech_params=np.tile([2.0, 1.0], (n_cells, 1)),
+        inter_params=np.tile([6.0, 2.0, 1.5], (n_cells, 1)),
+        species=species,
+    )
+
+
+def cell_sorting_scaled(n_cells: int, density_per_voxel: float = 7.1, **kw) -> Workload:
+    """cell_sorting at constant density: L is a multiple of the 18-unit voxel edge (SURVEY.md §8d:
+    C2 = 1 M cells in L = 936 = 52 * 18 => rho ~ 7.1; the benchmark rule of
+    cellular_raza-benchmarks/src/cell_sorting.rs:280-285 is rho ~ 2.5)."""
+    dim = kw.get("dim", 3)
+    n_side = max(int(round((n_cells / density_per_voxel) ** (1.0 / dim))), 1)
+    return cell_sorting(n_cells, 18.0 * n_side, **kw)
+
+
+def brownian_morse(
+    n_cells: int,
+    domain_size: float,
+    *,
+    seed: int = 2,
+    dim: int = 3,
+    dt: float = 0.01,
+    n_threads: int = 1,
+    noise_mode: int = _abi.CRB_NOISE_TABLE,
+    noise_steps: int = 0,
+    pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI,
+    solver_order: int = 2,
+    langevin: bool = False,
+) -> Workload:
+    """C3: Brownian3D{D 0.3, kT 0.3} (cell_sorting/src/main-brownian.rs:115-116) +
+    MorsePotential{radius 3, stiffness 0.5, strength 0.01} (tests/determinism_mechanics_interaction.rs:84-89)
+    with cutoff = voxel edge = 12."""
+    rng = np.random.default_rng(seed)
+    pos = _uniform_positions(rng, n_cells, dim, 0.0, domain_size)
+    if langevin:
+        vel = rng.normal(0.0, 0.1, size=(n_cells, dim))
+        mech = np.tile([1.0, 0.5, 0.3], (n_cells, 1))  # mass, damping, kT
+        kind = _abi.CRB_MECH_LANGEVIN
+    else:
+        vel = np.zeros((n_cells, dim))
+        mech = np.tile([0.3, 0.3], (n_cells, 1))
+        kind = _abi.CRB_MECH_BROWNIAN
+    mn = [0.0] * dim
+    mx = [domain_size] * dim
+    nv, dx = _domain_from_interaction_range(mn, mx, 12.0)
+    cfg = dict(
+        dim=dim,
+        mechanics_kind=kind,
+        interaction_kind=_abi.CRB_INT_MORSE,
+        domain_min=mn,
+        domain_max=mx,
+        n_voxels=nv,
+        dx=dx,
+        dt=dt,
+        solver_order=solver_order,
+        pair_weight_mode=pair_weight_mode,
+        ref_n_subdomains=n_threads,
+        noise_mode=noise_mode,
+        rng_seed=seed,
+    )
+    return Workload(
+        name=f"{'langevin' if langevin else 'brownian'}_morse_{dim}d_{n_cells}",
+        cfg_kwargs=cfg,
+        pos=pos,
+        vel=vel,
+        mech_params=mech,
+        inter_params=np.tile([3.0, 0.5, 12.0, 0.01], (n_cells, 1)),
+        species=None,
+        noise_steps=noise_steps,
+    )
+
+
+def noise_table(n_steps: int, n_ids: int, dim: int, seed: int = 7) -> np.ndarray:
+    """Standard-normal table z[step][agent id][d] fed to oracle and device alike."""
+    return np.random.default_rng(seed).standard_normal((n_steps, n_ids, dim))

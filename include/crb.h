@@ -1,0 +1,222 @@
+/*
+ * crb.h — C ABI of the B200-native mechanics/interaction backend for cellular_raza.
+ *
+ * This header is the drop-in boundary.  It plays the role that
+ *   cellular_raza-core/src/backend/cara/mod.rs:5-62   (#[repr(C)] Runner + extern "C" block)
+ * plays for the placeholder CUDA backend of the reference: a Rust host crate that sits beside
+ * `chili` binds exactly these symbols (see INTEGRATION.md for the `extern "C"` block and the
+ * `build.rs`), and the generated main loop of
+ *   cellular_raza-core-proc-macro/src/run_sim.rs:380-403
+ * is replaced by `crb_step` between save events and `crb_get_agents` at PartialSave iterations.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - every host pointer is borrowed for the duration of the call; outputs are written into
+ *    caller-allocated buffers.  All device memory is owned by the opaque handle.
+ *  - return value 0 on success, a negative crb_status otherwise (mirrors the SimulationError
+ *    variants used on this path, cellular_raza-core/src/backend/chili/errors.rs:73-121);
+ *    `crb_last_error` returns a human readable message for the last failure on that handle.
+ *  - a handle is NOT thread-safe (one host thread per handle, one handle per GPU).
+ *  - vectors are stored agent-major: pos[i*dim + d].
+ */
+#ifndef CRB_H
+#define CRB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+typedef enum crb_status {
+    CRB_OK = 0,
+    CRB_ERR_CALC = -1,        /* CalcError     (e.g. Mie potential at r == 0, interaction.rs:363-367) */
+    CRB_ERR_BOUNDARY = -2,    /* BoundaryError (agent still outside after one reflection,
+                                 cartesian_cuboid_n.rs:616-625)                                   */
+    CRB_ERR_INDEX = -3,       /* IndexError    (voxel lookup failed at setup, domain.rs:372-377)  */
+    CRB_ERR_DIVISION = -4,    /* DivisionError (rod division failed, bacterial_rods.rs:623-626)   */
+    CRB_ERR_DECOMPOSE = -5,   /* DecomposeError (get_decomp_res found nothing)                    */
+    CRB_ERR_INVALID_ARG = -16,
+    CRB_ERR_CAPACITY = -17,   /* more agents than `capacity` (set_agents, division, migration)    */
+    CRB_ERR_CUDA = -18,       /* CUDA runtime failure; message holds cudaGetErrorString           */
+    CRB_ERR_STATE = -19       /* call sequence violation (e.g. step before set_agents)            */
+} crb_status;
+
+/* ---- model selection ---------------------------------------------------------------------- */
+/* Mechanics kinds and their per-agent parameter rows (mech_params[i*n_mech + k]).
+ * reference: cellular_raza-building-blocks/src/cell_building_blocks/mechanics.rs */
+typedef enum crb_mechanics_kind {
+    CRB_MECH_NEWTON_DAMPED = 0, /* [damping_constant, mass]                 mechanics.rs:158-173 */
+    CRB_MECH_BROWNIAN = 1,      /* [diffusion_constant, kb_temperature]     mechanics.rs:336-357 */
+    CRB_MECH_LANGEVIN = 2,      /* [mass, damping, kb_temperature]          mechanics.rs:434-463 */
+    CRB_MECH_ROD = 3            /* [diffusion_constant, spring_tension, rigidity, spring_length,
+                                    damping, growth_rate, spring_length_threshold]
+                                    bacterial_rods.rs:157-240 + examples/bacterial_rods/src/main.rs */
+} crb_mechanics_kind;
+
+/* Interaction kinds and their per-agent parameter rows (inter_params[i*n_inter + k]).
+ * reference: cellular_raza-building-blocks/src/cell_building_blocks/interaction.rs,
+ *            cellular_raza-examples/cell_sorting/src/main.rs:43-97 */
+typedef enum crb_interaction_kind {
+    CRB_INT_CELL_SORTING = 0,       /* [cell_radius, potential_strength, relative_interaction_range]
+                                       + species byte; sign convention of the example            */
+    CRB_INT_CELL_SORTING_BENCH = 1, /* same potential, sign convention of
+                                       cellular_raza-benchmarks/src/cell_sorting.rs:79-86        */
+    CRB_INT_MORSE = 2,              /* [radius, potential_stiffness, cutoff, strength]  :151-260 */
+    CRB_INT_BOUND_LJ = 3,           /* [epsilon, sigma, bound, cutoff]                  :122-138 */
+    CRB_INT_MIE = 4                 /* [radius, strength, bound, cutoff, en, em]        :345-389 */
+} crb_interaction_kind;
+
+/* How the two half-forces of a pair are weighted (SURVEY.md finding 2).
+ * CHILI reproduces cellular_raza-core/src/backend/chili/update_mechanics.rs:206-234 as written:
+ * the return force of a neighbour voxel inside the same subdomain is dropped, so a pair in
+ * different voxels of one subdomain acts with weight 1/2; `ref_n_subdomains` is the `n_threads`
+ * of the chili run that is being matched.  PHYSICAL applies both halves everywhere. */
+typedef enum crb_pair_weight_mode {
+    CRB_WEIGHT_CHILI = 0,
+    CRB_WEIGHT_PHYSICAL = 1
+} crb_pair_weight_mode;
+
+/* Source of the standard-normal numbers consumed by stochastic mechanics. */
+typedef enum crb_noise_mode {
+    CRB_NOISE_NONE = 0,   /* random contribution is zero (deterministic mechanics)              */
+    CRB_NOISE_TABLE = 1,  /* z[step][agent id][d] uploaded with crb_set_noise (parity runs)     */
+    CRB_NOISE_PHILOX = 2  /* counter-based generator on the device keyed by (seed, id, step)    */
+} crb_noise_mode;
+
+#define CRB_MAX_DIM 3
+#define CRB_MAX_MECH_PARAMS 8
+#define CRB_MAX_INTER_PARAMS 6
+#define CRB_MAX_ROD_VERTICES 8
+
+/* ---- configuration ------------------------------------------------------------------------ */
+typedef struct crb_config {
+    uint32_t abi_version;      /* CRB_ABI_VERSION                                                */
+    uint32_t dim;              /* 2 or 3                                                         */
+    uint32_t mechanics_kind;   /* crb_mechanics_kind                                             */
+    uint32_t interaction_kind; /* crb_interaction_kind                                           */
+    uint32_t solver_order;     /* `mechanics_solver_order` kwarg of run_simulation!: N in
+                                  MechanicsAdamsBashforthSolver<N>; 2 (default) | 1 | 0
+                                  (run_sim.rs:131-159, solvers.rs:80-139)                        */
+    uint32_t pair_weight_mode; /* crb_pair_weight_mode                                           */
+    uint32_t ref_n_subdomains; /* chili n_threads to emulate in CRB_WEIGHT_CHILI (>= 1)          */
+    uint32_t noise_mode;       /* crb_noise_mode                                                 */
+    uint32_t rod_n_vertices;   /* CRB_MECH_ROD only: rows of the position matrix (<= 8)          */
+    uint32_t device;           /* CUDA device ordinal                                            */
+    /* slab decomposition along axis 0.  Single GPU: rank 0 of 1.                */
+    uint32_t rank;
+    uint32_t world_size;
+    uint64_t n_voxels[CRB_MAX_DIM]; /* CartesianCuboid::n_voxels (cartesian_cuboid_n.rs:61-70)   */
+    double domain_min[CRB_MAX_DIM]; /* CartesianCuboid::min                                      */
+    double domain_max[CRB_MAX_DIM]; /* CartesianCuboid::max                                      */
+    double dx[CRB_MAX_DIM];         /* CartesianCuboid::dx, computed by the host exactly as
+                                       cartesian_cuboid_n.rs:183-222 / 226-256 do               */
+    double dt;                      /* FixedStepsize::dt                                         */
+    uint64_t rng_seed;              /* CartesianCuboid::rng_seed                                 */
+    uint64_t capacity;              /* max number of agents resident on this device              */
+} crb_config;
+
+typedef struct crb_sim crb_sim; /* opaque */
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+/* replaces construct_simulation_runner (chili/datastructures.rs:51-217): builds the voxel
+ * grid, plain indices and the emulated chili subdomain map on the device. */
+int crb_create(const crb_config* cfg, crb_sim** out);
+/* replaces Drop for the runner (cara/mod.rs:16-22). */
+void crb_destroy(crb_sim* sim);
+/* message of the last failure on `sim` (or of the last failed crb_create when sim == NULL). */
+const char* crb_last_error(const crb_sim* sim);
+/* ABI version of the loaded library. */
+uint32_t crb_abi_version(void);
+/* number of per-agent parameters for a mechanics / interaction kind (0 if unknown). */
+uint32_t crb_n_mech_params(uint32_t mechanics_kind);
+uint32_t crb_n_inter_params(uint32_t interaction_kind);
+
+/* ---- agents ------------------------------------------------------------------------------- */
+/* replaces SubDomainBox::insert_initial_cells (chili/datastructures.rs:278-299): copies n agents
+ * to the device, bins them with CartesianCuboid::get_voxel_index_of_raw semantics
+ * (cartesian_cuboid_n.rs:320-337; pos <= min or index >= n_voxels is CRB_ERR_BOUNDARY /
+ * CRB_ERR_INDEX) and sorts them by voxel keeping input order inside a voxel.  AuxStorage starts
+ * empty.  pos/vel: n*dim*V doubles (V = rod_n_vertices for rods, else 1; rods are stored
+ * vertex-major per agent: pos[(i*V + v)*dim + d]).  species may be NULL (all 0), ids may be
+ * NULL (0..n-1). */
+int crb_set_agents(crb_sim* sim, uint64_t n, const double* pos, const double* vel,
+                   const double* mech_params, const double* inter_params,
+                   const uint8_t* species, const uint64_t* ids);
+
+/* number of agents currently resident. */
+uint64_t crb_n_agents(const crb_sim* sim);
+
+/* replaces the read side of save_cells (chili/datastructures.rs:373-396): copies the agents in
+ * device order (ascending voxel, chili in-voxel order).  Any output pointer may be NULL.
+ * `voxel` receives the VoxelPlainIndex of each agent.  cap = number of agents the buffers hold. */
+int crb_get_agents(crb_sim* sim, uint64_t cap, double* pos, double* vel, uint64_t* ids,
+                   uint64_t* voxel);
+/* mutable model state that is not pos/vel (rod spring_length, growth_rate …). */
+int crb_get_params(crb_sim* sim, uint64_t cap, double* mech_params, double* inter_params,
+                   uint8_t* species);
+
+/* AuxStorageMechanics (chili/aux_storage.rs:41-130) in device order: the ring buffers of
+ * previous increments oldest-first (hist_dx/hist_dv: cap*2*dim*V doubles, hist_len: entries
+ * used, 0..2) and current_force (zero between steps). */
+int crb_get_aux(crb_sim* sim, uint64_t cap, double* hist_dx, double* hist_dv, uint32_t* hist_len);
+/* restores AuxStorage for agents given in the order of the preceding crb_set_agents call. */
+int crb_set_aux(crb_sim* sim, uint64_t n, const double* hist_dx, const double* hist_dv,
+                const uint32_t* hist_len);
+
+/* z[(step*n_ids + id)*dim*V + k] standard normal numbers for the next n_steps steps, indexed by
+ * agent id (ids must be < n_ids).  CRB_NOISE_TABLE only. */
+int crb_set_noise(crb_sim* sim, const double* z, uint64_t n_steps, uint64_t n_ids);
+
+/* ---- stepping ----------------------------------------------------------------------------- */
+/* replaces n iterations of the generated loop body (run_sim.rs:380-403) for
+ * aspects [Mechanics, Interaction]: update_mechanics_interaction_step_1/2/3, local_mechanics_update,
+ * apply_boundary, sort_cells_in_voxels_step_1/2 (chili/update_mechanics.rs). Asynchronous errors
+ * raised on the device (CalcError, BoundaryError) are latched and returned here. */
+int crb_step(crb_sim* sim, uint64_t n_steps);
+/* blocks until all queued device work of the handle is done and returns the latched status. */
+int crb_sync(crb_sim* sim);
+/* number of steps taken since creation. */
+uint64_t crb_iteration(const crb_sim* sim);
+
+/* ---- parity taps (used by tests; not needed by a production host) ------------------------- */
+/* forces that the next step would integrate (AuxStorageMechanics::current_force after
+ * update_mechanics_interaction_step_3), device order, cap*dim*V doubles; does not advance. */
+int crb_debug_forces(crb_sim* sim, uint64_t cap, double* force);
+/* migration set of the last step: (id, old VoxelPlainIndex, new VoxelPlainIndex) triples of
+ * every agent that changed voxel in sort_cells_in_voxels.  Returns the count in *n_out. */
+int crb_get_migrations(crb_sim* sim, uint64_t cap, uint64_t* ids, uint64_t* old_voxel,
+                       uint64_t* new_voxel, uint64_t* n_out);
+/* number of agents in every voxel (n_voxels_total entries, plain index order). */
+int crb_get_voxel_counts(crb_sim* sim, uint64_t cap, uint32_t* counts);
+/* ordered candidate pairs evaluated by one force pass for the current state. */
+int crb_count_candidate_pairs(crb_sim* sim, uint64_t* n_pairs);
+/* number of kernels launched by this handle so far (bench.py `gpu_launches`). */
+uint64_t crb_kernel_launches(const crb_sim* sim);
+/* device time in milliseconds spent in a named stage since the last crb_reset_timers
+ * (CUDA events on the handle's stream; only recorded after crb_enable_timers(sim, 1)).
+ * stage: 0 force+integrate, 1 scan, 2 reorder, 3 halo, 4 migration. */
+int crb_enable_timers(crb_sim* sim, int on);
+int crb_reset_timers(crb_sim* sim);
+int crb_stage_time_ms(crb_sim* sim, uint32_t stage, double* ms, uint64_t* launches);
+
+/* ---- helpers that restate reference setup arithmetic on the host -------------------------- */
+/* get_decomp_res (cartesian_cuboid_n.rs:19-59): returns 0 and (n, m, average_len) or
+ * CRB_ERR_DECOMPOSE. */
+int crb_decomp_res(uint64_t n_voxel, uint64_t n_regions, uint64_t* n, uint64_t* m,
+                   uint64_t* average_len);
+/* CartesianCuboid::from_boundaries_and_interaction_range (cartesian_cuboid_n.rs:183-222):
+ * fills n_voxels and dx for `dim` axes. */
+int crb_domain_from_interaction_range(uint32_t dim, const double* min, const double* max,
+                                      double interaction_range, uint64_t* n_voxels, double* dx);
+/* CartesianCuboid::from_boundaries_and_n_voxels (cartesian_cuboid_n.rs:226-256). */
+int crb_domain_from_n_voxels(uint32_t dim, const double* min, const double* max,
+                             const uint64_t* n_voxels, double* dx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRB_H */

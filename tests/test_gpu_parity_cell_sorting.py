@@ -1,0 +1,162 @@
+"""Device (CUDA, through the C ABI) vs oracle for the cell_sorting path — BASELINE.json configs 1/2.
+
+Tolerances (BASELINE.json north_star): voxel assignment / membership / migration sets bit-exact,
+forces 1e-12 relative, 100-step trajectories 1e-9 of the domain size.
+"""
+import numpy as np
+import pytest
+
+from cellular_raza_b200 import _abi, workloads
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-12
+TRAJ_TOL = 1e-9
+
+
+@pytest.mark.parametrize("n_threads", [1, 4])
+@pytest.mark.parametrize("mode", [_abi.CRB_WEIGHT_CHILI, _abi.CRB_WEIGHT_PHYSICAL])
+def test_c1_forces_and_membership(oracle_lib, crb_lib, n_threads, mode):
+    w = workloads.cell_sorting(n_threads=n_threads, pair_weight_mode=mode)
+    dev, ora = parity.make_pair(w)
+    parity.assert_same_membership(dev, ora)
+    assert dev.count_candidate_pairs() == ora.count_candidate_pairs()
+    err, fd, fo = parity.force_errors(dev, ora)
+    assert err.max() <= FORCE_TOL, f"worst agent {err.argmax()} err {err.max():.3e}"
+
+
+def test_c1_in_voxel_order_matches_chili_single_subdomain(oracle_lib, crb_lib):
+    w = workloads.cell_sorting(n_threads=1)
+    dev, ora = parity.make_pair(w)
+    dev.step(25)
+    ora.step(25)
+    _, _, ids_d, vox_d = dev.get_agents()
+    _, _, ids_o, vox_o = ora.get_agents()
+    np.testing.assert_array_equal(vox_d, vox_o)
+    np.testing.assert_array_equal(ids_d, ids_o)
+
+
+@pytest.mark.parametrize("n_threads", [1, 4])
+def test_c1_one_step_increments_and_migration(oracle_lib, crb_lib, n_threads):
+    w = workloads.cell_sorting(n_threads=n_threads)
+    dev, ora = parity.make_pair(w)
+    for _ in range(3):
+        dev.step(1)
+        ora.step(1)
+        perr, verr, key_diff = parity.state_errors(dev, ora, 110.0)
+        assert perr <= 1e-13 and verr <= 1e-12
+        assert not key_diff.any()
+        md = set(zip(*[a.tolist() for a in dev.get_migrations()]))
+        mo = set(zip(*[a.tolist() for a in ora.get_migrations()]))
+        assert md == mo
+    hx_d, hv_d, hl_d = dev.get_aux()
+    hx_o, hv_o, hl_o = ora.get_aux()
+    _, _, ids_d, _ = dev.get_agents()
+    _, _, ids_o, _ = ora.get_agents()
+    hx_d, hv_d, hl_d = parity.by_id(ids_d, hx_d, hv_d, hl_d)
+    hx_o, hv_o, hl_o = parity.by_id(ids_o, hx_o, hv_o, hl_o)
+    np.testing.assert_array_equal(hl_d, hl_o)
+    assert np.abs(hx_d - hx_o).max() <= 1e-12
+    assert np.abs(hv_d - hv_o).max() <= 1e-11
+
+
+@pytest.mark.parametrize("n_threads,mode", [(1, 0), (4, 0), (1, 1)])
+def test_c1_trajectory_100_steps(oracle_lib, crb_lib, n_threads, mode):
+    w = workloads.cell_sorting(n_threads=n_threads, pair_weight_mode=mode)
+    dev, ora = parity.make_pair(w)
+    dev.step(100)
+    ora.step(100)
+    perr, verr, key_diff = parity.state_errors(dev, ora, 110.0)
+    assert perr <= TRAJ_TOL, perr
+    # a differing key is only tolerated for an agent within 1e-9 L of a voxel face
+    assert key_diff.sum() <= 2
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_solver_orders(oracle_lib, crb_lib, order):
+    w = workloads.cell_sorting(n_cells=400, domain_size=72.0, solver_order=order, n_threads=2)
+    dev, ora = parity.make_pair(w)
+    dev.step(20)
+    ora.step(20)
+    perr, verr, key_diff = parity.state_errors(dev, ora, 72.0)
+    assert perr <= TRAJ_TOL
+    assert not key_diff.any()
+
+
+def test_bench_sign_convention(oracle_lib, crb_lib):
+    """benchmark copy of the potential returns the forces with the opposite sign
+    (cellular_raza-benchmarks/src/cell_sorting.rs:79-86)."""
+    w = workloads.cell_sorting(n_cells=400, domain_size=72.0, bench_sign=True, n_threads=1)
+    dev, ora = parity.make_pair(w)
+    err, fd, fo = parity.force_errors(dev, ora)
+    assert err.max() <= FORCE_TOL
+    w2 = workloads.cell_sorting(n_cells=400, domain_size=72.0, bench_sign=False, n_threads=1)
+    dev2, ora2 = parity.make_pair(w2)
+    _, fd2, _ = parity.force_errors(dev2, ora2)
+    np.testing.assert_array_equal(fd2, -fd)
+
+
+def test_2d_cell_sorting(oracle_lib, crb_lib):
+    w = workloads.cell_sorting(n_cells=500, domain_size=200.0, dim=2, n_threads=3)
+    dev, ora = parity.make_pair(w)
+    parity.assert_same_membership(dev, ora)
+    err, _, _ = parity.force_errors(dev, ora)
+    assert err.max() <= FORCE_TOL
+    dev.step(50)
+    ora.step(50)
+    perr, _, key_diff = parity.state_errors(dev, ora, 200.0)
+    assert perr <= TRAJ_TOL and not key_diff.any()
+
+
+def test_heterogeneous_parameters(oracle_lib, crb_lib):
+    """per-agent radius/strength/range/damping/mass: the two halves of a pair use different `self`
+    parameters (own = i vs own = j)."""
+    w = workloads.cell_sorting(n_cells=600, domain_size=90.0, n_threads=2)
+    rng = np.random.default_rng(5)
+    w.inter_params = np.column_stack(
+        [rng.uniform(4.0, 6.0, w.n), rng.uniform(1.0, 3.0, w.n), rng.uniform(1.2, 1.5, w.n)]
+    )
+    w.mech_params = np.column_stack([rng.uniform(1.0, 3.0, w.n), rng.uniform(0.5, 2.0, w.n)])
+    dev, ora = parity.make_pair(w)
+    err, _, _ = parity.force_errors(dev, ora)
+    assert err.max() <= FORCE_TOL
+    dev.step(30)
+    ora.step(30)
+    perr, _, key_diff = parity.state_errors(dev, ora, 90.0)
+    assert perr <= TRAJ_TOL and not key_diff.any()
+
+
+def test_rerun_is_bitwise_identical(crb_lib):
+    """tests/determinism_mechanics_interaction.rs:44-62: same simulation twice => identical bits."""
+    w = workloads.cell_sorting(n_threads=4)
+    out = []
+    for _ in range(3):
+        from cellular_raza_b200.device import DeviceSimulation
+
+        dev = DeviceSimulation(w.config())
+        dev.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+        dev.step(40)
+        out.append(dev.get_agents())
+        dev.close()
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            np.testing.assert_array_equal(a, b)
+
+
+def test_c2_one_million_cells(oracle_lib, crb_lib):
+    """BASELINE.json config 2: 1 M cells, 52^3 voxels: bit-exact cell lists, forces 1e-12."""
+    w = workloads.cell_sorting_scaled(1_000_000, n_threads=1)
+    dev, ora = parity.make_pair(w, n_threads_oracle=8)
+    parity.assert_same_membership(dev, ora)
+    assert dev.count_candidate_pairs() == ora.count_candidate_pairs()
+    err, _, _ = parity.force_errors(dev, ora)
+    assert err.max() <= FORCE_TOL
+    dev.step(2)
+    ora.step(2)
+    perr, _, key_diff = parity.state_errors(dev, ora, 936.0)
+    assert perr <= 1e-13 and not key_diff.any()
+    md = set(zip(*[a.tolist() for a in dev.get_migrations()]))
+    mo = set(zip(*[a.tolist() for a in ora.get_migrations()]))
+    assert md == mo
