@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the mechanics/interaction hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of chili on host cores
+
+A "step" is one full pass of the hot path (pair forces -> AB3 update -> boundary -> cell-list
+rebuild/migration) over the whole population.  Workload: 3-D cell_sorting (NewtonDamped3D + species
+potential) at the density of the shipped example (rho ~ 7.1 agents per 18^3 voxel), `--cells-per-gpu`
+agents per GPU (weak scaling, BASELINE.json configs[4] = 8 M -> 64 M at 1/2/4/8 GPUs).
+Prints ONE JSON line (see the task contract / DESIGN.md §6 for the meaning of every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "agent_steps_per_s"
+UNIT = "agent-steps/s"
+FLOP_PER_PAIR = 50.0  # species potential counted as written, per ordered candidate pair
+# k_fill + k_reorder per agent (uniform parameters): dynamic state read+write 2*(pos 24 + vel 24 +
+# increments 48 + hlen 1) + id 16 + species 2 + fill (newkey 4, rank 4, tmp_idx 4) + reorder
+# (tmp_idx 4, newkey 4, sortkey 8, key_out 4) = 244 B  
+REORDER_BYTES_PER_AGENT = 2 * (24 + 24 + 48 + 1) + 16 + 2 + 12 + 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells-per-gpu", type=int, default=8_000_000)
+    ap.add_argument("--density", type=float, default=7.1, help="agents per voxel")
+    ap.add_argument("--n-threads-ref", type=int, default=1,
+                    help="chili n_threads whose pair weights are reproduced (CRB_WEIGHT_CHILI)")
+    ap.add_argument("--cpu-sample-cells", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.tmp = None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.split(",") for r in Path(self.tmp.name).read_text().strip().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def measured_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return {}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps: int, warmup: int, sample_cells: int):
+    """Times the CPU restatement of chili (oracle/) on the host cores: one emulated chili subdomain
+    per core, `sample_cells` agents at the workload's density.  The Rust reference itself cannot be
+    built in this image, so kind = "port"."""
+    from cellular_raza_b200 import workloads
+    from oracle.chili_oracle import ChiliOracle
+
+    cores = host_cores()
+    w = workloads.cell_sorting_scaled(sample_cells, args.density, n_threads=cores)
+    o = ChiliOracle(w.config(), n_threads=cores)
+    o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+    if warmup:
+        o.step(warmup)
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    val = w.n * steps / dt
+    sample = (f"{w.n} cells ({w.cfg_kwargs['n_voxels'][0]}^3 voxels, same density) x {steps} steps, "
+              f"{cores} threads = {cores} emulated chili subdomains, {dt:.1f} s")
+    o.close()
+    return val, cores, sample, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    sample_cells = args.cpu_sample_cells if total <= 30 else max(args.cpu_sample_cells // 4, 50_000)
+    val, cores, sample, ms = cpu_reference_run(args, args.steps, args.warmup, sample_cells)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args) -> dict:
+    n_total = args.cells_per_gpu * args.gpus
+    return {
+        "workload": "cell_sorting_3d_weak_scaling (BASELINE.json configs[4]; configs[1] with --cells-per-gpu 1000000)",
+        "cells_per_gpu": args.cells_per_gpu, "cells_total": n_total, "agents_per_voxel": args.density,
+        "mechanics": "NewtonDamped3D", "interaction": "cell_sorting species potential", "solver": "AB3 (order 2)",
+        "pair_weights": f"chili-as-written(n_threads={args.n_threads_ref})", "dt": 0.2,
+        "l2_policy": "working set larger than L2 (3 state copies x >= 100 B/agent x cells_per_gpu)",
+        "decomposition": f"slab{args.gpus}" if args.gpus > 1 else "single",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    from cellular_raza_b200 import workloads
+    from cellular_raza_b200.device import DeviceSimulation, measure_fp64_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus != 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with WORLD_SIZE={args.gpus} (got {world})")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if args.gpus > 1:
+        from cellular_raza_b200 import multi_gpu_bench
+
+        return multi_gpu_bench.run(args, rank, world, local_rank)
+
+    dev_id = local_rank
+    torch.cuda.set_device(dev_id)
+    n = args.cells_per_gpu
+    w = workloads.cell_sorting_scaled(n, args.density, n_threads=args.n_threads_ref)
+    sim = DeviceSimulation(w.config(device=dev_id))
+    sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
+    sim.set_agents(w.pos, w.vel, None, None, w.species)
+    stream = torch.cuda.ExternalStream(sim.stream, device=dev_id)
+    pairs = sim.count_candidate_pairs()
+
+    sim.step(max(args.warmup, 3))
+    fp64_peak, _ = measure_fp64_peak(dev_id)
+
+    # ---- timed region: K steps, device-resident ---------------------------------------------------
+    sampler = ClockSampler(dev_id)
+    sampler.start()
+    time.sleep(0.3)
+    sim.enable_timers(True)
+    sim.reset_timers()
+    l0 = sim.kernel_launches
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = sim.kernel_launches - l0
+    force_ms, force_launches = sim.stage_time_ms(0)
+    scan_ms, _ = sim.stage_time_ms(1)
+    reorder_ms, reorder_launches = sim.stage_time_ms(2)
+    sim.enable_timers(False)
+    clocks = sampler.stop()
+    pairs_after = sim.count_candidate_pairs()
+    value = n * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (force + integrate): FP64 pipe --------------------------
+    pairs_per_launch = 0.5 * (pairs + pairs_after)
+    force_avg_ms = force_ms / max(force_launches, 1)
+    achieved_tf = pairs_per_launch * FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
+    peaks = measured_peaks()
+    roofline = {
+        "kernel": "k_force_integrate", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+        "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+        "traffic": None, "share_of_step": force_ms / ms_total,
+        "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+        "pair_forces_per_s": pairs_per_launch / (force_avg_ms * 1e-3),
+    }
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    reorder_avg_ms = reorder_ms / max(args.steps, 1)
+    reorder_gbs = n * REORDER_BYTES_PER_AGENT / (reorder_avg_ms * 1e-3) / 1e9
+    roofline_hbm = {
+        "kernel": "k_fill+k_reorder (cell-list rebuild / migration scatter)", "bound": "hbm",
+        "achieved": reorder_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": reorder_gbs / hbm_peak,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+        "traffic": None, "share_of_step": reorder_ms / ms_total, "scan_share_of_step": scan_ms / ms_total,
+        "algorithmic_bytes_per_agent": REORDER_BYTES_PER_AGENT,
+    }
+
+    # ---- e2e: host buffers in, host buffers out, every step --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hp = torch.from_numpy(w.pos).pin_memory()
+        hv = torch.from_numpy(w.vel).pin_memory()
+        hs = torch.from_numpy(w.species).pin_memory()
+        op = torch.empty_like(hp).pin_memory()
+        ov = torch.empty_like(hv).pin_memory()
+        lib, h = sim._lib, sim._h
+        e2e_steps = args.steps
+        for k in range(2 + e2e_steps):
+            if k == 2:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            rc = lib.crb_set_agents(h, n, hp.data_ptr(), hv.data_ptr(), None, None, hs.data_ptr(), None)
+            rc = rc or lib.crb_step(h, 1)
+            rc = rc or lib.crb_get_agents(h, n, op.data_ptr(), ov.data_ptr(), None, None)
+            if rc:
+                raise RuntimeError(lib.crb_last_error(h))
+            hp, op = op, hp
+            hv, ov = ov, hv
+        torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t0
+        e2e = {
+            "value": n * e2e_steps / dt_e2e, "unit": UNIT,
+            "h2d_bytes_per_step": int(n * (24 + 24 + 1)), "d2h_bytes_per_step": int(n * 48),
+            "ms_per_step": dt_e2e / e2e_steps * 1e3,
+            "what": "crb_set_agents(pinned host pos, vel, species) + crb_step(1) + crb_get_agents(host pos, vel) per step",
+        }
+
+    # ---- CPU baseline (oracle, bounded sample) ----------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_run(args, 1, 0, min(args.cpu_sample_cells, n))
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args), "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "stage_ms_per_step": {"force_integrate": force_ms / args.steps, "scan": scan_ms / args.steps,
+                              "reorder": reorder_ms / args.steps},
+        "published_reference": "chili on Threadripper 3960X: 2.02e4 (1 thread, 1.3 M cells), best 1.01e5 (43 threads, 20 k cells); BASELINE.md",
+    }
+    print(json.dumps(line), flush=True)
+    sim.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,7 @@ SYMBOLS = [
     ("crb_n_mech_params", C.c_uint32, [C.c_uint32]),
     ("crb_n_inter_params", C.c_uint32, [C.c_uint32]),
     ("crb_set_agents", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("crb_set_uniform_params", C.c_int, [_vp, _vp, _vp]),
     ("crb_n_agents", C.c_uint64, [_vp]),
     ("crb_get_agents", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp]),
     ("crb_get_params", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp]),
@@ -138,6 +139,8 @@ SYMBOLS = [
     ("crb_enable_timers", C.c_int, [_vp, C.c_int]),
     ("crb_reset_timers", C.c_int, [_vp]),
     ("crb_stage_time_ms", C.c_int, [_vp, C.c_uint32, _f64p, _u64p]),
+    ("crb_stream", C.c_void_p, [_vp]),
+    ("crb_measure_fp64_peak", C.c_int, [C.c_uint32, _f64p, _f64p]),
     ("crb_decomp_res", C.c_int, [C.c_uint64, C.c_uint64, _u64p, _u64p, _u64p]),
     ("crb_domain_from_interaction_range", C.c_int, [C.c_uint32, _f64p, _f64p, C.c_double, _u64p, _f64p]),
     ("crb_domain_from_n_voxels", C.c_int, [C.c_uint32, _f64p, _f64p, _u64p, _f64p]),

@@ -33,6 +33,7 @@ struct crb_sim {
     int D = 3, V = 1;
     int n_mp = 0, n_ip = 0;
     bool uniform = true;
+    bool uniform_declared = false;
     Uniform uni;
     u64 cap = 0, n = 0;
     u64 nvox = 0;
@@ -519,19 +520,24 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
                    const uint64_t* ids) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (n > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
-    if (n && (!pos || !mech_params || !inter_params))
-        return fail(s, CRB_ERR_INVALID_ARG, "pos, mech_params and inter_params are required");
+    if (n && !pos) return fail(s, CRB_ERR_INVALID_ARG, "pos is required");
     CU(s, cudaSetDevice((int)s->cfg.device));
     const int D = s->D;
     // uniform-parameter fast path: all agents share one parameter row
-    s->uniform = true;
-    for (int k = 0; k < s->n_mp; ++k) s->uni.mp[k] = n ? mech_params[k] : 0.0;
-    for (int k = 0; k < s->n_ip; ++k) s->uni.ip[k] = n ? inter_params[k] : 0.0;
-    for (u64 i = 1; i < n && s->uniform; ++i) {
-        for (int k = 0; k < s->n_mp; ++k)
-            if (mech_params[i * s->n_mp + k] != s->uni.mp[k]) s->uniform = false;
-        for (int k = 0; k < s->n_ip; ++k)
-            if (inter_params[i * s->n_ip + k] != s->uni.ip[k]) s->uniform = false;
+    if (s->uniform_declared) {
+        s->uniform = true;
+    } else {
+        if (n && (!mech_params || !inter_params))
+            return fail(s, CRB_ERR_INVALID_ARG, "mech_params and inter_params are required");
+        s->uniform = true;
+        for (int k = 0; k < s->n_mp; ++k) s->uni.mp[k] = n ? mech_params[k] : 0.0;
+        for (int k = 0; k < s->n_ip; ++k) s->uni.ip[k] = n ? inter_params[k] : 0.0;
+        for (u64 i = 1; i < n && s->uniform; ++i) {
+            for (int k = 0; k < s->n_mp; ++k)
+                if (mech_params[i * s->n_mp + k] != s->uni.mp[k]) s->uniform = false;
+            for (int k = 0; k < s->n_ip; ++k)
+                if (inter_params[i * s->n_ip + k] != s->uni.ip[k]) s->uniform = false;
+        }
     }
     int rc;
     if ((rc = upload_rows(s, pos, D, s->T.pos, n))) return rc;
@@ -583,6 +589,52 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
     s->aux_settable = true;
     s->last_step_n = 0;
     s->noise_cursor = 0;
+    return 0;
+}
+
+int crb_set_uniform_params(crb_sim* s, const double* mech_row, const double* inter_row) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!mech_row && !inter_row) {
+        s->uniform_declared = false;
+        return 0;
+    }
+    if (!mech_row || !inter_row) return fail(s, CRB_ERR_INVALID_ARG, "both rows are required");
+    for (int k = 0; k < s->n_mp; ++k) s->uni.mp[k] = mech_row[k];
+    for (int k = 0; k < s->n_ip; ++k) s->uni.ip[k] = inter_row[k];
+    s->uniform_declared = true;
+    return 0;
+}
+
+void* crb_stream(crb_sim* s) { return s ? (void*)s->stream : nullptr; }
+
+int crb_measure_fp64_peak(uint32_t device, double* tflops, double* ms_out) {
+    if (!tflops) return CRB_ERR_INVALID_ARG;
+    if (cudaSetDevice((int)device) != cudaSuccess) return CRB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, (int)device) != cudaSuccess) return CRB_ERR_CUDA;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return CRB_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        k_dfma_peak<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return CRB_ERR_CUDA;
+    const double flops = 2.0 * 64.0 * (double)iters * threads * blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
     return 0;
 }
 

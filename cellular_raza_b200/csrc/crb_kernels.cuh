@@ -715,6 +715,28 @@ __global__ void k_collect_migrations(const u64* __restrict__ sortkey, const u32*
     newv[slot] = (u64)newkey[i] + (u64)g.p0 * g.ng[1] * g.ng[2];
 }
 
+// DFMA-only kernel: 8 independent chains per thread, 2 flop per fma.  Roofline denominator of the
+// force kernel.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    const double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == 123.456) out[0] = r;
+}
+
 __global__ void k_iota_u64(u64* a, u64 n) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;

@@ -109,8 +109,10 @@ class DeviceSimulation:
         n = pos.shape[0]
         pos = _f64(pos, (n, self.dim))
         vel = None if vel is None else _f64(vel, (n, self.dim))
-        mech_params = _f64(np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, self.n_mech)))
-        inter_params = _f64(np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, self.n_inter)))
+        if mech_params is not None:
+            mech_params = _f64(np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, self.n_mech)))
+        if inter_params is not None:
+            inter_params = _f64(np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, self.n_inter)))
         species = None if species is None else np.ascontiguousarray(species, dtype=np.uint8)
         ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
         self._check(
@@ -118,6 +120,20 @@ class DeviceSimulation:
                 self._h, n, _ptr(pos), _ptr(vel), _ptr(mech_params), _ptr(inter_params), _ptr(species), _ptr(ids)
             )
         )
+
+    def set_uniform_params(self, mech_row=None, inter_row=None):
+        """All agents share one parameter row; set_agents may then omit the parameter arrays."""
+        if mech_row is None and inter_row is None:
+            self._check(self._lib.crb_set_uniform_params(self._h, None, None))
+            return
+        m = _f64(mech_row, (self.n_mech,))
+        i = _f64(inter_row, (self.n_inter,))
+        self._check(self._lib.crb_set_uniform_params(self._h, _ptr(m), _ptr(i)))
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the handle (for CUDA-event timing)."""
+        return int(self._lib.crb_stream(self._h) or 0)
 
     @property
     def n_agents(self) -> int:
@@ -220,3 +236,14 @@ class DeviceSimulation:
         ln = C.c_uint64(0)
         self._check(self._lib.crb_stage_time_ms(self._h, stage, C.byref(ms), C.byref(ln)))
         return ms.value, ln.value
+
+
+def measure_fp64_peak(device: int = 0):
+    """-> (TFLOP/s, ms) of the DFMA-only micro-kernel (roofline denominator of the force kernel)."""
+    lib = _abi.load_library()
+    t = C.c_double(0)
+    ms = C.c_double(0)
+    rc = lib.crb_measure_fp64_peak(device, C.byref(t), C.byref(ms))
+    if rc != 0:
+        raise SimulationError(rc, "crb_measure_fp64_peak failed")
+    return t.value, ms.value

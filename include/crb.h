@@ -147,6 +147,11 @@ int crb_set_agents(crb_sim* sim, uint64_t n, const double* pos, const double* ve
                    const double* mech_params, const double* inter_params,
                    const uint8_t* species, const uint64_t* ids);
 
+/* declares that every agent shares one parameter row (the common case for the building-block
+ * examples); afterwards crb_set_agents may be called with mech_params == inter_params == NULL
+ * and skips the per-agent parameter columns entirely.  Passing NULL, NULL reverts. */
+int crb_set_uniform_params(crb_sim* sim, const double* mech_row, const double* inter_row);
+
 /* number of agents currently resident. */
 uint64_t crb_n_agents(const crb_sim* sim);
 
@@ -202,6 +207,12 @@ uint64_t crb_kernel_launches(const crb_sim* sim);
 int crb_enable_timers(crb_sim* sim, int on);
 int crb_reset_timers(crb_sim* sim);
 int crb_stage_time_ms(crb_sim* sim, uint32_t stage, double* ms, uint64_t* launches);
+
+/* the cudaStream_t all work of this handle is queued on (for CUDA-event timing by the caller). */
+void* crb_stream(crb_sim* sim);
+/* DFMA-only micro-kernel on `device`: measured FP64 FMA throughput in TFLOP/s (2 flop per FMA);
+ * the roofline denominator of the force kernel (MEASURED_PEAKS.json holds no FP64 figure). */
+int crb_measure_fp64_peak(uint32_t device, double* tflops, double* ms);
 
 /* ---- helpers that restate reference setup arithmetic on the host -------------------------- */
 /* get_decomp_res (cartesian_cuboid_n.rs:19-59): returns 0 and (n, m, average_len) or
