@@ -6,11 +6,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
-#include "crb_kernels.cuh"
+#include "crb_force_tile.cuh"
 
 using namespace crb;
 
@@ -58,6 +59,12 @@ struct crb_sim {
     bool have_agents = false;
     bool aux_settable = false;
     u64 last_step_n = 0;  // agents that took part in the last step (migration tap)
+    // k_force_tile geometry (chosen in crb_set_agents from the mean density)
+    TileLaunch tile;
+    bool tile_ok = false;
+    int tile_threads = kTileThreadsMax;
+    size_t tile_smem = 0;
+    int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 tile kernel (env CRB_FORCE_KERNEL)
     bool timers_on = false;
     StageTimer timers[kNumStages];
     std::vector<void*> allocs;
@@ -105,6 +112,7 @@ int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
             if ((rc = dalloc(s, &st.h0v[d], c))) return rc;
         }
         if ((rc = dalloc(s, &st.hlen, s->cap))) return rc;
+        if ((rc = dalloc(s, &st.posf, s->cap))) return rc;
     }
     if (stat) {
         if ((rc = dalloc(s, &st.id, s->cap))) return rc;
@@ -210,11 +218,95 @@ void launch_force_d(crb_sim* s, const KParams& P, bool force_only) {
     }
 }
 
-void launch_force(crb_sim* s, const KParams& P, bool force_only) {
+// ---- k_force_tile -------------------------------------------------------------------------------
+// interaction cutoff of a uniform parameter row (beyond it every potential of the set is exactly 0)
+double uniform_cutoff(const crb_sim* s) {
+    const double* ip = s->uni.ip;
+    switch (s->cfg.interaction_kind) {
+        case CRB_INT_CELL_SORTING:
+        case CRB_INT_CELL_SORTING_BENCH: return ip[2] * (ip[0] + ip[0]);  // range * (R1 + R2)
+        case CRB_INT_MORSE: return ip[2];
+        case CRB_INT_BOUND_LJ: return ip[3];
+        case CRB_INT_MIE: return ip[3];
+    }
+    return INFINITY;
+}
+
+// chooses the pencil geometry from the mean density; called whenever the population changes
+void plan_tile(crb_sim* s) {
+    s->tile_ok = false;
+    if (!s->uniform || s->n == 0 || s->kernel_choice == 1) return;
+    const Grid& g = s->g;
+    const int n2 = g.ng[2];
+    const int nrows = s->D == 3 ? 9 : 3;
+    const double owned_vox = (double)(g.own_hi - g.own_lo) * g.ng[1] * n2;
+    const double rho = std::max((double)s->n / std::max(owned_vox, 1.0), 1e-3);
+    const u32 cap = 2048;
+    int seg_max = (int)std::floor(cap / (nrows * rho * 1.2)) - 2;
+    const int by_targets = (int)std::ceil(1.75 * kTileThreadsMax / rho);
+    seg_max = std::max(1, std::min(seg_max, by_targets));
+    const int nseg = (n2 + seg_max - 1) / seg_max;
+    TileLaunch& T = s->tile;
+    T.nseg = nseg;
+    T.seg_len = (n2 + nseg - 1) / nseg;
+    T.x_begin = g.own_lo;
+    T.x_count = g.own_hi - g.own_lo;
+    T.cap = cap;
+    T.kmax = T.seg_len + 2;
+    // conservative FP32 filter radius: |d_f32 - d| <= 2^-22.5 * extent per axis (crb_force_tile.cuh)
+    double ext = 0;
+    for (int d = 0; d < s->D; ++d) ext = std::max(ext, g.mx[d] - g.mn[d]);
+    const double cutoff = uniform_cutoff(s);
+    float cut2f = INFINITY;
+    if (std::isfinite(cutoff) && cutoff > 0) {
+        const double c = (cutoff + 2.0 * ext * std::ldexp(1.0, -22)) * (1.0 + std::ldexp(1.0, -19));
+        const double c2 = c * c;
+        cut2f = (float)c2;
+        if ((double)cut2f < c2) cut2f = std::nextafterf(cut2f, INFINITY);
+    }
+    T.cut2f = cut2f;
+    s->tile_threads = kTileThreadsMax;
+    s->tile_smem = tile_smem_bytes(T.cap, T.kmax, s->tile_threads);
+    s->tile_ok = s->tile_smem <= 227 * 1024;
+}
+
+template <int D, int INTER>
+int launch_tile_t(crb_sim* s, const KParams& P, bool force_only) {
+    const TileLaunch& T = s->tile;
+    const u32 grid = (u32)T.x_count * (u32)s->g.ng[1] * (u32)T.nseg;
+    if (!grid) return 0;
+    if (force_only) {
+        auto k = k_force_tile<D, INTER, true>;
+        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile_smem));
+        k<<<grid, s->tile_threads, s->tile_smem, s->stream>>>(P, T);
+    } else {
+        auto k = k_force_tile<D, INTER, false>;
+        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile_smem));
+        k<<<grid, s->tile_threads, s->tile_smem, s->stream>>>(P, T);
+    }
+    return 0;
+}
+
+template <int D>
+int launch_tile_d(crb_sim* s, const KParams& P, bool force_only) {
+    switch (s->cfg.interaction_kind) {
+        case CRB_INT_CELL_SORTING: return launch_tile_t<D, CRB_INT_CELL_SORTING>(s, P, force_only);
+        case CRB_INT_CELL_SORTING_BENCH:
+            return launch_tile_t<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only);
+        case CRB_INT_MORSE: return launch_tile_t<D, CRB_INT_MORSE>(s, P, force_only);
+        case CRB_INT_BOUND_LJ: return launch_tile_t<D, CRB_INT_BOUND_LJ>(s, P, force_only);
+        case CRB_INT_MIE: return launch_tile_t<D, CRB_INT_MIE>(s, P, force_only);
+    }
+    return 0;
+}
+
+int launch_force(crb_sim* s, const KParams& P, bool force_only) {
+    if (s->tile_ok) return s->D == 3 ? launch_tile_d<3>(s, P, force_only) : launch_tile_d<2>(s, P, force_only);
     if (s->D == 3)
         launch_force_d<3>(s, P, force_only);
     else
         launch_force_d<2>(s, P, force_only);
+    return 0;
 }
 
 // scan count_new -> start_alt, fill, reorder T(+X static) -> Y, swap
@@ -248,6 +340,7 @@ int sort_into_place(crb_sim* s, u64 n_src, bool save_prev, bool ingest) {
         R.n_ip = s->uniform ? 0 : s->n_ip;
         R.save_prev = save_prev ? 1 : 0;
         R.has_species = 1;
+        for (int d = 0; d < 3; ++d) R.mn[d] = d < s->D ? s->g.mn[d] : 0.0;
         k_reorder<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(R);
     }
     stage_end(s, 2, n_src ? 2 : 0);
@@ -455,6 +548,10 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     g.sm_switch = sn * savg;
     g.sm_nsub = nsub;
     s->nvox = g.nvox_local();
+    if (const char* kc = std::getenv("CRB_FORCE_KERNEL")) {
+        if (!std::strcmp(kc, "agent")) s->kernel_choice = 1;
+        if (!std::strcmp(kc, "tile")) s->kernel_choice = 2;
+    }
 
     auto bail = [&](int rc) {
         g_create_error = s->error;
@@ -585,6 +682,7 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
     }
     if ((rc = sort_into_place(s, n, true, true))) return rc;
     CU(s, cudaStreamSynchronize(s->stream));
+    plan_tile(s);
     s->have_agents = true;
     s->aux_settable = true;
     s->last_step_n = 0;
@@ -636,6 +734,23 @@ int crb_measure_fp64_peak(uint32_t device, double* tflops, double* ms_out) {
     *tflops = flops / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
     return 0;
+}
+
+int crb_debug_rsqrt(uint32_t device, const double* x, double* y, uint64_t n) {
+    if (!x || !y) return CRB_ERR_INVALID_ARG;
+    if (cudaSetDevice((int)device) != cudaSuccess) return CRB_ERR_CUDA;
+    double *dx = nullptr, *dy = nullptr;
+    if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess) return CRB_ERR_CUDA;
+    if (cudaMalloc(&dy, n * sizeof(double)) != cudaSuccess) {
+        cudaFree(dx);
+        return CRB_ERR_CUDA;
+    }
+    cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    k_rsqrt_test<<<blocks_for(n, 256), 256>>>(dx, dy, n);
+    cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    return cudaGetLastError() == cudaSuccess ? 0 : CRB_ERR_CUDA;
 }
 
 int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t* ids,
@@ -842,10 +957,10 @@ int crb_step(crb_sim* s, uint64_t n_steps) {
         KParams P = make_params(s);
         P.save_prev = last ? 1 : 0;
         stage_begin(s, 0);
-        launch_force(s, P, false);
+        int rc;
+        if ((rc = launch_force(s, P, false))) return rc;
         stage_end(s, 0, s->n ? 1 : 0);
         CU(s, cudaGetLastError());
-        int rc;
         s->last_step_n = s->n;
         if ((rc = sort_into_place(s, s->n, last, false))) return rc;
         s->iteration++;
@@ -869,7 +984,7 @@ int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
     if (!s->force_out)
         if ((rc = dalloc(s, &s->force_out, s->cap * 3))) return rc;
     KParams P = make_params(s);
-    launch_force(s, P, true);
+    if ((rc = launch_force(s, P, true))) return rc;
     s->launches += s->n ? 1 : 0;
     CU(s, cudaGetLastError());
     const double* cols[8] = {s->force_out, s->force_out + s->cap, s->force_out + 2 * s->cap, 0, 0, 0, 0, 0};

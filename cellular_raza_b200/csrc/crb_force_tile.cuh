@@ -1,0 +1,407 @@
+// crb_force_tile.cuh — shared-memory tiled neighbour-force kernel (uniform parameters), sm_100a.
+//
+// Replaces SubDomainBox::update_mechanics_interaction_step_1/2/3
+// (cellular_raza-core/src/backend/chili/update_mechanics.rs:153-238, 285-382) +
+// local_mechanics_update (:530-559) + apply_boundary (:387-406) for the closed model set.
+//
+// One CTA owns a pencil of voxels: one (a0, a1) row of the voxel grid and a segment [za, zb) of the
+// fastest axis.  Because agents are sorted by VoxelPlainIndex, the candidates of the whole pencil are
+// <= 9 (3-D) / 3 (2-D) CONTIGUOUS index ranges (one per neighbouring row, voxels za-1 .. zb), which
+// are staged once in shared memory:
+//     f64  sx, sy, sz        exact positions (used by the potential)
+//     f32x4 sposf            {x - min_x, y - min_y, z - min_z, voxel index}  (used by the filter)
+//     u8   ssp               species
+// Work of one warp = 32 consecutive target agents of the pencil:
+//   filter  every staged candidate of the (at most 9 x (zspan+2)) voxels around the warp's targets is
+//           broadcast from shared memory (one LDS.128 per candidate per warp) and tested against the
+//           32 targets at once in FP32: conservative distance test (cutoff inflated by the FP32
+//           rounding bound of the coordinates) AND voxel adjacency (chili only pairs agents of
+//           neighbouring voxels).  The result is one bit per (target, candidate) in a 32-candidate
+//           mask word per lane.
+//   drain   every lane walks the set bits of its own masks in ascending candidate order and evaluates
+//           the potential in FP64 exactly as the per-agent kernel does (same coef(), same pair
+//           weights), accumulating in registers.  A candidate the filter rejected has coefficient
+//           exactly zero (every potential of the model set is zero beyond its cutoff), so skipping it
+//           does not change the result; the summation order per target is ascending candidate
+//           index, a pure function of the sorted state => bitwise run-to-run determinism.
+//   fused epilogue: integrate_agent() (increment, AB/Euler, boundary, new key, histogram).
+// If the candidates of a pencil exceed the staging capacity the pencil is processed in several
+// z-windows; a single voxel whose 3^D neighbourhood alone exceeds it takes the per-agent path
+// (force_from_global) inside the same kernel.
+#pragma once
+#include "crb_kernels.cuh"
+
+namespace crb {
+
+constexpr int kTileRows = 9;
+constexpr int kTileMaxChunks = 20;  // mask words buffered per lane between two drains
+constexpr int kTileThreadsMax = 256;
+
+struct TileLaunch {
+    int seg_len;   // voxels of the fastest axis per CTA
+    int nseg;      // segments per row
+    int x_begin;   // first local plane whose agents are targets
+    int x_count;   // number of such planes
+    u32 cap;       // staged-candidate capacity
+    int kmax;      // max voxels of a window + 1 (row stride of the wst table)
+    float cut2f;   // conservative FP32 cutoff^2 of the filter
+};
+
+__host__ __device__ inline size_t tile_smem_bytes(u32 cap, int kmax, int threads) {
+    const size_t c = cap + 32;  // padding: the filter reads up to 7 entries past a range
+    size_t b = 0;
+    b += 3 * c * sizeof(double);
+    b += c * sizeof(float4);
+    b += (size_t)kTileRows * (kmax + 1) * sizeof(u32);
+    b += (size_t)kTileMaxChunks * threads * sizeof(u32);
+    b += (size_t)(threads / 32) * kTileMaxChunks * sizeof(u32);
+    b += (c + 15) / 16 * 16;
+    return b + 64;
+}
+
+// per-target state of the drain
+template <int D>
+struct TileTarget {
+    double x[D];
+    double acc[D];
+    u32 my_v;       // local voxel index
+    u32 subv_lo;    // local voxel range of the target's chili subdomain (len 0 => weights 1)
+    u32 subv_len;
+    u8 sp;
+    int calc_flag;
+};
+
+template <int D, int INTER>
+__device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
+                                          const double* __restrict__ sx, const double* __restrict__ sy,
+                                          const double* __restrict__ sz, const float4* __restrict__ sposf,
+                                          const u8* __restrict__ ssp, const u32 j) {
+    double z[D];
+    z[0] = t.x[0] - sx[j];
+    if (D == 3) {
+        z[1] = t.x[1] - sy[j];
+        z[2] = t.x[2] - sz[j];
+    } else {
+        z[1] = t.x[1] - sy[j];
+    }
+    double r2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) r2 = fma(z[c], z[c], r2);
+    const u32 cvj = __float_as_uint(sposf[j].w);
+    const bool same_voxel = cvj == t.my_v;
+    const bool same_sub = (u32)(cvj - t.subv_lo) < t.subv_len;
+    const bool keep = same_voxel | !same_sub;
+    const bool same_species = Pot<INTER>::kUsesSpecies ? (ssp[j] == t.sp) : true;
+    double cf = own.coef(r2, ext_radius, same_species, &t.calc_flag);
+    cf = keep ? cf : 0.5 * cf;
+#pragma unroll
+    for (int c = 0; c < D; ++c) t.acc[c] = fma(z[c], cf, t.acc[c]);
+}
+
+// per-agent path over global memory (same arithmetic as k_force_integrate, uniform parameters)
+template <int D, int INTER>
+__device__ __forceinline__ void force_from_global(const KParams& P, const u64 i, const u32 v, const int i0,
+                                               const int i1, const int i2, const double* xi,
+                                               double* acc) {
+    const Grid& g = P.g;
+    const int n1 = g.ng[1], n2 = g.ng[2];
+    Pot<INTER> own;
+    own.init(P.u.ip);
+    const u8 spi = Pot<INTER>::kUsesSpecies ? P.A.species[i] : 0;
+    const u32 own_lo = P.start[v], own_hi = P.start[v + 1];
+    u32 sub_lo = 0, sub_hi = 0;
+    if (P.weight_mode == CRB_WEIGHT_CHILI) {
+        const u64 plane = (u64)n1 * n2;
+        const u64 gp = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
+        const u64 s = g.sub_of(gp);
+        const u64 base = (u64)g.p0 * plane, nloc = g.nvox_local();
+        u64 f = g.sub_first_voxel(s), l = g.sub_first_voxel(s + 1);
+        f = f < base ? 0 : (f - base > nloc ? nloc : f - base);
+        l = l < base ? 0 : (l - base > nloc ? nloc : l - base);
+        sub_lo = P.start[f];
+        sub_hi = P.start[l];
+    }
+    int calc_flag = 0;
+    const int z_lo = i2 > 0 ? i2 - 1 : 0;
+    const int z_hi = i2 + 1 < n2 ? i2 + 1 : n2 - 1;
+    for (int d0 = -1; d0 <= 1; ++d0) {
+        const int X = i0 + d0;
+        if (X < 0 || X >= g.L0) continue;
+        for (int d1 = -1; d1 <= 1; ++d1) {
+            const int Y = i1 + d1;
+            if (Y < 0 || Y >= n1) continue;
+            const u32 row = ((u32)X * (u32)n1 + (u32)Y) * (u32)n2;
+            const u32 jb = P.start[row + z_lo], je = P.start[row + z_hi + 1];
+            for (u32 j = jb; j < je; ++j) {
+                if (j == (u32)i) continue;
+                double z[D];
+                double r2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    z[c] = xi[c] - __ldg(&P.A.pos[c][j]);
+                    r2 = fma(z[c], z[c], r2);
+                }
+                const bool same_voxel = (j >= own_lo) & (j < own_hi);
+                const bool same_sub = (j >= sub_lo) & (j < sub_hi);
+                const bool keep = same_voxel | !same_sub;
+                const u8 spj = Pot<INTER>::kUsesSpecies ? __ldg(&P.A.species[j]) : 0;
+                double cf = own.coef(r2, P.u.ip[0], spi == spj, &calc_flag);
+                cf = keep ? cf : 0.5 * cf;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[c] = fma(z[c], cf, acc[c]);
+            }
+        }
+    }
+    if (calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
+}
+
+template <int D, int INTER, bool FORCE_ONLY>
+__global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams P, const TileLaunch T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = nthreads >> 5;
+    const Grid& g = P.g;
+    const int n1 = g.ng[1], n2 = g.ng[2];
+
+    // ---- carve shared memory -----------------------------------------------------------------------
+    const u32 capp = T.cap + 32;
+    double* sx = reinterpret_cast<double*>(smem_raw);
+    double* sy = sx + capp;
+    double* sz = sy + capp;
+    float4* sposf = reinterpret_cast<float4*>(sz + capp);
+    u32* wst = reinterpret_cast<u32*>(sposf + capp);             // [kTileRows][kmax + 1]
+    u32* masks = wst + kTileRows * (T.kmax + 1);                 // [kTileMaxChunks][nthreads]
+    u32* cbase = masks + kTileMaxChunks * nthreads;              // [nwarps][kTileMaxChunks]
+    u8* ssp = reinterpret_cast<u8*>(cbase + nwarps * kTileMaxChunks);
+    __shared__ u32 s_rowvox[kTileRows];   // first voxel (local plain index) of every neighbour row
+    __shared__ u32 s_g0[kTileRows];       // first global agent index staged per row
+    __shared__ u32 s_rs[kTileRows + 1];   // staged index of the first candidate of every row
+    __shared__ int s_valid[kTileRows];
+    __shared__ int s_kc;
+
+    // ---- which pencil ------------------------------------------------------------------------------
+    const int seg = blockIdx.x % T.nseg;
+    const int rowid = blockIdx.x / T.nseg;
+    const int Y = rowid % n1;
+    const int X = T.x_begin + rowid / n1;
+    const int za = seg * T.seg_len;
+    const int zb = min(za + T.seg_len, n2);
+    if (tid < kTileRows) {
+        const int d0 = tid / 3 - 1, d1 = tid % 3 - 1;
+        const int XX = X + d0, YY = Y + d1;
+        const bool ok = XX >= 0 && XX < g.L0 && YY >= 0 && YY < n1 && (D == 3 || d1 == 0);
+        s_valid[tid] = ok ? 1 : 0;
+        s_rowvox[tid] = ok ? ((u32)XX * (u32)n1 + (u32)YY) * (u32)n2 : 0u;
+    }
+    __syncthreads();
+    const u32 rv_c = s_rowvox[4];
+
+    Pot<INTER> own;
+    own.init(P.u.ip);
+    const double ext_radius = P.u.ip[0];
+
+    int z = za;
+    while (z < zb) {
+        // ---- window size: largest kc with all candidates of voxels [z-1, z+kc] staged ---------------
+        if (tid == 0) s_kc = 0;
+        __syncthreads();
+        {
+            // common case first: the whole remaining segment fits
+            int found = 0;
+            for (int kk = zb - z - tid; kk >= 1 && !found; kk -= nthreads) {
+                const int wa = max(z - 1, 0), wb = min(z + kk + 1, n2);
+                u32 total = 0;
+#pragma unroll
+                for (int r = 0; r < kTileRows; ++r)
+                    if (s_valid[r]) total += P.start[s_rowvox[r] + wb] - P.start[s_rowvox[r] + wa];
+                if (total <= T.cap) {
+                    atomicMax(&s_kc, kk);
+                    found = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int kc = s_kc;
+        if (kc == 0) {
+            // the neighbourhood of voxel z alone exceeds the staging capacity: per-agent path
+            const u32 v = rv_c + (u32)z;
+            const u32 t0 = P.start[v], t1 = P.start[v + 1];
+            for (u32 i = t0 + tid; i < t1; i += nthreads) {
+                double xi[D], acc[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    xi[c] = P.A.pos[c][i];
+                    acc[c] = 0.0;
+                }
+                force_from_global<D, INTER>(P, i, v, X, Y, z, xi, acc);
+                if constexpr (FORCE_ONLY) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
+                } else {
+                    integrate_agent<D, true>(P, i, v, t0, X, Y, z, xi, acc);
+                }
+            }
+            z += 1;
+            __syncthreads();
+            continue;
+        }
+        const int wa = max(z - 1, 0), wb = min(z + kc + 1, n2);
+        const int W = wb - wa;  // voxels in the window
+
+        // ---- row ranges -------------------------------------------------------------------------------
+        if (warp == 0) {
+            u32 a = 0, n = 0;
+            if (lane < kTileRows && s_valid[lane]) {
+                a = P.start[s_rowvox[lane] + wa];
+                n = P.start[s_rowvox[lane] + wb] - a;
+            }
+            u32 incl = n;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane < kTileRows) {
+                s_g0[lane] = a;
+                s_rs[lane] = incl - n;
+            }
+            if (lane == kTileRows - 1) s_rs[kTileRows] = incl;
+        }
+        __syncthreads();
+
+        // ---- stage candidates (coalesced) and the per-voxel offsets ------------------------------------
+        {
+            const u32 total = s_rs[kTileRows];
+            int r = 0;
+            for (u32 k = tid; k < total; k += nthreads) {
+                while (k >= s_rs[r + 1]) ++r;
+                const u32 gi = s_g0[r] + (k - s_rs[r]);
+                sx[k] = P.A.pos[0][gi];
+                sy[k] = P.A.pos[1][gi];
+                if (D == 3) sz[k] = P.A.pos[2][gi];
+                sposf[k] = P.A.posf[gi];
+                if (Pot<INTER>::kUsesSpecies) ssp[k] = P.A.species[gi];
+            }
+            // zero the padding the filter may read
+            if (tid < 32) sposf[total + tid] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
+            const int stride = T.kmax + 1;
+            for (int idx = tid; idx < kTileRows * (W + 1); idx += nthreads) {
+                const int rr = idx / (W + 1), k = idx - rr * (W + 1);
+                wst[rr * stride + k] =
+                    s_valid[rr] ? s_rs[rr] + (P.start[s_rowvox[rr] + wa + k] - s_g0[rr]) : s_rs[rr];
+            }
+        }
+        __syncthreads();
+
+        // ---- targets ------------------------------------------------------------------------------------
+        const u32 t0 = P.start[rv_c + z], t1 = P.start[rv_c + z + kc];
+        const int ngroups = (int)((t1 - t0 + 31) >> 5);
+        const int stride = T.kmax + 1;
+        for (int grp = warp; grp < ngroups; grp += nwarps) {
+            const u32 i_raw = t0 + (u32)grp * 32u + (u32)lane;
+            const bool valid = i_raw < t1;
+            const u32 i = valid ? i_raw : t1 - 1;
+            const u32 sj_self = s_rs[4] + (i - s_g0[4]);
+            const float4 pf = sposf[sj_self];
+            TileTarget<D> t;
+            t.x[0] = sx[sj_self];
+            t.x[1] = sy[sj_self];
+            if (D == 3) t.x[2] = sz[sj_self];
+#pragma unroll
+            for (int c = 0; c < D; ++c) t.acc[c] = 0.0;
+            t.my_v = __float_as_uint(pf.w);
+            t.sp = Pot<INTER>::kUsesSpecies ? ssp[sj_self] : 0;
+            t.calc_flag = 0;
+            t.subv_lo = 0;
+            t.subv_len = 0;
+            const int zt = (int)(t.my_v - rv_c);
+            if (P.weight_mode == CRB_WEIGHT_CHILI && g.sm_nsub <= 1) {
+                t.subv_len = (u32)g.nvox_local();  // one chili subdomain: everything is "local"
+            } else if (P.weight_mode == CRB_WEIGHT_CHILI) {
+                const u64 plane = (u64)n1 * n2;
+                const u64 gp = ((u64)(X + g.p0) * n1 + Y) * n2 + zt;
+                const u64 s = g.sub_of(gp);
+                const u64 base = (u64)g.p0 * plane, nloc = g.nvox_local();
+                u64 f = g.sub_first_voxel(s), l = g.sub_first_voxel(s + 1);
+                f = f < base ? 0 : (f - base > nloc ? nloc : f - base);
+                l = l < base ? 0 : (l - base > nloc ? nloc : l - base);
+                t.subv_lo = (u32)f;
+                t.subv_len = (u32)(l - f);
+            }
+            // filter coordinates; lanes without a target never pass
+            const float qnan = __uint_as_float(0x7fc00000u);
+            const float xf = valid ? pf.x : qnan, yf = pf.y, zf = pf.z;
+            const int zmin = __shfl_sync(0xffffffffu, zt, 0);
+            const int zmax = __shfl_sync(0xffffffffu, zt, 31);
+            const int klo = max(zmin - 1, wa) - wa, khi = min(zmax + 2, wb) - wa;
+
+            int nch = 0;
+            auto drain = [&]() {
+                __syncwarp();
+                int c = 0;
+                u32 m = 0, base = 0;
+                while (true) {
+                    while (m == 0) {
+                        if (c >= nch) break;
+                        m = masks[c * nthreads + tid];
+                        base = cbase[warp * kTileMaxChunks + c];
+                        ++c;
+                    }
+                    if (m == 0) break;
+                    const u32 b = __ffs(m) - 1;
+                    m &= m - 1;
+                    tile_eval<D, INTER>(t, own, ext_radius, sx, sy, sz, sposf, ssp, base + b);
+                }
+                __syncwarp();
+                nch = 0;
+            };
+
+            for (int r = 0; r < kTileRows; ++r) {
+                const u32 lo = wst[r * stride + klo], hi = wst[r * stride + khi];
+                if (lo >= hi) continue;  // warp-uniform
+                // candidate voxel must be within +-1 of the target's voxel along the fastest axis
+                const u32 rowv = t.my_v + (s_rowvox[r] - rv_c) - 1u;
+                for (u32 base = lo; base < hi; base += 32) {
+                    const u32 cnt = min(32u, hi - base);
+                    u32 m = 0;
+                    for (u32 k0 = 0; k0 < cnt; k0 += 8) {
+                        u32 m8 = 0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 cnd = sposf[base + k0 + u];
+                            const float dx = cnd.x - xf, dy = cnd.y - yf, dz = cnd.z - zf;
+                            float d2 = dx * dx;
+                            d2 = fmaf(dy, dy, d2);
+                            if (D == 3) d2 = fmaf(dz, dz, d2);
+                            const bool adj = (u32)(__float_as_uint(cnd.w) - rowv) <= 2u;
+                            if (adj && d2 <= T.cut2f) m8 |= 1u << u;
+                        }
+                        m |= m8 << k0;
+                    }
+                    if (cnt < 32u) m &= (1u << cnt) - 1u;
+                    const u32 dself = sj_self - base;
+                    if (dself < 32u) m &= ~(1u << dself);
+                    masks[nch * nthreads + tid] = m;
+                    if (lane == 0) cbase[warp * kTileMaxChunks + nch] = base;
+                    ++nch;
+                    if (nch == kTileMaxChunks) drain();
+                }
+            }
+            drain();
+
+            if (valid) {
+                if (t.calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
+                if constexpr (FORCE_ONLY) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = t.acc[c];
+                } else {
+                    integrate_agent<D, true>(P, i, t.my_v, P.start[t.my_v], X, Y, zt, t.x, t.acc);
+                }
+            }
+        }
+        z += kc;
+        __syncthreads();
+    }
+}
+
+}  // namespace crb

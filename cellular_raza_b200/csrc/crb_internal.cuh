@@ -61,6 +61,10 @@ struct State {
     u64* id;
     u8* species;
     u8* hlen;  // entries held by the ring buffers (0..solver_order)
+    // FP32 filter copy written by the reorder pass: {x - min_x, y - min_y, z - min_z (0 in 2-D),
+    // bit pattern of the local voxel index}.  Only read by the conservative distance pre-test of
+    // k_force_tile; never enters a result.
+    float4* posf;
 };
 
 struct Uniform {

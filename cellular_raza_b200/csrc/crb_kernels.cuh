@@ -61,6 +61,22 @@ __device__ __forceinline__ bool voxel_of(const Grid& g, const double* p, int* i0
 // why reciprocal square roots and multiplication chains replace the reference's
 // norm/normalize/powf sequence (SURVEY.md "hard parts").
 // ------------------------------------------------------------------------------------------------
+// 1/sqrt(x) for normal, positive x: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, ~20 good bits) refined by
+// two Newton steps y <- y + (y/2)(1 - x y^2)  => relative error < 2^-52 (checked on the device by
+// tests/test_gpu_kernels.py::test_rsqrt_accuracy).  Replaces CUDA's rsqrt(), whose slow path for
+// denormals/inf costs a CALL per pair.  x == 0 gives inf/NaN: callers test r2 == 0 themselves.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double e = fma(-hx * y, y, 0.5);  // (1 - x y^2) / 2
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
 template <int INTER>
 struct Pot;
 
@@ -81,7 +97,7 @@ struct PotCellSorting {
     __device__ __forceinline__ double coef(double r2, double ext_radius, bool same_species,
                                            int* flag) const {
         if (r2 == 0.0) return 0.0;  // own_pos == ext_pos -> zero force (:60-63)
-        const double rinv = rsqrt(r2);
+        const double rinv = rsqrt_nr(r2);
         const double r_true = r2 * rinv;
         const bool clamp = r_true < rmin;  // (:51-52, 67-68): r is clamped, dir is not
         const double r = clamp ? rmin : r_true;
@@ -119,7 +135,7 @@ struct Pot<CRB_INT_MORSE> {
     }
     __device__ __forceinline__ double coef(double r2, double ext_radius, bool, int*) const {
         if (r2 == 0.0) return 0.0;
-        const double rinv = rsqrt(r2);
+        const double rinv = rsqrt_nr(r2);
         const double dist = r2 * rinv;
         if (dist > cutoff) return 0.0;
         const double e = exp(-a * (dist - (radius + ext_radius)));
@@ -141,7 +157,7 @@ struct Pot<CRB_INT_BOUND_LJ> {
     }
     __device__ __forceinline__ double coef(double r2, double, bool, int*) const {
         if (r2 == 0.0) return __longlong_as_double(0x7ff8000000000000ll);
-        const double rinv = rsqrt(r2);
+        const double rinv = rsqrt_nr(r2);
         const double r = r2 * rinv;
         const double x = sigma * rinv;
         const double x2 = x * x;
@@ -175,7 +191,7 @@ struct Pot<CRB_INT_MIE> {
             *flag = 1;  // CalcError: identical position for two objects
             return 0.0;
         }
-        const double rinv = rsqrt(r2);
+        const double rinv = rsqrt_nr(r2);
         const double r = r2 * rinv;
         if (r > cutoff) return 0.0;
         const double sigma = sig_factor * (radius + ext_radius);
@@ -244,109 +260,16 @@ __device__ __forceinline__ void philox_normal4(u64 seed, u64 id, u64 iter, u32 s
 }
 
 // ------------------------------------------------------------------------------------------------
-// force + integrate + boundary + new key, one thread per agent of A (sorted by voxel).
-//
-// Pair weights (SURVEY.md finding 2; chili/update_mechanics.rs:186-234, 285-382): agent i always
-// receives 1/2 f_own(own = i, ext = j).  The other half, f_ext(own = j, ext = i), reaches i when j
-// is in the same voxel, in another chili subdomain, or always in PHYSICAL mode.  Because chili's
-// subdomains are contiguous plain-index chunks and agents are sorted by plain index, "same
-// voxel" and "same subdomain" are index-range tests on j.
+// A7-A10 for one agent: increment, Adams-Bashforth/Euler update, reflective boundary, new voxel key,
+// migration flag and histogram.  Shared by every force kernel (fused epilogue: the force never
+// travels through HBM).
 // ------------------------------------------------------------------------------------------------
-template <int D, int INTER, bool UNIFORM, bool FORCE_ONLY>
-__global__ void __launch_bounds__(kForceThreads)
-    k_force_integrate(const KParams P, const u64 first, const u64 count) {
-    const u64 t = (u64)blockIdx.x * kForceThreads + threadIdx.x;
-    if (t >= count) return;
-    const u64 i = first + t;
+template <int D, bool UNIFORM>
+__device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, const u32 v,
+                                                const u32 own_lo, const int i0, const int i1,
+                                                const int i2, const double* xi, const double* acc) {
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
-
-    double xi[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) xi[c] = P.A.pos[c][i];
-    double ipi[CRB_MAX_INTER_PARAMS];
-#pragma unroll
-    for (int k = 0; k < Pot<INTER>::NI; ++k) ipi[k] = UNIFORM ? P.u.ip[k] : P.A.ip[k][i];
-    Pot<INTER> own;
-    own.init(ipi);
-    const u8 spi = Pot<INTER>::kUsesSpecies ? P.A.species[i] : 0;
-
-    const u32 v = P.key[i];
-    const int i2 = (int)(v % (u32)n2);
-    const u32 tq = v / (u32)n2;
-    const int i1 = (int)(tq % (u32)n1);
-    const int i0 = (int)(tq / (u32)n1);  // local plane
-
-    const u32 own_lo = P.start[v], own_hi = P.start[v + 1];
-    u32 sub_lo = 0, sub_hi = 0;  // agents of i's chili subdomain (empty range => all weights 1)
-    if (P.weight_mode == CRB_WEIGHT_CHILI) {
-        const u64 plane = (u64)n1 * n2;
-        const u64 gp = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
-        const u64 s = g.sub_of(gp);
-        const u64 base = (u64)g.p0 * plane, nloc = g.nvox_local();
-        u64 f = g.sub_first_voxel(s), l = g.sub_first_voxel(s + 1);
-        f = f < base ? 0 : (f - base > nloc ? nloc : f - base);
-        l = l < base ? 0 : (l - base > nloc ? nloc : l - base);
-        sub_lo = P.start[f];
-        sub_hi = P.start[l];
-    }
-
-    double acc[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = 0.0;
-    int calc_flag = 0;
-
-    const int z_lo = i2 > 0 ? i2 - 1 : 0;
-    const int z_hi = i2 + 1 < n2 ? i2 + 1 : n2 - 1;
-    for (int d0 = -1; d0 <= 1; ++d0) {
-        const int X = i0 + d0;
-        if (X < 0 || X >= g.L0) continue;
-        for (int d1 = -1; d1 <= 1; ++d1) {
-            const int Y = i1 + d1;
-            if (Y < 0 || Y >= n1) continue;
-            const u32 row = ((u32)X * (u32)n1 + (u32)Y) * (u32)n2;
-            const u32 jb = P.start[row + z_lo], je = P.start[row + z_hi + 1];
-            for (u32 j = jb; j < je; ++j) {
-                double z[D];
-                double r2 = 0.0;
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    z[c] = xi[c] - __ldg(&P.A.pos[c][j]);
-                    r2 = fma(z[c], z[c], r2);
-                }
-                if (j == (u32)i) continue;
-                const bool same_voxel = (j >= own_lo) & (j < own_hi);
-                const bool same_sub = (j >= sub_lo) & (j < sub_hi);
-                const bool keep = same_voxel | !same_sub;  // second half reaches i
-                const u8 spj = Pot<INTER>::kUsesSpecies ? __ldg(&P.A.species[j]) : 0;
-                double cf;
-                if (UNIFORM) {
-                    const double ext_radius = ipi[0];
-                    cf = own.coef(r2, ext_radius, spi == spj, &calc_flag);
-                    cf = keep ? cf : 0.5 * cf;
-                } else {
-                    double ipj[CRB_MAX_INTER_PARAMS];
-#pragma unroll
-                    for (int k = 0; k < Pot<INTER>::NI; ++k) ipj[k] = __ldg(&P.A.ip[k][j]);
-                    const double ci = own.coef(r2, ipj[0], spi == spj, &calc_flag);
-                    cf = 0.5 * ci;
-                    if (keep) {
-                        Pot<INTER> other;
-                        other.init(ipj);
-                        cf += 0.5 * other.coef(r2, ipi[0], spi == spj, &calc_flag);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < D; ++c) acc[c] = fma(z[c], cf, acc[c]);
-            }
-        }
-    }
-    if (calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
-
-    if constexpr (FORCE_ONLY) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
-    } else {
     // ---- A7: Mechanics::calculate_increment / get_random_contribution ---------------------------
     double mp[CRB_MAX_MECH_PARAMS];
 #pragma unroll
@@ -478,7 +401,114 @@ __global__ void __launch_bounds__(kForceThreads)
         }
     }
     P.B.hlen[i] = (u8)n_prev;
-    }  // !FORCE_ONLY
+}
+
+// ------------------------------------------------------------------------------------------------
+// force + integrate + boundary + new key, one thread per agent of A (sorted by voxel).
+//
+// Pair weights (SURVEY.md finding 2; chili/update_mechanics.rs:186-234, 285-382): agent i always
+// receives 1/2 f_own(own = i, ext = j).  The other half, f_ext(own = j, ext = i), reaches i when j
+// is in the same voxel, in another chili subdomain, or always in PHYSICAL mode.  Because chili's
+// subdomains are contiguous plain-index chunks and agents are sorted by plain index, "same
+// voxel" and "same subdomain" are index-range tests on j.
+// ------------------------------------------------------------------------------------------------
+template <int D, int INTER, bool UNIFORM, bool FORCE_ONLY>
+__global__ void __launch_bounds__(kForceThreads)
+    k_force_integrate(const KParams P, const u64 first, const u64 count) {
+    const u64 t = (u64)blockIdx.x * kForceThreads + threadIdx.x;
+    if (t >= count) return;
+    const u64 i = first + t;
+    const Grid& g = P.g;
+    const int n1 = g.ng[1], n2 = g.ng[2];
+
+    double xi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) xi[c] = P.A.pos[c][i];
+    double ipi[CRB_MAX_INTER_PARAMS];
+#pragma unroll
+    for (int k = 0; k < Pot<INTER>::NI; ++k) ipi[k] = UNIFORM ? P.u.ip[k] : P.A.ip[k][i];
+    Pot<INTER> own;
+    own.init(ipi);
+    const u8 spi = Pot<INTER>::kUsesSpecies ? P.A.species[i] : 0;
+
+    const u32 v = P.key[i];
+    const int i2 = (int)(v % (u32)n2);
+    const u32 tq = v / (u32)n2;
+    const int i1 = (int)(tq % (u32)n1);
+    const int i0 = (int)(tq / (u32)n1);  // local plane
+
+    const u32 own_lo = P.start[v], own_hi = P.start[v + 1];
+    u32 sub_lo = 0, sub_hi = 0;  // agents of i's chili subdomain (empty range => all weights 1)
+    if (P.weight_mode == CRB_WEIGHT_CHILI) {
+        const u64 plane = (u64)n1 * n2;
+        const u64 gp = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
+        const u64 s = g.sub_of(gp);
+        const u64 base = (u64)g.p0 * plane, nloc = g.nvox_local();
+        u64 f = g.sub_first_voxel(s), l = g.sub_first_voxel(s + 1);
+        f = f < base ? 0 : (f - base > nloc ? nloc : f - base);
+        l = l < base ? 0 : (l - base > nloc ? nloc : l - base);
+        sub_lo = P.start[f];
+        sub_hi = P.start[l];
+    }
+
+    double acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.0;
+    int calc_flag = 0;
+
+    const int z_lo = i2 > 0 ? i2 - 1 : 0;
+    const int z_hi = i2 + 1 < n2 ? i2 + 1 : n2 - 1;
+    for (int d0 = -1; d0 <= 1; ++d0) {
+        const int X = i0 + d0;
+        if (X < 0 || X >= g.L0) continue;
+        for (int d1 = -1; d1 <= 1; ++d1) {
+            const int Y = i1 + d1;
+            if (Y < 0 || Y >= n1) continue;
+            const u32 row = ((u32)X * (u32)n1 + (u32)Y) * (u32)n2;
+            const u32 jb = P.start[row + z_lo], je = P.start[row + z_hi + 1];
+            for (u32 j = jb; j < je; ++j) {
+                double z[D];
+                double r2 = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    z[c] = xi[c] - __ldg(&P.A.pos[c][j]);
+                    r2 = fma(z[c], z[c], r2);
+                }
+                if (j == (u32)i) continue;
+                const bool same_voxel = (j >= own_lo) & (j < own_hi);
+                const bool same_sub = (j >= sub_lo) & (j < sub_hi);
+                const bool keep = same_voxel | !same_sub;  // second half reaches i
+                const u8 spj = Pot<INTER>::kUsesSpecies ? __ldg(&P.A.species[j]) : 0;
+                double cf;
+                if (UNIFORM) {
+                    const double ext_radius = ipi[0];
+                    cf = own.coef(r2, ext_radius, spi == spj, &calc_flag);
+                    cf = keep ? cf : 0.5 * cf;
+                } else {
+                    double ipj[CRB_MAX_INTER_PARAMS];
+#pragma unroll
+                    for (int k = 0; k < Pot<INTER>::NI; ++k) ipj[k] = __ldg(&P.A.ip[k][j]);
+                    const double ci = own.coef(r2, ipj[0], spi == spj, &calc_flag);
+                    cf = 0.5 * ci;
+                    if (keep) {
+                        Pot<INTER> other;
+                        other.init(ipj);
+                        cf += 0.5 * other.coef(r2, ipi[0], spi == spj, &calc_flag);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[c] = fma(z[c], cf, acc[c]);
+            }
+        }
+    }
+    if (calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
+
+    if constexpr (FORCE_ONLY) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
+    } else {
+        integrate_agent<D, UNIFORM>(P, i, v, own_lo, i0, i1, i2, xi, acc);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,6 +617,7 @@ struct ReorderParams {
     int n_mp, n_ip;  // per-agent parameter columns to move (0 when uniform)
     int save_prev;
     int has_species;
+    double mn[3];  // CartesianCuboid::min (origin of the FP32 filter coordinates)
 };
 
 __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
@@ -610,6 +641,12 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
             R.Y.h0x[c][d] = R.B.h0x[c][i];
             R.Y.h0v[c][d] = R.B.h0v[c][i];
         }
+    }
+    {
+        const double p0 = R.B.pos[0][i], p1 = R.B.pos[1][i];
+        const double p2 = R.D == 3 ? R.B.pos[2][i] : R.mn[2];
+        R.Y.posf[d] = make_float4((float)(p0 - R.mn[0]), (float)(p1 - R.mn[1]), (float)(p2 - R.mn[2]),
+                                  __uint_as_float(v));
     }
     R.Y.hlen[d] = R.B.hlen[i];
     R.Y.id[d] = R.A.id[i];
@@ -737,6 +774,10 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
     if (r == 123.456) out[0] = r;
 }
 
+__global__ void k_rsqrt_test(const double* x, double* y, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = rsqrt_nr(x[i]);
+}
 __global__ void k_iota_u64(u64* a, u64 n) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;

@@ -214,6 +214,9 @@ void* crb_stream(crb_sim* sim);
  * the roofline denominator of the force kernel (MEASURED_PEAKS.json holds no FP64 figure). */
 int crb_measure_fp64_peak(uint32_t device, double* tflops, double* ms);
 
+/* parity tap of the device reciprocal square root used by every potential (y[i] = 1/sqrt(x[i])). */
+int crb_debug_rsqrt(uint32_t device, const double* x, double* y, uint64_t n);
+
 /* ---- helpers that restate reference setup arithmetic on the host -------------------------- */
 /* get_decomp_res (cartesian_cuboid_n.rs:19-59): returns 0 and (n, m, average_len) or
  * CRB_ERR_DECOMPOSE. */
