@@ -62,7 +62,7 @@ struct crb_sim {
     // k_force_tile geometry (chosen in crb_set_agents from the mean density)
     TileLaunch tile;
     bool tile_ok = false;
-    int tile_threads = kTileThreadsMax;
+    int tile_threads = kTileThreads;
     size_t tile_smem = 0;
     int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 tile kernel (env CRB_FORCE_KERNEL)
     bool timers_on = false;
@@ -241,9 +241,13 @@ void plan_tile(crb_sim* s) {
     const int nrows = s->D == 3 ? 9 : 3;
     const double owned_vox = (double)(g.own_hi - g.own_lo) * g.ng[1] * n2;
     const double rho = std::max((double)s->n / std::max(owned_vox, 1.0), 1e-3);
-    const u32 cap = 2048;
-    int seg_max = (int)std::floor(cap / (nrows * rho * 1.2)) - 2;
-    const int by_targets = (int)std::ceil(1.75 * kTileThreadsMax / rho);
+    // ~110 targets per 128-thread CTA (headroom for the Poisson spread of the pencil population:
+    // a 5th group of 32 would cost a whole extra pass), candidates <= staging budget of 3 CTAs/SM
+    const size_t budget = 74 * 1024;
+    const size_t fixed = (size_t)(kTileQueue + 2) * kTileThreads * sizeof(unsigned short) + 2048;
+    const u32 cap = (u32)(((budget - fixed) / 41) / 32 * 32);
+    int seg_max = (int)std::floor((cap - kTileRows * kTileRowPad) / (nrows * rho * 1.2)) - 2;
+    const int by_targets = (int)std::floor(110.0 / rho);
     seg_max = std::max(1, std::min(seg_max, by_targets));
     const int nseg = (n2 + seg_max - 1) / seg_max;
     TileLaunch& T = s->tile;
@@ -265,7 +269,7 @@ void plan_tile(crb_sim* s) {
         if ((double)cut2f < c2) cut2f = std::nextafterf(cut2f, INFINITY);
     }
     T.cut2f = cut2f;
-    s->tile_threads = kTileThreadsMax;
+    s->tile_threads = kTileThreads;
     s->tile_smem = tile_smem_bytes(T.cap, T.kmax, s->tile_threads);
     s->tile_ok = s->tile_smem <= 227 * 1024;
 }

@@ -34,8 +34,10 @@
 namespace crb {
 
 constexpr int kTileRows = 9;
-constexpr int kTileMaxChunks = 20;  // mask words buffered per lane between two drains
-constexpr int kTileThreadsMax = 256;
+constexpr int kTileQueue = 64;      // in-range candidate indices buffered per lane between two drains
+constexpr int kTileThreads = 128;
+constexpr int kTileSub = 4;         // lanes per candidate-window sub-group
+constexpr int kTileRowPad = 8;      // sentinel entries staged after every row (filter over-read)
 
 struct TileLaunch {
     int seg_len;   // voxels of the fastest axis per CTA
@@ -48,13 +50,12 @@ struct TileLaunch {
 };
 
 __host__ __device__ inline size_t tile_smem_bytes(u32 cap, int kmax, int threads) {
-    const size_t c = cap + 32;  // padding: the filter reads up to 7 entries past a range
+    const size_t c = cap + 32;  // cap includes kTileRows * kTileRowPad sentinels; +32 safety
     size_t b = 0;
     b += 3 * c * sizeof(double);
     b += c * sizeof(float4);
     b += (size_t)kTileRows * (kmax + 1) * sizeof(u32);
-    b += (size_t)kTileMaxChunks * threads * sizeof(u32);
-    b += (size_t)(threads / 32) * kTileMaxChunks * sizeof(u32);
+    b += (size_t)(kTileQueue + 2) * threads * sizeof(unsigned short);
     b += (c + 15) / 16 * 16;
     return b + 64;
 }
@@ -72,30 +73,40 @@ struct TileTarget {
 };
 
 template <int D, int INTER>
-__device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
-                                          const double* __restrict__ sx, const double* __restrict__ sy,
-                                          const double* __restrict__ sz, const float4* __restrict__ sposf,
-                                          const u8* __restrict__ ssp, const u32 j) {
-    double z[D];
-    z[0] = t.x[0] - sx[j];
-    if (D == 3) {
-        z[1] = t.x[1] - sy[j];
-        z[2] = t.x[2] - sz[j];
-    } else {
-        z[1] = t.x[1] - sy[j];
+__device__ __forceinline__ void tile_eval2(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
+                                           const double* __restrict__ sx, const double* __restrict__ sy,
+                                           const double* __restrict__ sz, const float4* __restrict__ sfb,
+                                           const u8* __restrict__ ssp, const u32 j0, const bool h0,
+                                           const u32 j1, const bool h1) {
+    // straight-line code for both candidates (coef() is branch-free) so that the two dependent FP64
+    // chains interleave; an empty slot points at the target itself (z == 0) and contributes +0.
+    const u32 jj[2] = {j0, j1};
+    const bool hh[2] = {h0, h1};
+    double z[2][D], cf[2];
+    int flag[2] = {0, 0};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const u32 j = jj[e];
+        z[e][0] = t.x[0] - sx[j];
+        z[e][1] = t.x[1] - sy[j];
+        if (D == 3) z[e][2] = t.x[2] - sz[j];
+        double r2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) r2 = fma(z[e][c], z[e][c], r2);
+        const u32 cvj = reinterpret_cast<const u32*>(sfb + (j >> 1))[2 + (j & 1)];
+        const bool same_voxel = cvj == t.my_v;
+        const bool same_sub = (u32)(cvj - t.subv_lo) < t.subv_len;
+        const bool keep = same_voxel | !same_sub;
+        const bool same_species = Pot<INTER>::kUsesSpecies ? (ssp[j] == t.sp) : true;
+        const double c0 = own.coef(r2, ext_radius, same_species, &flag[e]);
+        const double w = hh[e] ? (keep ? 1.0 : 0.5) : 0.0;
+        cf[e] = hh[e] ? c0 * w : 0.0;
     }
-    double r2 = 0.0;
+    t.calc_flag |= (h0 ? flag[0] : 0) | (h1 ? flag[1] : 0);
 #pragma unroll
-    for (int c = 0; c < D; ++c) r2 = fma(z[c], z[c], r2);
-    const u32 cvj = __float_as_uint(sposf[j].w);
-    const bool same_voxel = cvj == t.my_v;
-    const bool same_sub = (u32)(cvj - t.subv_lo) < t.subv_len;
-    const bool keep = same_voxel | !same_sub;
-    const bool same_species = Pot<INTER>::kUsesSpecies ? (ssp[j] == t.sp) : true;
-    double cf = own.coef(r2, ext_radius, same_species, &t.calc_flag);
-    cf = keep ? cf : 0.5 * cf;
+    for (int e = 0; e < 2; ++e)
 #pragma unroll
-    for (int c = 0; c < D; ++c) t.acc[c] = fma(z[c], cf, t.acc[c]);
+        for (int c = 0; c < D; ++c) t.acc[c] = fma(z[e][c], cf[e], t.acc[c]);
 }
 
 // per-agent path over global memory (same arithmetic as k_force_integrate, uniform parameters)
@@ -156,10 +167,11 @@ __device__ __forceinline__ void force_from_global(const KParams& P, const u64 i,
 }
 
 template <int D, int INTER, bool FORCE_ONLY>
-__global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams P, const TileLaunch T) {
+__global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P, const TileLaunch T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = nthreads >> 5;
+    constexpr int nthreads = kTileThreads;  // launch contract: blockDim.x == kTileThreads
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = nthreads >> 5;
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
 
@@ -168,14 +180,17 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
     double* sx = reinterpret_cast<double*>(smem_raw);
     double* sy = sx + capp;
     double* sz = sy + capp;
-    float4* sposf = reinterpret_cast<float4*>(sz + capp);
-    u32* wst = reinterpret_cast<u32*>(sposf + capp);             // [kTileRows][kmax + 1]
-    u32* masks = wst + kTileRows * (T.kmax + 1);                 // [kTileMaxChunks][nthreads]
-    u32* cbase = masks + kTileMaxChunks * nthreads;              // [nwarps][kTileMaxChunks]
-    u8* ssp = reinterpret_cast<u8*>(cbase + nwarps * kTileMaxChunks);
+    // FP32 filter copy, two candidates per 2 x 16 B so that one LDS.128 feeds a packed f32x2 op:
+    //   sfa[p] = {x[2p], x[2p+1], y[2p], y[2p+1]},  sfb[p] = {z[2p], z[2p+1], cv[2p], cv[2p+1]}
+    float4* sfa = reinterpret_cast<float4*>(sz + capp);
+    float4* sfb = sfa + capp / 2;
+    u32* wst = reinterpret_cast<u32*>(sfb + capp / 2);           // [kTileRows][kmax + 1]
+    unsigned short* q = reinterpret_cast<unsigned short*>(wst + kTileRows * (T.kmax + 1));  // [kTileQueue + 2][nthreads]
+    u8* ssp = reinterpret_cast<u8*>(q + (kTileQueue + 2) * nthreads);
     __shared__ u32 s_rowvox[kTileRows];   // first voxel (local plain index) of every neighbour row
     __shared__ u32 s_g0[kTileRows];       // first global agent index staged per row
     __shared__ u32 s_rs[kTileRows + 1];   // staged index of the first candidate of every row
+    __shared__ u32 s_rn[kTileRows];       // candidates staged per row (without sentinels)
     __shared__ int s_valid[kTileRows];
     __shared__ int s_kc;
 
@@ -214,7 +229,7 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
 #pragma unroll
                 for (int r = 0; r < kTileRows; ++r)
                     if (s_valid[r]) total += P.start[s_rowvox[r] + wb] - P.start[s_rowvox[r] + wa];
-                if (total <= T.cap) {
+                if (total + kTileRows * kTileRowPad <= T.cap) {
                     atomicMax(&s_kc, kk);
                     found = 1;
                 }
@@ -255,7 +270,8 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
                 a = P.start[s_rowvox[lane] + wa];
                 n = P.start[s_rowvox[lane] + wb] - a;
             }
-            u32 incl = n;
+            const u32 np = lane < kTileRows ? n + kTileRowPad : 0u;  // row + sentinels
+            u32 incl = np;
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) {
                 const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
@@ -263,7 +279,8 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
             }
             if (lane < kTileRows) {
                 s_g0[lane] = a;
-                s_rs[lane] = incl - n;
+                s_rs[lane] = incl - np;
+                s_rn[lane] = n;
             }
             if (lane == kTileRows - 1) s_rs[kTileRows] = incl;
         }
@@ -275,15 +292,38 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
             int r = 0;
             for (u32 k = tid; k < total; k += nthreads) {
                 while (k >= s_rs[r + 1]) ++r;
-                const u32 gi = s_g0[r] + (k - s_rs[r]);
-                sx[k] = P.A.pos[0][gi];
-                sy[k] = P.A.pos[1][gi];
-                if (D == 3) sz[k] = P.A.pos[2][gi];
-                sposf[k] = P.A.posf[gi];
-                if (Pot<INTER>::kUsesSpecies) ssp[k] = P.A.species[gi];
+                const u32 o = k - s_rs[r];
+                float4 pf4;
+                if (o < s_rn[r]) {
+                    const u32 gi = s_g0[r] + o;
+                    sx[k] = P.A.pos[0][gi];
+                    sy[k] = P.A.pos[1][gi];
+                    if (D == 3) sz[k] = P.A.pos[2][gi];
+                    pf4 = P.A.posf[gi];
+                    if (Pot<INTER>::kUsesSpecies) ssp[k] = P.A.species[gi];
+                } else {
+                    // sentinel: NaN coordinates never pass the distance test (the voxel word alone is
+                    // not enough: rowv wraps to 0xffffffff for targets of local voxel 0)
+                    const float qn_ = __uint_as_float(0x7fc00000u);
+                    pf4 = make_float4(qn_, qn_, qn_, __uint_as_float(0xffffffffu));
+                }
+                float* fa = reinterpret_cast<float*>(sfa + (k >> 1)) + (k & 1);
+                float* fb = reinterpret_cast<float*>(sfb + (k >> 1)) + (k & 1);
+                fa[0] = pf4.x;
+                fa[2] = pf4.y;
+                fb[0] = pf4.z;
+                fb[2] = pf4.w;
             }
-            // zero the padding the filter may read
-            if (tid < 32) sposf[total + tid] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
+            if (tid < 32) {
+                const float qn_ = __uint_as_float(0x7fc00000u);
+                const u32 k = total + tid;
+                float* fa = reinterpret_cast<float*>(sfa + (k >> 1)) + (k & 1);
+                float* fb = reinterpret_cast<float*>(sfb + (k >> 1)) + (k & 1);
+                fa[0] = qn_;
+                fa[2] = qn_;
+                fb[0] = qn_;
+                fb[2] = __uint_as_float(0xffffffffu);
+            }
             const int stride = T.kmax + 1;
             for (int idx = tid; idx < kTileRows * (W + 1); idx += nthreads) {
                 const int rr = idx / (W + 1), k = idx - rr * (W + 1);
@@ -297,12 +337,18 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
         const u32 t0 = P.start[rv_c + z], t1 = P.start[rv_c + z + kc];
         const int ngroups = (int)((t1 - t0 + 31) >> 5);
         const int stride = T.kmax + 1;
+        const u32 limit = (s_rs[kTileRows] + 24) & ~1u;  // last safe (even) start of an 8-candidate block
         for (int grp = warp; grp < ngroups; grp += nwarps) {
             const u32 i_raw = t0 + (u32)grp * 32u + (u32)lane;
             const bool valid = i_raw < t1;
             const u32 i = valid ? i_raw : t1 - 1;
             const u32 sj_self = s_rs[4] + (i - s_g0[4]);
-            const float4 pf = sposf[sj_self];
+            float4 pf;
+            {
+                const float* fa = reinterpret_cast<const float*>(sfa + (sj_self >> 1)) + (sj_self & 1);
+                const float* fb = reinterpret_cast<const float*>(sfb + (sj_self >> 1)) + (sj_self & 1);
+                pf = make_float4(fa[0], fa[2], fb[0], fb[2]);
+            }
             TileTarget<D> t;
             t.x[0] = sx[sj_self];
             t.x[1] = sy[sj_self];
@@ -331,60 +377,78 @@ __global__ void __launch_bounds__(kTileThreadsMax, 2) k_force_tile(const KParams
             // filter coordinates; lanes without a target never pass
             const float qnan = __uint_as_float(0x7fc00000u);
             const float xf = valid ? pf.x : qnan, yf = pf.y, zf = pf.z;
-            const int zmin = __shfl_sync(0xffffffffu, zt, 0);
-            const int zmax = __shfl_sync(0xffffffffu, zt, 31);
+            // every sub-group of kTileSub consecutive lanes streams its OWN candidate window (the
+            // voxels zmin-1 .. zmax+1 of its targets): lanes of different sub-groups read different
+            // shared-memory addresses in the same LDS.128 (still one wavefront), and the number of
+            // (target, candidate) tests drops with the z-span of the sub-group instead of the warp's.
+            const int zmin = __shfl_sync(0xffffffffu, zt, 0, kTileSub);
+            const int zmax = __shfl_sync(0xffffffffu, zt, kTileSub - 1, kTileSub);
             const int klo = max(zmin - 1, wa) - wa, khi = min(zmax + 2, wb) - wa;
 
-            int nch = 0;
+            // per-lane FIFO of in-range candidate indices (ascending): q[k][tid]
+            // (32-bit shared-window address kept in a register: one predicated STS + one predicated
+            // IADD per accepted candidate)
+            unsigned short* const q0 = q + tid;
+            const u32 qa0 = (u32)__cvta_generic_to_shared(q0);
+            u32 qa = qa0;
             auto drain = [&]() {
-                __syncwarp();
-                int c = 0;
-                u32 m = 0, base = 0;
-                while (true) {
-                    while (m == 0) {
-                        if (c >= nch) break;
-                        m = masks[c * nthreads + tid];
-                        base = cbase[warp * kTileMaxChunks + c];
-                        ++c;
-                    }
-                    if (m == 0) break;
-                    const u32 b = __ffs(m) - 1;
-                    m &= m - 1;
-                    tile_eval<D, INTER>(t, own, ext_radius, sx, sy, sz, sposf, ssp, base + b);
+                const u32 nq = (qa - qa0) / (2u * nthreads);
+                const u32 nqmax = __reduce_max_sync(0xffffffffu, nq);
+                for (u32 k = 0; k < nqmax; k += 2) {
+                    // two candidates per iteration: two independent FP64 chains in flight per lane
+                    const u32 e0 = q0[k * nthreads], e1 = q0[(k + 1) * nthreads];
+                    const bool h0 = (k < nq) & (e0 != sj_self), h1 = (k + 1 < nq) & (e1 != sj_self);
+                    const u32 j0 = h0 ? e0 : sj_self, j1 = h1 ? e1 : sj_self;
+                    tile_eval2<D, INTER>(t, own, ext_radius, sx, sy, sz, sfb, ssp, j0, h0, j1, h1);
                 }
-                __syncwarp();
-                nch = 0;
+                qa = qa0;
             };
+            const u32 qfull = qa0 + 2u * (kTileQueue - 8) * nthreads;
+            const float2 xf2 = make_float2(-xf, -xf), yf2 = make_float2(-yf, -yf), zf2 = make_float2(-zf, -zf);
 
             for (int r = 0; r < kTileRows; ++r) {
                 const u32 lo = wst[r * stride + klo], hi = wst[r * stride + khi];
-                if (lo >= hi) continue;  // warp-uniform
+                const u32 lo2 = lo & ~1u;  // blocks start at an even candidate (pair layout); the extra
+                                           // leading candidate is voxel zmin-2 or a sentinel: not adjacent
+                const u32 n = hi - lo2;
+                const u32 nmax = __reduce_max_sync(0xffffffffu, n);
+                if (nmax == 0) continue;  // warp-uniform
                 // candidate voxel must be within +-1 of the target's voxel along the fastest axis
                 const u32 rowv = t.my_v + (s_rowvox[r] - rv_c) - 1u;
-                for (u32 base = lo; base < hi; base += 32) {
-                    const u32 cnt = min(32u, hi - base);
-                    u32 m = 0;
-                    for (u32 k0 = 0; k0 < cnt; k0 += 8) {
-                        u32 m8 = 0;
+                for (u32 k0 = 0; k0 < nmax; k0 += 8) {
+                    if (__any_sync(0xffffffffu, qa > qfull)) drain();
+                    // a block that starts inside the lane's range may over-read <= 7 entries: those are
+                    // later voxels of the same row or the row's sentinels, never adjacent.  A block past
+                    // the lane's range is disabled through rowv (no voxel index is within 2 of 2^31).
+                    const u32 rv = k0 < n ? rowv : 0x80000000u;
+                    const u32 b8 = min(lo2 + k0, limit);
+                    float4 ca[4], cb[4];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const float4 cnd = sposf[base + k0 + u];
-                            const float dx = cnd.x - xf, dy = cnd.y - yf, dz = cnd.z - zf;
-                            float d2 = dx * dx;
-                            d2 = fmaf(dy, dy, d2);
-                            if (D == 3) d2 = fmaf(dz, dz, d2);
-                            const bool adj = (u32)(__float_as_uint(cnd.w) - rowv) <= 2u;
-                            if (adj && d2 <= T.cut2f) m8 |= 1u << u;
-                        }
-                        m |= m8 << k0;
+                    for (int u = 0; u < 4; ++u) {  // all loads first: the queue stores below alias smem
+                        ca[u] = sfa[(b8 >> 1) + u];
+                        cb[u] = sfb[(b8 >> 1) + u];
                     }
-                    if (cnt < 32u) m &= (1u << cnt) - 1u;
-                    const u32 dself = sj_self - base;
-                    if (dself < 32u) m &= ~(1u << dself);
-                    masks[nch * nthreads + tid] = m;
-                    if (lane == 0) cbase[warp * kTileMaxChunks + nch] = base;
-                    ++nch;
-                    if (nch == kTileMaxChunks) drain();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 dx = __fadd2_rn(make_float2(ca[u].x, ca[u].y), xf2);
+                        const float2 dy = __fadd2_rn(make_float2(ca[u].z, ca[u].w), yf2);
+                        float2 d2 = __fmul2_rn(dx, dx);
+                        d2 = __ffma2_rn(dy, dy, d2);
+                        if (D == 3) {
+                            const float2 dz = __fadd2_rn(make_float2(cb[u].x, cb[u].y), zf2);
+                            d2 = __ffma2_rn(dz, dz, d2);
+                        }
+                        const bool p0 = ((u32)(__float_as_uint(cb[u].z) - rv) <= 2u) & (d2.x <= T.cut2f);
+                        const bool p1 = ((u32)(__float_as_uint(cb[u].w) - rv) <= 2u) & (d2.y <= T.cut2f);
+                        if (p0) {
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u)) : "memory");
+                            qa += 2u * nthreads;
+                        }
+                        if (p1) {
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u + 1)) : "memory");
+                            qa += 2u * nthreads;
+                        }
+                    }
                 }
             }
             drain();

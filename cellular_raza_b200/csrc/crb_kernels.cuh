@@ -96,7 +96,7 @@ struct PotCellSorting {
     }
     __device__ __forceinline__ double coef(double r2, double ext_radius, bool same_species,
                                            int* flag) const {
-        if (r2 == 0.0) return 0.0;  // own_pos == ext_pos -> zero force (:60-63)
+        // branch-free: r2 == 0 (own_pos == ext_pos -> zero force, :60-63) is selected at the end
         const double rinv = rsqrt_nr(r2);
         const double r_true = r2 * rinv;
         const bool clamp = r_true < rmin;  // (:51-52, 67-68): r is clamped, dir is not
@@ -112,7 +112,8 @@ struct PotCellSorting {
         if (!same_species) st = fmin(st, 0.0);  // only the repelling part acts between species
         // spatial_cutoff = (1 + signum(range*(R1+R2) - r)) / 2 ; signum(+0) = 1
         const double cut = (range * Rs - r >= 0.0) ? 1.0 : 0.0;
-        const double c = st * cut * rinv;
+        double c = st * cut * rinv;
+        c = r2 == 0.0 ? 0.0 : c;
         return BENCH ? c : -c;
     }
 };
@@ -134,12 +135,11 @@ struct Pot<CRB_INT_MORSE> {
         m2sa = -2.0 * ip[3] * ip[1];
     }
     __device__ __forceinline__ double coef(double r2, double ext_radius, bool, int*) const {
-        if (r2 == 0.0) return 0.0;
         const double rinv = rsqrt_nr(r2);
         const double dist = r2 * rinv;
-        if (dist > cutoff) return 0.0;
         const double e = exp(-a * (dist - (radius + ext_radius)));
-        return m2sa * e * (1.0 - e) * rinv;
+        const double c = m2sa * e * (1.0 - e) * rinv;
+        return (r2 == 0.0 || dist > cutoff) ? 0.0 : c;  // (:158-162) zero beyond the cutoff / at r = 0
     }
 };
 
