@@ -195,7 +195,7 @@ def run_b200(args):
     if args.gpus > 1:
         from cellular_raza_b200 import multi_gpu_bench
 
-        return multi_gpu_bench.run(args, rank, world, local_rank)
+        return multi_gpu_bench.run(args, rank, world, local_rank, sys.modules[__name__])
 
     dev_id = local_rank
     torch.cuda.set_device(dev_id)

@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-CRB_ABI_VERSION = 1
+CRB_ABI_VERSION = 2
 CRB_MAX_DIM = 3
 
 # crb_status
@@ -78,6 +78,8 @@ class CrbConfig(C.Structure):
         ("dt", C.c_double),
         ("rng_seed", C.c_uint64),
         ("capacity", C.c_uint64),
+        ("ghost_capacity", C.c_uint64),
+        ("migration_capacity", C.c_uint64),
     ]
 
 
@@ -131,6 +133,15 @@ SYMBOLS = [
     ("crb_step", C.c_int, [_vp, C.c_uint64]),
     ("crb_sync", C.c_int, [_vp]),
     ("crb_iteration", C.c_uint64, [_vp]),
+    ("crb_slab_halo_bytes", C.c_uint64, [_vp]),
+    ("crb_slab_migration_bytes", C.c_uint64, [_vp]),
+    ("crb_slab_info", C.c_int, [_vp, _u64p]),
+    ("crb_slab_halo_export", C.c_int, [_vp, _vp, _vp]),
+    ("crb_slab_halo_import", C.c_int, [_vp, _vp, _vp]),
+    ("crb_slab_compute", C.c_int, [_vp, C.c_int]),
+    ("crb_slab_migration_export", C.c_int, [_vp, _vp, _vp, _u64p]),
+    ("crb_slab_migration_import", C.c_int, [_vp, _vp, _vp, _u64p]),
+    ("crb_slab_finish", C.c_int, [_vp, C.c_int]),
     ("crb_debug_forces", C.c_int, [_vp, C.c_uint64, _vp]),
     ("crb_get_migrations", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _u64p]),
     ("crb_get_voxel_counts", C.c_int, [_vp, C.c_uint64, _vp]),

@@ -36,8 +36,19 @@ struct crb_sim {
     bool uniform = true;
     bool uniform_declared = false;
     Uniform uni;
-    u64 cap = 0, n = 0;
+    u64 cap = 0, n = 0;  // owned-agent capacity / owned agents
+    u64 G = 0;           // ghost capacity per side = index of the first owned agent in every column
+    u64 cap_total = 0;   // cap + 2 G
+    u64 mcap = 0;        // migration capacity per side and step
     u64 nvox = 0;
+    // slab decomposition
+    int rank = 0, world = 1;
+    bool has_lo = false, has_hi = false;  // neighbours below / above along axis 0
+    HaloLayout hl;
+    MigLayout ml;
+    bool step_open = false;  // crb_slab_compute done, crb_slab_finish pending
+    u64 n_src = 0;           // unsorted sources of the open step (owned + arrivals)
+    u64 n_gone = 0;          // agents exported in the open step
     cudaStream_t stream = nullptr;
     State X, T, Y;  // X: sorted state read by the force pass, T: integrated, Y: reorder target
     u32 *key = nullptr, *key_alt = nullptr;
@@ -100,7 +111,7 @@ int dalloc(crb_sim* s, T** p, u64 count) {
 
 int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
     std::memset(&st, 0, sizeof(st));
-    const u64 c = s->cap * s->V;
+    const u64 c = s->cap_total * s->V;
     int rc;
     if (dynamic) {
         for (int d = 0; d < s->D; ++d) {
@@ -111,16 +122,16 @@ int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
             if ((rc = dalloc(s, &st.h0x[d], c))) return rc;
             if ((rc = dalloc(s, &st.h0v[d], c))) return rc;
         }
-        if ((rc = dalloc(s, &st.hlen, s->cap))) return rc;
-        if ((rc = dalloc(s, &st.posf, s->cap))) return rc;
+        if ((rc = dalloc(s, &st.hlen, s->cap_total))) return rc;
+        if ((rc = dalloc(s, &st.posf, s->cap_total))) return rc;
     }
     if (stat) {
-        if ((rc = dalloc(s, &st.id, s->cap))) return rc;
-        if ((rc = dalloc(s, &st.species, s->cap))) return rc;
+        if ((rc = dalloc(s, &st.id, s->cap_total))) return rc;
+        if ((rc = dalloc(s, &st.species, s->cap_total))) return rc;
         for (int k = 0; k < s->n_mp; ++k)
-            if ((rc = dalloc(s, &st.mp[k], s->cap))) return rc;
+            if ((rc = dalloc(s, &st.mp[k], s->cap_total))) return rc;
         for (int k = 0; k < s->n_ip; ++k)
-            if ((rc = dalloc(s, &st.ip[k], s->cap))) return rc;
+            if ((rc = dalloc(s, &st.ip[k], s->cap_total))) return rc;
     }
     return 0;
 }
@@ -163,7 +174,8 @@ KParams make_params(crb_sim* s) {
     P.B = s->T;
     P.u = s->uni;
     P.n = s->n;
-    P.cap = s->cap;
+    P.first = s->G;
+    P.cap = s->cap_total;
     P.key = s->key;
     P.start = s->start;
     P.newkey = s->newkey;
@@ -192,9 +204,9 @@ void launch_force_t(crb_sim* s, const KParams& P, bool force_only) {
     const u32 grid = blocks_for(P.n, kForceThreads);
     if (!grid) return;
     if (force_only)
-        k_force_integrate<D, INTER, UNIFORM, true><<<grid, kForceThreads, 0, s->stream>>>(P, 0, P.n);
+        k_force_integrate<D, INTER, UNIFORM, true><<<grid, kForceThreads, 0, s->stream>>>(P, P.first, P.n);
     else
-        k_force_integrate<D, INTER, UNIFORM, false><<<grid, kForceThreads, 0, s->stream>>>(P, 0, P.n);
+        k_force_integrate<D, INTER, UNIFORM, false><<<grid, kForceThreads, 0, s->stream>>>(P, P.first, P.n);
 }
 
 template <int D, int INTER>
@@ -313,19 +325,26 @@ int launch_force(crb_sim* s, const KParams& P, bool force_only) {
     return 0;
 }
 
-// scan count_new -> start_alt, fill, reorder T(+X static) -> Y, swap
-int sort_into_place(crb_sim* s, u64 n_src, bool save_prev, bool ingest) {
+// scan count_new -> start_alt, fill, reorder T(+X static) -> Y, swap.
+// n_src: unsorted sources at [G, G + n_src) (owned agents of the step + arrivals, some of them marked
+// CRB_KEY_GONE); n_new: agents that remain = destination slots [G, G + n_new).
+int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool ingest) {
     const u64 nv = s->nvox;
     stage_begin(s, 1);
     k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt,
                                                             s->tile_sums, nv);
-    k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv);
+    k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv,
+                                                    (u32)s->G);
     k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
     stage_end(s, 1, 3);
     stage_begin(s, 2);
+    int nl = 0;
     if (n_src) {
         k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt,
-                                                             s->tmp_idx, n_src);
+                                                             s->tmp_idx, s->G, n_src);
+        ++nl;
+    }
+    if (n_new) {
         ReorderParams R;
         std::memset(&R, 0, sizeof(R));
         R.A = s->X;
@@ -337,7 +356,8 @@ int sort_into_place(crb_sim* s, u64 n_src, bool save_prev, bool ingest) {
         R.sortkey = s->sortkey;
         R.key_out = s->key_alt;
         R.slot_of_src = ingest ? s->slot_of_src : nullptr;
-        R.n = n_src;
+        R.n = n_new;
+        R.first = s->G;
         R.D = s->D;
         R.V = s->V;
         R.n_mp = s->uniform ? 0 : s->n_mp;
@@ -345,9 +365,10 @@ int sort_into_place(crb_sim* s, u64 n_src, bool save_prev, bool ingest) {
         R.save_prev = save_prev ? 1 : 0;
         R.has_species = 1;
         for (int d = 0; d < 3; ++d) R.mn[d] = d < s->D ? s->g.mn[d] : 0.0;
-        k_reorder<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(R);
+        k_reorder<<<blocks_for(n_new, 256), 256, 0, s->stream>>>(R);
+        ++nl;
     }
-    stage_end(s, 2, n_src ? 2 : 0);
+    stage_end(s, 2, nl);
     std::swap(s->X, s->Y);
     std::swap(s->key, s->key_alt);
     std::swap(s->start, s->start_alt);
@@ -387,7 +408,7 @@ int upload_rows(crb_sim* s, const double* host, int width, double* const* cols, 
     CU(s, cudaMemcpyAsync(s->stage, host, n * width * sizeof(double), cudaMemcpyHostToDevice,
                           s->stream));
     double* c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < width; ++k) c[k] = cols[k];
+    for (int k = 0; k < width; ++k) c[k] = cols[k] ? cols[k] + s->G : nullptr;  // owned agents start at G
     k_unpack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, width, c[0], c[1], c[2], c[3],
                                                             c[4], c[5], c[6], c[7], n);
     s->launches++;
@@ -397,7 +418,7 @@ int upload_rows(crb_sim* s, const double* host, int width, double* const* cols, 
 int download_rows(crb_sim* s, double* host, int width, const double* const* cols, u64 n) {
     if (!n) return 0;
     const double* c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < width; ++k) c[k] = cols[k];
+    for (int k = 0; k < width; ++k) c[k] = cols[k] ? cols[k] + s->G : nullptr;
     k_pack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, width, c[0], c[1], c[2], c[3],
                                                           c[4], c[5], c[6], c[7], n);
     s->launches++;
@@ -502,8 +523,10 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
     if (cfg->solver_order > 2)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "solver_order must be 0, 1 or 2");
-    if (cfg->world_size != 1 || cfg->rank != 0)
-        return fail(nullptr, CRB_ERR_INVALID_ARG, "use crb_create with world_size 1 (slabs: crb_mgpu.h)");
+    if (cfg->world_size == 0 || cfg->rank >= cfg->world_size)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "rank must be < world_size");
+    if (cfg->world_size > cfg->n_voxels[0])
+        return fail(nullptr, CRB_ERR_DECOMPOSE, "DecomposeError: more slabs than voxel planes along axis 0");
     if (!(cfg->dt > 0.0)) return fail(nullptr, CRB_ERR_INVALID_ARG, "dt must be positive");
     const int D = (int)cfg->dim;
     u64 nv = 1;
@@ -512,9 +535,8 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
             return fail(nullptr, CRB_ERR_BOUNDARY, "Min must be smaller than Max for domain boundaries");
         nv *= cfg->n_voxels[i];
     }
-    if (nv >= (1ull << 31)) return fail(nullptr, CRB_ERR_INVALID_ARG, "more than 2^31 voxels");
-    if (cfg->capacity == 0 || cfg->capacity >= (1ull << 32) - 1)
-        return fail(nullptr, CRB_ERR_INVALID_ARG, "capacity must be in [1, 2^32-2]");
+    if (cfg->capacity == 0 || cfg->capacity >= (1ull << 31))
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "capacity must be in [1, 2^31)");
 
     crb_sim* s = new crb_sim();
     s->cfg = *cfg;
@@ -523,6 +545,10 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     s->n_mp = (int)crb_n_mech_params(cfg->mechanics_kind);
     s->n_ip = (int)crb_n_inter_params(cfg->interaction_kind);
     s->cap = cfg->capacity;
+    s->rank = (int)cfg->rank;
+    s->world = (int)cfg->world_size;
+    s->has_lo = s->rank > 0;
+    s->has_hi = s->rank + 1 < s->world;
     Grid& g = s->g;
     std::memset(&g, 0, sizeof(g));
     g.D = D;
@@ -532,10 +558,18 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     g.cax[0] = 0;
     g.cax[1] = D == 3 ? 1 : -1;
     g.cax[2] = D - 1;
-    g.L0 = g.ng[0];
-    g.p0 = 0;
-    g.own_lo = 0;
-    g.own_hi = g.ng[0];
+    {
+        // slab of whole voxel planes along axis 0: ranks below `rem` own one plane more; one ghost
+        // plane towards every neighbour
+        const int n0 = g.ng[0], W = s->world, r = s->rank;
+        const int base = n0 / W, rem = n0 % W;
+        const int nown = base + (r < rem ? 1 : 0);
+        const int gp_lo = r * base + std::min(r, rem);
+        g.own_lo = s->has_lo ? 1 : 0;
+        g.own_hi = g.own_lo + nown;
+        g.L0 = g.own_hi + (s->has_hi ? 1 : 0);
+        g.p0 = gp_lo - g.own_lo;
+    }
     for (int i = 0; i < D; ++i) {
         g.mn[i] = cfg->domain_min[i];
         g.mx[i] = cfg->domain_max[i];
@@ -552,6 +586,58 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     g.sm_switch = sn * savg;
     g.sm_nsub = nsub;
     s->nvox = g.nvox_local();
+    if (s->nvox >= (1ull << 31)) {
+        delete s;
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "more than 2^31 voxels on one device");
+    }
+    {
+        const u64 plane = (u64)g.ng[1] * g.ng[2];
+        const u64 nown = (u64)(g.own_hi - g.own_lo);
+        if (s->world > 1) {
+            s->G = cfg->ghost_capacity ? cfg->ghost_capacity : (s->cap / nown) * 3 / 2 + 4096;
+            s->mcap = cfg->migration_capacity ? cfg->migration_capacity : std::max<u64>(s->G / 4, 4096);
+        }
+        s->cap_total = s->cap + 2 * s->G + (s->world > 1 ? 2 * s->mcap : 0);
+        if (s->cap_total >= (1ull << 32) - 2) {
+            delete s;
+            return fail(nullptr, CRB_ERR_INVALID_ARG, "capacity + ghost capacity exceeds 2^32");
+        }
+        // exchange buffer layouts
+        HaloLayout& H = s->hl;
+        std::memset(&H, 0, sizeof(H));
+        H.gcap = s->G;
+        H.plane = plane;
+        H.D = D;
+        H.n_ip = s->n_ip;  // columns are reserved; only copied when the parameters are not uniform
+        u64 off = 64;
+        auto take = [&](u64 bytes) {
+            const u64 o = off;
+            off += (bytes + 63) / 64 * 64;
+            return o;
+        };
+        H.off_rel = take((plane + 1) * sizeof(u32));
+        for (int c = 0; c < D; ++c) H.off_pos[c] = take(H.gcap * sizeof(double));
+        H.off_posf = take(H.gcap * sizeof(float4));
+        H.off_sp = take(H.gcap);
+        for (int k = 0; k < s->n_ip; ++k) H.off_ip[k] = take(H.gcap * sizeof(double));
+        H.bytes = off;
+        MigLayout& M = s->ml;
+        std::memset(&M, 0, sizeof(M));
+        M.mcap = s->mcap;
+        M.D = D;
+        M.n_mp = s->n_mp;
+        M.n_ip = s->n_ip;
+        off = 64;
+        for (int c = 0; c < 6 * D; ++c) M.off_dyn[c] = take(M.mcap * sizeof(double));
+        for (int k = 0; k < s->n_mp; ++k) M.off_mp[k] = take(M.mcap * sizeof(double));
+        for (int k = 0; k < s->n_ip; ++k) M.off_ip[k] = take(M.mcap * sizeof(double));
+        M.off_id = take(M.mcap * sizeof(u64));
+        M.off_sortkey = take(M.mcap * sizeof(u64));
+        M.off_gvox = take(M.mcap * sizeof(u64));
+        M.off_hlen = take(M.mcap);
+        M.off_sp = take(M.mcap);
+        M.bytes = off;
+    }
     if (const char* kc = std::getenv("CRB_FORCE_KERNEL")) {
         if (!std::strcmp(kc, "agent")) s->kernel_choice = 1;
         if (!std::strcmp(kc, "tile")) s->kernel_choice = 2;
@@ -577,12 +663,12 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     if ((rc = alloc_state(s, s->Y, true, true))) return bail(rc);
     if ((rc = alloc_state(s, s->T, true, false))) return bail(rc);
     s->n_tiles = (u32)((s->nvox + kScanTile - 1) / kScanTile);
-    if ((rc = dalloc(s, &s->key, s->cap)) || (rc = dalloc(s, &s->key_alt, s->cap)) ||
+    if ((rc = dalloc(s, &s->key, s->cap_total)) || (rc = dalloc(s, &s->key_alt, s->cap_total)) ||
         (rc = dalloc(s, &s->start, s->nvox + 1)) || (rc = dalloc(s, &s->start_alt, s->nvox + 1)) ||
-        (rc = dalloc(s, &s->count_new, s->nvox + 1)) || (rc = dalloc(s, &s->newkey, s->cap)) ||
-        (rc = dalloc(s, &s->rank_arb, s->cap)) || (rc = dalloc(s, &s->tmp_idx, s->cap)) ||
-        (rc = dalloc(s, &s->slot_of_src, s->cap)) || (rc = dalloc(s, &s->sortkey, s->cap)) ||
-        (rc = dalloc(s, &s->tile_sums, s->n_tiles + 1)) || (rc = dalloc(s, &s->stage, s->cap * 8)) ||
+        (rc = dalloc(s, &s->count_new, s->nvox + 1)) || (rc = dalloc(s, &s->newkey, s->cap_total)) ||
+        (rc = dalloc(s, &s->rank_arb, s->cap_total)) || (rc = dalloc(s, &s->tmp_idx, s->cap_total)) ||
+        (rc = dalloc(s, &s->slot_of_src, s->cap_total)) || (rc = dalloc(s, &s->sortkey, s->cap_total)) ||
+        (rc = dalloc(s, &s->tile_sums, s->n_tiles + 1)) || (rc = dalloc(s, &s->stage, s->cap_total * 8)) ||
         (rc = dalloc(s, &s->err, 4)) || (rc = dalloc(s, &s->scratch_u64, 16)))
         return bail(rc);
     e = cudaMallocHost((void**)&s->err_host, 4 * sizeof(int));
@@ -646,27 +732,27 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
         if ((rc = upload_rows(s, vel, D, s->T.vel, n))) return rc;
     } else {
         for (int d = 0; d < D; ++d)
-            CU(s, cudaMemsetAsync(s->T.vel[d], 0, n * sizeof(double), s->stream));
+            CU(s, cudaMemsetAsync(s->T.vel[d] + s->G, 0, n * sizeof(double), s->stream));
     }
     for (int d = 0; d < D; ++d) {
-        CU(s, cudaMemsetAsync(s->T.h1x[d], 0, n * sizeof(double), s->stream));
-        CU(s, cudaMemsetAsync(s->T.h1v[d], 0, n * sizeof(double), s->stream));
-        CU(s, cudaMemsetAsync(s->T.h0x[d], 0, n * sizeof(double), s->stream));
-        CU(s, cudaMemsetAsync(s->T.h0v[d], 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h1x[d] + s->G, 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h1v[d] + s->G, 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h0x[d] + s->G, 0, n * sizeof(double), s->stream));
+        CU(s, cudaMemsetAsync(s->T.h0v[d] + s->G, 0, n * sizeof(double), s->stream));
     }
-    CU(s, cudaMemsetAsync(s->T.hlen, 0, n, s->stream));
+    CU(s, cudaMemsetAsync(s->T.hlen + s->G, 0, n, s->stream));
     if (!s->uniform) {
         if ((rc = upload_rows(s, mech_params, s->n_mp, s->X.mp, n))) return rc;
         if ((rc = upload_rows(s, inter_params, s->n_ip, s->X.ip, n))) return rc;
     }
     if (species)
-        CU(s, cudaMemcpyAsync(s->X.species, species, n, cudaMemcpyHostToDevice, s->stream));
+        CU(s, cudaMemcpyAsync(s->X.species + s->G, species, n, cudaMemcpyHostToDevice, s->stream));
     else
-        CU(s, cudaMemsetAsync(s->X.species, 0, n, s->stream));
+        CU(s, cudaMemsetAsync(s->X.species + s->G, 0, n, s->stream));
     if (ids)
-        CU(s, cudaMemcpyAsync(s->X.id, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+        CU(s, cudaMemcpyAsync(s->X.id + s->G, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
     else if (n) {
-        k_iota_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X.id, n);
+        k_iota_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X.id + s->G, n);
         s->launches++;
     }
     CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
@@ -684,7 +770,7 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
         s->have_agents = false;
         return rc;
     }
-    if ((rc = sort_into_place(s, n, true, true))) return rc;
+    if ((rc = sort_into_place(s, n, n, true, true))) return rc;
     CU(s, cudaStreamSynchronize(s->stream));
     plan_tile(s);
     s->have_agents = true;
@@ -776,10 +862,10 @@ int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t*
             CU(s, cudaStreamSynchronize(s->stream));
         }
     }
-    if (ids) CU(s, cudaMemcpyAsync(ids, s->X.id, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    if (ids) CU(s, cudaMemcpyAsync(ids, s->X.id + s->G, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     if (voxel && n) {
         const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
-        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key, (u64*)s->stage, base, n);
+        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key + s->G, (u64*)s->stage, base, n);
         s->launches++;
         CU(s, cudaMemcpyAsync(voxel, s->stage, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     }
@@ -813,7 +899,7 @@ int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_
         }
     }
     if (species)
-        CU(s, cudaMemcpyAsync(species, s->X.species, n, cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaMemcpyAsync(species, s->X.species + s->G, n, cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -825,7 +911,7 @@ int crb_get_aux(crb_sim* s, uint64_t cap, double* hist_dx, double* hist_dv, uint
     const u64 n = s->n;
     const int D = s->D;
     std::vector<u8> hl(n);
-    CU(s, cudaMemcpyAsync(hl.data(), s->X.hlen, n, cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaMemcpyAsync(hl.data(), s->X.hlen + s->G, n, cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
     int rc;
     // rows of [h0 (older), h1 (newest)], re-packed oldest-first per agent below
@@ -857,9 +943,10 @@ int crb_get_aux(crb_sim* s, uint64_t cap, double* hist_dx, double* hist_dv, uint
 }
 
 namespace {
-__global__ void k_scatter_aux(State X, State T, const u32* __restrict__ slot, int D, u64 n) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void k_scatter_aux(State X, State T, const u32* __restrict__ slot, int D, u64 first, u64 n) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u64 i = first + t;
     const u32 d = slot[i];
     for (int c = 0; c < D; ++c) {
         X.h0x[c][d] = T.h0x[c][i];
@@ -915,9 +1002,9 @@ int crb_set_aux(crb_sim* s, uint64_t n, const double* hist_dx, const double* his
     if ((rc = upload_rows(s, rx.data(), 2 * D, cx, n))) return rc;
     CU(s, cudaStreamSynchronize(s->stream));
     if ((rc = upload_rows(s, rv.data(), 2 * D, cv, n))) return rc;
-    CU(s, cudaMemcpyAsync(s->T.hlen, hl.data(), n, cudaMemcpyHostToDevice, s->stream));
+    CU(s, cudaMemcpyAsync(s->T.hlen + s->G, hl.data(), n, cudaMemcpyHostToDevice, s->stream));
     if (n) {
-        k_scatter_aux<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X, s->T, s->slot_of_src, D, n);
+        k_scatter_aux<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X, s->T, s->slot_of_src, D, s->G, n);
         s->launches++;
     }
     CU(s, cudaStreamSynchronize(s->stream));
@@ -946,31 +1033,254 @@ int crb_set_noise(crb_sim* s, const double* z, uint64_t n_steps, uint64_t n_ids)
     return 0;
 }
 
+namespace {
+// stage A of one step: pair forces over the 3^D neighbourhood + fused integrate/boundary/new key for
+// the owned agents (ghost planes must hold the neighbours' boundary agents on a slab)
+int step_compute(crb_sim* s, bool save_prev) {
+    const bool stochastic = s->cfg.noise_mode == CRB_NOISE_TABLE &&
+                            s->cfg.mechanics_kind != CRB_MECH_NEWTON_DAMPED;
+    if (stochastic && s->noise_cursor >= s->noise_steps)
+        return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
+    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    KParams P = make_params(s);
+    P.save_prev = save_prev ? 1 : 0;
+    stage_begin(s, 0);
+    int rc;
+    if ((rc = launch_force(s, P, false))) return rc;
+    stage_end(s, 0, s->n ? 1 : 0);
+    CU(s, cudaGetLastError());
+    s->last_step_n = s->n;
+    s->n_src = s->n;
+    s->n_gone = 0;
+    return 0;
+}
+// stage B: cell-list rebuild (scan + stable counting-sort scatter of the whole state)
+int step_finish(crb_sim* s, bool save_prev) {
+    const u64 n_new = s->n_src - s->n_gone;
+    if (n_new > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity after migration");
+    int rc;
+    if ((rc = sort_into_place(s, s->n_src, n_new, save_prev, false))) return rc;
+    s->n = n_new;
+    s->iteration++;
+    s->noise_cursor++;
+    return 0;
+}
+}  // namespace
+
 int crb_step(crb_sim* s, uint64_t n_steps) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "crb_step before crb_set_agents");
+    if (s->world > 1)
+        return fail(s, CRB_ERR_STATE, "slab handle: drive the step with crb_slab_* (halo/migration exchange)");
     CU(s, cudaSetDevice((int)s->cfg.device));
-    const bool stochastic = s->cfg.noise_mode == CRB_NOISE_TABLE &&
-                            s->cfg.mechanics_kind != CRB_MECH_NEWTON_DAMPED;
     s->aux_settable = false;
     for (u64 it = 0; it < n_steps; ++it) {
-        if (stochastic && s->noise_cursor >= s->noise_steps)
-            return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
         const bool last = it + 1 == n_steps;
-        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
-        KParams P = make_params(s);
-        P.save_prev = last ? 1 : 0;
-        stage_begin(s, 0);
         int rc;
-        if ((rc = launch_force(s, P, false))) return rc;
-        stage_end(s, 0, s->n ? 1 : 0);
-        CU(s, cudaGetLastError());
-        s->last_step_n = s->n;
-        if ((rc = sort_into_place(s, s->n, last, false))) return rc;
-        s->iteration++;
-        s->noise_cursor++;
+        if ((rc = step_compute(s, last))) return rc;
+        if ((rc = step_finish(s, last))) return rc;
     }
     return check_latch(s);
+}
+
+// ---- slab protocol (one handle per device; the caller moves the buffers between devices) -----------
+uint64_t crb_slab_halo_bytes(const crb_sim* s) { return s ? s->hl.bytes : 0; }
+uint64_t crb_slab_migration_bytes(const crb_sim* s) { return s ? s->ml.bytes : 0; }
+
+int crb_slab_info(const crb_sim* s, uint64_t out[8]) {
+    if (!s || !out) return CRB_ERR_INVALID_ARG;
+    out[0] = (u64)s->g.p0 + s->g.own_lo;              // first owned global plane
+    out[1] = (u64)(s->g.own_hi - s->g.own_lo);        // owned planes
+    out[2] = s->has_lo;
+    out[3] = s->has_hi;
+    out[4] = s->G;
+    out[5] = s->mcap;
+    out[6] = s->cap;
+    out[7] = (u64)s->g.ng[1] * s->g.ng[2];
+    return 0;
+}
+
+int crb_slab_halo_export(crb_sim* s, void* lo_buf, void* hi_buf) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const u64 plane = s->hl.plane;
+    const u32 threads = 256;
+    const u32 grid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
+    HaloLayout L = s->hl;
+    if (s->uniform) L.n_ip = 0;
+    stage_begin(s, 3);
+    int nl = 0;
+    if (s->has_lo && lo_buf) {
+        k_halo_export<<<grid, threads, 0, s->stream>>>(s->X, s->start, (u32)(s->g.own_lo * plane), L,
+                                                      (unsigned char*)lo_buf, s->err);
+        ++nl;
+    }
+    if (s->has_hi && hi_buf) {
+        k_halo_export<<<grid, threads, 0, s->stream>>>(s->X, s->start, (u32)((s->g.own_hi - 1) * plane), L,
+                                                      (unsigned char*)hi_buf, s->err);
+        ++nl;
+    }
+    stage_end(s, 3, nl);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
+int crb_slab_halo_import(crb_sim* s, const void* lo_buf, const void* hi_buf) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const u64 plane = s->hl.plane;
+    const u32 threads = 256;
+    const u32 grid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
+    HaloLayout L = s->hl;
+    if (s->uniform) L.n_ip = 0;
+    stage_begin(s, 3);
+    int nl = 0;
+    if (s->has_lo) {
+        if (!lo_buf) return fail(s, CRB_ERR_INVALID_ARG, "lower halo buffer missing");
+        k_halo_import<<<grid, threads, 0, s->stream>>>(s->X, s->start, 0u, s->G, 1, L,
+                                                      (const unsigned char*)lo_buf, s->err);
+        ++nl;
+    }
+    if (s->has_hi) {
+        if (!hi_buf) return fail(s, CRB_ERR_INVALID_ARG, "upper halo buffer missing");
+        k_halo_import<<<grid, threads, 0, s->stream>>>(s->X, s->start, (u32)((s->g.L0 - 1) * plane),
+                                                      s->G + s->n, 0, L, (const unsigned char*)hi_buf,
+                                                      s->err);
+        ++nl;
+    }
+    stage_end(s, 3, nl);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
+int crb_slab_compute(crb_sim* s, int save_prev) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    if (s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_finish pending");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    s->aux_settable = false;
+    int rc;
+    if ((rc = step_compute(s, save_prev != 0))) return rc;
+    s->step_open = true;
+    return 0;
+}
+
+int crb_slab_migration_export(crb_sim* s, void* lo_buf, void* hi_buf, uint64_t n_out[2]) {
+    if (!s || !n_out) return CRB_ERR_INVALID_ARG;
+    if (!s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_compute first");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    n_out[0] = n_out[1] = 0;
+    if (s->world == 1) return 0;
+    const u64 plane = s->hl.plane;
+    CU(s, cudaMemsetAsync(s->scratch_u64, 0, 2 * sizeof(u64), s->stream));
+    stage_begin(s, 4);
+    int nl = 0;
+    if (s->n) {
+        MigExportParams M;
+        std::memset(&M, 0, sizeof(M));
+        M.A = s->X;
+        M.B = s->T;
+        M.newkey = s->newkey;
+        M.sortkey = s->sortkey;
+        M.first = s->G;
+        M.n = s->n;
+        M.lo_end = s->has_lo ? (u32)plane : 0u;
+        M.hi_begin = s->has_hi ? (u32)((s->g.L0 - 1) * plane) : 0xffffffffu;
+        M.vox_base = (u64)s->g.p0 * plane;
+        M.L = s->ml;
+        M.buf[0] = (unsigned char*)lo_buf;
+        M.buf[1] = (unsigned char*)hi_buf;
+        M.counter = s->scratch_u64;
+        M.err = s->err;
+        M.uniform = s->uniform ? 1 : 0;
+        if ((s->has_lo && !lo_buf) || (s->has_hi && !hi_buf))
+            return fail(s, CRB_ERR_INVALID_ARG, "migration buffer missing");
+        k_mig_export<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(M);
+        ++nl;
+    }
+    // the leavers were counted in the histogram of the ghost planes: they take no slot here
+    if (s->has_lo) CU(s, cudaMemsetAsync(s->count_new, 0, plane * sizeof(u32), s->stream));
+    if (s->has_hi)
+        CU(s, cudaMemsetAsync(s->count_new + (s->g.L0 - 1) * plane, 0, plane * sizeof(u32), s->stream));
+    // headers
+    if (s->has_lo) CU(s, cudaMemcpyAsync(lo_buf, s->scratch_u64, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+    if (s->has_hi) CU(s, cudaMemcpyAsync(hi_buf, s->scratch_u64 + 1, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+    stage_end(s, 4, nl);
+    u64 cnt[2] = {0, 0};
+    CU(s, cudaMemcpyAsync(cnt, s->scratch_u64, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    CU(s, cudaGetLastError());
+    if (cnt[0] > s->mcap || cnt[1] > s->mcap)
+        return fail(s, CRB_ERR_CAPACITY, "more migrating agents than migration_capacity");
+    n_out[0] = cnt[0];
+    n_out[1] = cnt[1];
+    s->n_gone = cnt[0] + cnt[1];
+    return 0;
+}
+
+int crb_slab_migration_import(crb_sim* s, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_compute first");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    u64 cnt[2] = {0, 0};
+    if (s->has_lo) {
+        if (!lo_buf) return fail(s, CRB_ERR_INVALID_ARG, "lower migration buffer missing");
+        CU(s, cudaMemcpyAsync(&cnt[0], lo_buf, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (s->has_hi) {
+        if (!hi_buf) return fail(s, CRB_ERR_INVALID_ARG, "upper migration buffer missing");
+        CU(s, cudaMemcpyAsync(&cnt[1], hi_buf, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (cnt[0] > s->mcap || cnt[1] > s->mcap)
+        return fail(s, CRB_ERR_CAPACITY, "more arriving agents than migration_capacity");
+    if (s->n_src + cnt[0] + cnt[1] > s->cap + 2 * s->mcap)
+        return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
+    const u64 plane = s->hl.plane;
+    stage_begin(s, 4);
+    int nl = 0;
+    for (int side = 0; side < 2; ++side) {
+        if (!cnt[side]) continue;
+        MigImportParams M;
+        std::memset(&M, 0, sizeof(M));
+        M.A = s->X;
+        M.B = s->T;
+        M.newkey = s->newkey;
+        M.rank_arb = s->rank_arb;
+        M.count_new = s->count_new;
+        M.sortkey = s->sortkey;
+        M.dst = s->G + s->n_src;
+        M.n = cnt[side];
+        M.vox_base = (u64)s->g.p0 * plane;
+        M.nvox = s->nvox;
+        M.L = s->ml;
+        M.buf = (const unsigned char*)(side == 0 ? lo_buf : hi_buf);
+        M.err = s->err;
+        M.uniform = s->uniform ? 1 : 0;
+        k_mig_import<<<blocks_for(cnt[side], 256), 256, 0, s->stream>>>(M);
+        ++nl;
+        s->n_src += cnt[side];
+    }
+    stage_end(s, 4, nl);
+    CU(s, cudaGetLastError());
+    if (n_in) {
+        n_in[0] = cnt[0];
+        n_in[1] = cnt[1];
+    }
+    return 0;
+}
+
+int crb_slab_finish(crb_sim* s, int save_prev) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_compute first");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    s->step_open = false;
+    int rc;
+    if ((rc = step_finish(s, save_prev != 0))) return rc;
+    plan_tile(s);
+    return 0;
 }
 
 int crb_sync(crb_sim* s) {
@@ -986,12 +1296,12 @@ int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
     CU(s, cudaSetDevice((int)s->cfg.device));
     int rc;
     if (!s->force_out)
-        if ((rc = dalloc(s, &s->force_out, s->cap * 3))) return rc;
+        if ((rc = dalloc(s, &s->force_out, s->cap_total * 3))) return rc;
     KParams P = make_params(s);
     if ((rc = launch_force(s, P, true))) return rc;
     s->launches += s->n ? 1 : 0;
     CU(s, cudaGetLastError());
-    const double* cols[8] = {s->force_out, s->force_out + s->cap, s->force_out + 2 * s->cap, 0, 0, 0, 0, 0};
+    const double* cols[8] = {s->force_out, s->force_out + s->cap_total, s->force_out + 2 * s->cap_total, 0, 0, 0, 0, 0};
     if ((rc = download_rows(s, force, s->D, cols, s->n))) return rc;
     return check_latch(s);
 }
@@ -1010,7 +1320,7 @@ int crb_get_migrations(crb_sim* s, uint64_t cap, uint64_t* ids, uint64_t* old_vo
     d_new = d_old + std::max<u64>(cap, 1);
     cudaMemsetAsync(s->scratch_u64, 0, sizeof(u64), s->stream);
     k_collect_migrations<<<blocks_for(n, 256), 256, 0, s->stream>>>(
-        s->sortkey, s->newkey, s->Y.id, s->g, n, cap, d_ids, d_old, d_new, s->scratch_u64);
+        s->sortkey, s->newkey, s->Y.id, s->g, s->G, n, cap, d_ids, d_old, d_new, s->scratch_u64);
     s->launches++;
     u64 cnt = 0;
     cudaMemcpyAsync(&cnt, s->scratch_u64, sizeof(u64), cudaMemcpyDeviceToHost, s->stream);

@@ -84,8 +84,9 @@ struct KParams {
     Grid g;
     State A, B;
     Uniform u;
-    u64 n;            // agents in A
-    u64 cap;          // allocated agents per array
+    u64 n;            // owned agents in A
+    u64 first;        // index of the first owned agent (ghost capacity G; 0 on a single device)
+    u64 cap;          // allocated agents per array (owned capacity + 2 G)
     u32* key;         // local voxel index of every agent of A (sorted ascending)
     u32* start;       // exclusive scan of per-voxel counts of A, nvox_local + 1 entries
     u32* newkey;      // local voxel index after the step (per old slot)
@@ -102,5 +103,33 @@ struct KParams {
     double dt;
     int mech, inter, order, weight_mode, noise_mode, save_prev;
 };
+
+// ---- slab exchange buffers ----------------------------------------------------------
+// One halo buffer carries the boundary plane of a slab: every column at a fixed offset (capacity
+// gcap agents) so that the receiver needs no size from the host.
+struct HaloLayout {
+    u64 gcap, plane;  // agent capacity, voxels per plane
+    int D, n_ip;      // n_ip == 0 when the parameters are uniform
+    u64 off_rel;      // u32 rel[plane + 1]: index of the first agent of every voxel relative to the plane
+    u64 off_pos[3];   // f64
+    u64 off_posf;     // float4
+    u64 off_sp;       // u8
+    u64 off_ip[CRB_MAX_INTER_PARAMS];
+    u64 bytes;
+    // header: u64 n at byte 0
+};
+// One migration buffer carries complete agents (dynamic + static state) that changed slab.
+struct MigLayout {
+    u64 mcap;
+    int D, n_mp, n_ip;
+    u64 off_dyn[18];  // f64 columns: pos, vel, h1x, h1v, h0x, h0v (D each)
+    u64 off_mp[CRB_MAX_MECH_PARAMS], off_ip[CRB_MAX_INTER_PARAMS];
+    u64 off_id, off_sortkey, off_gvox;  // u64
+    u64 off_hlen, off_sp;               // u8
+    u64 bytes;
+    // header: u64 n at byte 0
+};
+
+#define CRB_KEY_GONE 0xffffffffu  // newkey of an agent that left this slab (skipped by the reorder)
 
 }  // namespace crb

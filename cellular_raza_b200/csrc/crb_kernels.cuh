@@ -569,9 +569,9 @@ __global__ void __launch_bounds__(kScanThreads)
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-    k_scan_sums(u32* __restrict__ tile_sums, u32 n_tiles, u32* __restrict__ grand_total) {
+    k_scan_sums(u32* __restrict__ tile_sums, u32 n_tiles, u32* __restrict__ grand_total, u32 base) {
     __shared__ u32 tot;
-    u32 carry = 0;
+    u32 carry = base;  // index of the first owned agent: start[] holds absolute agent indices
     for (u32 base = 0; base < n_tiles; base += kScanThreads) {
         const u32 idx = base + threadIdx.x;
         const u32 x = idx < n_tiles ? tile_sums[idx] : 0u;
@@ -598,10 +598,13 @@ __global__ void __launch_bounds__(kScanThreads)
 // moves the whole state B (dynamic fields) + A (static fields) -> Y.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_fill(const u32* __restrict__ newkey, const u32* __restrict__ rank_arb,
-                       const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 n) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    tmp_idx[start_new[newkey[i]] + rank_arb[i]] = (u32)i;
+                       const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 first, u64 n) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u64 i = first + t;
+    const u32 k = newkey[i];
+    if (k == CRB_KEY_GONE) return;  // migrated to a neighbouring slab
+    tmp_idx[start_new[k] + rank_arb[i]] = (u32)i;
 }
 
 struct ReorderParams {
@@ -612,7 +615,8 @@ struct ReorderParams {
     const u64* sortkey;
     u32* key_out;
     u32* slot_of_src;  // optional: destination slot of every source index (ingestion only)
-    u64 n;
+    u64 n;      // destination slots [first, first + n)
+    u64 first;
     int D, V;
     int n_mp, n_ip;  // per-agent parameter columns to move (0 when uniform)
     int save_prev;
@@ -621,8 +625,9 @@ struct ReorderParams {
 };
 
 __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= R.n) return;
+    const u64 tp = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tp >= R.n) return;
+    const u64 p = R.first + tp;
     const u32 i = R.tmp_idx[p];
     const u32 v = R.newkey[i];
     const u32 sb = R.start_new[v], se = R.start_new[v + 1];
@@ -680,8 +685,9 @@ __global__ void k_pack_rows(double* __restrict__ rows, int width, const double* 
 
 template <int D>
 __global__ void k_ingest_keys(const KParams P) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    const u64 i = P.first + t;
     const Grid& g = P.g;
     double p[D];
     bool below = false;
@@ -693,26 +699,27 @@ __global__ void k_ingest_keys(const KParams P) {
     int q0 = 0, q1 = 0, q2 = 0;
     u32 nk = 0;
     if (below || !(p[0] == p[0])) {
-        latch_error(P.err, CRB_ERR_BOUNDARY, i);
+        latch_error(P.err, CRB_ERR_BOUNDARY, t);
     } else if (!voxel_of<D>(g, p, &q0, &q1, &q2)) {
-        latch_error(P.err, CRB_ERR_INDEX, i);
+        latch_error(P.err, CRB_ERR_INDEX, t);
     } else {
         const int l0 = q0 - g.p0;
         if (l0 < g.own_lo || l0 >= g.own_hi)
-            latch_error(P.err, CRB_ERR_INDEX, i);  // not in this device's slab
+            latch_error(P.err, CRB_ERR_INDEX, t);  // not in this device's slab
         else
             nk = ((u32)l0 * (u32)g.ng[1] + (u32)q1) * (u32)g.ng[2] + (u32)q2;
     }
     P.newkey[i] = nk;
-    P.sortkey[i] = i;  // input order inside a voxel (chili/datastructures.rs:278-299)
+    P.sortkey[i] = t;  // input order inside a voxel (chili/datastructures.rs:278-299)
     P.rank_arb[i] = atomicAdd(&P.count_new[nk], 1u);
 }
 
 // ordered candidate pairs of the current state
 __global__ void k_count_pairs(const KParams P, u64* out) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 i = P.first + t;
     u64 c = 0;
-    if (i < P.n) {
+    if (t < P.n) {
         const Grid& g = P.g;
         const int n1 = g.ng[1], n2 = g.ng[2];
         const u32 v = P.key[i];
@@ -739,10 +746,11 @@ __global__ void k_count_pairs(const KParams P, u64* out) {
 
 // migration tap: (id, old plain, new plain) of every agent flagged as moved in the last step
 __global__ void k_collect_migrations(const u64* __restrict__ sortkey, const u32* __restrict__ newkey,
-                                     const u64* __restrict__ id_old, Grid g, u64 n, u64 cap,
+                                     const u64* __restrict__ id_old, Grid g, u64 first, u64 n, u64 cap,
                                      u64* ids, u64* oldv, u64* newv, u64* counter) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u64 i = first + t;
     const u64 sk = sortkey[i];
     if (!(sk & CRB_SK_MOVED)) return;
     const u64 slot = atomicAdd(counter, 1ull);
@@ -750,6 +758,164 @@ __global__ void k_collect_migrations(const u64* __restrict__ sortkey, const u32*
     ids[slot] = id_old[i];
     oldv[slot] = (sk & ~CRB_SK_MOVED) >> CRB_SK_RANK_BITS;
     newv[slot] = (u64)newkey[i] + (u64)g.p0 * g.ng[1] * g.ng[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab exchange (replaces PosInformation / SendCell messages of
+// chili/update_mechanics.rs:12-61 between subdomains that live on different devices)
+// ------------------------------------------------------------------------------------------------
+// boundary plane [v0, v0 + plane) of the sorted state -> halo buffer.  The agent range of a plane is
+// contiguous, so every column is a straight copy.
+__global__ void k_halo_export(const State A, const u32* __restrict__ start, u32 v0, HaloLayout L,
+                              unsigned char* __restrict__ buf, int* err) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 a = start[v0], b = start[v0 + (u32)L.plane];
+    const u64 n = b - a;
+    if (t == 0) {
+        *reinterpret_cast<u64*>(buf) = n;
+        if (n > L.gcap) latch_error(err, CRB_ERR_CAPACITY, n);
+    }
+    if (t <= L.plane) reinterpret_cast<u32*>(buf + L.off_rel)[t] = start[v0 + (u32)t] - a;
+    if (t < n && t < L.gcap) {
+        const u64 i = a + t;
+        for (int c = 0; c < L.D; ++c) reinterpret_cast<double*>(buf + L.off_pos[c])[t] = A.pos[c][i];
+        reinterpret_cast<float4*>(buf + L.off_posf)[t] = A.posf[i];
+        (buf + L.off_sp)[t] = A.species[i];
+        for (int k = 0; k < L.n_ip; ++k) reinterpret_cast<double*>(buf + L.off_ip[k])[t] = A.ip[k][i];
+    }
+}
+
+// halo buffer -> ghost plane.  lower ghost: agents end at `edge` (= first owned index); upper ghost:
+// agents begin at `edge` (= one past the last owned index).  posf.w is re-based to the local voxel
+// index of the ghost plane (the sender wrote its own local index).
+__global__ void k_halo_import(State A, u32* __restrict__ start, u32 v0, u64 edge, int lower, HaloLayout L,
+                              const unsigned char* __restrict__ buf, int* err) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 n = *reinterpret_cast<const u64*>(buf);
+    if (n > L.gcap) {
+        if (t == 0) latch_error(err, CRB_ERR_CAPACITY, n);
+        return;
+    }
+    const u64 base = lower ? edge - n : edge;
+    const u32* rel = reinterpret_cast<const u32*>(buf + L.off_rel);
+    if (t <= L.plane) start[v0 + t] = (u32)(base + rel[t]);
+    if (t < n) {
+        const u64 i = base + t;
+        for (int c = 0; c < L.D; ++c) A.pos[c][i] = reinterpret_cast<const double*>(buf + L.off_pos[c])[t];
+        // voxel of agent t: the last v with rel[v] <= t (binary search over the plane)
+        u32 lo = 0, hi = (u32)L.plane;
+        while (hi - lo > 1) {
+            const u32 mid = (lo + hi) >> 1;
+            if (rel[mid] <= t) lo = mid; else hi = mid;
+        }
+        float4 pf = reinterpret_cast<const float4*>(buf + L.off_posf)[t];
+        pf.w = __uint_as_float(v0 + lo);
+        A.posf[i] = pf;
+        A.species[i] = (buf + L.off_sp)[t];
+        for (int k = 0; k < L.n_ip; ++k) A.ip[k][i] = reinterpret_cast<const double*>(buf + L.off_ip[k])[t];
+    }
+}
+
+// agents whose new voxel lies in a ghost plane leave this slab: stream-compacted with their complete
+// state into the migration buffer of that side (chili: SendCell(old_voxel, CellBox, Aux),
+// update_mechanics.rs:457-470).  The order inside the buffer is arbitrary; the receiver's reorder
+// ranks arrivals by (source voxel, in-voxel rank) exactly like local movers (:492-511).
+struct MigExportParams {
+    State A, B;  // A: static fields (pre-step order), B: integrated dynamic fields
+    u32* newkey;
+    const u64* sortkey;
+    u64 first, n;
+    u32 lo_end;    // local voxels [0, lo_end) belong to the lower ghost plane (0 if none)
+    u32 hi_begin;  // local voxels [hi_begin, ...) belong to the upper ghost plane (0xffffffff if none)
+    u64 vox_base;  // global plain index of local voxel 0
+    MigLayout L;
+    unsigned char* buf[2];
+    u64* counter;  // [2]
+    int* err;
+    int uniform;
+};
+__global__ void k_mig_export(const MigExportParams M) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M.n) return;
+    const u64 i = M.first + t;
+    const u32 k = M.newkey[i];
+    int side;
+    if (k < M.lo_end) side = 0;
+    else if (k >= M.hi_begin && k != CRB_KEY_GONE) side = 1;
+    else return;
+    const u64 slot = atomicAdd(&M.counter[side], 1ull);
+    M.newkey[i] = CRB_KEY_GONE;
+    if (slot >= M.L.mcap) {
+        latch_error(M.err, CRB_ERR_CAPACITY, M.A.id[i]);
+        return;
+    }
+    unsigned char* buf = M.buf[side];
+    const MigLayout& L = M.L;
+    const int D = L.D;
+    for (int c = 0; c < D; ++c) {
+        reinterpret_cast<double*>(buf + L.off_dyn[0 * D + c])[slot] = M.B.pos[c][i];
+        reinterpret_cast<double*>(buf + L.off_dyn[1 * D + c])[slot] = M.B.vel[c][i];
+        reinterpret_cast<double*>(buf + L.off_dyn[2 * D + c])[slot] = M.B.h1x[c][i];
+        reinterpret_cast<double*>(buf + L.off_dyn[3 * D + c])[slot] = M.B.h1v[c][i];
+        reinterpret_cast<double*>(buf + L.off_dyn[4 * D + c])[slot] = M.B.h0x[c][i];
+        reinterpret_cast<double*>(buf + L.off_dyn[5 * D + c])[slot] = M.B.h0v[c][i];
+    }
+    if (!M.uniform) {
+        for (int q = 0; q < L.n_mp; ++q) reinterpret_cast<double*>(buf + L.off_mp[q])[slot] = M.A.mp[q][i];
+        for (int q = 0; q < L.n_ip; ++q) reinterpret_cast<double*>(buf + L.off_ip[q])[slot] = M.A.ip[q][i];
+    }
+    reinterpret_cast<u64*>(buf + L.off_id)[slot] = M.A.id[i];
+    reinterpret_cast<u64*>(buf + L.off_sortkey)[slot] = M.sortkey[i];
+    reinterpret_cast<u64*>(buf + L.off_gvox)[slot] = M.vox_base + k;
+    (buf + L.off_hlen)[slot] = M.B.hlen[i];
+    (buf + L.off_sp)[slot] = M.A.species[i];
+}
+
+struct MigImportParams {
+    State A, B;
+    u32 *newkey, *rank_arb, *count_new;
+    u64* sortkey;
+    u64 dst;       // index of the first arrival in the unsorted source range
+    u64 n;         // arrivals
+    u64 vox_base;  // global plain index of local voxel 0
+    u64 nvox;      // local voxels
+    MigLayout L;
+    const unsigned char* buf;
+    int* err;
+    int uniform;
+};
+__global__ void k_mig_import(const MigImportParams M) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M.n) return;
+    const u64 i = M.dst + t;
+    const MigLayout& L = M.L;
+    const unsigned char* buf = M.buf;
+    const int D = L.D;
+    for (int c = 0; c < D; ++c) {
+        M.B.pos[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[0 * D + c])[t];
+        M.B.vel[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[1 * D + c])[t];
+        M.B.h1x[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[2 * D + c])[t];
+        M.B.h1v[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[3 * D + c])[t];
+        M.B.h0x[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[4 * D + c])[t];
+        M.B.h0v[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[5 * D + c])[t];
+    }
+    if (!M.uniform) {
+        for (int q = 0; q < L.n_mp; ++q) M.A.mp[q][i] = reinterpret_cast<const double*>(buf + L.off_mp[q])[t];
+        for (int q = 0; q < L.n_ip; ++q) M.A.ip[q][i] = reinterpret_cast<const double*>(buf + L.off_ip[q])[t];
+    }
+    M.A.id[i] = reinterpret_cast<const u64*>(buf + L.off_id)[t];
+    M.sortkey[i] = reinterpret_cast<const u64*>(buf + L.off_sortkey)[t];
+    M.B.hlen[i] = (buf + L.off_hlen)[t];
+    M.A.species[i] = (buf + L.off_sp)[t];
+    const u64 gv = reinterpret_cast<const u64*>(buf + L.off_gvox)[t];
+    if (gv < M.vox_base || gv - M.vox_base >= M.nvox) {
+        latch_error(M.err, CRB_ERR_INDEX, M.A.id[i]);
+        M.newkey[i] = CRB_KEY_GONE;
+        return;
+    }
+    const u32 nk = (u32)(gv - M.vox_base);
+    M.newkey[i] = nk;
+    M.rank_arb[i] = atomicAdd(&M.count_new[nk], 1u);
 }
 
 // DFMA-only kernel: 8 independent chains per thread, 2 flop per fma.  Roofline denominator of the

@@ -1,0 +1,152 @@
+"""bench.py --gpus N (N > 1): weak scaling of the mechanics/interaction step over slabs, one process
+per GPU under torchrun (nccl over NVLink).  See bench.py for the meaning of the JSON keys."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+
+def run(args, rank: int, world: int, local_rank: int, helpers):
+    import torch
+    import torch.distributed as dist
+
+    from . import workloads
+    from .device import measure_fp64_peak
+    from .slabs import SlabSimulation
+
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.cells_per_gpu
+    w = workloads.cell_sorting_slab(n, rank, world, args.density, n_threads=args.n_threads_ref)
+    cfg = w.config(capacity=int(n * 1.1) + 4096, device=local_rank)
+    sim = SlabSimulation(cfg, device=local_rank)
+    sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
+    sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
+    slab = sim.slab
+    stream = slab.torch_stream
+
+    sim.halo_exchange()
+    pairs = slab.count_candidate_pairs()
+    sim.step(max(args.warmup, 3))
+    sim.sync()
+    fp64_peak, _ = measure_fp64_peak(local_rank)
+
+    sampler = helpers.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    slab.enable_timers(True)
+    slab.reset_timers()
+    l0 = slab.kernel_launches
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms_local = e0.elapsed_time(e1)
+    t = torch.tensor([ms_local], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    launches = slab.kernel_launches - l0
+    force_ms, force_launches = slab.stage_time_ms(0)
+    scan_ms, _ = slab.stage_time_ms(1)
+    reorder_ms, _ = slab.stage_time_ms(2)
+    halo_ms, _ = slab.stage_time_ms(3)
+    mig_ms, _ = slab.stage_time_ms(4)
+    slab.enable_timers(False)
+    clocks = sampler.stop() if rank == 0 else None
+    n_now = torch.tensor([float(slab.n_agents)], device="cuda")
+    dist.all_reduce(n_now)
+    sim.halo_exchange()
+    pairs_after = slab.count_candidate_pairs()
+    pr = torch.tensor([0.5 * (pairs + pairs_after)], device="cuda", dtype=torch.float64)
+    fm = torch.tensor([force_ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(pr)  # total pairs per step over all ranks
+    dist.all_reduce(fm, op=dist.ReduceOp.MAX)
+    value = n * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in / out every step (every rank its own slab) ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        hp = torch.from_numpy(w.pos).pin_memory()
+        hv = torch.from_numpy(w.vel).pin_memory()
+        hs = torch.from_numpy(w.species).pin_memory()
+        hi = torch.from_numpy(w.extra["ids"]).pin_memory()
+        op = torch.empty_like(hp).pin_memory()
+        ov = torch.empty_like(hv).pin_memory()
+        lib, h = slab._lib, slab._h
+        e2e_steps = max(args.steps // 2, 3)
+        for k in range(2 + e2e_steps):
+            if k == 2:
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+            rc = lib.crb_set_agents(h, n, hp.data_ptr(), hv.data_ptr(), None, None, hs.data_ptr(), hi.data_ptr())
+            if rc:
+                raise RuntimeError(lib.crb_last_error(h))
+            sim.step(1)
+            m = slab.n_agents
+            rc = lib.crb_get_agents(h, m, op.data_ptr() if m <= n else None, ov.data_ptr() if m <= n else None, None, None)
+            if rc:
+                raise RuntimeError(lib.crb_last_error(h))
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
+        dt_e2e = float(dt_e2e.item())
+        e2e = {
+            "value": n * world * e2e_steps / dt_e2e, "unit": helpers.UNIT,
+            "h2d_bytes_per_step": int(world * n * (24 + 24 + 1 + 8)), "d2h_bytes_per_step": int(world * n * 48),
+            "ms_per_step": dt_e2e / e2e_steps * 1e3,
+            "what": "per rank: crb_set_agents(pinned host pos, vel, species, ids) + slab step (halo + migration over nccl) + crb_get_agents(host pos, vel)",
+        }
+
+    if rank == 0:
+        peaks = helpers.measured_peaks()
+        pairs_per_launch = float(pr.item()) / world  # per GPU
+        force_avg_ms = float(fm.item()) / max(force_launches, 1)
+        achieved_tf = pairs_per_launch * helpers.FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
+        roofline = {
+            "kernel": "k_force_tile (per GPU, slowest rank)", "bound": "fp64", "achieved": achieved_tf,
+            "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+            "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+            "traffic": None, "share_of_step": float(fm.item()) / ms_total,
+            "algorithmic_flop_per_pair": helpers.FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+            "pair_forces_per_s": pairs_per_launch * world / (force_avg_ms * 1e-3),
+        }
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        reorder_avg_ms = reorder_ms / max(args.steps, 1)
+        reorder_gbs = n * helpers.REORDER_BYTES_PER_AGENT / (reorder_avg_ms * 1e-3) / 1e9
+        roofline_hbm = {
+            "kernel": "k_fill+k_reorder (rank 0)", "bound": "hbm", "achieved": reorder_gbs, "peak": hbm_peak,
+            "unit": "GB/s", "frac": reorder_gbs / hbm_peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "traffic": None, "share_of_step": reorder_ms / ms_total,
+            "algorithmic_bytes_per_agent": helpers.REORDER_BYTES_PER_AGENT,
+        }
+        cfgd = helpers.workload_config(args)
+        cfgd.update({"halo_bytes_per_face": slab.halo_bytes, "migration_bytes_per_face": slab.mig_bytes,
+                     "exchange": "ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), 2 phases per step, no force return"})
+        line = {
+            "metric": helpers.METRIC, "value": value, "unit": helpers.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgd,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": None, "e2e": e2e,
+            "gpu_launches": int(launches) * world, "clocks": clocks,
+            "stage_ms_per_step": {"force_integrate": force_ms / args.steps, "scan": scan_ms / args.steps,
+                                  "reorder": reorder_ms / args.steps, "halo_pack_unpack": halo_ms / args.steps,
+                                  "migration_pack_unpack": mig_ms / args.steps},
+            "agents_after": float(n_now.item()),
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    dist.destroy_process_group()

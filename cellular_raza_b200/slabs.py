@@ -1,0 +1,314 @@
+"""Slab decomposition over several GPUs: host-side orchestration of the
+``crb_slab_*`` entry points of ``include/crb.h``.
+
+chili cuts the voxel list into ``n_threads`` contiguous chunks, one ``SubDomainBox`` per OS thread,
+and moves ``PosInformation`` / ``ForceInformation`` / ``SendCell`` messages through crossbeam channels
+separated by a global barrier (cellular_raza-core/src/backend/chili/simulation_flow.rs:350-423,
+438-450, 689-707; update_mechanics.rs:153-238, 418-513).  Here the domain is cut into slabs of whole
+voxel planes along axis 0, one ``crb_sim`` handle per GPU; per step every rank sends ONE halo buffer
+(boundary plane: positions + interaction information) and ONE migration buffer (complete agents that
+crossed the face) to each of its at most two neighbours.  There is no force return message: each side
+evaluates its own half of a cross-slab pair, exactly as chili evaluates every pair from both sides.
+
+Two transports move the fixed-size device buffers:
+
+* :class:`LocalSlabGroup` — all handles live in this process (same or different devices); buffers are
+  moved with device copies.  Used by the tests (several slabs on ONE GPU reproduce the single-handle
+  run bit for bit) and usable for one-process multi-GPU runs.
+* :class:`SlabSimulation` — one process per GPU (``torch.distributed``, backend ``nccl``): buffers
+  travel with ``ncclSend/ncclRecv`` over NVLink (``torch.distributed.batch_isend_irecv``).
+
+torch is used for device buffers, streams and the NCCL plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _abi
+from .device import DeviceSimulation
+
+
+def slab_planes(n_planes: int, world: int) -> list[tuple[int, int]]:
+    """(first global plane, number of planes) of every rank: ranks below ``n_planes % world`` own one
+    plane more.  Same rule as crb_create (csrc/crb_api.cu) and as chili's chunking of the voxel list
+    into sizes ceil/floor (cartesian_cuboid_n.rs:19-59)."""
+    if world < 1 or world > n_planes:
+        raise ValueError("need 1 <= world <= n_planes")
+    base, rem = divmod(n_planes, world)
+    out = []
+    for r in range(world):
+        out.append((r * base + min(r, rem), base + (1 if r < rem else 0)))
+    return out
+
+
+def rank_of_position(x0: np.ndarray, domain_min0: float, dx0: float, n_planes: int, world: int) -> np.ndarray:
+    """slab that owns agents with axis-0 coordinate ``x0`` (voxel index as get_voxel_index_of_raw,
+    cartesian_cuboid_n.rs:320-337)."""
+    plane = np.floor((np.asarray(x0, dtype=np.float64) - domain_min0) / dx0).astype(np.int64)
+    plane = np.clip(plane, 0, n_planes - 1)
+    firsts = np.array([f for f, _ in slab_planes(n_planes, world)], dtype=np.int64)
+    return np.searchsorted(firsts, plane, side="right") - 1
+
+
+def neighbor_exchange(dist, rank: int, world: int, outs, ins, group=None):
+    """Posts the at most four point-to-point operations of one exchange phase: ``outs[0]`` goes to
+    rank-1 and ``ins[0]`` comes from it, ``outs[1]`` / ``ins[1]`` likewise for rank+1.  Works with any
+    ``torch.distributed`` backend (nccl on device buffers; gloo on CPU tensors in the tests).
+    Returns the work handles (already waited: for nccl the wait is stream-ordered)."""
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, outs[0], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, ins[0], rank - 1, group))
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, outs[1], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, ins[1], rank + 1, group))
+    works = dist.batch_isend_irecv(ops) if ops else []
+    for w in works:
+        w.wait()
+    return works
+
+
+class SlabRank(DeviceSimulation):
+    """One slab: a ``crb_sim`` handle created with (rank, world_size) plus its exchange buffers."""
+
+    def __init__(self, cfg: _abi.CrbConfig, rank: int, world: int, device: int = 0,
+                 ghost_capacity: int = 0, migration_capacity: int = 0):
+        import torch
+
+        cfg.rank = rank
+        cfg.world_size = world
+        cfg.device = device
+        cfg.ghost_capacity = ghost_capacity
+        cfg.migration_capacity = migration_capacity
+        super().__init__(cfg)
+        self.rank, self.world, self.device = rank, world, device
+        info = (C.c_uint64 * 8)()
+        self._check(self._lib.crb_slab_info(self._h, info))
+        self.first_plane, self.n_planes = int(info[0]), int(info[1])
+        self.has_lo, self.has_hi = bool(info[2]), bool(info[3])
+        self.halo_bytes = int(self._lib.crb_slab_halo_bytes(self._h))
+        self.mig_bytes = int(self._lib.crb_slab_migration_bytes(self._h))
+        dev = torch.device("cuda", device)
+        self.torch_stream = torch.cuda.ExternalStream(self.stream, device=dev)
+
+        def buf(nbytes, present):
+            return torch.zeros(nbytes, dtype=torch.uint8, device=dev) if present else None
+
+        # [lo, hi] per direction
+        self.halo_out = [buf(self.halo_bytes, self.has_lo), buf(self.halo_bytes, self.has_hi)]
+        self.halo_in = [buf(self.halo_bytes, self.has_lo), buf(self.halo_bytes, self.has_hi)]
+        self.mig_out = [buf(self.mig_bytes, self.has_lo), buf(self.mig_bytes, self.has_hi)]
+        self.mig_in = [buf(self.mig_bytes, self.has_lo), buf(self.mig_bytes, self.has_hi)]
+        self.last_migration = (0, 0, 0, 0)  # out lo, out hi, in lo, in hi
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    # -- the six phases of one step ---------------------------------------------------------------
+    def halo_export(self):
+        self._check(self._lib.crb_slab_halo_export(self._h, self._p(self.halo_out[0]), self._p(self.halo_out[1])))
+
+    def halo_import(self):
+        self._check(self._lib.crb_slab_halo_import(self._h, self._p(self.halo_in[0]), self._p(self.halo_in[1])))
+
+    def compute(self, save_prev: bool = True):
+        self._check(self._lib.crb_slab_compute(self._h, 1 if save_prev else 0))
+
+    def migration_export(self):
+        n = (C.c_uint64 * 2)()
+        self._check(self._lib.crb_slab_migration_export(self._h, self._p(self.mig_out[0]), self._p(self.mig_out[1]), n))
+        return int(n[0]), int(n[1])
+
+    def migration_import(self):
+        n = (C.c_uint64 * 2)()
+        self._check(self._lib.crb_slab_migration_import(self._h, self._p(self.mig_in[0]), self._p(self.mig_in[1]), n))
+        return int(n[0]), int(n[1])
+
+    def finish(self, save_prev: bool = True):
+        self._check(self._lib.crb_slab_finish(self._h, 1 if save_prev else 0))
+
+    def step(self, n_steps: int = 1):  # pragma: no cover - guarded in C as well
+        raise RuntimeError("a slab is stepped by its group (LocalSlabGroup.step / SlabSimulation.step)")
+
+
+def split_agents_by_slab(cfg: _abi.CrbConfig, world: int, pos: np.ndarray) -> np.ndarray:
+    return rank_of_position(pos[:, 0], cfg.domain_min[0], cfg.dx[0], int(cfg.n_voxels[0]), world)
+
+
+class LocalSlabGroup:
+    """``world`` slabs driven by one process.  ``devices[r]`` is the CUDA device of rank r (all 0 to
+    run several slabs on one GPU)."""
+
+    def __init__(self, make_cfg, world: int, devices: Sequence[int] | None = None, **caps):
+        devices = list(devices) if devices is not None else [0] * world
+        self.world = world
+        self.ranks = [SlabRank(make_cfg(), r, world, devices[r], **caps) for r in range(world)]
+        self.cfg = self.ranks[0].cfg
+        self.dim = self.ranks[0].dim
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
+
+    # -- population -------------------------------------------------------------------------------
+    def set_agents(self, pos, vel, mech_params, inter_params, species=None, ids=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        n = pos.shape[0]
+        owner = split_agents_by_slab(self.cfg, self.world, pos)
+        ids = np.arange(n, dtype=np.uint64) if ids is None else np.asarray(ids, dtype=np.uint64)
+
+        def sel(a, m, width=None):
+            if a is None:
+                return None
+            a = np.asarray(a)
+            if width is not None:
+                a = np.broadcast_to(a, (n, width))
+            return np.ascontiguousarray(a[m])
+
+        for r, rk in enumerate(self.ranks):
+            m = owner == r
+            rk.set_agents(pos[m], sel(vel, m), sel(mech_params, m, rk.n_mech), sel(inter_params, m, rk.n_inter),
+                          sel(species, m), ids[m])
+
+    def set_noise(self, z):
+        for rk in self.ranks:
+            rk.set_noise(z)
+
+    # -- exchange ---------------------------------------------------------------------------------
+    def _exchange(self, out_attr: str, in_attr: str):
+        """rank r's 'hi' out-buffer -> rank r+1's 'lo' in-buffer and vice versa (device copies ordered
+        after the producer's stream and before the consumer's)."""
+        import torch
+
+        for r in range(self.world - 1):
+            a, b = self.ranks[r], self.ranks[r + 1]
+            for src_rank, src, dst_rank, dst in (
+                (a, getattr(a, out_attr)[1], b, getattr(b, in_attr)[0]),
+                (b, getattr(b, out_attr)[0], a, getattr(a, in_attr)[1]),
+            ):
+                with torch.cuda.stream(src_rank.torch_stream):
+                    dst.copy_(src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(src_rank.torch_stream)
+                dst_rank.torch_stream.wait_event(ev)
+
+    def halo_exchange(self):
+        for rk in self.ranks:
+            rk.halo_export()
+        self._exchange("halo_out", "halo_in")
+        for rk in self.ranks:
+            rk.halo_import()
+
+    def step(self, n_steps: int = 1):
+        for it in range(n_steps):
+            last = it + 1 == n_steps
+            self.halo_exchange()
+            for rk in self.ranks:
+                rk.compute(last)
+            outs = [rk.migration_export() for rk in self.ranks]
+            self._exchange("mig_out", "mig_in")
+            ins = [rk.migration_import() for rk in self.ranks]
+            for rk, o, i in zip(self.ranks, outs, ins):
+                rk.last_migration = (*o, *i)
+                rk.finish(last)
+        for rk in self.ranks:
+            rk.sync()
+
+    # -- gathered views (device order inside a slab, slabs in rank order) --------------------------
+    @property
+    def n_agents(self) -> int:
+        return sum(rk.n_agents for rk in self.ranks)
+
+    def get_agents(self):
+        parts = [rk.get_agents() for rk in self.ranks]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(4))
+
+    def get_aux(self):
+        parts = [rk.get_aux() for rk in self.ranks]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
+
+    def debug_forces(self):
+        self.halo_exchange()
+        return np.concatenate([rk.debug_forces() for rk in self.ranks])
+
+    def get_voxel_counts(self):
+        return np.concatenate([rk.get_voxel_counts()[: rk.n_planes * self._plane()] for rk in self.ranks])
+
+    def _plane(self):
+        nv = [int(self.cfg.n_voxels[i]) for i in range(self.dim)]
+        return int(np.prod(nv[1:]))
+
+    def count_candidate_pairs(self):
+        self.halo_exchange()
+        return sum(rk.count_candidate_pairs() for rk in self.ranks)
+
+    @property
+    def kernel_launches(self):
+        return sum(rk.kernel_launches for rk in self.ranks)
+
+
+class SlabSimulation:
+    """One slab per process (``torch.distributed`` must be initialised with the nccl backend); halo and
+    migration buffers travel with ncclSend/ncclRecv over NVLink."""
+
+    def __init__(self, cfg: _abi.CrbConfig, device: int | None = None, group=None, **caps):
+        import torch
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        device = torch.cuda.current_device() if device is None else device
+        self.slab = SlabRank(cfg, self.rank, self.world, device, **caps)
+        self.cfg = self.slab.cfg
+        self.dim = self.slab.dim
+
+    def close(self):
+        self.slab.close()
+
+    def set_agents(self, pos, vel, mech_params, inter_params, species=None, ids=None):
+        """``pos`` … are THIS rank's agents (axis-0 coordinate inside the slab)."""
+        self.slab.set_agents(pos, vel, mech_params, inter_params, species, ids)
+
+    def set_uniform_params(self, mech_row=None, inter_row=None):
+        self.slab.set_uniform_params(mech_row, inter_row)
+
+    def _exchange(self, outs, ins):
+        import torch
+
+        with torch.cuda.stream(self.slab.torch_stream):
+            # stream-ordered for nccl: the waits block the handle's stream, not the host
+            neighbor_exchange(self.dist, self.rank, self.world, outs, ins, self.group)
+
+    def halo_exchange(self):
+        s = self.slab
+        s.halo_export()
+        self._exchange(s.halo_out, s.halo_in)
+        s.halo_import()
+
+    def step(self, n_steps: int = 1):
+        s = self.slab
+        for it in range(n_steps):
+            last = it + 1 == n_steps
+            self.halo_exchange()
+            s.compute(last)
+            out = s.migration_export()
+            self._exchange(s.mig_out, s.mig_in)
+            inn = s.migration_import()
+            s.last_migration = (*out, *inn)
+            s.finish(last)
+
+    def sync(self):
+        self.slab.sync()
+
+    @property
+    def n_agents(self):
+        return self.slab.n_agents
+
+    def get_agents(self):
+        return self.slab.get_agents()

@@ -172,3 +172,43 @@ def brownian_morse(
 def noise_table(n_steps: int, n_ids: int, dim: int, seed: int = 7) -> np.ndarray:
     """Standard-normal table z[step][agent id][d] fed to oracle and device alike."""
     return np.random.default_rng(seed).standard_normal((n_steps, n_ids, dim))
+
+
+def cell_sorting_slab(cells_per_rank: int, rank: int, world: int, density_per_voxel: float = 7.1, *,
+                      seed: int = 1, n_threads: int = 1, dt: float = 0.2,
+                      pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI) -> Workload:
+    """Weak-scaling population (BASELINE.json configs[4]): the global domain is ``world`` cubes of
+    ``cells_per_rank`` agents stacked along axis 0; only THIS rank's agents are generated (independent
+    PCG64 stream per rank), ids are globally unique.  ``cfg_kwargs`` describe the GLOBAL domain."""
+    n_side = max(int(round((cells_per_rank / density_per_voxel) ** (1.0 / 3.0))), 1)
+    edge = 18.0 * n_side
+    rng = np.random.default_rng([seed, rank])
+    pos = _uniform_positions(rng, cells_per_rank, 3, 0.0, edge)
+    pos[:, 0] += rank * edge
+    if rank > 0:
+        # the plane index of x == rank * edge must be the slab's first plane
+        np.maximum(pos[:, 0], rank * edge, out=pos[:, 0])
+    half = cells_per_rank // 2
+    species = (np.arange(cells_per_rank) <= half).astype(np.uint8)
+    mn = [0.0, 0.0, 0.0]
+    mx = [edge * world, edge, edge]
+    nv, dx = _domain_from_interaction_range(mn, mx, 18.0)
+    cfg = dict(
+        dim=3,
+        mechanics_kind=_abi.CRB_MECH_NEWTON_DAMPED,
+        interaction_kind=_abi.CRB_INT_CELL_SORTING,
+        domain_min=mn, domain_max=mx, n_voxels=nv, dx=dx, dt=dt, solver_order=2,
+        pair_weight_mode=pair_weight_mode, ref_n_subdomains=n_threads,
+    )
+    w = Workload(
+        name=f"cell_sorting_slab_{cells_per_rank}x{world}",
+        cfg_kwargs=cfg,
+        pos=pos,
+        vel=np.zeros((cells_per_rank, 3)),
+        mech_params=np.tile([2.0, 1.0], (cells_per_rank, 1)),
+        inter_params=np.tile([6.0, 2.0, 1.5], (cells_per_rank, 1)),
+        species=species,
+    )
+    w.extra["ids"] = (np.arange(cells_per_rank, dtype=np.uint64) + np.uint64(rank) * np.uint64(cells_per_rank))
+    w.extra["n_side"] = n_side
+    return w

@@ -16,7 +16,7 @@
  *  - return value 0 on success, a negative crb_status otherwise (mirrors the SimulationError
  *    variants used on this path, cellular_raza-core/src/backend/chili/errors.rs:73-121);
  *    `crb_last_error` returns a human readable message for the last failure on that handle.
- *  - a handle is NOT thread-safe (one host thread per handle, one handle per GPU).
+ *  - a handle is NOT thread-safe (one host thread per handle, one handle per GPU slab).
  *  - vectors are stored agent-major: pos[i*dim + d].
  */
 #ifndef CRB_H
@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 1
+#define CRB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 typedef enum crb_status {
@@ -116,7 +116,9 @@ typedef struct crb_config {
                                        cartesian_cuboid_n.rs:183-222 / 226-256 do               */
     double dt;                      /* FixedStepsize::dt                                         */
     uint64_t rng_seed;              /* CartesianCuboid::rng_seed                                 */
-    uint64_t capacity;              /* max number of agents resident on this device              */
+    uint64_t capacity;              /* max number of OWNED agents resident on this device        */
+    uint64_t ghost_capacity;        /* slabs: max agents of one boundary plane (0 = 1.5 x mean)  */
+    uint64_t migration_capacity;    /* slabs: max agents crossing one slab face per step (0=auto)*/
 } crb_config;
 
 typedef struct crb_sim crb_sim; /* opaque */
@@ -186,6 +188,38 @@ int crb_step(crb_sim* sim, uint64_t n_steps);
 int crb_sync(crb_sim* sim);
 /* number of steps taken since creation. */
 uint64_t crb_iteration(const crb_sim* sim);
+
+/* ---- slab decomposition over several devices --------------------------------------
+ * Replaces the Communicator / ChannelComm traffic of chili between subdomains
+ * (cellular_raza-core/src/backend/chili/simulation_flow.rs:438-450, 689-707; message types
+ * PosInformation / SendCell, chili/update_mechanics.rs:12-61) and its barrier
+ * (simulation_flow.rs:350-423).  The domain is cut into world_size slabs of whole voxel planes along
+ * axis 0; every rank owns one handle created with (rank, world_size) and keeps one ghost plane per
+ * neighbour.  No ForceInformation message exists: each side evaluates its own half of a
+ * cross-slab pair.  The caller moves the fixed-size device buffers between neighbouring devices
+ * (ncclSend/ncclRecv, cudaMemcpyPeer, or a plain device copy when two handles share a device):
+ *
+ *     crb_slab_halo_export(lo_out, hi_out)            my boundary planes            -> neighbours
+ *     crb_slab_halo_import(lo_in, hi_in)              neighbours' boundary planes   -> ghost planes
+ *     crb_slab_compute(save_prev)                     forces + integrate + new voxel keys
+ *     crb_slab_migration_export(lo_out, hi_out, n)    agents that left the slab     -> neighbours
+ *     crb_slab_migration_import(lo_in, hi_in, n)      arrivals
+ *     crb_slab_finish(save_prev)                      cell-list rebuild (sort_cells_in_voxels)
+ *
+ * "lo" is the neighbour with rank - 1, "hi" rank + 1; a buffer pointer may be NULL where there is no
+ * neighbour.  All pointers are DEVICE pointers of at least crb_slab_halo_bytes / _migration_bytes.
+ * save_prev != 0 keeps the older ring-buffer entry readable by crb_get_aux after this step. */
+uint64_t crb_slab_halo_bytes(const crb_sim* sim);
+uint64_t crb_slab_migration_bytes(const crb_sim* sim);
+/* out[0] first owned global plane, [1] owned planes, [2] has lower neighbour, [3] has upper neighbour,
+ * [4] ghost capacity, [5] migration capacity, [6] owned capacity, [7] voxels per plane. */
+int crb_slab_info(const crb_sim* sim, uint64_t out[8]);
+int crb_slab_halo_export(crb_sim* sim, void* lo_buf, void* hi_buf);
+int crb_slab_halo_import(crb_sim* sim, const void* lo_buf, const void* hi_buf);
+int crb_slab_compute(crb_sim* sim, int save_prev);
+int crb_slab_migration_export(crb_sim* sim, void* lo_buf, void* hi_buf, uint64_t n_out[2]);
+int crb_slab_migration_import(crb_sim* sim, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]);
+int crb_slab_finish(crb_sim* sim, int save_prev);
 
 /* ---- parity taps (used by tests; not needed by a production host) ------------------------- */
 /* forces that the next step would integrate (AuxStorageMechanics::current_force after
