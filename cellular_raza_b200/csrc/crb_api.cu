@@ -592,7 +592,8 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     }
     {
         const u64 plane = (u64)g.ng[1] * g.ng[2];
-        const u64 nown = (u64)(g.own_hi - g.own_lo);
+        // the same on every rank (buffer sizes must agree): floor(planes / world) owned planes
+        const u64 nown = std::max<u64>((u64)g.ng[0] / (u64)s->world, 1);
         if (s->world > 1) {
             s->G = cfg->ghost_capacity ? cfg->ghost_capacity : (s->cap / nown) * 3 / 2 + 4096;
             s->mcap = cfg->migration_capacity ? cfg->migration_capacity : std::max<u64>(s->G / 4, 4096);
