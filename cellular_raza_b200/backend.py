@@ -1,0 +1,388 @@
+"""Host-side mirror of the reference's user-facing interface for the mechanics/interaction path.
+
+A simulation written against cellular_raza's concepts API
+
+    run_simulation!(domain: domain, agents: agents, settings: settings, aspects: [Mechanics, Interaction])
+
+(cellular_raza-examples/cell_sorting/src/main.rs:165-170; macro kwargs
+cellular_raza-core-proc-macro/src/run_sim.rs:131-159) maps 1:1 onto :func:`run_simulation` here: the
+same names (``CartesianCuboid``, ``NewtonDamped3D``, ``Brownian3D``, ``Langevin3D``, ``MorsePotential``,
+``BoundLennardJones``, ``MiePotential``, ``Settings``, ``FixedStepsize``, ``StorageBuilder``,
+``StorageAccess``, ``SimulationError``), the same argument meaning and the same error behaviour.  The
+generated main loop (run_sim.rs:380-403) becomes ``crb_step`` between save events and
+``crb_get_agents``/``crb_get_aux`` at ``PartialSave`` iterations.  All arithmetic happens in
+``libcrb200.so``; this file only packs agents into parameter rows and writes snapshots in the
+reference's on-disk layout (cellular_raza-core/src/storage/concepts.rs:156-170, 702-790).
+
+The Rust host crate a maintainer would add does exactly the same through the same C ABI
+(INTEGRATION.md); it cannot be compiled in this image (no cargo).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import time as _time
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import SimulationError  # noqa: F401  (re-export: chili/errors.rs:73-121)
+from .device import DeviceSimulation, make_config
+
+
+# ---- domain (cellular_raza-building-blocks/src/domains/cartesian_cuboid_n.rs) ---------------------
+@dataclass
+class CartesianCuboid:
+    min: np.ndarray
+    max: np.ndarray
+    dx: np.ndarray
+    n_voxels: np.ndarray
+    rng_seed: int = 0
+
+    @staticmethod
+    def _check(mn, mx):
+        if np.any(mn >= mx):  # check_min_max (:149-162)
+            raise SimulationError(_abi.CRB_ERR_BOUNDARY, "Min must be smaller than Max for domain boundaries")
+
+    @classmethod
+    def from_boundaries_and_interaction_range(cls, min, max, interaction_range: float) -> "CartesianCuboid":
+        """:183-222 — n = floor((max - min) / range) clamped to >= 1, dx = (max - min) / n."""
+        mn, mx = np.asarray(min, dtype=np.float64), np.asarray(max, dtype=np.float64)
+        cls._check(mn, mx)
+        n = np.floor((mx - mn) / interaction_range)
+        nv = np.maximum(n.astype(np.uint64), 1)
+        with np.errstate(divide="ignore"):
+            dx = (mx - mn) / n
+        return cls(mn, mx, dx, nv)
+
+    @classmethod
+    def from_boundaries_and_n_voxels(cls, min, max, n_voxels) -> "CartesianCuboid":
+        """:226-256"""
+        mn, mx = np.asarray(min, dtype=np.float64), np.asarray(max, dtype=np.float64)
+        cls._check(mn, mx)
+        nv = np.asarray(n_voxels, dtype=np.uint64)
+        return cls(mn, mx, (mx - mn) / nv.astype(np.float64), nv)
+
+    @property
+    def dim(self) -> int:
+        return len(self.min)
+
+
+# ---- mechanics (cell_building_blocks/mechanics.rs) -------------------------------------------------
+@dataclass
+class _Mechanics:
+    pos: Sequence[float]
+    KIND = -1
+
+    def row(self) -> list[float]:
+        raise NotImplementedError
+
+    def velocity(self):
+        return getattr(self, "vel", [0.0] * len(self.pos))
+
+
+@dataclass
+class NewtonDamped3D(_Mechanics):  # :158-173 (2-D twin below)
+    vel: Sequence[float] = (0.0, 0.0, 0.0)
+    damping_constant: float = 0.0
+    mass: float = 1.0
+    KIND = _abi.CRB_MECH_NEWTON_DAMPED
+
+    def row(self):
+        return [self.damping_constant, self.mass]
+
+
+class NewtonDamped2D(NewtonDamped3D):
+    pass
+
+
+@dataclass
+class Brownian3D(_Mechanics):  # :336-357
+    diffusion_constant: float = 0.0
+    kb_temperature: float = 1.0
+    KIND = _abi.CRB_MECH_BROWNIAN
+
+    def row(self):
+        return [self.diffusion_constant, self.kb_temperature]
+
+
+class Brownian2D(Brownian3D):
+    pass
+
+
+@dataclass
+class Langevin3D(_Mechanics):  # :434-463
+    vel: Sequence[float] = (0.0, 0.0, 0.0)
+    mass: float = 1.0
+    damping: float = 0.0
+    kb_temperature: float = 0.0
+    KIND = _abi.CRB_MECH_LANGEVIN
+
+    def row(self):
+        return [self.mass, self.damping, self.kb_temperature]
+
+
+class Langevin2D(Langevin3D):
+    pass
+
+
+# ---- interaction (cell_building_blocks/interaction.rs; examples/cell_sorting/src/main.rs) ----------
+@dataclass
+class MorsePotential:  # :226-260
+    radius: float
+    potential_stiffness: float
+    cutoff: float
+    strength: float
+    KIND = _abi.CRB_INT_MORSE
+    species = 0
+
+    def row(self):
+        return [self.radius, self.potential_stiffness, self.cutoff, self.strength]
+
+
+@dataclass
+class BoundLennardJones:  # :122-138
+    epsilon: float
+    sigma: float
+    bound: float
+    cutoff: float
+    KIND = _abi.CRB_INT_BOUND_LJ
+    species = 0
+
+    def row(self):
+        return [self.epsilon, self.sigma, self.bound, self.cutoff]
+
+
+@dataclass
+class MiePotential:  # :345-389
+    radius: float
+    strength: float
+    bound: float
+    cutoff: float
+    en: float
+    em: float
+    KIND = _abi.CRB_INT_MIE
+    species = 0
+
+    def row(self):
+        return [self.radius, self.strength, self.bound, self.cutoff, self.en, self.em]
+
+
+@dataclass
+class CellSpecificInteraction:  # cellular_raza-examples/cell_sorting/src/main.rs:26-97
+    species: int  # 0 = RedCell, 1 = BlueCell
+    cell_radius: float
+    potential_strength: float
+    relative_interaction_range: float
+    KIND = _abi.CRB_INT_CELL_SORTING
+
+    def row(self):
+        return [self.cell_radius, self.potential_strength, self.relative_interaction_range]
+
+
+@dataclass
+class Agent:
+    """what ``#[derive(CellAgent)] struct Cell { #[Mechanics] mechanics, #[Interaction] interaction }``
+    is in the reference (cell_sorting/src/main.rs:99-105)."""
+
+    mechanics: _Mechanics
+    interaction: object
+
+
+# ---- time (cellular_raza-core/src/time.rs) ---------------------------------------------------------
+@dataclass
+class FixedStepsize:
+    t0: float
+    dt: float
+    save_iterations: list[int]
+    maximum_iterations: int
+
+    @classmethod
+    def from_partial_save_points(cls, t0: float, dt: float, points: Iterable[float]) -> "FixedStepsize":
+        """:173-239 — iteration of a save point = round((t - t0) / dt); the run ends at the last one."""
+        pts = sorted(points)
+        if not pts:
+            raise ValueError("No savepoints specified. Simulation will not save any results.")
+        if any(t0 > p for p in pts):
+            raise ValueError("Invalid time configuration! Evaluation time point is before starting time point.")
+        its = [int(round((p - t0) / dt)) for p in pts]
+        return cls(t0, dt, its, its[-1])
+
+    @classmethod
+    def from_partial_save_steps(cls, t0: float, dt: float, n_steps: int, save_interval: int) -> "FixedStepsize":
+        """:94-111 — save points t0 + k * save_interval * dt for k = 0 ..= ceil(n_steps / save_interval)."""
+        k = -(-n_steps // save_interval)
+        return cls.from_partial_save_points(t0, dt, [t0 + (save_interval * n) * dt for n in range(k + 1)])
+
+    @classmethod
+    def from_partial_save_interval(cls, t0: float, dt: float, t_max: float, save_interval: float) -> "FixedStepsize":
+        pts, t = [], t0
+        while t <= t_max:
+            pts.append(t)
+            t += save_interval
+        return cls.from_partial_save_points(t0, dt, pts)
+
+
+# ---- storage (cellular_raza-core/src/storage/concepts.rs) ------------------------------------------
+@dataclass
+class StorageBuilder:
+    """``StorageBuilder::new().priority([...]).location(path)`` (:226-331).  priority entries:
+    "Memory" and/or "SerdeJson"."""
+
+    location: str = "out"
+    priority: Sequence[str] = ("Memory",)
+    add_date: bool = True
+    suffix: str = ""
+
+
+class StorageManager:
+    """read side of ``StorageAccess.cells`` (``StorageInterfaceLoad``): iteration -> elements."""
+
+    def __init__(self, json_dir: Path | None):
+        self.json_dir = json_dir
+        self.memory: dict[int, dict] = {}
+
+    def get_all_iterations(self) -> list[int]:
+        its = set(self.memory)
+        if self.json_dir is not None and self.json_dir.exists():
+            its |= {int(p.name) for p in self.json_dir.iterdir() if p.is_dir()}
+        return sorted(its)
+
+    def load_all_elements_at_iteration(self, iteration: int) -> dict:
+        """-> {identifier tuple: {"pos", "vel", "id", "voxel", "aux"}}"""
+        if iteration in self.memory:
+            return self.memory[iteration]
+        out = {}
+        for f in sorted((self.json_dir / f"{iteration:020d}").glob("batch_*.json")):
+            for e in json.loads(f.read_text())["data"]:
+                cell, aux = e["element"]
+                ident = tuple(e["identifier"].items())[0]
+                out[ident] = {"cell": cell["cell"], "aux": aux}
+        return out
+
+    def load_all_elements(self) -> dict[int, dict]:
+        return {it: self.load_all_elements_at_iteration(it) for it in self.get_all_iterations()}
+
+
+@dataclass
+class StorageAccess:  # chili/result.rs:5-10
+    cells: StorageManager
+    subdomains: StorageManager
+    path: Path | None = None
+
+
+@dataclass
+class Settings:  # chili/setup.rs:17-27
+    n_threads: int
+    time: FixedStepsize
+    storage: StorageBuilder = field(default_factory=StorageBuilder)
+    progressbar: str | None = None
+
+
+# ---- the entry point -------------------------------------------------------------------------------
+def _pack(agents: Sequence[Agent], dim: int):
+    n = len(agents)
+    if n == 0:
+        raise ValueError("no agents")
+    mk = {type(a.mechanics).KIND for a in agents}
+    ik = {type(a.interaction).KIND for a in agents}
+    if len(mk) != 1 or len(ik) != 1:
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "all agents must use the same mechanics and interaction types")
+    pos = np.array([a.mechanics.pos for a in agents], dtype=np.float64).reshape(n, dim)
+    vel = np.array([a.mechanics.velocity() for a in agents], dtype=np.float64).reshape(n, dim)
+    mp = np.array([a.mechanics.row() for a in agents], dtype=np.float64)
+    ip = np.array([a.interaction.row() for a in agents], dtype=np.float64)
+    sp = np.array([getattr(a.interaction, "species", 0) for a in agents], dtype=np.uint8)
+    return mk.pop(), ik.pop(), pos, vel, mp, ip, sp
+
+
+def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: Settings,
+                   aspects: Sequence[str] = ("Mechanics", "Interaction"), *,
+                   mechanics_solver_order: int = 2, determinism: bool = True,
+                   pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI, noise_mode: int | None = None,
+                   noise_table: np.ndarray | None = None, device: int = 0) -> StorageAccess:
+    """``run_simulation!`` of the B200 backend.  ``settings.n_threads`` is chili's subdomain count: it
+    does not create threads here, it selects the pair weights chili applies for that decomposition
+    (SURVEY.md finding 2); ``pair_weight_mode=CRB_WEIGHT_PHYSICAL`` applies both halves everywhere."""
+    unsupported = set(aspects) - {"Mechanics", "Interaction"}
+    if unsupported:
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, f"aspects {sorted(unsupported)} are outside the hot path (SURVEY.md §8)")
+    dim = domain.dim
+    mk, ik, pos, vel, mp, ip, sp = _pack(agents, dim)
+    if noise_mode is None:
+        noise_mode = _abi.CRB_NOISE_NONE if mk == _abi.CRB_MECH_NEWTON_DAMPED else (
+            _abi.CRB_NOISE_TABLE if noise_table is not None else _abi.CRB_NOISE_PHILOX)
+    cfg = make_config(dim=dim, mechanics_kind=mk, interaction_kind=ik, domain_min=domain.min, domain_max=domain.max,
+                      n_voxels=domain.n_voxels, dx=domain.dx, dt=settings.time.dt, capacity=len(agents),
+                      solver_order=mechanics_solver_order, pair_weight_mode=pair_weight_mode,
+                      ref_n_subdomains=max(settings.n_threads, 1), noise_mode=noise_mode,
+                      rng_seed=domain.rng_seed, device=device)
+    sim = DeviceSimulation(cfg)
+    try:
+        sim.set_agents(pos, vel, mp, ip, sp)
+        if noise_table is not None:
+            sim.set_noise(noise_table)
+        sb = settings.storage
+        root = None
+        if "SerdeJson" in sb.priority:
+            root = Path(sb.location)
+            if sb.add_date:
+                root = root / _time.strftime("%Y-%m-%d-T%H-%M-%S")
+            if sb.suffix:
+                root = root / sb.suffix
+        cells = StorageManager(None if root is None else root / "cells" / "json")
+        subdomains = StorageManager(None if root is None else root / "subdomains" / "json")
+        ts = settings.time
+        save_its = sorted(set(ts.save_iterations))
+        agent_rows = {"mech": type(agents[0].mechanics).__name__, "inter": type(agents[0].interaction).__name__}
+        if save_its and save_its[0] == 0:  # save_initial (time.rs:243-255)
+            _save(sim, cells, 0, sb, agent_rows)
+        it = 0
+        for target in [s for s in save_its if s > 0]:
+            sim.step(target - it)  # replaces (target - it) iterations of run_sim.rs:380-403
+            it = target
+            _save(sim, cells, it, sb, agent_rows)
+        if it < ts.maximum_iterations:
+            sim.step(ts.maximum_iterations - it)
+        return StorageAccess(cells, subdomains, root)
+    finally:
+        sim.close()
+
+
+def _save(sim: DeviceSimulation, cells: StorageManager, iteration: int, sb: StorageBuilder, names: dict):
+    """save_cells (chili/datastructures.rs:373-396) -> store_batch_elements (storage/concepts.rs:766-790)."""
+    pos, vel, ids, vox = sim.get_agents()
+    hx, hv, hl = sim.get_aux()
+    mp, ip, sp = sim.get_params()
+    if "Memory" in sb.priority:
+        cells.memory[iteration] = {
+            ("Initial", int(i)): {"pos": pos[k], "vel": vel[k], "voxel": int(vox[k]),
+                                  "aux": {"positions": hx[k, : hl[k]], "velocities": hv[k, : hl[k]]}}
+            for k, i in enumerate(ids)
+        }
+    if cells.json_dir is not None:
+        d = cells.json_dir / f"{iteration:020d}"
+        d.mkdir(parents=True, exist_ok=True)
+        k = 0
+        while (d / f"batch_{0:020d}_{k:020d}.json").exists():
+            k += 1
+        dim = pos.shape[1]
+        data = []
+        for a in range(len(ids)):
+            ident = {"Initial": int(ids[a])}
+            data.append({
+                "identifier": ident,
+                "element": [
+                    {"identifier": ident, "parent": None,
+                     "cell": {"mechanics": {"pos": pos[a].tolist(), "vel": vel[a].tolist(), "type": names["mech"],
+                                            "params": mp[a].tolist()},
+                              "interaction": {"type": names["inter"], "params": ip[a].tolist(), "species": int(sp[a])}}},
+                    {"mechanics": {"positions": hx[a, : hl[a]].tolist(), "velocities": hv[a, : hl[a]].tolist(),
+                                   "current_force": [0.0] * dim, "zero_force": [0.0] * dim}},
+                ],
+            })
+        (d / f"batch_{0:020d}_{k:020d}.json").write_text(json.dumps({"data": data}, indent=2))

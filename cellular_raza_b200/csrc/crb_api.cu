@@ -253,22 +253,27 @@ void plan_tile(crb_sim* s) {
     const int nrows = s->D == 3 ? 9 : 3;
     const double owned_vox = (double)(g.own_hi - g.own_lo) * g.ng[1] * n2;
     const double rho = std::max((double)s->n / std::max(owned_vox, 1.0), 1e-3);
-    // ~110 targets per 128-thread CTA (headroom for the Poisson spread of the pencil population:
-    // a 5th group of 32 would cost a whole extra pass), candidates <= staging budget of 3 CTAs/SM
+    // 128-thread CTAs; every CTA takes ~118 targets of one row (count-balanced, snapped to voxel
+    // boundaries: <= 128 with high probability, so the four warps run one full pass each); candidates
+    // <= staging budget of 3 CTAs/SM
     const size_t budget = 74 * 1024;
-    const size_t fixed = (size_t)(kTileQueue + 2) * kTileThreads * sizeof(unsigned short) + 2048;
-    const u32 cap = (u32)(((budget - fixed) / 41) / 32 * 32);
-    int seg_max = (int)std::floor((cap - kTileRows * kTileRowPad) / (nrows * rho * 1.2)) - 2;
-    const int by_targets = (int)std::floor(110.0 / rho);
-    seg_max = std::max(1, std::min(seg_max, by_targets));
-    const int nseg = (n2 + seg_max - 1) / seg_max;
     TileLaunch& T = s->tile;
-    T.nseg = nseg;
-    T.seg_len = (n2 + nseg - 1) / nseg;
+    T.chunk_len = std::min(n2, 64);
+    T.nchunks = (n2 + T.chunk_len - 1) / T.chunk_len;
+    T.kmax = T.chunk_len + 2;
+    const size_t fixed = (size_t)(kTileQueue + 4) * kTileThreads * sizeof(unsigned short) +
+                         (size_t)kTileRows * (T.kmax + 1) * sizeof(u32) + 2048;
+    const u32 cap = (u32)(((budget - fixed) / 42) / 32 * 32);
+    // candidates of a segment of t targets: nrows * (t + 2 voxels' worth) (+ sentinels)
+    // (10 % slack ~ 3 sigma of the Poisson spread; an overflowing pencil is split into z-windows)
+    const double per_target = nrows * 1.1;
+    double tseg = (cap - kTileRows * kTileRowPad - nrows * 2.0 * rho * 1.1) / per_target;
+    tseg = std::max(8.0, std::min(tseg, 118.0));
+    T.tseg = (u32)tseg;
+    T.nseg = (int)std::ceil(T.chunk_len * rho * 1.6 / T.tseg) + 1;
     T.x_begin = g.own_lo;
     T.x_count = g.own_hi - g.own_lo;
     T.cap = cap;
-    T.kmax = T.seg_len + 2;
     // conservative FP32 filter radius: |d_f32 - d| <= 2^-22.5 * extent per axis (crb_force_tile.cuh)
     double ext = 0;
     for (int d = 0; d < s->D; ++d) ext = std::max(ext, g.mx[d] - g.mn[d]);
@@ -289,7 +294,7 @@ void plan_tile(crb_sim* s) {
 template <int D, int INTER>
 int launch_tile_t(crb_sim* s, const KParams& P, bool force_only) {
     const TileLaunch& T = s->tile;
-    const u32 grid = (u32)T.x_count * (u32)s->g.ng[1] * (u32)T.nseg;
+    const u32 grid = (u32)T.x_count * (u32)s->g.ng[1] * (u32)T.nseg * (u32)T.nchunks;
     if (!grid) return 0;
     if (force_only) {
         auto k = k_force_tile<D, INTER, true>;

@@ -40,13 +40,15 @@ constexpr int kTileSub = 4;         // lanes per candidate-window sub-group
 constexpr int kTileRowPad = 8;      // sentinel entries staged after every row (filter over-read)
 
 struct TileLaunch {
-    int seg_len;   // voxels of the fastest axis per CTA
-    int nseg;      // segments per row
-    int x_begin;   // first local plane whose agents are targets
-    int x_count;   // number of such planes
-    u32 cap;       // staged-candidate capacity
-    int kmax;      // max voxels of a window + 1 (row stride of the wst table)
-    float cut2f;   // conservative FP32 cutoff^2 of the filter
+    int chunk_len;  // voxels of the fastest axis per chunk (bounds the window table)
+    int nchunks;    // chunks per row
+    int nseg;       // count-balanced segments per chunk (CTAs beyond the chunk's population exit)
+    u32 tseg;       // target agents per segment
+    int x_begin;    // first local plane whose agents are targets
+    int x_count;    // number of such planes
+    u32 cap;        // staged-candidate capacity (incl. sentinels)
+    int kmax;       // max voxels of a window + 1 (row stride of the wst table)
+    float cut2f;    // conservative FP32 cutoff^2 of the filter
 };
 
 __host__ __device__ inline size_t tile_smem_bytes(u32 cap, int kmax, int threads) {
@@ -55,8 +57,8 @@ __host__ __device__ inline size_t tile_smem_bytes(u32 cap, int kmax, int threads
     b += 3 * c * sizeof(double);
     b += c * sizeof(float4);
     b += (size_t)kTileRows * (kmax + 1) * sizeof(u32);
-    b += (size_t)(kTileQueue + 2) * threads * sizeof(unsigned short);
-    b += (c + 15) / 16 * 16;
+    b += (size_t)(kTileQueue + 4) * threads * sizeof(unsigned short);
+    b += 2 * ((c + 15) / 16 * 16);  // species + window-relative z voxel
     return b + 64;
 }
 
@@ -68,24 +70,23 @@ struct TileTarget {
     u32 my_v;       // local voxel index
     u32 subv_lo;    // local voxel range of the target's chili subdomain (len 0 => weights 1)
     u32 subv_len;
+    u32 zw;         // voxel of the target along the fastest axis, relative to the staged window
     u8 sp;
     int calc_flag;
 };
 
-template <int D, int INTER>
-__device__ __forceinline__ void tile_eval2(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
-                                           const double* __restrict__ sx, const double* __restrict__ sy,
-                                           const double* __restrict__ sz, const float4* __restrict__ sfb,
-                                           const u8* __restrict__ ssp, const u32 j0, const bool h0,
-                                           const u32 j1, const bool h1) {
-    // straight-line code for both candidates (coef() is branch-free) so that the two dependent FP64
-    // chains interleave; an empty slot points at the target itself (z == 0) and contributes +0.
-    const u32 jj[2] = {j0, j1};
-    const bool hh[2] = {h0, h1};
-    double z[2][D], cf[2];
-    int flag[2] = {0, 0};
+template <int D, int INTER, int NE>
+__device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
+                                          const double* __restrict__ sx, const double* __restrict__ sy,
+                                          const double* __restrict__ sz, const float4* __restrict__ sfb,
+                                          const u8* __restrict__ ssp, const u8* __restrict__ szv,
+                                          const u32 (&jj)[NE], const bool (&hh)[NE]) {
+    // straight-line code for NE candidates (coef() is branch-free) so that the dependent FP64 chains
+    // interleave; an empty slot points at the target itself (z == 0) and contributes +0.
+    double z[NE][D], cf[NE];
+    int flag[NE];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
+    for (int e = 0; e < NE; ++e) {
         const u32 j = jj[e];
         z[e][0] = t.x[0] - sx[j];
         z[e][1] = t.x[1] - sy[j];
@@ -97,16 +98,23 @@ __device__ __forceinline__ void tile_eval2(TileTarget<D>& t, const Pot<INTER>& o
         const bool same_voxel = cvj == t.my_v;
         const bool same_sub = (u32)(cvj - t.subv_lo) < t.subv_len;
         const bool keep = same_voxel | !same_sub;
+        // chili only pairs agents of neighbouring voxels: the candidate rows are x/y-adjacent by
+        // construction, the fastest axis is checked here (the FP32 filter tests the distance only)
+        const bool adj = (u32)((u32)szv[j] - t.zw + 1u) <= 2u;
         const bool same_species = Pot<INTER>::kUsesSpecies ? (ssp[j] == t.sp) : true;
+        flag[e] = 0;
         const double c0 = own.coef(r2, ext_radius, same_species, &flag[e]);
-        const double w = hh[e] ? (keep ? 1.0 : 0.5) : 0.0;
-        cf[e] = hh[e] ? c0 * w : 0.0;
+        const bool use = hh[e] & adj;
+        const double w = keep ? 1.0 : 0.5;
+        cf[e] = use ? c0 * w : 0.0;
+        if (!use) flag[e] = 0;
     }
-    t.calc_flag |= (h0 ? flag[0] : 0) | (h1 ? flag[1] : 0);
 #pragma unroll
-    for (int e = 0; e < 2; ++e)
+    for (int e = 0; e < NE; ++e) {
+        t.calc_flag |= flag[e];
 #pragma unroll
         for (int c = 0; c < D; ++c) t.acc[c] = fma(z[e][c], cf[e], t.acc[c]);
+    }
 }
 
 // per-agent path over global memory (same arithmetic as k_force_integrate, uniform parameters)
@@ -172,6 +180,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     constexpr int nthreads = kTileThreads;  // launch contract: blockDim.x == kTileThreads
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = nthreads >> 5;
+    constexpr int NE = 4;  // candidates evaluated per drain iteration and lane
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
 
@@ -185,22 +194,24 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     float4* sfa = reinterpret_cast<float4*>(sz + capp);
     float4* sfb = sfa + capp / 2;
     u32* wst = reinterpret_cast<u32*>(sfb + capp / 2);           // [kTileRows][kmax + 1]
-    unsigned short* q = reinterpret_cast<unsigned short*>(wst + kTileRows * (T.kmax + 1));  // [kTileQueue + 2][nthreads]
-    u8* ssp = reinterpret_cast<u8*>(q + (kTileQueue + 2) * nthreads);
+    unsigned short* q = reinterpret_cast<unsigned short*>(wst + kTileRows * (T.kmax + 1));  // [kTileQueue + NE][nthreads]
+    u8* ssp = reinterpret_cast<u8*>(q + (kTileQueue + NE) * nthreads);
+    u8* szv = ssp + (capp + 15) / 16 * 16;
     __shared__ u32 s_rowvox[kTileRows];   // first voxel (local plain index) of every neighbour row
     __shared__ u32 s_g0[kTileRows];       // first global agent index staged per row
     __shared__ u32 s_rs[kTileRows + 1];   // staged index of the first candidate of every row
     __shared__ u32 s_rn[kTileRows];       // candidates staged per row (without sentinels)
     __shared__ int s_valid[kTileRows];
-    __shared__ int s_kc;
+    __shared__ int s_kc, s_za, s_zb;
 
-    // ---- which pencil ------------------------------------------------------------------------------
+    // ---- which pencil: row, chunk of the fastest axis, count-balanced segment of the chunk -----------
     const int seg = blockIdx.x % T.nseg;
-    const int rowid = blockIdx.x / T.nseg;
+    const int chunk = (blockIdx.x / T.nseg) % T.nchunks;
+    const int rowid = blockIdx.x / (T.nseg * T.nchunks);
     const int Y = rowid % n1;
     const int X = T.x_begin + rowid / n1;
-    const int za = seg * T.seg_len;
-    const int zb = min(za + T.seg_len, n2);
+    const int ca = chunk * T.chunk_len;
+    const int cb = min(ca + T.chunk_len, n2);
     if (tid < kTileRows) {
         const int d0 = tid / 3 - 1, d1 = tid % 3 - 1;
         const int XX = X + d0, YY = Y + d1;
@@ -208,8 +219,28 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
         s_valid[tid] = ok ? 1 : 0;
         s_rowvox[tid] = ok ? ((u32)XX * (u32)n1 + (u32)YY) * (u32)n2 : 0u;
     }
+    if (tid == 0) {
+        s_za = cb;
+        s_zb = cb;
+    }
     __syncthreads();
     const u32 rv_c = s_rowvox[4];
+    {
+        // segment k owns the voxels whose first agent has in-chunk index in [k, k+1) * tseg: every CTA
+        // gets ~tseg targets whatever the local density (the last segment takes the remainder)
+        const u32 r0 = P.start[rv_c + ca];
+        const u32 lo_cnt = (u32)seg * T.tseg;
+        const u32 hi_cnt = seg == T.nseg - 1 ? 0xffffffffu : lo_cnt + T.tseg;
+        for (int zz = ca + tid; zz < cb; zz += nthreads) {
+            const u32 c = P.start[rv_c + zz] - r0;
+            if (c >= lo_cnt) atomicMin(&s_za, zz);
+            if (c >= hi_cnt) atomicMin(&s_zb, zz);
+        }
+    }
+    __syncthreads();
+    const int za = s_za, zb = s_zb;
+    if (za >= zb) return;
+    if (P.start[rv_c + zb] == P.start[rv_c + za]) return;  // no targets
 
     Pot<INTER> own;
     own.init(P.u.ip);
@@ -218,10 +249,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     int z = za;
     while (z < zb) {
         // ---- window size: largest kc with all candidates of voxels [z-1, z+kc] staged ---------------
+        __syncthreads();
         if (tid == 0) s_kc = 0;
         __syncthreads();
         {
-            // common case first: the whole remaining segment fits
             int found = 0;
             for (int kk = zb - z - tid; kk >= 1 && !found; kk -= nthreads) {
                 const int wa = max(z - 1, 0), wb = min(z + kk + 1, n2);
@@ -229,7 +260,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
 #pragma unroll
                 for (int r = 0; r < kTileRows; ++r)
                     if (s_valid[r]) total += P.start[s_rowvox[r] + wb] - P.start[s_rowvox[r] + wa];
-                if (total + kTileRows * kTileRowPad <= T.cap) {
+                if (total + kTileRows * kTileRowPad <= T.cap && wb - wa <= T.kmax) {
                     atomicMax(&s_kc, kk);
                     found = 1;
                 }
@@ -257,7 +288,6 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                 }
             }
             z += 1;
-            __syncthreads();
             continue;
         }
         const int wa = max(z - 1, 0), wb = min(z + kc + 1, n2);
@@ -286,26 +316,32 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
         }
         __syncthreads();
 
-        // ---- stage candidates (coalesced) and the per-voxel offsets ------------------------------------
+        // ---- per-voxel offsets, then the candidates (coalesced) ------------------------------------------
+        const int stride = T.kmax + 1;
+        for (int idx = tid; idx < kTileRows * (W + 1); idx += nthreads) {
+            const int rr = idx / (W + 1), k = idx - rr * (W + 1);
+            wst[rr * stride + k] =
+                s_valid[rr] ? s_rs[rr] + (P.start[s_rowvox[rr] + wa + k] - s_g0[rr]) : s_rs[rr];
+        }
         {
             const u32 total = s_rs[kTileRows];
+            const float qn_ = __uint_as_float(0x7fc00000u);
             int r = 0;
-            for (u32 k = tid; k < total; k += nthreads) {
-                while (k >= s_rs[r + 1]) ++r;
-                const u32 o = k - s_rs[r];
-                float4 pf4;
-                if (o < s_rn[r]) {
-                    const u32 gi = s_g0[r] + o;
-                    sx[k] = P.A.pos[0][gi];
-                    sy[k] = P.A.pos[1][gi];
-                    if (D == 3) sz[k] = P.A.pos[2][gi];
-                    pf4 = P.A.posf[gi];
-                    if (Pot<INTER>::kUsesSpecies) ssp[k] = P.A.species[gi];
-                } else {
-                    // sentinel: NaN coordinates never pass the distance test (the voxel word alone is
-                    // not enough: rowv wraps to 0xffffffff for targets of local voxel 0)
-                    const float qn_ = __uint_as_float(0x7fc00000u);
-                    pf4 = make_float4(qn_, qn_, qn_, __uint_as_float(0xffffffffu));
+            for (u32 k = tid; k < total + 32; k += nthreads) {
+                float4 pf4 = make_float4(qn_, qn_, qn_, __uint_as_float(0xffffffffu));  // sentinel: NaN never passes
+                u32 zv = 0xff;
+                if (k < total) {
+                    while (k >= s_rs[r + 1]) ++r;
+                    const u32 o = k - s_rs[r];
+                    if (o < s_rn[r]) {
+                        const u32 gi = s_g0[r] + o;
+                        sx[k] = P.A.pos[0][gi];
+                        sy[k] = P.A.pos[1][gi];
+                        if (D == 3) sz[k] = P.A.pos[2][gi];
+                        pf4 = P.A.posf[gi];
+                        if (Pot<INTER>::kUsesSpecies) ssp[k] = P.A.species[gi];
+                        zv = __float_as_uint(pf4.w) - s_rowvox[r] - (u32)wa;  // window-relative voxel (< kmax <= 250)
+                    }
                 }
                 float* fa = reinterpret_cast<float*>(sfa + (k >> 1)) + (k & 1);
                 float* fb = reinterpret_cast<float*>(sfb + (k >> 1)) + (k & 1);
@@ -313,35 +349,21 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                 fa[2] = pf4.y;
                 fb[0] = pf4.z;
                 fb[2] = pf4.w;
-            }
-            if (tid < 32) {
-                const float qn_ = __uint_as_float(0x7fc00000u);
-                const u32 k = total + tid;
-                float* fa = reinterpret_cast<float*>(sfa + (k >> 1)) + (k & 1);
-                float* fb = reinterpret_cast<float*>(sfb + (k >> 1)) + (k & 1);
-                fa[0] = qn_;
-                fa[2] = qn_;
-                fb[0] = qn_;
-                fb[2] = __uint_as_float(0xffffffffu);
-            }
-            const int stride = T.kmax + 1;
-            for (int idx = tid; idx < kTileRows * (W + 1); idx += nthreads) {
-                const int rr = idx / (W + 1), k = idx - rr * (W + 1);
-                wst[rr * stride + k] =
-                    s_valid[rr] ? s_rs[rr] + (P.start[s_rowvox[rr] + wa + k] - s_g0[rr]) : s_rs[rr];
+                szv[k] = (u8)zv;
             }
         }
         __syncthreads();
 
-        // ---- targets ------------------------------------------------------------------------------------
+        // ---- targets: split evenly over the warps ---------------------------------------------------------
         const u32 t0 = P.start[rv_c + z], t1 = P.start[rv_c + z + kc];
-        const int ngroups = (int)((t1 - t0 + 31) >> 5);
-        const int stride = T.kmax + 1;
+        const u32 ntar = t1 - t0;
+        const u32 per = (ntar + nwarps - 1) / nwarps;
+        const u32 w_begin = t0 + (u32)warp * per, w_end = min(w_begin + per, t1);
         const u32 limit = (s_rs[kTileRows] + 24) & ~1u;  // last safe (even) start of an 8-candidate block
-        for (int grp = warp; grp < ngroups; grp += nwarps) {
-            const u32 i_raw = t0 + (u32)grp * 32u + (u32)lane;
-            const bool valid = i_raw < t1;
-            const u32 i = valid ? i_raw : t1 - 1;
+        for (u32 gb = w_begin; gb < w_end; gb += 32) {
+            const u32 i_raw = gb + (u32)lane;
+            const bool valid = i_raw < w_end;
+            const u32 i = valid ? i_raw : w_end - 1;
             const u32 sj_self = s_rs[4] + (i - s_g0[4]);
             float4 pf;
             {
@@ -361,6 +383,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
             t.subv_lo = 0;
             t.subv_len = 0;
             const int zt = (int)(t.my_v - rv_c);
+            t.zw = (u32)(zt - wa);
             if (P.weight_mode == CRB_WEIGHT_CHILI && g.sm_nsub <= 1) {
                 t.subv_len = (u32)g.nvox_local();  // one chili subdomain: everything is "local"
             } else if (P.weight_mode == CRB_WEIGHT_CHILI) {
@@ -394,12 +417,16 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
             auto drain = [&]() {
                 const u32 nq = (qa - qa0) / (2u * nthreads);
                 const u32 nqmax = __reduce_max_sync(0xffffffffu, nq);
-                for (u32 k = 0; k < nqmax; k += 2) {
-                    // two candidates per iteration: two independent FP64 chains in flight per lane
-                    const u32 e0 = q0[k * nthreads], e1 = q0[(k + 1) * nthreads];
-                    const bool h0 = (k < nq) & (e0 != sj_self), h1 = (k + 1 < nq) & (e1 != sj_self);
-                    const u32 j0 = h0 ? e0 : sj_self, j1 = h1 ? e1 : sj_self;
-                    tile_eval2<D, INTER>(t, own, ext_radius, sx, sy, sz, sfb, ssp, j0, h0, j1, h1);
+                for (u32 k = 0; k < nqmax; k += NE) {
+                    u32 jj[NE];
+                    bool hh[NE];
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        const u32 ent = q0[(k + e) * nthreads];
+                        hh[e] = (k + e < nq) & (ent != sj_self);
+                        jj[e] = hh[e] ? ent : sj_self;
+                    }
+                    tile_eval<D, INTER, NE>(t, own, ext_radius, sx, sy, sz, sfb, ssp, szv, jj, hh);
                 }
                 qa = qa0;
             };
@@ -409,42 +436,38 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
             for (int r = 0; r < kTileRows; ++r) {
                 const u32 lo = wst[r * stride + klo], hi = wst[r * stride + khi];
                 const u32 lo2 = lo & ~1u;  // blocks start at an even candidate (pair layout); the extra
-                                           // leading candidate is voxel zmin-2 or a sentinel: not adjacent
+                                           // leading candidate is voxel zmin-2 or a sentinel: rejected
+                                           // by the distance test or by the adjacency test of the drain
                 const u32 n = hi - lo2;
                 const u32 nmax = __reduce_max_sync(0xffffffffu, n);
                 if (nmax == 0) continue;  // warp-uniform
-                // candidate voxel must be within +-1 of the target's voxel along the fastest axis
-                const u32 rowv = t.my_v + (s_rowvox[r] - rv_c) - 1u;
                 for (u32 k0 = 0; k0 < nmax; k0 += 8) {
                     if (__any_sync(0xffffffffu, qa > qfull)) drain();
-                    // a block that starts inside the lane's range may over-read <= 7 entries: those are
-                    // later voxels of the same row or the row's sentinels, never adjacent.  A block past
-                    // the lane's range is disabled through rowv (no voxel index is within 2 of 2^31).
-                    const u32 rv = k0 < n ? rowv : 0x80000000u;
+                    // a block past the lane's range is disabled through the threshold; a block that
+                    // starts inside may over-read <= 7 entries (later voxels of the row or sentinels)
+                    const float cut = k0 < n ? T.cut2f : -1.0f;
                     const u32 b8 = min(lo2 + k0, limit);
-                    float4 ca[4], cb[4];
+                    float4 ca4[4], cb4[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {  // all loads first: the queue stores below alias smem
-                        ca[u] = sfa[(b8 >> 1) + u];
-                        cb[u] = sfb[(b8 >> 1) + u];
+                        ca4[u] = sfa[(b8 >> 1) + u];
+                        if (D == 3) cb4[u] = sfb[(b8 >> 1) + u];
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float2 dx = __fadd2_rn(make_float2(ca[u].x, ca[u].y), xf2);
-                        const float2 dy = __fadd2_rn(make_float2(ca[u].z, ca[u].w), yf2);
+                        const float2 dx = __fadd2_rn(make_float2(ca4[u].x, ca4[u].y), xf2);
+                        const float2 dy = __fadd2_rn(make_float2(ca4[u].z, ca4[u].w), yf2);
                         float2 d2 = __fmul2_rn(dx, dx);
                         d2 = __ffma2_rn(dy, dy, d2);
                         if (D == 3) {
-                            const float2 dz = __fadd2_rn(make_float2(cb[u].x, cb[u].y), zf2);
+                            const float2 dz = __fadd2_rn(make_float2(cb4[u].x, cb4[u].y), zf2);
                             d2 = __ffma2_rn(dz, dz, d2);
                         }
-                        const bool p0 = ((u32)(__float_as_uint(cb[u].z) - rv) <= 2u) & (d2.x <= T.cut2f);
-                        const bool p1 = ((u32)(__float_as_uint(cb[u].w) - rv) <= 2u) & (d2.y <= T.cut2f);
-                        if (p0) {
+                        if (d2.x <= cut) {
                             asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u)) : "memory");
                             qa += 2u * nthreads;
                         }
-                        if (p1) {
+                        if (d2.y <= cut) {
                             asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u + 1)) : "memory");
                             qa += 2u * nthreads;
                         }
@@ -464,7 +487,6 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
             }
         }
         z += kc;
-        __syncthreads();
     }
 }
 

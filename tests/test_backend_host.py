@@ -1,0 +1,54 @@
+"""Host-side mirror of the reference interface (cellular_raza_b200/backend.py): pure host logic on CPU."""
+import numpy as np
+import pytest
+
+from cellular_raza_b200 import backend as cr
+
+
+def test_domain_constructors_match_reference_tests():
+    # cartesian_cuboid_n.rs:167-182
+    d = cr.CartesianCuboid.from_boundaries_and_interaction_range([2.0, 3.0, 1.0], [10.0, 10.0, 20.0], 2.0)
+    assert d.n_voxels.tolist() == [4, 3, 9]
+    np.testing.assert_allclose(d.dx, [2.0, 7.0 / 3.0, 19.0 / 9.0])
+    d = cr.CartesianCuboid.from_boundaries_and_n_voxels([0.0, 0.0], [10.0, 5.0], [5, 5])
+    np.testing.assert_array_equal(d.dx, [2.0, 1.0])
+    with pytest.raises(cr.SimulationError):
+        cr.CartesianCuboid.from_boundaries_and_n_voxels([0.0, 6.0], [10.0, 5.0], [5, 5])
+
+
+def test_fixed_stepsize_event_schedule():
+    # time.rs:94-111: n_steps = 10, save_interval = 11 -> save points 0 and 11 => 11 iterations
+    # (the benchmark's `from_partial_save_steps(0, dt, n, n + 1)` quirk)
+    t = cr.FixedStepsize.from_partial_save_steps(0.0, 0.2, 10, 11)
+    assert t.save_iterations == [0, 11] and t.maximum_iterations == 11
+    t = cr.FixedStepsize.from_partial_save_steps(0.0, 0.2, 10_000, 20)
+    assert t.save_iterations[:3] == [0, 20, 40] and t.maximum_iterations == 10_000
+    t = cr.FixedStepsize.from_partial_save_interval(0.0, 0.1, 20.0, 2.0)
+    assert t.save_iterations[1] == 20 and t.maximum_iterations == 200
+    t = cr.FixedStepsize.from_partial_save_points(1.0, 0.2, [3.0, 5.0, 11.0, 20.0])
+    assert t.save_iterations == [10, 20, 50, 95]
+    with pytest.raises(ValueError):
+        cr.FixedStepsize.from_partial_save_points(1.0, 0.2, [0.5])
+    with pytest.raises(ValueError):
+        cr.FixedStepsize.from_partial_save_points(1.0, 0.2, [])
+
+
+def test_agent_packing():
+    agents = [cr.Agent(cr.NewtonDamped3D([1.0, 2.0, 3.0], [0.1, 0.0, 0.0], 2.0, 1.0),
+                       cr.CellSpecificInteraction(k % 2, 6.0, 2.0, 1.5)) for k in range(4)]
+    mk, ik, pos, vel, mp, ip, sp = cr._pack(agents, 3)
+    assert (mk, ik) == (0, 0) and pos.shape == (4, 3) and sp.tolist() == [0, 1, 0, 1]
+    assert mp[0].tolist() == [2.0, 1.0] and ip[0].tolist() == [6.0, 2.0, 1.5]
+    b = cr.Agent(cr.Brownian3D([1.0, 1.0, 1.0], 0.3, 0.3), cr.MorsePotential(3.0, 0.5, 12.0, 0.01))
+    mk, ik, pos, vel, mp, ip, sp = cr._pack([b], 3)
+    assert (mk, ik) == (1, 2) and vel.tolist() == [[0.0, 0.0, 0.0]] and ip[0].tolist() == [3.0, 0.5, 12.0, 0.01]
+    with pytest.raises(cr.SimulationError):
+        cr._pack(agents + [b], 3)
+
+
+def test_unsupported_aspects_are_rejected():
+    d = cr.CartesianCuboid.from_boundaries_and_n_voxels([0.0] * 3, [10.0] * 3, [2, 2, 2])
+    s = cr.Settings(1, cr.FixedStepsize.from_partial_save_steps(0.0, 0.1, 2, 1))
+    a = [cr.Agent(cr.NewtonDamped3D([1.0, 1.0, 1.0]), cr.MorsePotential(1.0, 1.0, 2.0, 0.1))]
+    with pytest.raises(cr.SimulationError):
+        cr.run_simulation(d, a, s, aspects=["Mechanics", "Reactions"])

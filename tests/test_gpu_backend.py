@@ -1,0 +1,58 @@
+"""run_simulation (reference-shaped entry point) on the device: the reference's own whole-loop checks."""
+import json
+
+import numpy as np
+import pytest
+
+from cellular_raza_b200 import backend as cr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_free_motion_like_chili_doctest(crb_lib):
+    """chili/mod.rs:134-157: no force, pos = key + iteration * dt * vel within 1e-5, 10 cells, every
+    stored iteration holds all cells with Initial identifiers."""
+    vel = 0.1
+    agents = [cr.Agent(cr.NewtonDamped3D([1.0 + n, 5.0, 5.0], [vel, 0.0, 0.0], 0.0, 1.0),
+                       cr.MorsePotential(0.1, 1.0, 0.05, 0.0)) for n in range(10)]
+    domain = cr.CartesianCuboid.from_boundaries_and_n_voxels([0.0] * 3, [20.0, 10.0, 10.0], [4, 2, 2])
+    settings = cr.Settings(1, cr.FixedStepsize.from_partial_save_interval(0.0, 0.1, 20.0, 2.0),
+                           cr.StorageBuilder(priority=["Memory"]))
+    acc = cr.run_simulation(domain, agents, settings, mechanics_solver_order=2)
+    hist = acc.cells.load_all_elements()
+    assert sorted(hist) == list(range(0, 201, 20))
+    for it, cells in hist.items():
+        assert len(cells) == 10
+        for (kind, key), c in cells.items():
+            assert kind == "Initial"
+            assert abs(c["pos"][0] - (1.0 + key + it * 0.1 * vel)) < 1e-5
+
+
+def test_cell_sorting_example_with_json_storage(crb_lib, tmp_path):
+    """cell_sorting as shipped, shortened: JSON snapshots land in
+    <location>/<date>/cells/json/<iteration:020>/batch_<instance:020>_<k:020>.json with
+    {"data": [{"identifier", "element": [CellBox, AuxStorage]}]} (storage/concepts.rs:156-170, 702-743)."""
+    rng = np.random.default_rng(1)
+    n = 400
+    pos = rng.uniform(0.5, 72.0, (n, 3))
+    agents = [cr.Agent(cr.NewtonDamped3D(pos[k].tolist(), [0.0] * 3, 2.0, 1.0),
+                       cr.CellSpecificInteraction(int(k <= n // 2), 6.0, 2.0, 1.5)) for k in range(n)]
+    domain = cr.CartesianCuboid.from_boundaries_and_interaction_range([0.0] * 3, [72.0] * 3, 18.0)
+    settings = cr.Settings(4, cr.FixedStepsize.from_partial_save_steps(0.0, 0.2, 40, 20),
+                           cr.StorageBuilder(location=str(tmp_path), priority=["SerdeJson", "Memory"]))
+    acc = cr.run_simulation(domain, agents, settings)
+    its = acc.cells.get_all_iterations()
+    assert its == [0, 20, 40]
+    f = acc.path / "cells" / "json" / f"{20:020d}" / f"batch_{0:020d}_{0:020d}.json"
+    assert f.exists()
+    body = json.loads(f.read_text())
+    e = body["data"][0]
+    assert set(e) == {"identifier", "element"} and "Initial" in e["identifier"]
+    cbox, aux = e["element"]
+    assert set(cbox) == {"identifier", "parent", "cell"} and cbox["parent"] is None
+    assert set(aux["mechanics"]) == {"positions", "velocities", "current_force", "zero_force"}
+    assert len(aux["mechanics"]["positions"]) == 2  # ring of N = 2 increments, oldest first
+    mem = acc.cells.memory[40]
+    assert len(mem) == n
+    moved = np.array([np.abs(mem[("Initial", k)]["pos"] - pos[k]).max() for k in range(n)])
+    assert moved.max() > 1e-3  # the cells interact
