@@ -124,6 +124,7 @@ int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
         }
         if ((rc = dalloc(s, &st.hlen, s->cap_total))) return rc;
         if ((rc = dalloc(s, &st.posf, s->cap_total))) return rc;
+        if ((rc = dalloc(s, &st.meta, s->cap_total))) return rc;
     }
     if (stat) {
         if ((rc = dalloc(s, &st.id, s->cap_total))) return rc;
@@ -258,19 +259,19 @@ void plan_tile(crb_sim* s) {
     // <= staging budget of 3 CTAs/SM
     const size_t budget = 74 * 1024;
     TileLaunch& T = s->tile;
-    T.chunk_len = std::min(n2, 64);
+    T.chunk_len = std::min(n2, 56);
     T.nchunks = (n2 + T.chunk_len - 1) / T.chunk_len;
     T.kmax = T.chunk_len + 2;
     const size_t fixed = (size_t)(kTileQueue + 4) * kTileThreads * sizeof(unsigned short) +
                          (size_t)kTileRows * (T.kmax + 1) * sizeof(u32) + 2048;
-    const u32 cap = (u32)(((budget - fixed) / 42) / 32 * 32);
+    const u32 cap = (u32)(((budget - fixed) / 44) / 32 * 32);
     // candidates of a segment of t targets: nrows * (t + 2 voxels' worth) (+ sentinels)
     // (10 % slack ~ 3 sigma of the Poisson spread; an overflowing pencil is split into z-windows)
     const double per_target = nrows * 1.1;
     double tseg = (cap - kTileRows * kTileRowPad - nrows * 2.0 * rho * 1.1) / per_target;
-    tseg = std::max(8.0, std::min(tseg, 118.0));
+    tseg = std::max(8.0, std::min(tseg, 124.0));
     T.tseg = (u32)tseg;
-    T.nseg = (int)std::ceil(T.chunk_len * rho * 1.6 / T.tseg) + 1;
+    T.nseg = (int)std::ceil(T.chunk_len * rho * 1.3 / T.tseg) + 1;
     T.x_begin = g.own_lo;
     T.x_count = g.own_hi - g.own_lo;
     T.cap = cap;
@@ -370,6 +371,7 @@ int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool inges
         R.save_prev = save_prev ? 1 : 0;
         R.has_species = 1;
         for (int d = 0; d < 3; ++d) R.mn[d] = d < s->D ? s->g.mn[d] : 0.0;
+        R.n2 = (u32)s->g.ng[2];
         k_reorder<<<blocks_for(n_new, 256), 256, 0, s->stream>>>(R);
         ++nl;
     }
@@ -624,6 +626,7 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         H.off_rel = take((plane + 1) * sizeof(u32));
         for (int c = 0; c < D; ++c) H.off_pos[c] = take(H.gcap * sizeof(double));
         H.off_posf = take(H.gcap * sizeof(float4));
+        H.off_meta = take(H.gcap * sizeof(u32));
         H.off_sp = take(H.gcap);
         for (int k = 0; k < s->n_ip; ++k) H.off_ip[k] = take(H.gcap * sizeof(double));
         H.bytes = off;

@@ -34,7 +34,7 @@
 namespace crb {
 
 constexpr int kTileRows = 9;
-constexpr int kTileQueue = 64;      // in-range candidate indices buffered per lane between two drains
+constexpr int kTileQueue = 56;      // in-range candidate indices buffered per lane between two drains
 constexpr int kTileThreads = 128;
 constexpr int kTileSub = 4;         // lanes per candidate-window sub-group
 constexpr int kTileRowPad = 8;      // sentinel entries staged after every row (filter over-read)
@@ -52,13 +52,13 @@ struct TileLaunch {
 };
 
 __host__ __device__ inline size_t tile_smem_bytes(u32 cap, int kmax, int threads) {
-    const size_t c = cap + 32;  // cap includes kTileRows * kTileRowPad sentinels; +32 safety
+    const size_t c = cap + 34;  // cap includes kTileRows * kTileRowPad sentinels; +34 filter over-read
     size_t b = 0;
-    b += 3 * c * sizeof(double);
-    b += c * sizeof(float4);
-    b += (size_t)kTileRows * (kmax + 1) * sizeof(u32);
-    b += (size_t)(kTileQueue + 4) * threads * sizeof(unsigned short);
-    b += 2 * ((c + 15) / 16 * 16);  // species + window-relative z voxel
+    b += 3 * c * sizeof(double);                                       // sx, sy, sz
+    b += c * sizeof(float4);                                           // FP32 filter copy (pair layout)
+    b += c * sizeof(u32);                                              // species | z voxel
+    b += (size_t)kTileRows * (kmax + 1) * sizeof(u32);                 // start[] of the 9 rows
+    b += (size_t)(kTileQueue + 4) * threads * sizeof(unsigned short);  // per-lane FIFOs
     return b + 64;
 }
 
@@ -70,7 +70,7 @@ struct TileTarget {
     u32 my_v;       // local voxel index
     u32 subv_lo;    // local voxel range of the target's chili subdomain (len 0 => weights 1)
     u32 subv_len;
-    u32 zw;         // voxel of the target along the fastest axis, relative to the staged window
+    u32 zw;         // voxel index of the target along the fastest axis, low 8 bits
     u8 sp;
     int calc_flag;
 };
@@ -78,8 +78,8 @@ struct TileTarget {
 template <int D, int INTER, int NE>
 __device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
                                           const double* __restrict__ sx, const double* __restrict__ sy,
-                                          const double* __restrict__ sz, const float4* __restrict__ sfb,
-                                          const u8* __restrict__ ssp, const u8* __restrict__ szv,
+                                          const double* __restrict__ sz, const float4* __restrict__ sf,
+                                          const u32* __restrict__ smeta,
                                           const u32 (&jj)[NE], const bool (&hh)[NE]) {
     // straight-line code for NE candidates (coef() is branch-free) so that the dependent FP64 chains
     // interleave; an empty slot points at the target itself (z == 0) and contributes +0.
@@ -94,14 +94,15 @@ __device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& ow
         double r2 = 0.0;
 #pragma unroll
         for (int c = 0; c < D; ++c) r2 = fma(z[e][c], z[e][c], r2);
-        const u32 cvj = reinterpret_cast<const u32*>(sfb + (j >> 1))[2 + (j & 1)];
+        const u32 cvj = reinterpret_cast<const u32*>(sf + (j | 1u))[2 + (j & 1)];  // sf[2p+1] = {z0,z1,cv0,cv1}
+        const u32 mj = smeta[j];
         const bool same_voxel = cvj == t.my_v;
         const bool same_sub = (u32)(cvj - t.subv_lo) < t.subv_len;
         const bool keep = same_voxel | !same_sub;
         // chili only pairs agents of neighbouring voxels: the candidate rows are x/y-adjacent by
         // construction, the fastest axis is checked here (the FP32 filter tests the distance only)
-        const bool adj = (u32)((u32)szv[j] - t.zw + 1u) <= 2u;
-        const bool same_species = Pot<INTER>::kUsesSpecies ? (ssp[j] == t.sp) : true;
+        const bool adj = (((mj >> 8) - t.zw + 1u) & 0xffu) <= 2u;
+        const bool same_species = Pot<INTER>::kUsesSpecies ? ((mj & 0xffu) == (u32)t.sp) : true;
         flag[e] = 0;
         const double c0 = own.coef(r2, ext_radius, same_species, &flag[e]);
         const bool use = hh[e] & adj;
@@ -174,6 +175,19 @@ __device__ __forceinline__ void force_from_global(const KParams& P, const u64 i,
     if (calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
 }
 
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int D, int INTER, bool FORCE_ONLY>
 __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P, const TileLaunch T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -185,18 +199,17 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     const int n1 = g.ng[1], n2 = g.ng[2];
 
     // ---- carve shared memory -----------------------------------------------------------------------
-    const u32 capp = T.cap + 32;
+    const u32 capp = T.cap + 34;
     double* sx = reinterpret_cast<double*>(smem_raw);
     double* sy = sx + capp;
     double* sz = sy + capp;
     // FP32 filter copy, two candidates per 2 x 16 B so that one LDS.128 feeds a packed f32x2 op:
-    //   sfa[p] = {x[2p], x[2p+1], y[2p], y[2p+1]},  sfb[p] = {z[2p], z[2p+1], cv[2p], cv[2p+1]}
-    float4* sfa = reinterpret_cast<float4*>(sz + capp);
-    float4* sfb = sfa + capp / 2;
-    u32* wst = reinterpret_cast<u32*>(sfb + capp / 2);           // [kTileRows][kmax + 1]
-    unsigned short* q = reinterpret_cast<unsigned short*>(wst + kTileRows * (T.kmax + 1));  // [kTileQueue + NE][nthreads]
-    u8* ssp = reinterpret_cast<u8*>(q + (kTileQueue + NE) * nthreads);
-    u8* szv = ssp + (capp + 15) / 16 * 16;
+    //   sf[2p] = {x[2p], x[2p+1], y[2p], y[2p+1]},  sf[2p+1] = {z[2p], z[2p+1], cv[2p], cv[2p+1]}
+    // (staged as one float4 {x, y, z, cv} per candidate by cp.async, then transposed pairwise in place)
+    float4* sf = reinterpret_cast<float4*>(sz + capp);
+    u32* smeta = reinterpret_cast<u32*>(sf + capp);              // species | (z voxel & 0xff) << 8
+    u32* sst = smeta + capp;                                     // [kTileRows][kmax + 1] copy of start[]
+    unsigned short* q = reinterpret_cast<unsigned short*>(sst + kTileRows * (T.kmax + 1));  // [kTileQueue + NE][nthreads]
     __shared__ u32 s_rowvox[kTileRows];   // first voxel (local plain index) of every neighbour row
     __shared__ u32 s_g0[kTileRows];       // first global agent index staged per row
     __shared__ u32 s_rs[kTileRows + 1];   // staged index of the first candidate of every row
@@ -225,14 +238,31 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     }
     __syncthreads();
     const u32 rv_c = s_rowvox[4];
+    // ---- ONE round of global loads: start[] of the 9 rows over the chunk +- 1 voxel -> shared -------
+    const int zb0 = max(ca - 1, 0), ztop = min(cb + 1, n2);
+    const int sstride = T.kmax + 1;  // >= ztop - zb0 + 1
     {
-        // segment k owns the voxels whose first agent has in-chunk index in [k, k+1) * tseg: every CTA
-        // gets ~tseg targets whatever the local density (the last segment takes the remainder)
-        const u32 r0 = P.start[rv_c + ca];
-        const u32 lo_cnt = (u32)seg * T.tseg;
-        const u32 hi_cnt = seg == T.nseg - 1 ? 0xffffffffu : lo_cnt + T.tseg;
+        const int ns = ztop - zb0 + 1;
+        for (int idx = tid; idx < kTileRows * ns; idx += nthreads) {
+            const int r = idx / ns, k = idx - r * ns;
+            sst[r * sstride + k] = s_valid[r] ? P.start[s_rowvox[r] + (u32)(zb0 + k)] : 0u;
+        }
+    }
+    __syncthreads();
+#define SS(r, zz) sst[(r) * sstride + ((zz) - zb0)]
+    {
+        // segment k owns the voxels whose first agent has in-chunk index in [k, k+1) * tsr, balanced per
+        // row (ceil(R / tseg) segments of equal size): every CTA gets <= ~tseg targets whatever the
+        // local density
+        const u32 r0 = SS(4, ca);
+        const u32 R = SS(4, cb) - r0;
+        const u32 nsr = min((R + T.tseg - 1) / T.tseg, (u32)T.nseg);
+        if ((u32)seg >= nsr) return;  // uniform: no barrier is pending
+        const u32 tsr = (R + nsr - 1) / nsr;
+        const u32 lo_cnt = (u32)seg * tsr;
+        const u32 hi_cnt = (u32)seg == nsr - 1 ? 0xffffffffu : lo_cnt + tsr;
         for (int zz = ca + tid; zz < cb; zz += nthreads) {
-            const u32 c = P.start[rv_c + zz] - r0;
+            const u32 c = SS(4, zz) - r0;
             if (c >= lo_cnt) atomicMin(&s_za, zz);
             if (c >= hi_cnt) atomicMin(&s_zb, zz);
         }
@@ -240,7 +270,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     __syncthreads();
     const int za = s_za, zb = s_zb;
     if (za >= zb) return;
-    if (P.start[rv_c + zb] == P.start[rv_c + za]) return;  // no targets
+    if (SS(4, zb) == SS(4, za)) return;  // no targets
 
     Pot<INTER> own;
     own.init(P.u.ip);
@@ -258,9 +288,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                 const int wa = max(z - 1, 0), wb = min(z + kk + 1, n2);
                 u32 total = 0;
 #pragma unroll
-                for (int r = 0; r < kTileRows; ++r)
-                    if (s_valid[r]) total += P.start[s_rowvox[r] + wb] - P.start[s_rowvox[r] + wa];
-                if (total + kTileRows * kTileRowPad <= T.cap && wb - wa <= T.kmax) {
+                for (int r = 0; r < kTileRows; ++r) total += SS(r, wb) - SS(r, wa);
+                if (total + kTileRows * kTileRowPad <= T.cap) {
                     atomicMax(&s_kc, kk);
                     found = 1;
                 }
@@ -271,7 +300,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
         if (kc == 0) {
             // the neighbourhood of voxel z alone exceeds the staging capacity: per-agent path
             const u32 v = rv_c + (u32)z;
-            const u32 t0 = P.start[v], t1 = P.start[v + 1];
+            const u32 t0 = SS(4, z), t1 = SS(4, z + 1);
             for (u32 i = t0 + tid; i < t1; i += nthreads) {
                 double xi[D], acc[D];
 #pragma unroll
@@ -284,21 +313,20 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
 #pragma unroll
                     for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
                 } else {
-                    integrate_agent<D, true>(P, i, v, t0, X, Y, z, xi, acc);
+                    integrate_agent<D, true>(P, i, v, t0, X, Y, z, xi, acc, load_agent_dyn<D>(P, i));
                 }
             }
             z += 1;
             continue;
         }
         const int wa = max(z - 1, 0), wb = min(z + kc + 1, n2);
-        const int W = wb - wa;  // voxels in the window
 
         // ---- row ranges -------------------------------------------------------------------------------
         if (warp == 0) {
             u32 a = 0, n = 0;
-            if (lane < kTileRows && s_valid[lane]) {
-                a = P.start[s_rowvox[lane] + wa];
-                n = P.start[s_rowvox[lane] + wb] - a;
+            if (lane < kTileRows) {
+                a = SS(lane, wa);
+                n = SS(lane, wb) - a;
             }
             const u32 np = lane < kTileRows ? n + kTileRowPad : 0u;  // row + sentinels
             u32 incl = np;
@@ -316,59 +344,59 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
         }
         __syncthreads();
 
-        // ---- per-voxel offsets, then the candidates (coalesced) ------------------------------------------
-        const int stride = T.kmax + 1;
-        for (int idx = tid; idx < kTileRows * (W + 1); idx += nthreads) {
-            const int rr = idx / (W + 1), k = idx - rr * (W + 1);
-            wst[rr * stride + k] =
-                s_valid[rr] ? s_rs[rr] + (P.start[s_rowvox[rr] + wa + k] - s_g0[rr]) : s_rs[rr];
-        }
+        // ---- stage the candidates: asynchronous copies, nothing waits until all are in flight ----------
         {
             const u32 total = s_rs[kTileRows];
+            const u32 tend = (total + 33) & ~1u;  // even, >= total + 32: whole pairs of sentinels
             const float qn_ = __uint_as_float(0x7fc00000u);
             int r = 0;
-            for (u32 k = tid; k < total + 32; k += nthreads) {
-                float4 pf4 = make_float4(qn_, qn_, qn_, __uint_as_float(0xffffffffu));  // sentinel: NaN never passes
-                u32 zv = 0xff;
+            for (u32 k = tid; k < tend; k += nthreads) {
+                bool real = false;
                 if (k < total) {
                     while (k >= s_rs[r + 1]) ++r;
                     const u32 o = k - s_rs[r];
                     if (o < s_rn[r]) {
                         const u32 gi = s_g0[r] + o;
-                        sx[k] = P.A.pos[0][gi];
-                        sy[k] = P.A.pos[1][gi];
-                        if (D == 3) sz[k] = P.A.pos[2][gi];
-                        pf4 = P.A.posf[gi];
-                        if (Pot<INTER>::kUsesSpecies) ssp[k] = P.A.species[gi];
-                        zv = __float_as_uint(pf4.w) - s_rowvox[r] - (u32)wa;  // window-relative voxel (< kmax <= 250)
+                        cp_async_8(sx + k, P.A.pos[0] + gi);
+                        cp_async_8(sy + k, P.A.pos[1] + gi);
+                        if (D == 3) cp_async_8(sz + k, P.A.pos[2] + gi);
+                        cp_async_16(sf + k, P.A.posf + gi);
+                        cp_async_4(smeta + k, P.A.meta + gi);
+                        real = true;
                     }
                 }
-                float* fa = reinterpret_cast<float*>(sfa + (k >> 1)) + (k & 1);
-                float* fb = reinterpret_cast<float*>(sfb + (k >> 1)) + (k & 1);
-                fa[0] = pf4.x;
-                fa[2] = pf4.y;
-                fb[0] = pf4.z;
-                fb[2] = pf4.w;
-                szv[k] = (u8)zv;
+                if (!real) {  // sentinel: NaN coordinates never pass the distance test
+                    sf[k] = make_float4(qn_, qn_, qn_, __uint_as_float(0xffffffffu));
+                    smeta[k] = 0xffffu;
+                }
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            // pairwise in-place transpose {x,y,z,cv} x 2 -> {x0,x1,y0,y1}, {z0,z1,cv0,cv1}
+            for (u32 p = tid; 2 * p + 1 < tend; p += nthreads) {
+                const float4 a = sf[2 * p], b = sf[2 * p + 1];
+                sf[2 * p] = make_float4(a.x, b.x, a.y, b.y);
+                sf[2 * p + 1] = make_float4(a.z, b.z, a.w, b.w);
             }
         }
         __syncthreads();
 
-        // ---- targets: split evenly over the warps ---------------------------------------------------------
-        const u32 t0 = P.start[rv_c + z], t1 = P.start[rv_c + z + kc];
-        const u32 ntar = t1 - t0;
-        const u32 per = (ntar + nwarps - 1) / nwarps;
-        const u32 w_begin = t0 + (u32)warp * per, w_end = min(w_begin + per, t1);
+        // ---- targets: groups of 32 consecutive agents, one warp each ---------------------------------------
+        const u32 t0 = SS(4, z), t1 = SS(4, z + kc);
+        const u32 w_end = t1;
         const u32 limit = (s_rs[kTileRows] + 24) & ~1u;  // last safe (even) start of an 8-candidate block
-        for (u32 gb = w_begin; gb < w_end; gb += 32) {
+        for (u32 gb = t0 + 32u * (u32)warp; gb < w_end; gb += 32u * nwarps) {
             const u32 i_raw = gb + (u32)lane;
             const bool valid = i_raw < w_end;
             const u32 i = valid ? i_raw : w_end - 1;
+            // integrator inputs: issued now, consumed after the pair loop
+            AgentDyn<D> dyn;
+            if constexpr (!FORCE_ONLY) dyn = load_agent_dyn<D>(P, i);
             const u32 sj_self = s_rs[4] + (i - s_g0[4]);
             float4 pf;
             {
-                const float* fa = reinterpret_cast<const float*>(sfa + (sj_self >> 1)) + (sj_self & 1);
-                const float* fb = reinterpret_cast<const float*>(sfb + (sj_self >> 1)) + (sj_self & 1);
+                const float* fa = reinterpret_cast<const float*>(sf + (sj_self & ~1u)) + (sj_self & 1);
+                const float* fb = reinterpret_cast<const float*>(sf + (sj_self | 1u)) + (sj_self & 1);
                 pf = make_float4(fa[0], fa[2], fb[0], fb[2]);
             }
             TileTarget<D> t;
@@ -378,12 +406,13 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
 #pragma unroll
             for (int c = 0; c < D; ++c) t.acc[c] = 0.0;
             t.my_v = __float_as_uint(pf.w);
-            t.sp = Pot<INTER>::kUsesSpecies ? ssp[sj_self] : 0;
+            const u32 mself = smeta[sj_self];
+            t.sp = (u8)(mself & 0xffu);
+            t.zw = mself >> 8;
             t.calc_flag = 0;
             t.subv_lo = 0;
             t.subv_len = 0;
             const int zt = (int)(t.my_v - rv_c);
-            t.zw = (u32)(zt - wa);
             if (P.weight_mode == CRB_WEIGHT_CHILI && g.sm_nsub <= 1) {
                 t.subv_len = (u32)g.nvox_local();  // one chili subdomain: everything is "local"
             } else if (P.weight_mode == CRB_WEIGHT_CHILI) {
@@ -406,7 +435,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
             // (target, candidate) tests drops with the z-span of the sub-group instead of the warp's.
             const int zmin = __shfl_sync(0xffffffffu, zt, 0, kTileSub);
             const int zmax = __shfl_sync(0xffffffffu, zt, kTileSub - 1, kTileSub);
-            const int klo = max(zmin - 1, wa) - wa, khi = min(zmax + 2, wb) - wa;
+            const int zlo = max(zmin - 1, wa), zhi = min(zmax + 2, wb);
 
             // per-lane FIFO of in-range candidate indices (ascending): q[k][tid]
             // (32-bit shared-window address kept in a register: one predicated STS + one predicated
@@ -426,7 +455,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                         hh[e] = (k + e < nq) & (ent != sj_self);
                         jj[e] = hh[e] ? ent : sj_self;
                     }
-                    tile_eval<D, INTER, NE>(t, own, ext_radius, sx, sy, sz, sfb, ssp, szv, jj, hh);
+                    tile_eval<D, INTER, NE>(t, own, ext_radius, sx, sy, sz, sf, smeta, jj, hh);
                 }
                 qa = qa0;
             };
@@ -434,7 +463,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
             const float2 xf2 = make_float2(-xf, -xf), yf2 = make_float2(-yf, -yf), zf2 = make_float2(-zf, -zf);
 
             for (int r = 0; r < kTileRows; ++r) {
-                const u32 lo = wst[r * stride + klo], hi = wst[r * stride + khi];
+                const u32 off = s_rs[r] - s_g0[r];
+                const u32 lo = off + SS(r, zlo), hi = off + SS(r, zhi);
                 const u32 lo2 = lo & ~1u;  // blocks start at an even candidate (pair layout); the extra
                                            // leading candidate is voxel zmin-2 or a sentinel: rejected
                                            // by the distance test or by the adjacency test of the drain
@@ -450,8 +480,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                     float4 ca4[4], cb4[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {  // all loads first: the queue stores below alias smem
-                        ca4[u] = sfa[(b8 >> 1) + u];
-                        if (D == 3) cb4[u] = sfb[(b8 >> 1) + u];
+                        ca4[u] = sf[b8 + 2 * u];
+                        if (D == 3) cb4[u] = sf[b8 + 2 * u + 1];
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -482,12 +512,13 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
 #pragma unroll
                     for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = t.acc[c];
                 } else {
-                    integrate_agent<D, true>(P, i, t.my_v, P.start[t.my_v], X, Y, zt, t.x, t.acc);
+                    integrate_agent<D, true>(P, i, t.my_v, SS(4, zt), X, Y, zt, t.x, t.acc, dyn);
                 }
             }
         }
         z += kc;
     }
+#undef SS
 }
 
 }  // namespace crb

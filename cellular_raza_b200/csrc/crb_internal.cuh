@@ -65,6 +65,7 @@ struct State {
     // bit pattern of the local voxel index}.  Only read by the conservative distance pre-test of
     // k_force_tile; never enters a result.
     float4* posf;
+    u32* meta;  // species | (voxel index along the fastest axis & 0xff) << 8  (k_force_tile drain)
 };
 
 struct Uniform {
@@ -113,6 +114,7 @@ struct HaloLayout {
     u64 off_rel;      // u32 rel[plane + 1]: index of the first agent of every voxel relative to the plane
     u64 off_pos[3];   // f64
     u64 off_posf;     // float4
+    u64 off_meta;     // u32
     u64 off_sp;       // u8
     u64 off_ip[CRB_MAX_INTER_PARAMS];
     u64 bytes;

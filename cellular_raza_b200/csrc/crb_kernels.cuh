@@ -107,13 +107,16 @@ struct PotCellSorting {
         const double bound = 4.0 + sinv;
         const double s2 = sinv * sinv;
         double val = s2 - s2 * s2;  // (1/sigma)^2 - (1/sigma)^4
-        val = fmax(fmin(val, bound), -bound);
-        double st = strength * val;
-        if (!same_species) st = fmin(st, 0.0);  // only the repelling part acts between species
-        // spatial_cutoff = (1 + signum(range*(R1+R2) - r)) / 2 ; signum(+0) = 1
-        const double cut = (range * Rs - r >= 0.0) ? 1.0 : 0.0;
-        double c = st * cut * rinv;
-        c = r2 == 0.0 ? 0.0 : c;
+        // clamp(val, -bound, bound): x - x^2 <= 1/4 < 4 <= bound whenever 1/sigma >= 0, so the upper
+        // clamp can only act for a negative radius sum (kept for that case; the branch is warp-uniform
+        // with uniform parameters)
+        if (Rs < 0.0) val = fmin(val, bound);
+        val = fmax(val, -bound);
+        const double st = strength * val;
+        // attracting part only between equal species (:88-96); spatial_cutoff =
+        // (1 + signum(range*(R1+R2) - r)) / 2 with signum(+0) = 1 (:74-75)
+        const bool on = (same_species | (st < 0.0)) & (range * Rs - r >= 0.0) & (r2 != 0.0);
+        const double c = on ? st * rinv : 0.0;
         return BENCH ? c : -c;
     }
 };
@@ -264,10 +267,32 @@ __device__ __forceinline__ void philox_normal4(u64 seed, u64 id, u64 iter, u32 s
 // migration flag and histogram.  Shared by every force kernel (fused epilogue: the force never
 // travels through HBM).
 // ------------------------------------------------------------------------------------------------
+// per-agent inputs of the integrator; loaded early (before the pair loop) so that their global-memory
+// latency overlaps the force computation
+template <int D>
+struct AgentDyn {
+    double vel[D], oldx[D], oldv[D];
+    int hlen;
+};
+template <int D>
+__device__ __forceinline__ AgentDyn<D> load_agent_dyn(const KParams& P, const u64 i) {
+    AgentDyn<D> a;
+    const bool brownian = P.mech == CRB_MECH_BROWNIAN;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        a.vel[c] = brownian ? 0.0 : P.A.vel[c][i];  // Brownian::velocity() == 0 (mechanics.rs:371-378)
+        a.oldx[c] = P.A.h1x[c][i];
+        a.oldv[c] = P.A.h1v[c][i];
+    }
+    a.hlen = P.A.hlen[i];
+    return a;
+}
+
 template <int D, bool UNIFORM>
 __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, const u32 v,
                                                 const u32 own_lo, const int i0, const int i1,
-                                                const int i2, const double* xi, const double* acc) {
+                                                const int i2, const double* xi, const double* acc,
+                                                const AgentDyn<D>& dyn) {
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
     // ---- A7: Mechanics::calculate_increment / get_random_contribution ---------------------------
@@ -278,7 +303,7 @@ __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, c
     const bool brownian = P.mech == CRB_MECH_BROWNIAN;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-        vel[c] = brownian ? 0.0 : P.A.vel[c][i];  // Brownian::velocity() == 0 (mechanics.rs:371-378)
+        vel[c] = dyn.vel[c];
         rx[c] = 0.0;
         rv[c] = 0.0;
     }
@@ -333,13 +358,13 @@ __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, c
 
     // ---- A8: local_mechanics_update (chili/solvers.rs:156-300) -----------------------------------
     const int N = P.order;
-    const int hlen = P.A.hlen[i];
+    const int hlen = dyn.hlen;
     const int n_prev = N == 0 ? 0 : (hlen + 1 < N ? hlen + 1 : N);  // ring size AFTER the push
     double p_new[D], v_new[D], oldx[D], oldv[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-        oldx[c] = P.A.h1x[c][i];
-        oldv[c] = P.A.h1v[c][i];
+        oldx[c] = dyn.oldx[c];
+        oldv[c] = dyn.oldv[c];
         if (N == 2 && n_prev == 2) {
             // ring = [previous, current] oldest first; dx = [current, ring[0], ring[1]]
             p_new[c] = helper_ab3(xi[c], dxv[c], oldx[c], dxv[c], P.dt, rx[c]);
@@ -507,7 +532,7 @@ __global__ void __launch_bounds__(kForceThreads)
 #pragma unroll
         for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
     } else {
-        integrate_agent<D, UNIFORM>(P, i, v, own_lo, i0, i1, i2, xi, acc);
+        integrate_agent<D, UNIFORM>(P, i, v, own_lo, i0, i1, i2, xi, acc, load_agent_dyn<D>(P, i));
     }
 }
 
@@ -622,6 +647,7 @@ struct ReorderParams {
     int save_prev;
     int has_species;
     double mn[3];  // CartesianCuboid::min (origin of the FP32 filter coordinates)
+    u32 n2;        // voxels along the fastest axis
 };
 
 __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
@@ -652,6 +678,9 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
         const double p2 = R.D == 3 ? R.B.pos[2][i] : R.mn[2];
         R.Y.posf[d] = make_float4((float)(p0 - R.mn[0]), (float)(p1 - R.mn[1]), (float)(p2 - R.mn[2]),
                                   __uint_as_float(v));
+        // species | (voxel index along the fastest axis & 0xff) << 8: what the drain of k_force_tile
+        // needs besides the voxel index (one 4-byte word per staged candidate)
+        R.Y.meta[d] = (u32)(R.has_species ? R.A.species[i] : 0) | (((v % R.n2) & 0xffu) << 8);
     }
     R.Y.hlen[d] = R.B.hlen[i];
     R.Y.id[d] = R.A.id[i];
@@ -780,6 +809,7 @@ __global__ void k_halo_export(const State A, const u32* __restrict__ start, u32 
         const u64 i = a + t;
         for (int c = 0; c < L.D; ++c) reinterpret_cast<double*>(buf + L.off_pos[c])[t] = A.pos[c][i];
         reinterpret_cast<float4*>(buf + L.off_posf)[t] = A.posf[i];
+        reinterpret_cast<u32*>(buf + L.off_meta)[t] = A.meta[i];
         (buf + L.off_sp)[t] = A.species[i];
         for (int k = 0; k < L.n_ip; ++k) reinterpret_cast<double*>(buf + L.off_ip[k])[t] = A.ip[k][i];
     }
@@ -811,6 +841,7 @@ __global__ void k_halo_import(State A, u32* __restrict__ start, u32 v0, u64 edge
         float4 pf = reinterpret_cast<const float4*>(buf + L.off_posf)[t];
         pf.w = __uint_as_float(v0 + lo);
         A.posf[i] = pf;
+        A.meta[i] = reinterpret_cast<const u32*>(buf + L.off_meta)[t];
         A.species[i] = (buf + L.off_sp)[t];
         for (int k = 0; k < L.n_ip; ++k) A.ip[k][i] = reinterpret_cast<const double*>(buf + L.off_ip[k])[t];
     }
