@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-CRB_ABI_VERSION = 2
+CRB_ABI_VERSION = 3
 CRB_MAX_DIM = 3
 
 # crb_status
@@ -45,7 +45,7 @@ CRB_NOISE_NONE = 0
 CRB_NOISE_TABLE = 1
 CRB_NOISE_PHILOX = 2
 
-N_MECH_PARAMS = {CRB_MECH_NEWTON_DAMPED: 2, CRB_MECH_BROWNIAN: 2, CRB_MECH_LANGEVIN: 3, CRB_MECH_ROD: 7}
+N_MECH_PARAMS = {CRB_MECH_NEWTON_DAMPED: 2, CRB_MECH_BROWNIAN: 2, CRB_MECH_LANGEVIN: 3, CRB_MECH_ROD: 8}
 N_INTER_PARAMS = {
     CRB_INT_CELL_SORTING: 3,
     CRB_INT_CELL_SORTING_BENCH: 3,
@@ -129,6 +129,9 @@ SYMBOLS = [
     ("crb_get_params", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp]),
     ("crb_get_aux", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp]),
     ("crb_set_aux", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp]),
+    ("crb_get_identifiers", C.c_int, [_vp, C.c_uint64, _vp, _vp]),
+    ("crb_n_divisions", C.c_uint64, [_vp]),
+    ("crb_debug_neighbor_counts", C.c_int, [_vp, C.c_uint64, _vp]),
     ("crb_set_noise", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
     ("crb_step", C.c_int, [_vp, C.c_uint64]),
     ("crb_sync", C.c_int, [_vp]),

@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libcrb200.so"
 SOURCES = [CSRC / "crb_api.cu"]
-HEADERS = [CSRC / "crb_internal.cuh", CSRC / "crb_kernels.cuh", PKG.parent / "include" / "crb.h"]
+HEADERS = [p for p in CSRC.glob("*.cuh")] + [PKG.parent / "include" / "crb.h"]
 
 NVCC_FLAGS = [
     "-O3",

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "crb_force_tile.cuh"
+#include "crb_rods.cuh"
 
 using namespace crb;
 
@@ -78,6 +79,14 @@ struct crb_sim {
     int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 tile kernel (env CRB_FORCE_KERNEL)
     bool timers_on = false;
     StageTimer timers[kNumStages];
+    // bacterial rods (CRB_MECH_ROD): own state layout, see crb_rods.cuh
+    bool rods = false;
+    RodState RX, RT, RY;
+    u8* div_flag = nullptr;
+    u32* id_counter = nullptr;
+    u32* n_div_dev = nullptr;
+    u64* nb_out = nullptr;
+    u64 last_divisions = 0;
     std::vector<void*> allocs;
     std::string error;
 };
@@ -436,6 +445,8 @@ int download_rows(crb_sim* s, double* host, int width, const double* const* cols
 
 }  // namespace
 
+#include "crb_rods_host.cuh"
+
 // =================================================================================================
 extern "C" {
 
@@ -446,7 +457,7 @@ uint32_t crb_n_mech_params(uint32_t kind) {
         case CRB_MECH_NEWTON_DAMPED: return 2;
         case CRB_MECH_BROWNIAN: return 2;
         case CRB_MECH_LANGEVIN: return 3;
-        case CRB_MECH_ROD: return 7;
+        case CRB_MECH_ROD: return 8;
     }
     return 0;
 }
@@ -524,8 +535,20 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         return fail(nullptr, CRB_ERR_INVALID_ARG, "abi_version mismatch");
     if (cfg->dim != 2 && cfg->dim != 3)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "dim must be 2 or 3");
-    if (cfg->mechanics_kind > CRB_MECH_LANGEVIN)
-        return fail(nullptr, CRB_ERR_INVALID_ARG, "unsupported mechanics_kind for point agents");
+    if (cfg->mechanics_kind > CRB_MECH_ROD)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown mechanics_kind");
+    const bool rods = cfg->mechanics_kind == CRB_MECH_ROD;
+    if (rods) {
+        if (cfg->dim != 3 || cfg->interaction_kind != CRB_INT_MORSE)
+            return fail(nullptr, CRB_ERR_INVALID_ARG,
+                        "CRB_MECH_ROD needs dim == 3 and interaction_kind == CRB_INT_MORSE (RodInteraction<MorsePotential>)");
+        if (cfg->rod_n_vertices < 2 || cfg->rod_n_vertices > CRB_MAX_ROD_VERTICES)
+            return fail(nullptr, CRB_ERR_INVALID_ARG, "rod_n_vertices must be in [2, 8]");
+        if (cfg->world_size != 1)
+            return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: slab decomposition is not implemented yet");
+        if (cfg->noise_mode != CRB_NOISE_NONE)
+            return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: only CRB_NOISE_NONE (diffusion_constant 0)");
+    }
     if (cfg->interaction_kind > CRB_INT_MIE)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
     if (cfg->solver_order > 2)
@@ -548,7 +571,8 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     crb_sim* s = new crb_sim();
     s->cfg = *cfg;
     s->D = D;
-    s->V = 1;
+    s->V = rods ? (int)cfg->rod_n_vertices : 1;
+    s->rods = rods;
     s->n_mp = (int)crb_n_mech_params(cfg->mechanics_kind);
     s->n_ip = (int)crb_n_inter_params(cfg->interaction_kind);
     s->cap = cfg->capacity;
@@ -668,16 +692,20 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         return bail(CRB_ERR_CUDA);
     }
     int rc;
-    if ((rc = alloc_state(s, s->X, true, true))) return bail(rc);
-    if ((rc = alloc_state(s, s->Y, true, true))) return bail(rc);
-    if ((rc = alloc_state(s, s->T, true, false))) return bail(rc);
+    if (rods) {
+        if ((rc = rods_alloc(s))) return bail(rc);
+    } else {
+        if ((rc = alloc_state(s, s->X, true, true))) return bail(rc);
+        if ((rc = alloc_state(s, s->Y, true, true))) return bail(rc);
+        if ((rc = alloc_state(s, s->T, true, false))) return bail(rc);
+    }
     s->n_tiles = (u32)((s->nvox + kScanTile - 1) / kScanTile);
     if ((rc = dalloc(s, &s->key, s->cap_total)) || (rc = dalloc(s, &s->key_alt, s->cap_total)) ||
         (rc = dalloc(s, &s->start, s->nvox + 1)) || (rc = dalloc(s, &s->start_alt, s->nvox + 1)) ||
         (rc = dalloc(s, &s->count_new, s->nvox + 1)) || (rc = dalloc(s, &s->newkey, s->cap_total)) ||
         (rc = dalloc(s, &s->rank_arb, s->cap_total)) || (rc = dalloc(s, &s->tmp_idx, s->cap_total)) ||
         (rc = dalloc(s, &s->slot_of_src, s->cap_total)) || (rc = dalloc(s, &s->sortkey, s->cap_total)) ||
-        (rc = dalloc(s, &s->tile_sums, s->n_tiles + 1)) || (rc = dalloc(s, &s->stage, s->cap_total * 8)) ||
+        (rc = dalloc(s, &s->tile_sums, s->n_tiles + 1)) || (rc = dalloc(s, &s->stage, s->cap_total * (rods ? 3 * s->V : 8))) ||
         (rc = dalloc(s, &s->err, 4)) || (rc = dalloc(s, &s->scratch_u64, 16)))
         return bail(rc);
     e = cudaMallocHost((void**)&s->err_host, 4 * sizeof(int));
@@ -718,6 +746,7 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
     if (n > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
     if (n && !pos) return fail(s, CRB_ERR_INVALID_ARG, "pos is required");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_set_agents(s, n, pos, vel, mech_params, inter_params, (const u64*)ids);
     const int D = s->D;
     // uniform-parameter fast path: all agents share one parameter row
     if (s->uniform_declared) {
@@ -857,6 +886,7 @@ int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t*
     if (!s) return CRB_ERR_INVALID_ARG;
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_get_agents(s, cap, pos, vel, (u64*)ids, (u64*)voxel);
     int rc;
     const u64 n = s->n;
     if (pos) {
@@ -887,6 +917,7 @@ int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_
     if (!s) return CRB_ERR_INVALID_ARG;
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_get_params(s, cap, mech_params, inter_params, species);
     const u64 n = s->n;
     int rc;
     if (mech_params) {
@@ -917,6 +948,7 @@ int crb_get_aux(crb_sim* s, uint64_t cap, double* hist_dx, double* hist_dv, uint
     if (!s) return CRB_ERR_INVALID_ARG;
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_get_aux(s, cap, hist_dx, hist_dv, hist_len);
     const u64 n = s->n;
     const int D = s->D;
     std::vector<u8> hl(n);
@@ -970,6 +1002,7 @@ __global__ void k_scatter_aux(State X, State T, const u32* __restrict__ slot, in
 int crb_set_aux(crb_sim* s, uint64_t n, const double* hist_dx, const double* hist_dv,
                 const uint32_t* hist_len) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->rods) return fail(s, CRB_ERR_STATE, "crb_set_aux is not available for CRB_MECH_ROD");
     if (!s->aux_settable || n != s->n)
         return fail(s, CRB_ERR_STATE, "crb_set_aux must directly follow crb_set_agents with the same n");
     if (!hist_dx || !hist_dv || !hist_len) return fail(s, CRB_ERR_INVALID_ARG, "null argument");
@@ -1083,6 +1116,7 @@ int crb_step(crb_sim* s, uint64_t n_steps) {
         return fail(s, CRB_ERR_STATE, "slab handle: drive the step with crb_slab_* (halo/migration exchange)");
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->aux_settable = false;
+    if (s->rods) return rods_step(s, n_steps);
     for (u64 it = 0; it < n_steps; ++it) {
         const bool last = it + 1 == n_steps;
         int rc;
@@ -1303,6 +1337,7 @@ int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_debug_forces(s, force, nullptr);
     int rc;
     if (!s->force_out)
         if ((rc = dalloc(s, &s->force_out, s->cap_total * 3))) return rc;
@@ -1315,9 +1350,45 @@ int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
     return check_latch(s);
 }
 
+int crb_get_identifiers(crb_sim* s, uint64_t cap, uint64_t* ident, uint64_t* parent) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_get_identifiers(s, cap, (u64*)ident, (u64*)parent);
+    const u64 n = s->n;
+    std::vector<u64> ids(n);
+    CU(s, cudaMemcpyAsync(ids.data(), s->X.id + s->G, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    for (u64 i = 0; i < n; ++i) {
+        if (ident) {
+            ident[i * 3 + 0] = 1;  // Initial(id)
+            ident[i * 3 + 1] = ids[i];
+            ident[i * 3 + 2] = 0;
+        }
+        if (parent) {
+            parent[i * 3 + 0] = ~0ull;
+            parent[i * 3 + 1] = 0;
+            parent[i * 3 + 2] = 0;
+        }
+    }
+    return 0;
+}
+
+uint64_t crb_n_divisions(const crb_sim* s) { return s ? s->last_divisions : 0; }
+
+int crb_debug_neighbor_counts(crb_sim* s, uint64_t cap, uint64_t* counts) {
+    if (!s || !counts) return CRB_ERR_INVALID_ARG;
+    if (!s->rods) return fail(s, CRB_ERR_STATE, "neighbour sensing is only part of the CRB_MECH_ROD step");
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    return rods_debug_forces(s, nullptr, (u64*)counts);
+}
+
 int crb_get_migrations(crb_sim* s, uint64_t cap, uint64_t* ids, uint64_t* old_voxel,
                        uint64_t* new_voxel, uint64_t* n_out) {
     if (!s || !n_out) return CRB_ERR_INVALID_ARG;
+    if (s->rods) return fail(s, CRB_ERR_STATE, "crb_get_migrations is not available for CRB_MECH_ROD");
     CU(s, cudaSetDevice((int)s->cfg.device));
     *n_out = 0;
     const u64 n = s->last_step_n;

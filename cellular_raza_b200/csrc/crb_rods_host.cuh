@@ -1,0 +1,408 @@
+// crb_rods_host.cuh — host side of the bacterial-rods path (included by crb_api.cu after the
+// definition of crb_sim and its helpers).  Same C ABI entry points as the point-agent path; the
+// functions here are what those entry points dispatch to when mechanics_kind == CRB_MECH_ROD.
+#pragma once
+
+namespace {
+
+enum { RMP_DIFF = 0, RMP_TENSION, RMP_RIGIDITY, RMP_LENGTH, RMP_DAMPING, RMP_GROWTH, RMP_THRESHOLD, RMP_GROWTH_BASE };
+
+int rods_alloc_state(crb_sim* s, RodState& st, bool dynamic, bool stat) {
+    std::memset(&st, 0, sizeof(st));
+    const u64 c = s->cap_total, W = 3ull * s->V;
+    int rc;
+    if (dynamic) {
+        if ((rc = dalloc(s, &st.pos, c * W)) || (rc = dalloc(s, &st.vel, c * W)) ||
+            (rc = dalloc(s, &st.h1x, c * W)) || (rc = dalloc(s, &st.h1v, c * W)) ||
+            (rc = dalloc(s, &st.h0x, c * W)) || (rc = dalloc(s, &st.h0v, c * W)) ||
+            (rc = dalloc(s, &st.len, c)) || (rc = dalloc(s, &st.growth, c)) ||
+            (rc = dalloc(s, &st.cen, c * 4)) || (rc = dalloc(s, &st.hlen, c)))
+            return rc;
+    }
+    if (stat) {
+        if ((rc = dalloc(s, &st.ident, c * 3)) || (rc = dalloc(s, &st.parent, c * 3))) return rc;
+    }
+    return 0;
+}
+
+int rods_alloc(crb_sim* s) {
+    int rc;
+    if ((rc = rods_alloc_state(s, s->RX, true, true))) return rc;
+    if ((rc = rods_alloc_state(s, s->RY, true, true))) return rc;
+    if ((rc = rods_alloc_state(s, s->RT, true, false))) return rc;
+    if ((rc = dalloc(s, &s->div_flag, s->cap_total)) || (rc = dalloc(s, &s->id_counter, s->nvox + 1)) ||
+        (rc = dalloc(s, &s->n_div_dev, 4)))
+        return rc;
+    CU(s, cudaMemsetAsync(s->div_flag, 0, s->cap_total, s->stream));
+    CU(s, cudaMemsetAsync(s->id_counter, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    return 0;
+}
+
+// smallest double x with sqrt(x) >= c (sqrt correctly rounded, monotone): (norm < c) <=> (norm^2 < x)
+double sqrt_threshold(double c) {
+    double x = c * c;
+    while (std::sqrt(x) >= c) x = std::nextafter(x, 0.0);
+    while (std::sqrt(x) < c) x = std::nextafter(x, INFINITY);
+    return x;
+}
+
+RodParams rods_params(crb_sim* s) {
+    RodParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.g = s->g;
+    P.A = s->RX;
+    P.B = s->RT;
+    P.n = s->n;
+    P.cap = s->cap_total;
+    P.key = s->key;
+    P.start = s->start;
+    P.newkey = s->newkey;
+    P.rank_arb = s->rank_arb;
+    P.count_new = s->count_new;
+    P.sortkey = s->sortkey;
+    P.div_flag = s->div_flag;
+    P.id_counter = s->id_counter;
+    P.n_div = s->n_div_dev;
+    P.force_out = s->force_out;
+    P.nb_out = s->nb_out;
+    P.err = s->err;
+    P.dt = s->cfg.dt;
+    const double* mp = s->uni.mp;
+    const double* ip = s->uni.ip;
+    P.tension = mp[RMP_TENSION];
+    P.rigidity = mp[RMP_RIGIDITY];
+    P.damping = mp[RMP_DAMPING];
+    P.threshold = mp[RMP_THRESHOLD];
+    P.growth_base = mp[RMP_GROWTH_BASE];
+    P.radius = ip[0];
+    P.stiffness = ip[1];
+    P.cutoff = ip[2];
+    P.strength = ip[3];
+    const double two_r = 2.0 * P.radius;
+    P.reject = std::max(P.cutoff, two_r) * (1.0 + 1e-9);
+    P.nb_thresh2 = sqrt_threshold(two_r);
+    P.order = (int)s->cfg.solver_order;
+    P.weight_mode = (int)s->cfg.pair_weight_mode;
+    P.save_prev = 0;
+    return P;
+}
+
+template <int V>
+void rods_launch_force_v(crb_sim* s, const RodParams& P, bool force_only) {
+    const u32 grid = blocks_for(P.n, kRodThreads);
+    if (!grid) return;
+    if (force_only)
+        k_rod_force<V, true><<<grid, kRodThreads, 0, s->stream>>>(P);
+    else
+        k_rod_force<V, false><<<grid, kRodThreads, 0, s->stream>>>(P);
+}
+template <int V>
+void rods_launch_divide_v(crb_sim* s, const RodParams& P) {
+    const u32 grid = blocks_for(P.n, 128);
+    if (grid) k_rod_divide<V><<<grid, 128, 0, s->stream>>>(P);
+}
+template <int V>
+void rods_launch_ingest_v(crb_sim* s, const RodParams& P) {
+    const u32 grid = blocks_for(P.n, 256);
+    if (grid) k_rod_ingest<V><<<grid, 256, 0, s->stream>>>(P);
+}
+#define RODS_DISPATCH_V(s, CALL)                      \
+    switch ((s)->V) {                                 \
+        case 2: CALL(2); break;                       \
+        case 3: CALL(3); break;                       \
+        case 4: CALL(4); break;                       \
+        case 5: CALL(5); break;                       \
+        case 6: CALL(6); break;                       \
+        case 7: CALL(7); break;                       \
+        case 8: CALL(8); break;                       \
+    }
+
+void rods_launch_force(crb_sim* s, const RodParams& P, bool force_only) {
+#define CALL(VV) rods_launch_force_v<VV>(s, P, force_only)
+    RODS_DISPATCH_V(s, CALL)
+#undef CALL
+}
+void rods_launch_divide(crb_sim* s, const RodParams& P) {
+#define CALL(VV) rods_launch_divide_v<VV>(s, P)
+    RODS_DISPATCH_V(s, CALL)
+#undef CALL
+}
+void rods_launch_ingest(crb_sim* s, const RodParams& P) {
+#define CALL(VV) rods_launch_ingest_v<VV>(s, P)
+    RODS_DISPATCH_V(s, CALL)
+#undef CALL
+}
+
+// scan count_new -> start_alt, fill, reorder RT (+ RX identifiers) -> RY, swap
+int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev) {
+    const u64 nv = s->nvox;
+    stage_begin(s, 1);
+    k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, s->tile_sums, nv);
+    k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv, 0u);
+    k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
+    stage_end(s, 1, 3);
+    stage_begin(s, 2);
+    int nl = 0;
+    if (n_src) {
+        k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt, s->tmp_idx,
+                                                             0, n_src);
+        RodReorderParams R;
+        std::memset(&R, 0, sizeof(R));
+        R.A = s->RX;
+        R.B = s->RT;
+        R.Y = s->RY;
+        R.newkey = s->newkey;
+        R.start_new = s->start_alt;
+        R.tmp_idx = s->tmp_idx;
+        R.sortkey = s->sortkey;
+        R.key_out = s->key_alt;
+        R.n = n_src;
+        R.cap = s->cap_total;
+        R.W = 3 * s->V;
+        R.save_prev = save_prev ? 1 : 0;
+        k_rod_reorder<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(R);
+        nl = 2;
+    }
+    stage_end(s, 2, nl);
+    std::swap(s->RX, s->RY);
+    std::swap(s->key, s->key_alt);
+    std::swap(s->start, s->start_alt);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
+// agent-major host rows of width W -> planes of stride cap_total (through the staging buffer)
+int rods_upload_planes(crb_sim* s, const double* host, int W, double* planes, u64 n) {
+    if (!n) return 0;
+    CU(s, cudaMemcpyAsync(s->stage, host, n * W * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    k_rod_unpack<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, planes, W, s->cap_total, n);
+    s->launches++;
+    return 0;
+}
+int rods_download_planes(crb_sim* s, double* host, int W, const double* planes, u64 n) {
+    if (!n) return 0;
+    k_rod_pack<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, planes, W, s->cap_total, n);
+    s->launches++;
+    CU(s, cudaMemcpyAsync(host, s->stage, n * W * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, const double* mech_params,
+                    const double* inter_params, const u64* ids) {
+    const int W = 3 * s->V;
+    // RodMechanics / MorsePotential fields are uniform except spring_length and growth_rate
+    std::vector<double> len(n), growth(n);
+    if (s->uniform_declared && !mech_params) {
+        for (u64 i = 0; i < n; ++i) {
+            len[i] = s->uni.mp[RMP_LENGTH];
+            growth[i] = s->uni.mp[RMP_GROWTH];
+        }
+    } else {
+        if (n && (!mech_params || (!inter_params && !s->uniform_declared)))
+            return fail(s, CRB_ERR_INVALID_ARG, "mech_params and inter_params are required");
+        if (n) {
+            for (int k = 0; k < 8; ++k) s->uni.mp[k] = mech_params[k];
+            if (inter_params)
+                for (int k = 0; k < 4; ++k) s->uni.ip[k] = inter_params[k];
+        }
+        for (u64 i = 0; i < n; ++i) {
+            for (int k = 0; k < 8; ++k)
+                if (k != RMP_LENGTH && k != RMP_GROWTH && mech_params[i * 8 + k] != s->uni.mp[k])
+                    return fail(s, CRB_ERR_INVALID_ARG,
+                                "rods: all mechanics parameters except spring_length and growth_rate must be uniform");
+            if (inter_params)
+                for (int k = 0; k < 4; ++k)
+                    if (inter_params[i * 4 + k] != s->uni.ip[k])
+                        return fail(s, CRB_ERR_INVALID_ARG, "rods: interaction parameters must be uniform");
+            len[i] = mech_params[i * 8 + RMP_LENGTH];
+            growth[i] = mech_params[i * 8 + RMP_GROWTH];
+        }
+    }
+    if (s->uni.mp[RMP_DIFF] != 0.0)
+        return fail(s, CRB_ERR_INVALID_ARG,
+                    "rods: diffusion_constant != 0 is not supported (the example ships 0; noise contract A7 "
+                    "covers point agents only)");
+    s->uniform = true;
+    int rc;
+    if ((rc = rods_upload_planes(s, pos, W, s->RT.pos, n))) return rc;
+    if (vel) {
+        CU(s, cudaStreamSynchronize(s->stream));
+        if ((rc = rods_upload_planes(s, vel, W, s->RT.vel, n))) return rc;
+    } else {
+        CU(s, cudaMemsetAsync(s->RT.vel, 0, s->cap_total * W * sizeof(double), s->stream));
+    }
+    for (double* p : {s->RT.h1x, s->RT.h1v, s->RT.h0x, s->RT.h0v})
+        CU(s, cudaMemsetAsync(p, 0, s->cap_total * W * sizeof(double), s->stream));
+    CU(s, cudaMemsetAsync(s->RT.hlen, 0, s->cap_total, s->stream));
+    CU(s, cudaMemcpyAsync(s->RT.len, len.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(s, cudaMemcpyAsync(s->RT.growth, growth.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    u64* d_ids = nullptr;
+    if (ids && n) {
+        CU(s, cudaStreamSynchronize(s->stream));
+        d_ids = (u64*)s->stage;
+        CU(s, cudaMemcpyAsync(d_ids, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    }
+    if (n) {
+        k_rod_init_ident<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->RX, d_ids, s->cap_total, n);
+        s->launches++;
+    }
+    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    CU(s, cudaMemsetAsync(s->div_flag, 0, s->cap_total, s->stream));
+    s->n = n;
+    RodParams P = rods_params(s);
+    rods_launch_ingest(s, P);
+    s->launches += n ? 1 : 0;
+    if ((rc = check_latch(s))) {
+        s->n = 0;
+        s->have_agents = false;
+        return rc;
+    }
+    if ((rc = rods_sort_into_place(s, n, true))) return rc;
+    k_rod_init_counters<<<blocks_for(s->nvox, 256), 256, 0, s->stream>>>(s->start, s->id_counter, s->nvox);
+    s->launches++;
+    CU(s, cudaStreamSynchronize(s->stream));
+    CU(s, cudaGetLastError());
+    s->have_agents = true;
+    s->aux_settable = false;
+    s->last_step_n = 0;
+    s->last_divisions = 0;
+    return 0;
+}
+
+int rods_step(crb_sim* s, u64 n_steps) {
+    for (u64 it = 0; it < n_steps; ++it) {
+        const bool last = it + 1 == n_steps;
+        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+        CU(s, cudaMemsetAsync(s->n_div_dev, 0, sizeof(u32), s->stream));
+        RodParams P = rods_params(s);
+        P.save_prev = last ? 1 : 0;
+        stage_begin(s, 0);
+        rods_launch_force(s, P, false);
+        stage_end(s, 0, s->n ? 1 : 0);
+        stage_begin(s, 4);
+        rods_launch_divide(s, P);
+        if (s->n)
+            k_rod_bump_counters<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(s->div_flag, s->key, s->id_counter,
+                                                                             s->n);
+        stage_end(s, 4, s->n ? 2 : 0);
+        u32 n_div = 0;
+        CU(s, cudaMemcpyAsync(&n_div, s->n_div_dev, sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaStreamSynchronize(s->stream));
+        CU(s, cudaGetLastError());
+        if (s->n + n_div > s->cap) {
+            check_latch(s);
+            return fail(s, CRB_ERR_CAPACITY, "more agents than capacity after division");
+        }
+        s->last_step_n = s->n;
+        s->last_divisions = n_div;
+        int rc;
+        if ((rc = rods_sort_into_place(s, s->n + n_div, last))) return rc;
+        s->n += n_div;
+        s->iteration++;
+    }
+    return check_latch(s);
+}
+
+int rods_get_agents(crb_sim* s, u64 cap, double* pos, double* vel, u64* ids, u64* voxel) {
+    const u64 n = s->n;
+    const int W = 3 * s->V;
+    int rc;
+    if (pos && (rc = rods_download_planes(s, pos, W, s->RX.pos, n))) return rc;
+    if (vel && (rc = rods_download_planes(s, vel, W, s->RX.vel, n))) return rc;
+    if (ids)
+        CU(s, cudaMemcpyAsync(ids, s->RX.ident + s->cap_total, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    if (voxel && n) {
+        const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
+        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key, (u64*)s->stage, base, n);
+        s->launches++;
+        CU(s, cudaMemcpyAsync(voxel, s->stage, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(s, cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int rods_get_identifiers(crb_sim* s, u64 cap, u64* ident, u64* parent) {
+    const u64 n = s->n;
+    if (!n) return 0;
+    for (int which = 0; which < 2; ++which) {
+        u64* out = which == 0 ? ident : parent;
+        if (!out) continue;
+        k_rod_pack_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>((u64*)s->stage, which == 0 ? s->RX.ident : s->RX.parent,
+                                                                 3, s->cap_total, n);
+        s->launches++;
+        CU(s, cudaMemcpyAsync(out, s->stage, n * 3 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaStreamSynchronize(s->stream));
+    }
+    return 0;
+}
+
+int rods_get_params(crb_sim* s, u64 cap, double* mech_params, double* inter_params, u8* species) {
+    const u64 n = s->n;
+    if (mech_params) {
+        std::vector<double> len(n), growth(n);
+        CU(s, cudaMemcpyAsync(len.data(), s->RX.len, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaMemcpyAsync(growth.data(), s->RX.growth, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaStreamSynchronize(s->stream));
+        for (u64 i = 0; i < n; ++i) {
+            for (int k = 0; k < 8; ++k) mech_params[i * 8 + k] = s->uni.mp[k];
+            mech_params[i * 8 + RMP_LENGTH] = len[i];
+            mech_params[i * 8 + RMP_GROWTH] = growth[i];
+        }
+    }
+    if (inter_params)
+        for (u64 i = 0; i < n; ++i)
+            for (int k = 0; k < 4; ++k) inter_params[i * 4 + k] = s->uni.ip[k];
+    if (species) std::memset(species, 0, n);
+    return 0;
+}
+
+// ring buffers oldest-first: [n][2][V][3]
+int rods_get_aux(crb_sim* s, u64 cap, double* hist_dx, double* hist_dv, uint32_t* hist_len) {
+    const u64 n = s->n;
+    const int W = 3 * s->V;
+    std::vector<u8> hl(n);
+    CU(s, cudaMemcpyAsync(hl.data(), s->RX.hlen, n, cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    std::vector<double> older(n * W), newest(n * W);
+    int rc;
+    for (int which = 0; which < 2; ++which) {
+        double* outp = which == 0 ? hist_dx : hist_dv;
+        if (!outp) continue;
+        if ((rc = rods_download_planes(s, older.data(), W, which == 0 ? s->RX.h0x : s->RX.h0v, n))) return rc;
+        if ((rc = rods_download_planes(s, newest.data(), W, which == 0 ? s->RX.h1x : s->RX.h1v, n))) return rc;
+        for (u64 i = 0; i < n; ++i) {
+            double* o = outp + i * 2 * W;
+            for (int k = 0; k < 2 * W; ++k) o[k] = 0.0;
+            if (hl[i] == 2) {
+                for (int k = 0; k < W; ++k) {
+                    o[k] = older[i * W + k];
+                    o[W + k] = newest[i * W + k];
+                }
+            } else if (hl[i] == 1) {
+                for (int k = 0; k < W; ++k) o[k] = newest[i * W + k];
+            }
+        }
+    }
+    if (hist_len)
+        for (u64 i = 0; i < n; ++i) hist_len[i] = hl[i];
+    return 0;
+}
+
+int rods_debug_forces(crb_sim* s, double* force, u64* counts) {
+    int rc;
+    if (!s->force_out)
+        if ((rc = dalloc(s, &s->force_out, s->cap_total * 3 * s->V))) return rc;
+    if (!s->nb_out)
+        if ((rc = dalloc(s, &s->nb_out, s->cap_total))) return rc;
+    RodParams P = rods_params(s);
+    rods_launch_force(s, P, true);
+    s->launches += s->n ? 1 : 0;
+    CU(s, cudaGetLastError());
+    if (force && (rc = rods_download_planes(s, force, 3 * s->V, s->force_out, s->n))) return rc;
+    if (counts)
+        CU(s, cudaMemcpyAsync(counts, s->nb_out, s->n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    return check_latch(s);
+}
+
+}  // namespace

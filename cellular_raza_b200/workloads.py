@@ -212,3 +212,90 @@ def cell_sorting_slab(cells_per_rank: int, rank: int, world: int, density_per_vo
     w.extra["ids"] = (np.arange(cells_per_rank, dtype=np.uint64) + np.uint64(rank) * np.uint64(cells_per_rank))
     w.extra["n_side"] = n_side
     return w
+
+
+# ---------------------------------------------------------------------------------------------------
+MICRO_METRE = 1e-6
+MINUTE = 1.0
+
+
+def bacterial_rods(
+    n_tiles_x: int = 1,
+    n_tiles_z: int = 1,
+    *,
+    rods_per_tile: int = 5,
+    seed: int = 5,
+    n_vertices: int = 5,
+    dt: float = 0.1 * MINUTE,
+    n_threads: int = 8,
+    spring_length_range=(1.5, 2.5),
+    pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI,
+    solver_order: int = 2,
+    capacity_factor: float = 2.0,
+) -> Workload:
+    """cellular_raza-examples/bacterial_rods as shipped (src/main.rs:111-212), tiled: every tile is the
+    shipped domain (200 x 15 x 45 um, [8, 1, 2] voxels) holding ``rods_per_tile`` rods placed by the
+    shipped rule (:143-163: first vertex in [dx, 2dx] x [dx/3, 2dx/3] x [dx, 2dx] of the tile with
+    dx = 15 um, direction in the x-y plane with +-pi/8 jitter per segment, 3 um segments, spring length
+    drawn from ``spring_length_range`` um).  Tiles repeat along x and z, so the rod density of the shipped
+    example is kept (BASELINE.json configs[3]: "2 M rods ... domain scaled at constant rod density").
+    Units: metres and minutes like the example.  ChaCha8 cannot be reproduced here: numpy PCG64."""
+    rng = np.random.default_rng(seed)
+    V = n_vertices
+    um = MICRO_METRE
+    seg = 3.0 * um
+    delta_x = seg * V
+    domain_size = 50.0 * um
+    tile = np.array([4.0 * domain_size, delta_x, 3.0 * delta_x])
+    n = n_tiles_x * n_tiles_z * rods_per_tile
+    tx = np.repeat(np.arange(n_tiles_x), n_tiles_z * rods_per_tile)
+    tz = np.tile(np.repeat(np.arange(n_tiles_z), rods_per_tile), n_tiles_x)
+    pos = np.zeros((n, V, 3))
+    pos[:, 0, 0] = rng.uniform(delta_x, 2.0 * delta_x, n) + tx * tile[0]
+    pos[:, 0, 1] = rng.uniform(delta_x / 3.0, delta_x * 2.0 / 3.0, n)
+    pos[:, 0, 2] = rng.uniform(delta_x, 2.0 * delta_x, n) + tz * tile[2]
+    # directions are redrawn until every vertex lies inside the domain: a rod that starts across a wall
+    # is folded by the reflective boundary in the first step (bacterial_rods.rs:489-533) and the
+    # curvature force 2 * rigidity * tan(angle / 2) of a folded joint diverges
+    todo = np.arange(n)
+    margin = 0.25 * um
+    while todo.size:
+        theta = rng.uniform(0.0, 2.0 * np.pi, todo.size)
+        for i in range(1, V):
+            phi = theta + rng.uniform(-np.pi / 8.0, np.pi / 8.0, todo.size)
+            pos[todo, i, 0] = pos[todo, i - 1, 0] + seg * np.cos(phi)
+            pos[todo, i, 1] = pos[todo, i - 1, 1] + seg * np.sin(phi)
+            pos[todo, i, 2] = pos[todo, i - 1, 2]
+        y, x = pos[todo, :, 1], pos[todo, :, 0]
+        bad = ((y.min(axis=1) < margin) | (y.max(axis=1) > tile[1] - margin) | (x.min(axis=1) < margin)
+               | (x.max(axis=1) > tile[0] * n_tiles_x - margin))
+        todo = todo[bad]
+    spring_length = rng.uniform(spring_length_range[0], spring_length_range[1], n) * um
+    growth_base = 0.1 * um / MINUTE
+    mech = np.tile(
+        [0.0, 10.0 / MINUTE**2, 1.0 * um / MINUTE**2, 0.0, 1.5 / MINUTE, growth_base, 6.0 * um, growth_base],
+        (n, 1),
+    )
+    mech[:, 3] = spring_length
+    inter = np.tile([3.0 * um, 0.5 / um, 5.0 * um, 0.1 * um**2 / MINUTE**2], (n, 1))
+    mn = [0.0, 0.0, 0.0]
+    mx = [tile[0] * n_tiles_x, tile[1], tile[2] * n_tiles_z]
+    nv = np.array([8 * n_tiles_x, 1, 2 * n_tiles_z], dtype=np.uint64)
+    dx = (np.asarray(mx) - np.asarray(mn)) / nv.astype(np.float64)  # from_boundaries_and_n_voxels
+    cfg = dict(
+        dim=3,
+        mechanics_kind=_abi.CRB_MECH_ROD,
+        interaction_kind=_abi.CRB_INT_MORSE,
+        domain_min=mn, domain_max=mx, n_voxels=nv, dx=dx, dt=dt, solver_order=solver_order,
+        pair_weight_mode=pair_weight_mode, ref_n_subdomains=n_threads, rod_n_vertices=V,
+        capacity=max(int(n * capacity_factor), 16),
+    )
+    return Workload(
+        name=f"bacterial_rods_{n}",
+        cfg_kwargs=cfg,
+        pos=pos,
+        vel=np.zeros((n, V, 3)),
+        mech_params=mech,
+        inter_params=inter,
+        species=None,
+    )

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 2
+#define CRB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 typedef enum crb_status {
@@ -53,8 +53,15 @@ typedef enum crb_mechanics_kind {
     CRB_MECH_BROWNIAN = 1,      /* [diffusion_constant, kb_temperature]     mechanics.rs:336-357 */
     CRB_MECH_LANGEVIN = 2,      /* [mass, damping, kb_temperature]          mechanics.rs:434-463 */
     CRB_MECH_ROD = 3            /* [diffusion_constant, spring_tension, rigidity, spring_length,
-                                    damping, growth_rate, spring_length_threshold]
-                                    bacterial_rods.rs:157-240 + examples/bacterial_rods/src/main.rs */
+                                    damping, growth_rate, spring_length_threshold, growth_base_rate]
+                                    RodMechanics (bacterial_rods.rs:82-107, 157-240) + the Cycle /
+                                    NeighborSensing fields and GROWTH_BASE_RATE of the example agent
+                                    (cellular_raza-examples/bacterial_rods/src/main.rs:12-25, 48-109).
+                                    Needs interaction_kind CRB_INT_MORSE (RodInteraction<MorsePotential>),
+                                    dim 3 and 2 <= rod_n_vertices <= 8; the step then runs aspects
+                                    [Mechanics, Interaction, Cycle, NeighborSensing] (main.rs:202-210).
+                                    spring_length and growth_rate are per-agent state, the other
+                                    entries must be equal for all agents. */
 } crb_mechanics_kind;
 
 /* Interaction kinds and their per-agent parameter rows (inter_params[i*n_inter + k]).
@@ -178,6 +185,15 @@ int crb_set_aux(crb_sim* sim, uint64_t n, const double* hist_dx, const double* h
  * agent id (ids must be < n_ids).  CRB_NOISE_TABLE only. */
 int crb_set_noise(crb_sim* sim, const double* z, uint64_t n_steps, uint64_t n_ids);
 
+/* CellIdentifier and parent of every agent in device order (cellular_raza-concepts/src/cell.rs:18-25,
+ * 128-137): 3 words per agent {kind, a, b} with kind 0 = Division(voxel a, counter b), 1 = Initial(a),
+ * 2 = Inserted(a, b); parent kind = UINT64_MAX when the agent has no parent.  Point agents are always
+ * Initial(id).  Either pointer may be NULL. */
+int crb_get_identifiers(crb_sim* sim, uint64_t cap, uint64_t* ident, uint64_t* parent);
+/* rods: number of Division events carried out by the last step (update_cell_cycle_4,
+ * chili/update_cycle.rs:9-69). */
+uint64_t crb_n_divisions(const crb_sim* sim);
+
 /* ---- stepping ----------------------------------------------------------------------------- */
 /* replaces n iterations of the generated loop body (run_sim.rs:380-403) for
  * aspects [Mechanics, Interaction]: update_mechanics_interaction_step_1/2/3, local_mechanics_update,
@@ -225,6 +241,9 @@ int crb_slab_finish(crb_sim* sim, int save_prev);
 /* forces that the next step would integrate (AuxStorageMechanics::current_force after
  * update_mechanics_interaction_step_3), device order, cap*dim*V doubles; does not advance. */
 int crb_debug_forces(crb_sim* sim, uint64_t cap, double* force);
+/* rods: the NeighborSensing accumulator of every agent as the next step would see it in
+ * react_to_neighbors (examples/bacterial_rods/src/main.rs:48-78), device order; does not advance. */
+int crb_debug_neighbor_counts(crb_sim* sim, uint64_t cap, uint64_t* counts);
 /* migration set of the last step: (id, old VoxelPlainIndex, new VoxelPlainIndex) triples of
  * every agent that changed voxel in sort_cells_in_voxels.  Returns the count in *n_out. */
 int crb_get_migrations(crb_sim* sim, uint64_t cap, uint64_t* ids, uint64_t* old_voxel,

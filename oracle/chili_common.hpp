@@ -34,7 +34,7 @@ inline uint32_t n_mech_params(uint32_t kind) {
         case CRB_MECH_NEWTON_DAMPED: return 2;
         case CRB_MECH_BROWNIAN: return 2;
         case CRB_MECH_LANGEVIN: return 3;
-        case CRB_MECH_ROD: return 7;
+        case CRB_MECH_ROD: return 8;
     }
     return 0;
 }

@@ -1,0 +1,188 @@
+"""Bacterial rods (BASELINE.json configs[3]): device vs oracle
+through the C ABI.  Device order must equal chili's (voxel, in-voxel) order, so arrays are compared
+position by position; identifiers, voxel assignment, neighbour counts, growth and division sets are
+bit-exact, forces <= 1e-12 (metric of SURVEY §8d), trajectories <= 1e-9 of the domain extent."""
+import numpy as np
+import pytest
+
+from cellular_raza_b200 import _abi, workloads
+from cellular_raza_b200._abi import SimulationError
+from cellular_raza_b200.rods import RodSimulation
+from oracle.rods_oracle import RodsOracle
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-12
+TRAJ_TOL = 1e-9
+
+
+def make_pair(w, **over):
+    dev = RodSimulation(w.config(**over))
+    ora = RodsOracle(w.config(**over), n_threads=4)
+    for sim in (dev, ora):
+        sim.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    return dev, ora
+
+
+def assert_same_population(dev, ora):
+    pd, vd, idd, pad, xd = dev.get_agents()
+    po, vo, ido, pao, xo = ora.get_agents()
+    assert len(idd) == len(ido)
+    np.testing.assert_array_equal(idd, ido)   # same identifiers in the same (voxel, in-voxel) order
+    np.testing.assert_array_equal(pad, pao)
+    np.testing.assert_array_equal(xd, xo)
+    np.testing.assert_array_equal(dev.get_voxel_counts(), ora.get_voxel_counts())
+    return pd, vd, po, vo
+
+
+def force_check(dev, ora):
+    fd = dev.debug_forces()
+    nbd = dev.debug_neighbor_counts()
+    fo, ab, nbo = ora.forces()
+    np.testing.assert_array_equal(nbd, nbo)
+    num = np.abs(fd - fo).reshape(len(fd), -1).max(axis=1)
+    den = np.maximum(np.abs(fo).reshape(len(fo), -1).max(axis=1), ab)
+    den = np.where(den == 0, 1.0, den)
+    return (num / den).max(), int(nbo.sum())
+
+
+@pytest.mark.parametrize("mode,n_threads", [(_abi.CRB_WEIGHT_CHILI, 8), (_abi.CRB_WEIGHT_CHILI, 1),
+                                            (_abi.CRB_WEIGHT_PHYSICAL, 3)])
+def test_forces_and_neighbor_counts(crb_lib, mode, n_threads):
+    w = workloads.bacterial_rods(6, 5, rods_per_tile=24, n_threads=n_threads, pair_weight_mode=mode)
+    dev, ora = make_pair(w)
+    assert_same_population(dev, ora)
+    err, nb = force_check(dev, ora)
+    assert nb > 1000  # the population does interact
+    assert err <= FORCE_TOL, err
+    assert dev.count_candidate_pairs() == ora.count_candidate_pairs()
+
+
+def test_example_as_shipped_100_steps(crb_lib):
+    w = workloads.bacterial_rods(1, 1)  # 5 rods, [8, 1, 2] voxels, n_threads 8
+    dev, ora = make_pair(w)
+    dev.step(100)
+    ora.step(100)
+    pd, vd, po, vo = assert_same_population(dev, ora)
+    L = max(w.cfg_kwargs["domain_max"])
+    assert np.abs(pd - po).max() / L <= TRAJ_TOL
+    np.testing.assert_array_equal(dev.get_params()[:, [3, 5]], ora.get_params()[:, [3, 5]])
+
+
+@pytest.mark.parametrize("order", [2, 1, 0])
+def test_trajectory_with_growth_and_division(crb_lib, order):
+    # spring lengths close to the threshold (6 um): rods divide within the 100 steps
+    w = workloads.bacterial_rods(6, 5, rods_per_tile=6, spring_length_range=(5.6, 5.99), solver_order=order,
+                                 capacity_factor=3.0)
+    dev, ora = make_pair(w)
+    n_div = 0
+    for _ in range(10):
+        dev.step(10)
+        ora.step(10)
+        assert dev.n_agents == ora.n_agents
+    pd, vd, po, vo = assert_same_population(dev, ora)
+    n_div = dev.n_agents - w.n
+    assert n_div > 10, "the test population must divide"
+    L = max(w.cfg_kwargs["domain_max"])
+    assert np.abs(pd - po).max() / L <= TRAJ_TOL
+    # velocity error integrated over the run stays below the trajectory tolerance
+    assert np.abs(vd - vo).max() * (100 * 0.1) <= TRAJ_TOL * L
+    mpd, mpo = dev.get_params(), ora.get_params()
+    np.testing.assert_array_equal(mpd[:, 5], mpo[:, 5])  # growth rates: pure function of the counts
+    assert np.abs(mpd[:, 3] - mpo[:, 3]).max() <= 1e-15 * 6e-6 * 100
+    hxd, hvd, hld = dev.get_aux()
+    hxo, hvo, hlo = ora.get_aux()
+    np.testing.assert_array_equal(hld, hlo)
+    assert np.abs(hxd - hxo).max() <= 1e-9 * max(np.abs(hxo).max(), 1e-30)
+    err, _ = force_check(dev, ora)
+    # forces of the two evolved states (sanity: positions differ by ~1e-15 m, stiffness 5e5 / m)
+    assert err <= 1e-6
+
+
+def test_division_step_is_exact(crb_lib):
+    """one step from identical state in which rods divide: geometry of mother and daughter, identifiers
+    Division(voxel, counter), parents and the fresh AuxStorage of the daughter."""
+    w = workloads.bacterial_rods(4, 4, rods_per_tile=5, spring_length_range=(5.995, 5.9999), capacity_factor=3.0)
+    dev, ora = make_pair(w)
+    dev.step(1)
+    ora.step(1)
+    assert ora.n_divisions > 0
+    assert dev.n_divisions == ora.n_divisions
+    pd, vd, po, vo = assert_same_population(dev, ora)
+    L = max(w.cfg_kwargs["domain_max"])
+    assert np.abs(pd - po).max() / L <= 1e-15
+    _, _, ident, parent, _ = dev.get_agents()
+    div = ident[:, 0] == 0
+    assert div.sum() == 2 * dev.n_divisions
+    assert np.all(parent[div, 0] == 1)  # parents are Initial(n)
+    _, _, hl = dev.get_aux()
+    assert set(hl[div].tolist()) == {0, 1}  # daughters start empty, mothers keep their ring buffer
+    np.testing.assert_array_equal(dev.get_params()[:, 3], ora.get_params()[:, 3])
+
+
+def test_bitwise_reruns(crb_lib):
+    w = workloads.bacterial_rods(6, 5, rods_per_tile=6, spring_length_range=(5.6, 5.99), capacity_factor=3.0)
+    outs = []
+    for _ in range(3):
+        d = RodSimulation(w.config())
+        d.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+        d.step(60)
+        outs.append(d.get_agents())
+        d.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            np.testing.assert_array_equal(a, b)
+
+
+def test_invariants_physical_mode(crb_lib):
+    """PHYSICAL weights: interaction forces of a closed population sum to zero per axis."""
+    w = workloads.bacterial_rods(4, 4, rods_per_tile=20, pair_weight_mode=_abi.CRB_WEIGHT_PHYSICAL)
+    d = RodSimulation(w.config())
+    d.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    f = d.debug_forces()
+    scale = np.abs(f).sum()
+    assert scale > 0
+    assert np.abs(f.sum(axis=(0, 1))).max() <= 1e-12 * scale
+    d.step(20)
+    pos = d.get_agents()[0]
+    for c in range(3):
+        assert pos[:, :, c].min() >= 0 and pos[:, :, c].max() <= w.cfg_kwargs["domain_max"][c]
+
+
+def test_vertex_counts(crb_lib):
+    for V in (3, 4, 7):
+        w = workloads.bacterial_rods(3, 3, rods_per_tile=12, n_vertices=V, spring_length_range=(2.5, 3.2))
+        dev, ora = make_pair(w)
+        err, _ = force_check(dev, ora)
+        assert err <= FORCE_TOL
+        dev.step(20)
+        ora.step(20)
+        pd, vd, po, vo = assert_same_population(dev, ora)
+        assert np.abs(pd - po).max() / max(w.cfg_kwargs["domain_max"]) <= TRAJ_TOL
+
+
+def test_error_paths(crb_lib):
+    w = workloads.bacterial_rods(4, 4, rods_per_tile=5, spring_length_range=(5.995, 5.9999), capacity_factor=1.0)
+    d = RodSimulation(w.config(capacity=w.n))
+    d.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    with pytest.raises(SimulationError) as e:
+        d.step(3)
+    assert e.value.code == _abi.CRB_ERR_CAPACITY
+    d.close()
+    # a rod whose vertex mean lies at/below the domain minimum: BoundaryError at setup
+    w = workloads.bacterial_rods(1, 1)
+    bad = w.pos.copy()
+    bad[0, :, 1] = -1e-6
+    d = RodSimulation(w.config())
+    with pytest.raises(SimulationError) as e:
+        d.set_agents(bad, w.vel, w.mech_params, w.inter_params)
+    assert e.value.code == _abi.CRB_ERR_BOUNDARY
+    # non-uniform tension is rejected
+    mp = w.mech_params.copy()
+    mp[1, 1] *= 2
+    with pytest.raises(SimulationError) as e:
+        d.set_agents(w.pos, w.vel, mp, w.inter_params)
+    assert e.value.code == _abi.CRB_ERR_INVALID_ARG
+    d.close()
+    with pytest.raises(SimulationError):
+        RodSimulation(w.config(dim=2))
