@@ -93,7 +93,8 @@ def test_trajectory_with_growth_and_division(crb_lib, order):
     hxd, hvd, hld = dev.get_aux()
     hxo, hvo, hlo = ora.get_aux()
     np.testing.assert_array_equal(hld, hlo)
-    assert np.abs(hxd - hxo).max() <= 1e-9 * max(np.abs(hxo).max(), 1e-30)
+    # newest position increments are velocities (dx = vel): same integrated bound as the velocities
+    assert np.abs(hxd - hxo).max() * (100 * 0.1) <= TRAJ_TOL * L
     err, _ = force_check(dev, ora)
     # forces of the two evolved states (sanity: positions differ by ~1e-15 m, stiffness 5e5 / m)
     assert err <= 1e-6
