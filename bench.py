@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-cells", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: halo exchange before the force pass instead of behind its interior planes")
     return ap.parse_args()
 
 

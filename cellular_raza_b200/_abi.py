@@ -142,6 +142,8 @@ SYMBOLS = [
     ("crb_slab_halo_export", C.c_int, [_vp, _vp, _vp]),
     ("crb_slab_halo_import", C.c_int, [_vp, _vp, _vp]),
     ("crb_slab_compute", C.c_int, [_vp, C.c_int]),
+    ("crb_slab_compute_interior", C.c_int, [_vp, C.c_int]),
+    ("crb_slab_compute_boundary", C.c_int, [_vp]),
     ("crb_slab_migration_export", C.c_int, [_vp, _vp, _vp, _u64p]),
     ("crb_slab_migration_import", C.c_int, [_vp, _vp, _vp, _u64p]),
     ("crb_slab_finish", C.c_int, [_vp, C.c_int]),

@@ -51,6 +51,11 @@ struct crb_sim {
     u64 n_src = 0;           // unsorted sources of the open step (owned + arrivals)
     u64 n_gone = 0;          // agents exported in the open step
     cudaStream_t stream = nullptr;
+    // overlap of the halo exchange with interior force work: the interior planes run on `stream2`
+    // (lowest priority) while the halo travels on `stream` (highest priority)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_interior = nullptr;
+    int interior_state = 0;  // 0 none, 1 crb_slab_compute_interior done (boundary pending)
     State X, T, Y;  // X: sorted state read by the force pass, T: integrated, Y: reorder target
     u32 *key = nullptr, *key_alt = nullptr;
     u32 *start = nullptr, *start_alt = nullptr;
@@ -148,18 +153,18 @@ int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
 
 inline u32 blocks_for(u64 n, u32 threads) { return (u32)((n + threads - 1) / threads); }
 
-void stage_begin(crb_sim* s, int stage) {
+void stage_begin(crb_sim* s, int stage, cudaStream_t st = nullptr) {
     if (!s->timers_on) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    cudaEventRecord(a, s->stream);
+    cudaEventRecord(a, st ? st : s->stream);
     s->timers[stage].ev.emplace_back(a, b);
 }
-void stage_end(crb_sim* s, int stage, int n_launches) {
+void stage_end(crb_sim* s, int stage, int n_launches, cudaStream_t st = nullptr) {
     s->launches += n_launches;
     if (!s->timers_on) return;
-    cudaEventRecord(s->timers[stage].ev.back().second, s->stream);
+    cudaEventRecord(s->timers[stage].ev.back().second, st ? st : s->stream);
     s->timers[stage].launches += n_launches;
 }
 void timers_resolve(crb_sim* s) {
@@ -301,38 +306,50 @@ void plan_tile(crb_sim* s) {
     s->tile_ok = s->tile_smem <= 227 * 1024;
 }
 
+// plane range of a launch: x_count < 0 => all owned planes (TileLaunch as planned)
+struct PlaneRange {
+    int x_begin = 0, x_count = -1;
+    cudaStream_t st = nullptr;
+};
+
 template <int D, int INTER>
-int launch_tile_t(crb_sim* s, const KParams& P, bool force_only) {
-    const TileLaunch& T = s->tile;
+int launch_tile_t(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
+    TileLaunch T = s->tile;
+    if (pr.x_count >= 0) {
+        T.x_begin = pr.x_begin;
+        T.x_count = pr.x_count;
+    }
+    cudaStream_t st = pr.st ? pr.st : s->stream;
     const u32 grid = (u32)T.x_count * (u32)s->g.ng[1] * (u32)T.nseg * (u32)T.nchunks;
     if (!grid) return 0;
     if (force_only) {
         auto k = k_force_tile<D, INTER, true>;
         CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile_smem));
-        k<<<grid, s->tile_threads, s->tile_smem, s->stream>>>(P, T);
+        k<<<grid, s->tile_threads, s->tile_smem, st>>>(P, T);
     } else {
         auto k = k_force_tile<D, INTER, false>;
         CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile_smem));
-        k<<<grid, s->tile_threads, s->tile_smem, s->stream>>>(P, T);
+        k<<<grid, s->tile_threads, s->tile_smem, st>>>(P, T);
     }
     return 0;
 }
 
 template <int D>
-int launch_tile_d(crb_sim* s, const KParams& P, bool force_only) {
+int launch_tile_d(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
     switch (s->cfg.interaction_kind) {
-        case CRB_INT_CELL_SORTING: return launch_tile_t<D, CRB_INT_CELL_SORTING>(s, P, force_only);
+        case CRB_INT_CELL_SORTING: return launch_tile_t<D, CRB_INT_CELL_SORTING>(s, P, force_only, pr);
         case CRB_INT_CELL_SORTING_BENCH:
-            return launch_tile_t<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only);
-        case CRB_INT_MORSE: return launch_tile_t<D, CRB_INT_MORSE>(s, P, force_only);
-        case CRB_INT_BOUND_LJ: return launch_tile_t<D, CRB_INT_BOUND_LJ>(s, P, force_only);
-        case CRB_INT_MIE: return launch_tile_t<D, CRB_INT_MIE>(s, P, force_only);
+            return launch_tile_t<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only, pr);
+        case CRB_INT_MORSE: return launch_tile_t<D, CRB_INT_MORSE>(s, P, force_only, pr);
+        case CRB_INT_BOUND_LJ: return launch_tile_t<D, CRB_INT_BOUND_LJ>(s, P, force_only, pr);
+        case CRB_INT_MIE: return launch_tile_t<D, CRB_INT_MIE>(s, P, force_only, pr);
     }
     return 0;
 }
 
-int launch_force(crb_sim* s, const KParams& P, bool force_only) {
-    if (s->tile_ok) return s->D == 3 ? launch_tile_d<3>(s, P, force_only) : launch_tile_d<2>(s, P, force_only);
+int launch_force(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr = PlaneRange()) {
+    if (s->tile_ok)
+        return s->D == 3 ? launch_tile_d<3>(s, P, force_only, pr) : launch_tile_d<2>(s, P, force_only, pr);
     if (s->D == 3)
         launch_force_d<3>(s, P, force_only);
     else
@@ -686,7 +703,14 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         s->error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
         return bail(CRB_ERR_CUDA);
     }
-    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    {
+        int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        e = cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, prio_lo);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_interior, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         s->error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
         return bail(CRB_ERR_CUDA);
@@ -727,10 +751,14 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
 void crb_destroy(crb_sim* s) {
     if (!s) return;
     cudaSetDevice((int)s->cfg.device);
+    if (s->stream2) cudaStreamSynchronize(s->stream2);
     if (s->stream) cudaStreamSynchronize(s->stream);
     timers_resolve(s);
     for (void* p : s->allocs) cudaFree(p);
     if (s->err_host) cudaFreeHost(s->err_host);
+    if (s->ev_ready) cudaEventDestroy(s->ev_ready);
+    if (s->ev_interior) cudaEventDestroy(s->ev_interior);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1078,22 +1106,35 @@ int crb_set_noise(crb_sim* s, const double* z, uint64_t n_steps, uint64_t n_ids)
 namespace {
 // stage A of one step: pair forces over the 3^D neighbourhood + fused integrate/boundary/new key for
 // the owned agents (ghost planes must hold the neighbours' boundary agents on a slab)
-int step_compute(crb_sim* s, bool save_prev) {
+int step_prepare(crb_sim* s) {
     const bool stochastic = s->cfg.noise_mode == CRB_NOISE_TABLE &&
                             s->cfg.mechanics_kind != CRB_MECH_NEWTON_DAMPED;
     if (stochastic && s->noise_cursor >= s->noise_steps)
         return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
     CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    return 0;
+}
+// force + integrate for the targets of a plane range (default: all owned planes) on pr.st
+int step_launch(crb_sim* s, bool save_prev, const PlaneRange& pr) {
     KParams P = make_params(s);
     P.save_prev = save_prev ? 1 : 0;
-    stage_begin(s, 0);
+    stage_begin(s, 0, pr.st);
     int rc;
-    if ((rc = launch_force(s, P, false))) return rc;
-    stage_end(s, 0, s->n ? 1 : 0);
+    if ((rc = launch_force(s, P, false, pr))) return rc;
+    stage_end(s, 0, s->n ? 1 : 0, pr.st);
     CU(s, cudaGetLastError());
+    return 0;
+}
+void step_mark(crb_sim* s) {
     s->last_step_n = s->n;
     s->n_src = s->n;
     s->n_gone = 0;
+}
+int step_compute(crb_sim* s, bool save_prev) {
+    int rc;
+    if ((rc = step_prepare(s))) return rc;
+    if ((rc = step_launch(s, save_prev, PlaneRange()))) return rc;
+    step_mark(s);
     return 0;
 }
 // stage B: cell-list rebuild (scan + stable counting-sort scatter of the whole state)
@@ -1202,10 +1243,78 @@ int crb_slab_compute(crb_sim* s, int save_prev) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     if (s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_finish pending");
+    if (s->interior_state) return fail(s, CRB_ERR_STATE, "crb_slab_compute_boundary pending");
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->aux_settable = false;
     int rc;
     if ((rc = step_compute(s, save_prev != 0))) return rc;
+    s->step_open = true;
+    return 0;
+}
+
+// planes whose 3^D neighbourhood touches no ghost plane: [own_lo + has_lo, own_hi - has_hi)
+static void interior_planes(const crb_sim* s, int* b, int* e) {
+    *b = s->g.own_lo + (s->has_lo ? 1 : 0);
+    *e = s->g.own_hi - (s->has_hi ? 1 : 0);
+    if (*e < *b) *e = *b;
+}
+
+int crb_slab_compute_interior(crb_sim* s, int save_prev) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    if (s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_finish pending");
+    if (s->interior_state) return fail(s, CRB_ERR_STATE, "crb_slab_compute_boundary pending");
+    if (s->rods) return fail(s, CRB_ERR_STATE, "rods are not slab-decomposed");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    s->aux_settable = false;
+    int rc;
+    if ((rc = step_prepare(s))) return rc;
+    s->interior_state = save_prev ? 3 : 1;
+    int b, e;
+    interior_planes(s, &b, &e);
+    // the per-agent kernel (non-uniform parameters) is not split: everything runs in the boundary call
+    if (!s->tile_ok || e <= b || !s->n) return 0;
+    // the interior pass starts once the sorted state X of the previous step and the cleared histogram exist
+    CU(s, cudaEventRecord(s->ev_ready, s->stream));
+    CU(s, cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));
+    PlaneRange pr;
+    pr.x_begin = b;
+    pr.x_count = e - b;
+    pr.st = s->stream2;
+    if ((rc = step_launch(s, save_prev != 0, pr))) return rc;
+    CU(s, cudaEventRecord(s->ev_interior, s->stream2));
+    s->interior_state |= 4;  // something is running on stream2
+    return 0;
+}
+
+int crb_slab_compute_boundary(crb_sim* s) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->interior_state) return fail(s, CRB_ERR_STATE, "crb_slab_compute_interior first");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    const bool save_prev = (s->interior_state & 2) != 0;
+    const bool split = (s->interior_state & 4) != 0;
+    s->interior_state = 0;
+    int rc;
+    if (!split) {
+        if ((rc = step_launch(s, save_prev, PlaneRange()))) return rc;
+    } else {
+        int b, e;
+        interior_planes(s, &b, &e);
+        PlaneRange pr;
+        pr.st = s->stream;
+        if (b > s->g.own_lo) {
+            pr.x_begin = s->g.own_lo;
+            pr.x_count = b - s->g.own_lo;
+            if ((rc = step_launch(s, save_prev, pr))) return rc;
+        }
+        if (s->g.own_hi > e) {
+            pr.x_begin = e;
+            pr.x_count = s->g.own_hi - e;
+            if ((rc = step_launch(s, save_prev, pr))) return rc;
+        }
+        CU(s, cudaStreamWaitEvent(s->stream, s->ev_interior, 0));
+    }
+    step_mark(s);
     s->step_open = true;
     return 0;
 }

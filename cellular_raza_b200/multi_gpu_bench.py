@@ -19,11 +19,14 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
 
     torch.cuda.set_device(local_rank)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # the halo transfer must get SM slots while the interior force pass saturates the device:
+    # nccl kernels on a high-priority stream (the interior pass runs on the lowest priority)
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     n = args.cells_per_gpu
     w = workloads.cell_sorting_slab(n, rank, world, args.density, n_threads=args.n_threads_ref)
     cfg = w.config(capacity=int(n * 1.1) + 4096, device=local_rank)
-    sim = SlabSimulation(cfg, device=local_rank)
+    sim = SlabSimulation(cfg, device=local_rank, overlap=not args.no_overlap)
     sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
     sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
     slab = sim.slab
@@ -135,7 +138,8 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         }
         cfgd = helpers.workload_config(args)
         cfgd.update({"halo_bytes_per_face": slab.halo_bytes, "migration_bytes_per_face": slab.mig_bytes,
-                     "exchange": "ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), 2 phases per step, no force return"})
+                     "exchange": "ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), 2 phases per step, no force return",
+                     "halo_overlap": "off" if args.no_overlap else "interior planes on a second stream while the halo travels"})
         line = {
             "metric": helpers.METRIC, "value": value, "unit": helpers.UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -118,6 +118,14 @@ class SlabRank(DeviceSimulation):
     def compute(self, save_prev: bool = True):
         self._check(self._lib.crb_slab_compute(self._h, 1 if save_prev else 0))
 
+    def compute_interior(self, save_prev: bool = True):
+        """planes without a ghost neighbour, on the handle's second stream (needs no halo)"""
+        self._check(self._lib.crb_slab_compute_interior(self._h, 1 if save_prev else 0))
+
+    def compute_boundary(self):
+        """planes next to a ghost plane, after halo_import; joins the second stream"""
+        self._check(self._lib.crb_slab_compute_boundary(self._h))
+
     def migration_export(self):
         n = (C.c_uint64 * 2)()
         self._check(self._lib.crb_slab_migration_export(self._h, self._p(self.mig_out[0]), self._p(self.mig_out[1]), n))
@@ -143,9 +151,11 @@ class LocalSlabGroup:
     """``world`` slabs driven by one process.  ``devices[r]`` is the CUDA device of rank r (all 0 to
     run several slabs on one GPU)."""
 
-    def __init__(self, make_cfg, world: int, devices: Sequence[int] | None = None, **caps):
+    def __init__(self, make_cfg, world: int, devices: Sequence[int] | None = None, overlap: bool = True,
+                 **caps):
         devices = list(devices) if devices is not None else [0] * world
         self.world = world
+        self.overlap = overlap
         self.ranks = [SlabRank(make_cfg(), r, world, devices[r], **caps) for r in range(world)]
         self.cfg = self.ranks[0].cfg
         self.dim = self.ranks[0].dim
@@ -206,9 +216,17 @@ class LocalSlabGroup:
     def step(self, n_steps: int = 1):
         for it in range(n_steps):
             last = it + 1 == n_steps
-            self.halo_exchange()
-            for rk in self.ranks:
-                rk.compute(last)
+            if self.overlap:
+                # interior planes start at once; the halo travels meanwhile
+                for rk in self.ranks:
+                    rk.compute_interior(last)
+                self.halo_exchange()
+                for rk in self.ranks:
+                    rk.compute_boundary()
+            else:
+                self.halo_exchange()
+                for rk in self.ranks:
+                    rk.compute(last)
             outs = [rk.migration_export() for rk in self.ranks]
             self._exchange("mig_out", "mig_in")
             ins = [rk.migration_import() for rk in self.ranks]
@@ -255,12 +273,14 @@ class SlabSimulation:
     """One slab per process (``torch.distributed`` must be initialised with the nccl backend); halo and
     migration buffers travel with ncclSend/ncclRecv over NVLink."""
 
-    def __init__(self, cfg: _abi.CrbConfig, device: int | None = None, group=None, **caps):
+    def __init__(self, cfg: _abi.CrbConfig, device: int | None = None, group=None, overlap: bool = True,
+                 **caps):
         import torch
         import torch.distributed as dist
 
         self.dist = dist
         self.group = group
+        self.overlap = overlap
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         device = torch.cuda.current_device() if device is None else device
@@ -295,8 +315,15 @@ class SlabSimulation:
         s = self.slab
         for it in range(n_steps):
             last = it + 1 == n_steps
-            self.halo_exchange()
-            s.compute(last)
+            if self.overlap:
+                # interior planes on the second stream; pack, ncclSend/ncclRecv and unpack of the halo
+                # run meanwhile on the (high-priority) main stream, then the boundary planes
+                s.compute_interior(last)
+                self.halo_exchange()
+                s.compute_boundary()
+            else:
+                self.halo_exchange()
+                s.compute(last)
             out = s.migration_export()
             self._exchange(s.mig_out, s.mig_in)
             inn = s.migration_import()

@@ -222,6 +222,19 @@ uint64_t crb_iteration(const crb_sim* sim);
  *     crb_slab_migration_import(lo_in, hi_in, n)      arrivals
  *     crb_slab_finish(save_prev)                      cell-list rebuild (sort_cells_in_voxels)
  *
+ * Overlap of the halo exchange with interior force work: crb_slab_compute may be
+ * replaced by the pair
+ *
+ *     crb_slab_compute_interior(save_prev)   planes whose 3^D neighbourhood holds no ghost plane; needs
+ *                                            no halo, runs on the handle's second (low-priority) stream
+ *                                            and may be called BEFORE crb_slab_halo_import
+ *     crb_slab_compute_boundary()            the one or two owned planes next to a ghost plane, on the
+ *                                            main stream after crb_slab_halo_import; joins both streams
+ *
+ * so that the sequence  compute_interior, halo_export, <send/recv>, halo_import, compute_boundary  hides
+ * the transfer behind the interior pass.  Results are bit-identical to crb_slab_compute (every target
+ * sums its candidates in the same order whichever launch evaluates it).
+ *
  * "lo" is the neighbour with rank - 1, "hi" rank + 1; a buffer pointer may be NULL where there is no
  * neighbour.  All pointers are DEVICE pointers of at least crb_slab_halo_bytes / _migration_bytes.
  * save_prev != 0 keeps the older ring-buffer entry readable by crb_get_aux after this step. */
@@ -233,6 +246,8 @@ int crb_slab_info(const crb_sim* sim, uint64_t out[8]);
 int crb_slab_halo_export(crb_sim* sim, void* lo_buf, void* hi_buf);
 int crb_slab_halo_import(crb_sim* sim, const void* lo_buf, const void* hi_buf);
 int crb_slab_compute(crb_sim* sim, int save_prev);
+int crb_slab_compute_interior(crb_sim* sim, int save_prev);
+int crb_slab_compute_boundary(crb_sim* sim);
 int crb_slab_migration_export(crb_sim* sim, void* lo_buf, void* hi_buf, uint64_t n_out[2]);
 int crb_slab_migration_import(crb_sim* sim, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]);
 int crb_slab_finish(crb_sim* sim, int save_prev);

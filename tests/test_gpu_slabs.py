@@ -134,3 +134,31 @@ def test_migration_capacity_error(crb_lib):
         grp.step(3)
     assert e.value.code == _abi.CRB_ERR_CAPACITY
     grp.close()
+
+
+def test_overlapped_step_equals_plain_step(crb_lib):
+    """crb_slab_compute_interior + crb_slab_compute_boundary (halo exchange hidden behind the interior
+    planes, second stream) is bit-identical to crb_slab_compute after the halo import."""
+    w = workloads.cell_sorting_scaled(120_000, 7.1, n_threads=2)
+    a = LocalSlabGroup(lambda: w.config(), 3, overlap=True)
+    b = LocalSlabGroup(lambda: w.config(), 3, overlap=False)
+    for g in (a, b):
+        g.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+    for _ in range(3):
+        a.step(7)
+        b.step(7)
+        pa, va, ia, xa = _by_id(a)
+        pb, vb, ib, xb = _by_id(b)
+        assert np.array_equal(ia, ib) and np.array_equal(xa, xb)
+        assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+    # protocol errors: boundary without interior, compute while a boundary call is pending
+    rk = a.ranks[0]
+    with pytest.raises(Exception):
+        rk.compute_boundary()
+    rk.compute_interior(True)
+    with pytest.raises(Exception):
+        rk.compute(True)
+    a.halo_exchange()
+    rk.compute_boundary()
+    a.close()
+    b.close()

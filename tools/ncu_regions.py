@@ -14,7 +14,7 @@ tile = files["cellular_raza_b200/csrc/crb_force_tile.cuh"]
 def find(pat):
     return next(i + 1 for i, l in enumerate(tile) if pat in l)
 marks = [("prologue", find("k_force_tile(const KParams")), ("window_search", find("window size: largest kc")),
-         ("row_ranges", find("---- row ranges")), ("staging", find("per-voxel offsets, then the candidates")),
+         ("row_ranges", find("---- row ranges")), ("staging", find("---- stage the candidates")),
          ("target_setup", find("---- targets:")), ("drain_ctl", find("auto drain = [&]()")),
          ("filter", find("for (int r = 0; r < kTileRows; ++r) {")), ("epilogue", find("if (valid) {"))]
 def region(ln, text):
