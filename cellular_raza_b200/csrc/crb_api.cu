@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "crb_force_tile.cuh"
+#include "crb_force_tile2.cuh"
 #include "crb_rods.cuh"
 
 using namespace crb;
@@ -81,7 +82,11 @@ struct crb_sim {
     bool tile_ok = false;
     int tile_threads = kTileThreads;
     size_t tile_smem = 0;
-    int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 tile kernel (env CRB_FORCE_KERNEL)
+    // k_force_tile2 geometry (2 x 2-row tiles; preferred when it fits)
+    TileLaunch tile2;
+    bool tile2_ok = false;
+    size_t tile2_smem = 0;
+    int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 k_force_tile, 3 k_force_tile2 (env CRB_FORCE_KERNEL)
     bool timers_on = false;
     StageTimer timers[kNumStages];
     // bacterial rods (CRB_MECH_ROD): own state layout, see crb_rods.cuh
@@ -262,7 +267,12 @@ double uniform_cutoff(const crb_sim* s) {
 // chooses the pencil geometry from the mean density; called whenever the population changes
 void plan_tile(crb_sim* s) {
     s->tile_ok = false;
+    s->tile2_ok = false;
     if (!s->uniform || s->n == 0 || s->kernel_choice == 1) return;
+    // the tile kernel evaluates the species potential without its upper clamp (acts only for R1 + R2 < 0)
+    if ((s->cfg.interaction_kind == CRB_INT_CELL_SORTING || s->cfg.interaction_kind == CRB_INT_CELL_SORTING_BENCH) &&
+        s->uni.ip[0] < 0.0)
+        return;
     const Grid& g = s->g;
     const int n2 = g.ng[2];
     const int nrows = s->D == 3 ? 9 : 3;
@@ -278,7 +288,7 @@ void plan_tile(crb_sim* s) {
     T.kmax = T.chunk_len + 2;
     const size_t fixed = (size_t)(kTileQueue + 4) * kTileThreads * sizeof(unsigned short) +
                          (size_t)kTileRows * (T.kmax + 1) * sizeof(u32) + 2048;
-    const u32 cap = (u32)(((budget - fixed) / 44) / 32 * 32);
+    const u32 cap = (u32)(((budget - fixed) / (sizeof(TileCand) + sizeof(float4))) / 32 * 32);
     // candidates of a segment of t targets: nrows * (t + 2 voxels' worth) (+ sentinels)
     // (10 % slack ~ 3 sigma of the Poisson spread; an overflowing pencil is split into z-windows)
     const double per_target = nrows * 1.1;
@@ -304,6 +314,41 @@ void plan_tile(crb_sim* s) {
     s->tile_threads = kTileThreads;
     s->tile_smem = tile_smem_bytes(T.cap, T.kmax, s->tile_threads);
     s->tile_ok = s->tile_smem <= 227 * 1024;
+
+    // ---- k_force_tile2: 2 x 2 target rows per CTA, 16 staged rows ---------------------------------------
+    s->tile2_ok = false;
+    if (s->kernel_choice == 2) return;
+    TileLaunch& U = s->tile2;
+    U = T;
+    U.chunk_len = std::min(n2, 24);
+    U.nchunks = (n2 + U.chunk_len - 1) / U.chunk_len;
+    U.kmax = U.chunk_len + 2;
+    const int trows = s->D == 3 ? 4 : 2;   // target rows of a full tile
+    const int srows = s->D == 3 ? 16 : 4;  // staged rows that hold agents
+    // shared memory of one CTA: four CTAs per SM when that still feeds four full warps, else three
+    const size_t per_cand = sizeof(TileCand) + sizeof(float4) / 2 + sizeof(float2) / 2;
+    const size_t fixed2 = (size_t)(kTileQueue + 4) * kTileThreads * sizeof(unsigned short) +
+                          (size_t)kT2Rows * (U.kmax + 1) * sizeof(u32) + 64 + 34 * per_cand + 1024 /* static */;
+    for (int ctas = 4; ctas >= 2; --ctas) {
+        const size_t budget2 = (size_t)227 * 1024 / ctas - 1024;  // 1 KB per CTA is reserved by the driver
+        if (budget2 <= fixed2) continue;
+        const u32 cap2 = (u32)(((budget2 - fixed2) / per_cand) / 2 * 2);
+        const double halo = srows * 2.0 * rho * 1.05 + kT2Rows * (kT2Pad + 1);
+        const double per_t = (double)srows / trows * 1.05;
+        double ts = ((double)cap2 - halo) / per_t;
+        ts = std::min(ts, 116.0);  // + <= 12 padding slots: one pass of the four warps
+        if (ts < 96.0 && ctas > 2) continue;  // would leave a warp idle: take more shared memory instead
+        if (ts < 8.0) break;
+        U.tseg = (u32)ts;
+        U.cap = cap2;
+        U.nseg = (int)std::ceil(U.chunk_len * trows * rho * 1.2 / U.tseg) + 1;
+        s->tile2_smem = tile2_smem_bytes(U.cap, U.kmax, kTileThreads);
+        s->tile2_ok = s->tile2_smem <= budget2 + 1024;
+        if (std::getenv("CRB_DEBUG_PLAN"))
+            std::fprintf(stderr, "[crb] tile2 plan: ctas/SM %d smem %zu cap %u tseg %u nseg %d chunk %d x %d rho %.2f\n",
+                         ctas, s->tile2_smem, U.cap, U.tseg, U.nseg, U.chunk_len, U.nchunks, rho);
+        break;
+    }
 }
 
 // plane range of a launch: x_count < 0 => all owned planes (TileLaunch as planned)
@@ -334,6 +379,42 @@ int launch_tile_t(crb_sim* s, const KParams& P, bool force_only, const PlaneRang
     return 0;
 }
 
+template <int D, int INTER>
+int launch_tile2_t(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
+    TileLaunch T = s->tile2;
+    if (pr.x_count >= 0) {
+        T.x_begin = pr.x_begin;
+        T.x_count = pr.x_count;
+    }
+    cudaStream_t st = pr.st ? pr.st : s->stream;
+    const u32 nx2 = (u32)(T.x_count + 1) / 2, ny2 = (u32)(s->g.ng[1] + 1) / 2;
+    const u32 grid = nx2 * ny2 * (u32)T.nseg * (u32)T.nchunks;
+    if (!grid) return 0;
+    if (force_only) {
+        auto k = k_force_tile2<D, INTER, true>;
+        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile2_smem));
+        k<<<grid, kTileThreads, s->tile2_smem, st>>>(P, T);
+    } else {
+        auto k = k_force_tile2<D, INTER, false>;
+        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile2_smem));
+        k<<<grid, kTileThreads, s->tile2_smem, st>>>(P, T);
+    }
+    return 0;
+}
+
+template <int D>
+int launch_tile2_d(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
+    switch (s->cfg.interaction_kind) {
+        case CRB_INT_CELL_SORTING: return launch_tile2_t<D, CRB_INT_CELL_SORTING>(s, P, force_only, pr);
+        case CRB_INT_CELL_SORTING_BENCH:
+            return launch_tile2_t<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only, pr);
+        case CRB_INT_MORSE: return launch_tile2_t<D, CRB_INT_MORSE>(s, P, force_only, pr);
+        case CRB_INT_BOUND_LJ: return launch_tile2_t<D, CRB_INT_BOUND_LJ>(s, P, force_only, pr);
+        case CRB_INT_MIE: return launch_tile2_t<D, CRB_INT_MIE>(s, P, force_only, pr);
+    }
+    return 0;
+}
+
 template <int D>
 int launch_tile_d(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
     switch (s->cfg.interaction_kind) {
@@ -348,6 +429,8 @@ int launch_tile_d(crb_sim* s, const KParams& P, bool force_only, const PlaneRang
 }
 
 int launch_force(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr = PlaneRange()) {
+    if (s->tile2_ok)
+        return s->D == 3 ? launch_tile2_d<3>(s, P, force_only, pr) : launch_tile2_d<2>(s, P, force_only, pr);
     if (s->tile_ok)
         return s->D == 3 ? launch_tile_d<3>(s, P, force_only, pr) : launch_tile_d<2>(s, P, force_only, pr);
     if (s->D == 3)
@@ -691,6 +774,7 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     if (const char* kc = std::getenv("CRB_FORCE_KERNEL")) {
         if (!std::strcmp(kc, "agent")) s->kernel_choice = 1;
         if (!std::strcmp(kc, "tile")) s->kernel_choice = 2;
+        if (!std::strcmp(kc, "tile2")) s->kernel_choice = 3;
     }
 
     auto bail = [&](int rc) {
@@ -1273,7 +1357,7 @@ int crb_slab_compute_interior(crb_sim* s, int save_prev) {
     int b, e;
     interior_planes(s, &b, &e);
     // the per-agent kernel (non-uniform parameters) is not split: everything runs in the boundary call
-    if (!s->tile_ok || e <= b || !s->n) return 0;
+    if (!(s->tile_ok || s->tile2_ok) || e <= b || !s->n) return 0;
     // the interior pass starts once the sorted state X of the previous step and the cleared histogram exist
     CU(s, cudaEventRecord(s->ev_ready, s->stream));
     CU(s, cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));

@@ -51,12 +51,18 @@ struct TileLaunch {
     float cut2f;    // conservative FP32 cutoff^2 of the filter
 };
 
+// exact data of one staged candidate: one address computation and two LDS.128 per evaluated pair
+struct __align__(16) TileCand {
+    double x, y, z;
+    u32 meta;  // species | (z voxel & 0xff) << 8
+    u32 cv;    // local voxel index
+};
+
 __host__ __device__ inline size_t tile_smem_bytes(u32 cap, int kmax, int threads) {
     const size_t c = cap + 34;  // cap includes kTileRows * kTileRowPad sentinels; +34 filter over-read
     size_t b = 0;
-    b += 3 * c * sizeof(double);                                       // sx, sy, sz
+    b += c * sizeof(TileCand);                                         // exact positions + meta + voxel
     b += c * sizeof(float4);                                           // FP32 filter copy (pair layout)
-    b += c * sizeof(u32);                                              // species | z voxel
     b += (size_t)kTileRows * (kmax + 1) * sizeof(u32);                 // start[] of the 9 rows
     b += (size_t)(kTileQueue + 4) * threads * sizeof(unsigned short);  // per-lane FIFOs
     return b + 64;
@@ -77,9 +83,7 @@ struct TileTarget {
 
 template <int D, int INTER, int NE>
 __device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
-                                          const double* __restrict__ sx, const double* __restrict__ sy,
-                                          const double* __restrict__ sz, const float4* __restrict__ sf,
-                                          const u32* __restrict__ smeta,
+                                          const TileCand* __restrict__ sc,
                                           const u32 (&jj)[NE], const bool (&hh)[NE]) {
     // straight-line code for NE candidates (coef() is branch-free) so that the dependent FP64 chains
     // interleave; an empty slot points at the target itself (z == 0) and contributes +0.
@@ -87,15 +91,16 @@ __device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& ow
     int flag[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const u32 j = jj[e];
-        z[e][0] = t.x[0] - sx[j];
-        z[e][1] = t.x[1] - sy[j];
-        if (D == 3) z[e][2] = t.x[2] - sz[j];
+        const double2* cp = reinterpret_cast<const double2*>(sc + jj[e]);
+        const double2 c0 = cp[0], c1 = cp[1];
+        z[e][0] = t.x[0] - c0.x;
+        z[e][1] = t.x[1] - c0.y;
+        if (D == 3) z[e][2] = t.x[2] - c1.x;
         double r2 = 0.0;
 #pragma unroll
         for (int c = 0; c < D; ++c) r2 = fma(z[e][c], z[e][c], r2);
-        const u32 cvj = reinterpret_cast<const u32*>(sf + (j | 1u))[2 + (j & 1)];  // sf[2p+1] = {z0,z1,cv0,cv1}
-        const u32 mj = smeta[j];
+        const u32 mj = (u32)__double2loint(c1.y);
+        const u32 cvj = (u32)__double2hiint(c1.y);
         const bool same_voxel = cvj == t.my_v;
         const bool same_sub = (u32)(cvj - t.subv_lo) < t.subv_len;
         const bool keep = same_voxel | !same_sub;
@@ -104,10 +109,10 @@ __device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& ow
         const bool adj = (((mj >> 8) - t.zw + 1u) & 0xffu) <= 2u;
         const bool same_species = Pot<INTER>::kUsesSpecies ? ((mj & 0xffu) == (u32)t.sp) : true;
         flag[e] = 0;
-        const double c0 = own.coef(r2, ext_radius, same_species, &flag[e]);
+        const double cc = coef_tile<INTER>(own, r2, ext_radius, same_species, &flag[e]);
         const bool use = hh[e] & adj;
         const double w = keep ? 1.0 : 0.5;
-        cf[e] = use ? c0 * w : 0.0;
+        cf[e] = use ? cc * w : 0.0;
         if (!use) flag[e] = 0;
     }
 #pragma unroll
@@ -200,15 +205,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
 
     // ---- carve shared memory -----------------------------------------------------------------------
     const u32 capp = T.cap + 34;
-    double* sx = reinterpret_cast<double*>(smem_raw);
-    double* sy = sx + capp;
-    double* sz = sy + capp;
+    TileCand* sc = reinterpret_cast<TileCand*>(smem_raw);
     // FP32 filter copy, two candidates per 2 x 16 B so that one LDS.128 feeds a packed f32x2 op:
     //   sf[2p] = {x[2p], x[2p+1], y[2p], y[2p+1]},  sf[2p+1] = {z[2p], z[2p+1], cv[2p], cv[2p+1]}
     // (staged as one float4 {x, y, z, cv} per candidate by cp.async, then transposed pairwise in place)
-    float4* sf = reinterpret_cast<float4*>(sz + capp);
-    u32* smeta = reinterpret_cast<u32*>(sf + capp);              // species | (z voxel & 0xff) << 8
-    u32* sst = smeta + capp;                                     // [kTileRows][kmax + 1] copy of start[]
+    float4* sf = reinterpret_cast<float4*>(sc + capp);
+    u32* sst = reinterpret_cast<u32*>(sf + capp);                // [kTileRows][kmax + 1] copy of start[]
     unsigned short* q = reinterpret_cast<unsigned short*>(sst + kTileRows * (T.kmax + 1));  // [kTileQueue + NE][nthreads]
     __shared__ u32 s_rowvox[kTileRows];   // first voxel (local plain index) of every neighbour row
     __shared__ u32 s_g0[kTileRows];       // first global agent index staged per row
@@ -225,6 +227,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
     const int X = T.x_begin + rowid / n1;
     const int ca = chunk * T.chunk_len;
     const int cb = min(ca + T.chunk_len, n2);
+    {
+        // CTAs beyond the segments this row needs leave before anything is staged (two broadcast loads)
+        const u32 rvc = ((u32)X * (u32)n1 + (u32)Y) * (u32)n2;
+        const u32 R = __ldg(P.start + rvc + cb) - __ldg(P.start + rvc + ca);
+        if ((u32)seg * T.tseg >= R) return;  // seg >= ceil(R / tseg); uniform
+    }
     if (tid < kTileRows) {
         const int d0 = tid / 3 - 1, d1 = tid % 3 - 1;
         const int XX = X + d0, YY = Y + d1;
@@ -357,17 +365,17 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                     const u32 o = k - s_rs[r];
                     if (o < s_rn[r]) {
                         const u32 gi = s_g0[r] + o;
-                        cp_async_8(sx + k, P.A.pos[0] + gi);
-                        cp_async_8(sy + k, P.A.pos[1] + gi);
-                        if (D == 3) cp_async_8(sz + k, P.A.pos[2] + gi);
+                        cp_async_8(&sc[k].x, P.A.pos[0] + gi);
+                        cp_async_8(&sc[k].y, P.A.pos[1] + gi);
+                        if (D == 3) cp_async_8(&sc[k].z, P.A.pos[2] + gi);
                         cp_async_16(sf + k, P.A.posf + gi);
-                        cp_async_4(smeta + k, P.A.meta + gi);
+                        cp_async_4(&sc[k].meta, P.A.meta + gi);
                         real = true;
                     }
                 }
                 if (!real) {  // sentinel: NaN coordinates never pass the distance test
                     sf[k] = make_float4(qn_, qn_, qn_, __uint_as_float(0xffffffffu));
-                    smeta[k] = 0xffffu;
+                    sc[k].meta = 0xffffu;
                 }
             }
             cp_async_wait_all();
@@ -377,6 +385,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                 const float4 a = sf[2 * p], b = sf[2 * p + 1];
                 sf[2 * p] = make_float4(a.x, b.x, a.y, b.y);
                 sf[2 * p + 1] = make_float4(a.z, b.z, a.w, b.w);
+                sc[2 * p].cv = __float_as_uint(a.w);
+                sc[2 * p + 1].cv = __float_as_uint(b.w);
             }
         }
         __syncthreads();
@@ -400,13 +410,13 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                 pf = make_float4(fa[0], fa[2], fb[0], fb[2]);
             }
             TileTarget<D> t;
-            t.x[0] = sx[sj_self];
-            t.x[1] = sy[sj_self];
-            if (D == 3) t.x[2] = sz[sj_self];
+            t.x[0] = sc[sj_self].x;
+            t.x[1] = sc[sj_self].y;
+            if (D == 3) t.x[2] = sc[sj_self].z;
 #pragma unroll
             for (int c = 0; c < D; ++c) t.acc[c] = 0.0;
             t.my_v = __float_as_uint(pf.w);
-            const u32 mself = smeta[sj_self];
+            const u32 mself = sc[sj_self].meta;
             t.sp = (u8)(mself & 0xffu);
             t.zw = mself >> 8;
             t.calc_flag = 0;
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_force_tile(const KParams P,
                         hh[e] = (k + e < nq) & (ent != sj_self);
                         jj[e] = hh[e] ? ent : sj_self;
                     }
-                    tile_eval<D, INTER, NE>(t, own, ext_radius, sx, sy, sz, sf, smeta, jj, hh);
+                    tile_eval<D, INTER, NE>(t, own, ext_radius, sc, jj, hh);
                 }
                 qa = qa0;
             };

@@ -94,8 +94,10 @@ struct PotCellSorting {
         rmin = R * 0.3162277660168379;
         inv_rmin = 1.0 / rmin;
     }
-    __device__ __forceinline__ double coef(double r2, double ext_radius, bool same_species,
-                                           int* flag) const {
+    // UPPER = false drops the upper clamp, which can only act for a negative radius sum (the tile
+    // kernel is not planned for such parameters, see plan_tile)
+    template <bool UPPER>
+    __device__ __forceinline__ double coef_t(double r2, double ext_radius, bool same_species) const {
         // branch-free: r2 == 0 (own_pos == ext_pos -> zero force, :60-63) is selected at the end
         const double rinv = rsqrt_nr(r2);
         const double r_true = r2 * rinv;
@@ -104,20 +106,26 @@ struct PotCellSorting {
         const double rcinv = clamp ? inv_rmin : rinv;
         const double Rs = R + ext_radius;
         const double sinv = Rs * rcinv;  // 1 / sigma
-        const double bound = 4.0 + sinv;
+        const double nbound = -4.0 - sinv;
         const double s2 = sinv * sinv;
         double val = s2 - s2 * s2;  // (1/sigma)^2 - (1/sigma)^4
         // clamp(val, -bound, bound): x - x^2 <= 1/4 < 4 <= bound whenever 1/sigma >= 0, so the upper
-        // clamp can only act for a negative radius sum (kept for that case; the branch is warp-uniform
-        // with uniform parameters)
-        if (Rs < 0.0) val = fmin(val, bound);
-        val = fmax(val, -bound);
+        // clamp can only act for a negative radius sum.  Compare-selects instead of fmin/fmax (no NaN
+        // reaches a selected result: r2 == 0 is masked below)
+        if (UPPER) {
+            if (Rs < 0.0) val = val > -nbound ? -nbound : val;
+        }
+        val = val < nbound ? nbound : val;
         const double st = strength * val;
         // attracting part only between equal species (:88-96); spatial_cutoff =
         // (1 + signum(range*(R1+R2) - r)) / 2 with signum(+0) = 1 (:74-75)
         const bool on = (same_species | (st < 0.0)) & (range * Rs - r >= 0.0) & (r2 != 0.0);
         const double c = on ? st * rinv : 0.0;
         return BENCH ? c : -c;
+    }
+    __device__ __forceinline__ double coef(double r2, double ext_radius, bool same_species,
+                                           int* flag) const {
+        return coef_t<true>(r2, ext_radius, same_species);
     }
 };
 template <>
@@ -204,6 +212,16 @@ struct Pot<CRB_INT_MIE> {
         return force * rinv;
     }
 };
+
+// coefficient as the tile kernel evaluates it (same arithmetic; cell sorting without the upper clamp)
+template <int INTER>
+__device__ __forceinline__ double coef_tile(const Pot<INTER>& p, double r2, double ext_radius,
+                                            bool same_species, int* flag) {
+    if constexpr (INTER == CRB_INT_CELL_SORTING || INTER == CRB_INT_CELL_SORTING_BENCH)
+        return p.template coef_t<false>(r2, ext_radius, same_species);
+    else
+        return p.coef(r2, ext_radius, same_species, flag);
+}
 
 // ------------------------------------------------------------------------------------------------
 // A8 helper formulas with the reference's operation order, no fma

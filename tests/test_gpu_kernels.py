@@ -49,10 +49,11 @@ def test_tile_kernel_equals_agent_kernel(crb_lib, monkeypatch, make):
     """same candidates, same coef(), same ascending-index summation order => identical forces"""
     w = make()
     fa = _forces(w, "agent", monkeypatch)
-    ft = _forces(w, "tile", monkeypatch)
     scale = np.abs(fa).max()
-    assert np.abs(fa - ft).max() <= 1e-14 * scale
-    assert np.array_equal(fa, ft), "tile and per-agent kernels should agree bitwise"
+    for kernel in ("tile", "tile2"):
+        ft = _forces(w, kernel, monkeypatch)
+        assert np.abs(fa - ft).max() <= 1e-14 * scale, kernel
+        assert np.array_equal(fa, ft), f"{kernel} and per-agent kernels should agree bitwise"
 
 
 def test_tile_kernel_dense_voxels_fall_back(crb_lib, monkeypatch):
@@ -60,5 +61,5 @@ def test_tile_kernel_dense_voxels_fall_back(crb_lib, monkeypatch):
     inside k_force_tile; results must not change."""
     w = workloads.cell_sorting(n_cells=6000, domain_size=54.0)  # 3^3 voxels, 222 agents per voxel
     fa = _forces(w, "agent", monkeypatch)
-    ft = _forces(w, "tile", monkeypatch)
-    assert np.array_equal(fa, ft)
+    for kernel in ("tile", "tile2"):
+        assert np.array_equal(fa, _forces(w, kernel, monkeypatch)), kernel
