@@ -86,6 +86,7 @@ struct crb_sim {
     TileLaunch tile2;
     bool tile2_ok = false;
     size_t tile2_smem = 0;
+    int tile2_threads = kTileThreads;
     int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 k_force_tile, 3 k_force_tile2 (env CRB_FORCE_KERNEL)
     bool timers_on = false;
     StageTimer timers[kNumStages];
@@ -318,36 +319,62 @@ void plan_tile(crb_sim* s) {
     // ---- k_force_tile2: 2 x 2 target rows per CTA, 16 staged rows ---------------------------------------
     s->tile2_ok = false;
     if (s->kernel_choice == 2) return;
-    TileLaunch& U = s->tile2;
-    U = T;
-    U.chunk_len = std::min(n2, 24);
-    U.nchunks = (n2 + U.chunk_len - 1) / U.chunk_len;
-    U.kmax = U.chunk_len + 2;
     const int trows = s->D == 3 ? 4 : 2;   // target rows of a full tile
     const int srows = s->D == 3 ? 16 : 4;  // staged rows that hold agents
-    // shared memory of one CTA: four CTAs per SM when that still feeds four full warps, else three
     const size_t per_cand = sizeof(TileCand) + sizeof(float4) / 2 + sizeof(float2) / 2;
-    const size_t fixed2 = (size_t)(kTileQueue + 4) * kTileThreads * sizeof(unsigned short) +
-                          (size_t)kT2Rows * (U.kmax + 1) * sizeof(u32) + 64 + 34 * per_cand + 1024 /* static */;
-    for (int ctas = 4; ctas >= 2; --ctas) {
+    const double per_t = (double)srows / trows * 1.05;  // staged candidates per target (+5 % spread)
+    const double halo = srows * 2.0 * rho * 1.05 + kT2Rows * (kT2Pad + 1);
+    const double col = trows * rho;  // targets per voxel column of a tile
+    // CTA shape: 256 threads x 2 CTAs/SM or 128 x 4 (16 warps per SM either way); the one that keeps
+    // more targets resident per SM wins.  A CTA wants ~NT - 12 targets (every row of targets is padded to
+    // a multiple of 4 slots); its chunk of the fastest axis holds m segments of that size, with 7 %
+    // head room for the spread of the counts so that ceil(R / tseg) segments almost always suffice.
+    double best = 0, plan_fill = 0;
+    const char* forced = std::getenv("CRB_TILE2_THREADS");
+    for (int nt : {256, 128}) {
+        if (forced && std::atoi(forced) != nt) continue;
+        const int ctas = 512 / nt;
         const size_t budget2 = (size_t)227 * 1024 / ctas - 1024;  // 1 KB per CTA is reserved by the driver
-        if (budget2 <= fixed2) continue;
-        const u32 cap2 = (u32)(((budget2 - fixed2) / per_cand) / 2 * 2);
-        const double halo = srows * 2.0 * rho * 1.05 + kT2Rows * (kT2Pad + 1);
-        const double per_t = (double)srows / trows * 1.05;
-        double ts = ((double)cap2 - halo) / per_t;
-        ts = std::min(ts, 116.0);  // + <= 12 padding slots: one pass of the four warps
-        if (ts < 96.0 && ctas > 2) continue;  // would leave a warp idle: take more shared memory instead
-        if (ts < 8.0) break;
-        U.tseg = (u32)ts;
-        U.cap = cap2;
-        U.nseg = (int)std::ceil(U.chunk_len * trows * rho * 1.2 / U.tseg) + 1;
-        s->tile2_smem = tile2_smem_bytes(U.cap, U.kmax, kTileThreads);
-        s->tile2_ok = s->tile2_smem <= budget2 + 1024;
-        if (std::getenv("CRB_DEBUG_PLAN"))
-            std::fprintf(stderr, "[crb] tile2 plan: ctas/SM %d smem %zu cap %u tseg %u nseg %d chunk %d x %d rho %.2f\n",
-                         ctas, s->tile2_smem, U.cap, U.tseg, U.nseg, U.chunk_len, U.nchunks, rho);
-        break;
+        const double lanes = nt - 12.0;
+        // chunks of the fastest axis (the start[] table holds chunk_len + 3 entries for each of the 16
+        // rows): the split whose ceil(R / tseg) equal segments come closest to the lane budget, with
+        // 5 % head room for the spread of the counts
+        for (int nchunks = 1; nchunks <= n2; ++nchunks) {
+            const int chunk_len = (n2 + nchunks - 1) / nchunks;
+            if (chunk_len > 61 && nchunks < n2) continue;
+            if (nchunks > 1 && (n2 + nchunks - 2) / (nchunks - 1) == chunk_len) continue;  // same length, more chunks
+            const int kmax = chunk_len + 2;
+            const size_t fixed2 = (size_t)(kTileQueue + 4) * nt * sizeof(unsigned short) +
+                                  (size_t)kT2Rows * (kmax + 1) * sizeof(u32) + 64 + 34 * per_cand + 1024 /* static */;
+            if (budget2 <= fixed2) continue;
+            const u32 cap2 = (u32)std::min<size_t>(((budget2 - fixed2) / per_cand) / 2 * 2, 60000);
+            const double ts = std::min(((double)cap2 - halo) / per_t, lanes);
+            if (ts < 8.0) continue;
+            const double Rc = chunk_len * col;
+            const int mseg = std::max(1, (int)std::ceil(Rc * 1.05 / ts));
+            const double fill = Rc / mseg;  // expected targets per CTA
+            const double score = fill * ctas;
+            if (score <= best * 1.001) continue;
+            best = score;
+            TileLaunch& U = s->tile2;
+            U = T;
+            U.chunk_len = chunk_len;
+            U.nchunks = (n2 + chunk_len - 1) / chunk_len;
+            U.kmax = kmax;
+            U.tseg = (u32)ts;
+            U.cap = cap2;
+            U.nseg = mseg + 1;
+            s->tile2_threads = nt;
+            s->tile2_smem = tile2_smem_bytes(U.cap, U.kmax, nt);
+            s->tile2_ok = s->tile2_smem <= budget2 + 1024;
+            plan_fill = fill;
+        }
+    }
+    if (s->tile2_ok && std::getenv("CRB_DEBUG_PLAN")) {
+        const TileLaunch& U = s->tile2;
+        std::fprintf(stderr, "[crb] tile2 plan: threads %d smem %zu cap %u tseg %u nseg %d chunk %d x %d "
+                             "rho %.2f expected targets/CTA %.0f\n",
+                     s->tile2_threads, s->tile2_smem, U.cap, U.tseg, U.nseg, U.chunk_len, U.nchunks, rho, plan_fill);
     }
 }
 
@@ -390,16 +417,14 @@ int launch_tile2_t(crb_sim* s, const KParams& P, bool force_only, const PlaneRan
     const u32 nx2 = (u32)(T.x_count + 1) / 2, ny2 = (u32)(s->g.ng[1] + 1) / 2;
     const u32 grid = nx2 * ny2 * (u32)T.nseg * (u32)T.nchunks;
     if (!grid) return 0;
-    if (force_only) {
-        auto k = k_force_tile2<D, INTER, true>;
+    auto go = [&](auto k) -> int {
         CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile2_smem));
-        k<<<grid, kTileThreads, s->tile2_smem, st>>>(P, T);
-    } else {
-        auto k = k_force_tile2<D, INTER, false>;
-        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile2_smem));
-        k<<<grid, kTileThreads, s->tile2_smem, st>>>(P, T);
-    }
-    return 0;
+        k<<<grid, s->tile2_threads, s->tile2_smem, st>>>(P, T);
+        return 0;
+    };
+    if (s->tile2_threads == 256)
+        return force_only ? go(k_force_tile2<D, INTER, true, 256>) : go(k_force_tile2<D, INTER, false, 256>);
+    return force_only ? go(k_force_tile2<D, INTER, true, 128>) : go(k_force_tile2<D, INTER, false, 128>);
 }
 
 template <int D>

@@ -41,10 +41,10 @@ __host__ __device__ inline size_t tile2_smem_bytes(u32 cap, int kmax, int thread
     return b + 64;
 }
 
-template <int D, int INTER, bool FORCE_ONLY>
-__global__ void __launch_bounds__(kTileThreads, 4) k_force_tile2(const KParams P, const TileLaunch T) {
+template <int D, int INTER, bool FORCE_ONLY, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, const TileLaunch T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int nthreads = kTileThreads;  // launch contract: blockDim.x == kTileThreads
+    constexpr int nthreads = NT;  // launch contract: blockDim.x == NT (128: 4 CTAs/SM, 256: 2 CTAs/SM)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = nthreads >> 5;
     constexpr int NE = 4;  // candidates evaluated per drain iteration and lane

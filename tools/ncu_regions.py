@@ -1,37 +1,40 @@
 #!/usr/bin/env python
-"""Aggregate an .ncu-rep source page by code region of k_force_tile (instructions + stall samples)."""
-import csv, io, subprocess, sys, re
+"""Aggregate an .ncu-rep source page by code region of the tile force kernels (instructions + stall
+samples).  usage: ncu_regions.py rep [tile|tile2]"""
+import csv, io, subprocess, sys
 rep = sys.argv[1]
+which = sys.argv[2] if len(sys.argv) > 2 else "tile2"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(k for k, r in enumerate(rows) if "Source" in r and len(r) > 5)
 hh = rows[hi]
 ii, st = hh.index("Instructions Executed"), hh.index("Warp Stall Sampling (All Samples)")
-files = {}
-for f in ("cellular_raza_b200/csrc/crb_force_tile.cuh", "cellular_raza_b200/csrc/crb_kernels.cuh"):
-    files[f] = open(f).read().splitlines()
-tile = files["cellular_raza_b200/csrc/crb_force_tile.cuh"]
+D = "cellular_raza_b200/csrc/"
+files = {f: open(D + f).read().splitlines() for f in ("crb_force_tile.cuh", "crb_force_tile2.cuh", "crb_kernels.cuh")}
+main = files["crb_force_tile2.cuh" if which == "tile2" else "crb_force_tile.cuh"]
 def find(pat):
-    return next(i + 1 for i, l in enumerate(tile) if pat in l)
-marks = [("prologue", find("k_force_tile(const KParams")), ("window_search", find("window size: largest kc")),
+    return next(i + 1 for i, l in enumerate(main) if pat in l)
+marks = [("prologue", find("const KParams P, const TileLaunch T)")), ("window_search", find("window size: largest kc")),
          ("row_ranges", find("---- row ranges")), ("staging", find("---- stage the candidates")),
          ("target_setup", find("---- targets:")), ("drain_ctl", find("auto drain = [&]()")),
-         ("filter", find("for (int r = 0; r < kTileRows; ++r) {")), ("epilogue", find("if (valid) {"))]
+         ("filter", find("for (int r = 0; r < 9; ++r)" if which == "tile2" else "for (int r = 0; r < kTileRows; ++r) {")), ("epilogue", find("if (valid) {"))]
+def at(f, ln, t):
+    L = files[f]
+    return 0 < ln <= len(L) and L[ln - 1].strip() == t
 def region(ln, text):
     t = text.strip()
-    in_tile = 0 < ln <= len(tile) and tile[ln - 1].strip() == t
-    k = files["cellular_raza_b200/csrc/crb_kernels.cuh"]
-    in_k = 0 < ln <= len(k) and k[ln - 1].strip() == t
-    if in_tile and not in_k:
+    mainf = "crb_force_tile2.cuh" if which == "tile2" else "crb_force_tile.cuh"
+    if at(mainf, ln, t) and not at("crb_kernels.cuh", ln, t) and not (which == "tile2" and at("crb_force_tile.cuh", ln, t) and 60 < ln < 135):
         if ln < marks[0][1]:
-            return "eval(tile_eval)" if ln > 60 else "other"
+            return "eval(tile_eval)" if (which != "tile2" and ln > 60) else "other"
         r = "prologue"
         for name, start in marks:
             if ln >= start: r = name
         return r
-    if in_k:
-        if ln < 250: return "eval(coef/rsqrt)"
-        return "epilogue(integrate)"
+    if which == "tile2" and at("crb_force_tile.cuh", ln, t) and ln < 200:
+        return "eval(tile_eval)"
+    if at("crb_kernels.cuh", ln, t):
+        return "eval(coef/rsqrt)" if ln < 260 else "epilogue(integrate)"
     if "fadd2" in t or "ffma2" in t or "fmul2" in t: return "filter"
     if "reduce_max" in t or "vote_any" in t: return "filter"
     return "other:" + t[:30]
