@@ -123,6 +123,16 @@ def measured_peaks() -> dict:
     return {}
 
 
+def ncu_traffic(cells: int, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, from the committed ncu
+    capture at this population (profiles/traffic.json; null when that size was not captured)."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text())[str(cells)][kernel]
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_run(args, steps: int, warmup: int, sample_cells: int):
     """Times the CPU restatement of chili (oracle/) on the host cores: one emulated chili subdomain
@@ -241,10 +251,10 @@ def run_b200(args):
     achieved_tf = pairs_per_launch * FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
     peaks = measured_peaks()
     roofline = {
-        "kernel": "k_force_integrate", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+        "kernel": sim.force_kernel_name, "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
         "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-        "traffic": None, "share_of_step": force_ms / ms_total,
+        "traffic": ncu_traffic(n, "force"), "share_of_step": force_ms / ms_total,
         "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
         "pair_forces_per_s": pairs_per_launch / (force_avg_ms * 1e-3),
     }
@@ -255,7 +265,7 @@ def run_b200(args):
         "kernel": "k_fill+k_reorder (cell-list rebuild / migration scatter)", "bound": "hbm",
         "achieved": reorder_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": reorder_gbs / hbm_peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-        "traffic": None, "share_of_step": reorder_ms / ms_total, "scan_share_of_step": scan_ms / ms_total,
+        "traffic": ncu_traffic(n, "reorder"), "share_of_step": reorder_ms / ms_total, "scan_share_of_step": scan_ms / ms_total,
         "algorithmic_bytes_per_agent": REORDER_BYTES_PER_AGENT,
     }
 

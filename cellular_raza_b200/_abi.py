@@ -136,6 +136,11 @@ SYMBOLS = [
     ("crb_step", C.c_int, [_vp, C.c_uint64]),
     ("crb_sync", C.c_int, [_vp]),
     ("crb_iteration", C.c_uint64, [_vp]),
+    ("crb_force_kernel_name", C.c_char_p, [_vp]),
+    ("crb_snapshot_async", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("crb_snapshot_wait", C.c_int, [_vp, _u64p]),
+    ("crb_host_alloc", C.c_void_p, [C.c_uint64]),
+    ("crb_host_free", None, [C.c_void_p]),
     ("crb_slab_halo_bytes", C.c_uint64, [_vp]),
     ("crb_slab_migration_bytes", C.c_uint64, [_vp]),
     ("crb_slab_info", C.c_int, [_vp, _u64p]),

@@ -20,6 +20,7 @@ The Rust host crate a maintainer would add does exactly the same through the sam
 from __future__ import annotations
 
 import json
+import threading
 import math
 import os
 import time as _time
@@ -339,25 +340,75 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
         ts = settings.time
         save_its = sorted(set(ts.save_iterations))
         agent_rows = {"mech": type(agents[0].mechanics).__name__, "inter": type(agents[0].interaction).__name__}
+        # Snapshots do not stop the stepping loop: crb_snapshot_async packs the state on the device and
+        # copies it to pinned host memory on a side stream while the next steps run; the JSON / memory
+        # store is written by a writer thread (ctypes releases the GIL inside crb_step).
+        # mechanics / interaction parameters do not change on this path: fetched once, looked up by
+        # identifier for every snapshot (the device order changes with every cell-list rebuild)
+        ids0 = sim.get_agents()[2]
+        o0 = np.argsort(ids0, kind="stable")
+        ids_sorted = ids0[o0]
+        params_sorted = tuple(a[o0] for a in sim.get_params())
+        writer: threading.Thread | None = None
+        pending = None  # (iteration, snapshot token)
+        errors: list[BaseException] = []
+
+        def flush():
+            nonlocal writer, pending
+            if writer is not None:
+                writer.join()
+                writer = None
+            if errors:
+                raise errors[0]
+            if pending is not None:
+                it_p, token = pending
+                pending = None
+                state = sim.snapshot_wait(token)
+
+                def work():
+                    try:
+                        k = np.searchsorted(ids_sorted, state[2])
+                        _store(state, tuple(a[k] for a in params_sorted), cells, it_p, sb, agent_rows)
+                    except BaseException as e:  # surfaced by the next flush()
+                        errors.append(e)
+
+                writer = threading.Thread(target=work, name=f"crb-save-{it_p}")
+                writer.start()
+
+        def save(iteration):
+            nonlocal pending
+            flush()  # one snapshot in flight: finish the previous one first
+            pending = (iteration, sim.snapshot_async(aux=True))
+
         if save_its and save_its[0] == 0:  # save_initial (time.rs:243-255)
-            _save(sim, cells, 0, sb, agent_rows)
+            save(0)
         it = 0
         for target in [s for s in save_its if s > 0]:
             sim.step(target - it)  # replaces (target - it) iterations of run_sim.rs:380-403
             it = target
-            _save(sim, cells, it, sb, agent_rows)
+            save(it)
         if it < ts.maximum_iterations:
             sim.step(ts.maximum_iterations - it)
+        flush()
+        if writer is not None:
+            writer.join()
+        if errors:
+            raise errors[0]
         return StorageAccess(cells, subdomains, root)
     finally:
         sim.close()
 
 
 def _save(sim: DeviceSimulation, cells: StorageManager, iteration: int, sb: StorageBuilder, names: dict):
+    """blocking variant: download and store (used by tests)"""
+    state = (*sim.get_agents(), *sim.get_aux())
+    _store(state, sim.get_params(), cells, iteration, sb, names)
+
+
+def _store(state, params, cells: StorageManager, iteration: int, sb: StorageBuilder, names: dict):
     """save_cells (chili/datastructures.rs:373-396) -> store_batch_elements (storage/concepts.rs:766-790)."""
-    pos, vel, ids, vox = sim.get_agents()
-    hx, hv, hl = sim.get_aux()
-    mp, ip, sp = sim.get_params()
+    pos, vel, ids, vox, hx, hv, hl = state
+    mp, ip, sp = params
     if "Memory" in sb.priority:
         cells.memory[iteration] = {
             ("Initial", int(i)): {"pos": pos[k], "vel": vel[k], "voxel": int(vox[k]),

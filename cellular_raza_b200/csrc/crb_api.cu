@@ -57,6 +57,16 @@ struct crb_sim {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_interior = nullptr;
     int interior_state = 0;  // 0 none, 1 crb_slab_compute_interior done (boundary pending)
+    // storage snapshots: packed on `stream` into `snap`, copied to the caller's host buffers on `stream_io`
+    cudaStream_t stream_io = nullptr;
+    cudaEvent_t ev_snap_packed = nullptr, ev_snap_done = nullptr;
+    double* snap = nullptr;
+    u64 snap_cap = 0;
+    bool snap_pending = false;
+    u64 snap_n = 0;
+    u8* snap_hlen_host = nullptr;  // pinned
+    double *snap_hx_host = nullptr, *snap_hv_host = nullptr;
+    uint32_t* snap_hl_out = nullptr;
     State X, T, Y;  // X: sorted state read by the force pass, T: integrated, Y: reorder target
     u32 *key = nullptr, *key_alt = nullptr;
     u32 *start = nullptr, *start_alt = nullptr;
@@ -865,6 +875,13 @@ void crb_destroy(crb_sim* s) {
     timers_resolve(s);
     for (void* p : s->allocs) cudaFree(p);
     if (s->err_host) cudaFreeHost(s->err_host);
+    if (s->snap_pending) cudaEventSynchronize(s->ev_snap_done);
+    if (s->stream_io) cudaStreamSynchronize(s->stream_io);
+    if (s->ev_snap_packed) cudaEventDestroy(s->ev_snap_packed);
+    if (s->ev_snap_done) cudaEventDestroy(s->ev_snap_done);
+    if (s->stream_io) cudaStreamDestroy(s->stream_io);
+    if (s->snap) cudaFree(s->snap);
+    if (s->snap_hlen_host) cudaFreeHost(s->snap_hlen_host);
     if (s->ev_ready) cudaEventDestroy(s->ev_ready);
     if (s->ev_interior) cudaEventDestroy(s->ev_interior);
     if (s->stream2) cudaStreamDestroy(s->stream2);
@@ -875,6 +892,13 @@ void crb_destroy(crb_sim* s) {
 uint64_t crb_n_agents(const crb_sim* s) { return s ? s->n : 0; }
 uint64_t crb_iteration(const crb_sim* s) { return s ? s->iteration : 0; }
 uint64_t crb_kernel_launches(const crb_sim* s) { return s ? s->launches : 0; }
+const char* crb_force_kernel_name(const crb_sim* s) {
+    if (!s) return "";
+    if (s->rods) return "k_rod_force";
+    if (s->tile2_ok) return s->tile2_threads == 256 ? "k_force_tile2<256 threads, 2 CTAs/SM>" : "k_force_tile2<128 threads, 4 CTAs/SM>";
+    if (s->tile_ok) return "k_force_tile";
+    return "k_force_integrate";
+}
 
 int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
                    const double* mech_params, const double* inter_params, const uint8_t* species,
@@ -1541,6 +1565,134 @@ int crb_slab_finish(crb_sim* s, int save_prev) {
     int rc;
     if ((rc = step_finish(s, save_prev != 0))) return rc;
     plan_tile(s);
+    return 0;
+}
+
+// ---- storage snapshots (save_cells at PartialSave iterations, chili/datastructures.rs:373-396) -----
+void* crb_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void crb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int crb_snapshot_wait(crb_sim* s, uint64_t* n_agents) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->snap_pending) return fail(s, CRB_ERR_STATE, "no snapshot in flight");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    CU(s, cudaEventSynchronize(s->ev_snap_done));
+    s->snap_pending = false;
+    const u64 n = s->snap_n;
+    const int D = s->D;
+    // ring buffers oldest-first, unused entries zero (as crb_get_aux)
+    for (double* o : {s->snap_hx_host, s->snap_hv_host}) {
+        if (!o) continue;
+        for (u64 i = 0; i < n; ++i) {
+            double* r = o + i * 2 * D;
+            const u8 hl = s->snap_hlen_host[i];
+            if (hl == 1) {
+                for (int d = 0; d < D; ++d) {
+                    r[d] = r[D + d];
+                    r[D + d] = 0.0;
+                }
+            } else if (hl == 0) {
+                for (int k = 0; k < 2 * D; ++k) r[k] = 0.0;
+            }
+        }
+    }
+    if (s->snap_hl_out)
+        for (u64 i = 0; i < n; ++i) s->snap_hl_out[i] = s->snap_hlen_host[i];
+    if (n_agents) *n_agents = n;
+    return 0;
+}
+
+int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t* ids, uint64_t* voxel,
+                       double* hist_dx, double* hist_dv, uint32_t* hist_len) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    if (s->rods) return fail(s, CRB_ERR_STATE, "rods: use crb_get_agents / crb_get_aux");
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, "snapshot inside an open slab step");
+    if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    int rc;
+    if (s->snap_pending && (rc = crb_snapshot_wait(s, nullptr))) return rc;
+    if (!s->stream_io) {
+        CU(s, cudaStreamCreateWithFlags(&s->stream_io, cudaStreamNonBlocking));
+        CU(s, cudaEventCreateWithFlags(&s->ev_snap_packed, cudaEventDisableTiming));
+        CU(s, cudaEventCreateWithFlags(&s->ev_snap_done, cudaEventDisableTiming));
+    }
+    const u64 n = s->n;
+    const int D = s->D;
+    const u64 per = (u64)(2 * D + 2 + 4 * D + 1);  // doubles per agent: pos, vel, id, voxel, hx, hv, hlen (padded)
+    if (s->snap_cap < s->cap) {
+        if (s->snap) cudaFree(s->snap);
+        if (s->snap_hlen_host) cudaFreeHost(s->snap_hlen_host);
+        s->snap = nullptr;
+        s->snap_hlen_host = nullptr;
+        s->snap_cap = 0;
+        CU(s, cudaMalloc((void**)&s->snap, s->cap * per * sizeof(double)));
+        CU(s, cudaMallocHost((void**)&s->snap_hlen_host, s->cap));
+        s->snap_cap = s->cap;
+    }
+    double* b_pos = s->snap;
+    double* b_vel = b_pos + n * D;
+    u64* b_id = (u64*)(b_vel + n * D);
+    u64* b_vox = b_id + n;
+    double* b_hx = (double*)(b_vox + n);
+    double* b_hv = b_hx + n * 2 * D;
+    u8* b_hl = (u8*)(b_hv + n * 2 * D);
+    auto pack = [&](double* dst, int width, const double* const* cols) {
+        const double* c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < width; ++k) c[k] = cols[k] ? cols[k] + s->G : nullptr;
+        k_pack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(dst, width, c[0], c[1], c[2], c[3], c[4], c[5],
+                                                              c[6], c[7], n);
+        s->launches++;
+    };
+    if (n) {
+        if (pos) pack(b_pos, D, s->X.pos);
+        if (vel) {
+            if (s->cfg.mechanics_kind == CRB_MECH_BROWNIAN)
+                CU(s, cudaMemsetAsync(b_vel, 0, n * D * sizeof(double), s->stream));
+            else
+                pack(b_vel, D, s->X.vel);
+        }
+        if (ids) CU(s, cudaMemcpyAsync(b_id, s->X.id + s->G, n * sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+        if (voxel) {
+            const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
+            k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key + s->G, b_vox, base, n);
+            s->launches++;
+        }
+        for (int which = 0; which < 2; ++which) {
+            if (!(which == 0 ? hist_dx : hist_dv)) continue;
+            const double* cols[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int d = 0; d < D; ++d) {
+                cols[d] = which == 0 ? s->X.h0x[d] : s->X.h0v[d];
+                cols[D + d] = which == 0 ? s->X.h1x[d] : s->X.h1v[d];
+            }
+            pack(which == 0 ? b_hx : b_hv, 2 * D, cols);
+        }
+        CU(s, cudaMemcpyAsync(b_hl, s->X.hlen + s->G, n, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    CU(s, cudaGetLastError());
+    CU(s, cudaEventRecord(s->ev_snap_packed, s->stream));
+    CU(s, cudaStreamWaitEvent(s->stream_io, s->ev_snap_packed, 0));
+    if (n) {
+        if (pos) CU(s, cudaMemcpyAsync(pos, b_pos, n * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream_io));
+        if (vel) CU(s, cudaMemcpyAsync(vel, b_vel, n * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream_io));
+        if (ids) CU(s, cudaMemcpyAsync(ids, b_id, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream_io));
+        if (voxel) CU(s, cudaMemcpyAsync(voxel, b_vox, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream_io));
+        if (hist_dx) CU(s, cudaMemcpyAsync(hist_dx, b_hx, n * 2 * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream_io));
+        if (hist_dv) CU(s, cudaMemcpyAsync(hist_dv, b_hv, n * 2 * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream_io));
+        CU(s, cudaMemcpyAsync(s->snap_hlen_host, b_hl, n, cudaMemcpyDeviceToHost, s->stream_io));
+    }
+    CU(s, cudaEventRecord(s->ev_snap_done, s->stream_io));
+    s->snap_pending = true;
+    s->snap_n = n;
+    s->snap_hx_host = hist_dx;
+    s->snap_hv_host = hist_dv;
+    s->snap_hl_out = hist_len;
     return 0;
 }
 

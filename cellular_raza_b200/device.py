@@ -84,8 +84,10 @@ class DeviceSimulation:
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.crb_destroy(self._h)
+            self._lib.crb_destroy(self._h)  # waits for a snapshot in flight
             self._h = None
+            for ptr, _ in self.__dict__.pop("_pin_pool", {}).values():
+                self._lib.crb_host_free(C.c_void_p(ptr))
 
     def __del__(self):
         try:
@@ -147,6 +149,10 @@ class DeviceSimulation:
     def kernel_launches(self) -> int:
         return int(self._lib.crb_kernel_launches(self._h))
 
+    @property
+    def force_kernel_name(self) -> str:
+        return self._lib.crb_force_kernel_name(self._h).decode()
+
     def get_agents(self):
         """-> (pos[n,D], vel[n,D], ids[n], voxel[n]) in device order."""
         n = self.n_agents
@@ -156,6 +162,54 @@ class DeviceSimulation:
         vox = np.empty(n, dtype=np.uint64)
         self._check(self._lib.crb_get_agents(self._h, n, _ptr(pos), _ptr(vel), _ptr(ids), _ptr(vox)))
         return pos, vel, ids, vox
+
+    # -- storage snapshots that do not stop the stepping loop (crb_snapshot_async / _wait) ------------
+    def _pinned(self, name, shape, dtype):
+        """numpy view of page-locked host memory (crb_host_alloc), one buffer per name, grown on demand"""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = max(count * dtype.itemsize, 1)
+        pool = self.__dict__.setdefault("_pin_pool", {})
+        ent = pool.get(name)
+        if ent is None or ent[1] < nbytes:
+            if ent is not None:
+                self._lib.crb_host_free(C.c_void_p(ent[0]))
+            ptr = self._lib.crb_host_alloc(nbytes)
+            if not ptr:
+                raise MemoryError("crb_host_alloc failed")
+            ent = (ptr, nbytes)
+            pool[name] = ent
+        buf = (C.c_char * nbytes).from_address(ent[0])
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def snapshot_async(self, aux: bool = True):
+        """starts a snapshot of the current state; ``step`` may be called while it is copied.  Returns a
+        token for :meth:`snapshot_wait`."""
+        n = self.n_agents
+        bufs = {
+            "pos": self._pinned("pos", (n, self.dim), np.float64),
+            "vel": self._pinned("vel", (n, self.dim), np.float64),
+            "ids": self._pinned("ids", (n,), np.uint64),
+            "vox": self._pinned("vox", (n,), np.uint64),
+        }
+        if aux:
+            bufs["hx"] = self._pinned("hx", (n, 2, self.dim), np.float64)
+            bufs["hv"] = self._pinned("hv", (n, 2, self.dim), np.float64)
+            bufs["hl"] = self._pinned("hl", (n,), np.uint32)
+        p = lambda k: _ptr(bufs[k]) if k in bufs else None
+        self._check(self._lib.crb_snapshot_async(self._h, n, p("pos"), p("vel"), p("ids"), p("vox"),
+                                                 p("hx"), p("hv"), p("hl")))
+        return bufs
+
+    def snapshot_wait(self, bufs):
+        """-> copies (pos, vel, ids, voxel[, hist_dx, hist_dv, hist_len]) of a finished snapshot"""
+        n = C.c_uint64(0)
+        self._check(self._lib.crb_snapshot_wait(self._h, C.byref(n)))
+        m = int(n.value)
+        out = [bufs[k][:m].copy() for k in ("pos", "vel", "ids", "vox")]
+        if "hx" in bufs:
+            out += [bufs[k][:m].copy() for k in ("hx", "hv", "hl")]
+        return tuple(out)
 
     def get_params(self):
         n = self.n_agents

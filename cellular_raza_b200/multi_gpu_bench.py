@@ -119,7 +119,7 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         force_avg_ms = float(fm.item()) / max(force_launches, 1)
         achieved_tf = pairs_per_launch * helpers.FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
         roofline = {
-            "kernel": "k_force_tile (per GPU, slowest rank)", "bound": "fp64", "achieved": achieved_tf,
+            "kernel": slab.force_kernel_name + " (per GPU, slowest rank)", "bound": "fp64", "achieved": achieved_tf,
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
             "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
             "traffic": None, "share_of_step": float(fm.item()) / ms_total,

@@ -252,6 +252,21 @@ int crb_slab_migration_export(crb_sim* sim, void* lo_buf, void* hi_buf, uint64_t
 int crb_slab_migration_import(crb_sim* sim, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]);
 int crb_slab_finish(crb_sim* sim, int save_prev);
 
+/* ---- storage snapshots without stopping the stepping loop ---------------------------------------
+ * Replaces the blocking save_cells of chili at PartialSave iterations (chili/datastructures.rs:373-396,
+ * run_sim.rs:432-444).  crb_snapshot_async packs the CURRENT state (same layouts and order as
+ * crb_get_agents / crb_get_aux; any pointer may be NULL) into a device-side snapshot buffer on the
+ * handle's stream and starts the device-to-host copies on a side stream; it returns at once and
+ * crb_step may be called while the copies run.  The host buffers (pinned memory from crb_host_alloc
+ * for a truly asynchronous copy) belong to the library until crb_snapshot_wait returns; one snapshot
+ * is in flight at a time (a second call waits for the first). */
+int crb_snapshot_async(crb_sim* sim, uint64_t cap, double* pos, double* vel, uint64_t* ids,
+                       uint64_t* voxel, double* hist_dx, double* hist_dv, uint32_t* hist_len);
+int crb_snapshot_wait(crb_sim* sim, uint64_t* n_agents);
+/* page-locked host memory for snapshot / upload buffers. */
+void* crb_host_alloc(uint64_t bytes);
+void crb_host_free(void* p);
+
 /* ---- parity taps (used by tests; not needed by a production host) ------------------------- */
 /* forces that the next step would integrate (AuxStorageMechanics::current_force after
  * update_mechanics_interaction_step_3), device order, cap*dim*V doubles; does not advance. */
@@ -269,6 +284,8 @@ int crb_get_voxel_counts(crb_sim* sim, uint64_t cap, uint32_t* counts);
 int crb_count_candidate_pairs(crb_sim* sim, uint64_t* n_pairs);
 /* number of kernels launched by this handle so far (bench.py `gpu_launches`). */
 uint64_t crb_kernel_launches(const crb_sim* sim);
+/* name of the force kernel the planner chose for the current population (bench / profile labels). */
+const char* crb_force_kernel_name(const crb_sim* sim);
 /* device time in milliseconds spent in a named stage since the last crb_reset_timers
  * (CUDA events on the handle's stream; only recorded after crb_enable_timers(sim, 1)).
  * stage: 0 force+integrate, 1 scan, 2 reorder, 3 halo, 4 migration. */

@@ -56,3 +56,30 @@ def test_cell_sorting_example_with_json_storage(crb_lib, tmp_path):
     assert len(mem) == n
     moved = np.array([np.abs(mem[("Initial", k)]["pos"] - pos[k]).max() for k in range(n)])
     assert moved.max() > 1e-3  # the cells interact
+
+
+def test_snapshot_async_equals_blocking_download(crb_lib):
+    """crb_snapshot_async / crb_snapshot_wait (side-stream D2H into pinned memory) return exactly what
+    crb_get_agents / crb_get_aux return at the same iteration, although the stepping loop went on
+    while the copy was in flight."""
+    from cellular_raza_b200 import workloads
+    from cellular_raza_b200.device import DeviceSimulation
+
+    w = workloads.cell_sorting_scaled(60_000, 7.1)
+    sim = DeviceSimulation(w.config())
+    sim.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+    sim.step(3)
+    ref = (*sim.get_agents(), *sim.get_aux())
+    token = sim.snapshot_async()
+    sim.step(5)  # overwrites every state buffer at least twice
+    snap = sim.snapshot_wait(token)
+    for a, b in zip(ref, snap):
+        assert np.array_equal(a, b)
+    # a second snapshot while one is pending waits for the first; wait without a snapshot is an error
+    t1 = sim.snapshot_async(aux=False)
+    now = sim.get_agents()
+    got = sim.snapshot_wait(t1)
+    assert all(np.array_equal(a, b) for a, b in zip(now, got))
+    with pytest.raises(cr.SimulationError):
+        sim.snapshot_wait(t1)
+    sim.close()
