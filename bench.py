@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--n-threads-ref", type=int, default=1,
                     help="chili n_threads whose pair weights are reproduced (CRB_WEIGHT_CHILI)")
     ap.add_argument("--cpu-sample-cells", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="cell_sorting", choices=["cell_sorting", "brownian_morse", "bacterial_rods"],
+                    help="cell_sorting = the headline (BASELINE.json configs[1]/[4]); brownian_morse = configs[2] "
+                         "(N > 1: ONE cube of cells-per-gpu x N agents cut into slabs); bacterial_rods = configs[3] (1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
@@ -177,8 +180,30 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def flop_per_pair(args) -> float:
+    # species potential 50 flop, Morse 30 flop (+ 1 exp, not counted) per ordered candidate pair
+    return 30.0 if args.workload == "brownian_morse" else FLOP_PER_PAIR
+
+
+def make_workload(args, n: int):
+    from cellular_raza_b200 import _abi, workloads
+
+    if args.workload == "brownian_morse":
+        return workloads.brownian_morse_scaled(n, 4.0, n_threads=args.n_threads_ref, noise_mode=_abi.CRB_NOISE_PHILOX)
+    return workloads.cell_sorting_scaled(n, args.density, n_threads=args.n_threads_ref)
+
+
 def workload_config(args) -> dict:
     n_total = args.cells_per_gpu * args.gpus
+    if args.workload == "brownian_morse":
+        return {
+            "workload": "brownian3d_morse (BASELINE.json configs[2])", "cells_per_gpu": args.cells_per_gpu,
+            "cells_total": n_total, "agents_per_voxel": 4.0, "mechanics": "Brownian3D{D 0.3, kT 0.3}",
+            "interaction": "MorsePotential{radius 3, stiffness 0.5, cutoff 12, strength 0.01}",
+            "solver": "AB3 (order 2)", "noise": "counter-based Philox normal per (seed, id, step)",
+            "pair_weights": f"chili-as-written(n_threads={args.n_threads_ref})", "dt": 0.01,
+            "l2_policy": "working set larger than L2", "decomposition": f"slab{args.gpus}" if args.gpus > 1 else "single",
+        }
     return {
         "workload": "cell_sorting_3d_weak_scaling (BASELINE.json configs[4]; configs[1] with --cells-per-gpu 1000000)",
         "cells_per_gpu": args.cells_per_gpu, "cells_total": n_total, "agents_per_voxel": args.density,
@@ -212,7 +237,9 @@ def run_b200(args):
     dev_id = local_rank
     torch.cuda.set_device(dev_id)
     n = args.cells_per_gpu
-    w = workloads.cell_sorting_scaled(n, args.density, n_threads=args.n_threads_ref)
+    if args.workload == "bacterial_rods":
+        return run_rods(args, dev_id)
+    w = make_workload(args, n)
     sim = DeviceSimulation(w.config(device=dev_id))
     sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
     sim.set_agents(w.pos, w.vel, None, None, w.species)
@@ -248,14 +275,14 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (force + integrate): FP64 pipe --------------------------
     pairs_per_launch = 0.5 * (pairs + pairs_after)
     force_avg_ms = force_ms / max(force_launches, 1)
-    achieved_tf = pairs_per_launch * FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
+    achieved_tf = pairs_per_launch * flop_per_pair(args) / (force_avg_ms * 1e-3) / 1e12
     peaks = measured_peaks()
     roofline = {
         "kernel": sim.force_kernel_name, "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
         "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
         "traffic": ncu_traffic(n, "force"), "share_of_step": force_ms / ms_total,
-        "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+        "algorithmic_flop_per_pair": flop_per_pair(args), "pairs_per_launch": pairs_per_launch,
         "pair_forces_per_s": pairs_per_launch / (force_avg_ms * 1e-3),
     }
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -274,7 +301,8 @@ def run_b200(args):
     if not args.no_e2e:
         hp = torch.from_numpy(w.pos).pin_memory()
         hv = torch.from_numpy(w.vel).pin_memory()
-        hs = torch.from_numpy(w.species).pin_memory()
+        hs = torch.from_numpy(w.species).pin_memory() if w.species is not None else None
+        hs_ptr = hs.data_ptr() if hs is not None else None
         op = torch.empty_like(hp).pin_memory()
         ov = torch.empty_like(hv).pin_memory()
         lib, h = sim._lib, sim._h
@@ -283,7 +311,7 @@ def run_b200(args):
             if k == 2:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-            rc = lib.crb_set_agents(h, n, hp.data_ptr(), hv.data_ptr(), None, None, hs.data_ptr(), None)
+            rc = lib.crb_set_agents(h, n, hp.data_ptr(), hv.data_ptr(), None, None, hs_ptr, None)
             rc = rc or lib.crb_step(h, 1)
             rc = rc or lib.crb_get_agents(h, n, op.data_ptr(), ov.data_ptr(), None, None)
             if rc:
@@ -314,6 +342,55 @@ def run_b200(args):
         "stage_ms_per_step": {"force_integrate": force_ms / args.steps, "scan": scan_ms / args.steps,
                               "reorder": reorder_ms / args.steps},
         "published_reference": "chili on Threadripper 3960X: 2.02e4 (1 thread, 1.3 M cells), best 1.01e5 (43 threads, 20 k cells); BASELINE.md",
+    }
+    print(json.dumps(line), flush=True)
+    sim.close()
+
+
+def run_rods(args, dev_id: int):
+    """BASELINE.json configs[3]: bacterial_rods (RodMechanics + RodInteraction, growth / division => the rod
+    count changes inside the timed region; agent-steps = sum over steps of the current count, here
+    steps x mean(count before, count after))."""
+    import torch
+
+    from cellular_raza_b200 import workloads
+    from cellular_raza_b200.rods import RodSimulation
+
+    n = args.cells_per_gpu
+    per_tile = 5
+    side = max(int(round((n / per_tile) ** 0.5)), 1)
+    # spring lengths up to the division threshold (6 um): ~10 % of the rods divide inside the timed region
+    w = workloads.bacterial_rods(side, side, rods_per_tile=per_tile, n_threads=args.n_threads_ref,
+                                 spring_length_range=(4.0, 6.0))
+    sim = RodSimulation(w.config(device=dev_id))
+    sim.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    stream = torch.cuda.ExternalStream(sim.stream, device=dev_id)
+    sim.step(max(args.warmup, 3))
+    sampler = ClockSampler(dev_id)
+    sampler.start()
+    time.sleep(0.3)
+    l0, n0 = sim.kernel_launches, sim.n_agents
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    n1 = sim.n_agents
+    clocks = sampler.stop()
+    value = 0.5 * (n0 + n1) * args.steps / (ms_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "bacterial_rods (BASELINE.json configs[3])", "rods_initial": w.n, "rods_before": n0,
+                   "rods_after": n1, "vertices": 5, "tiles": [side, side],
+                   "aspects": "Mechanics, Interaction, Cycle, NeighborSensing", "dt_min": 0.1,
+                   "l2_policy": "working set larger than L2" if w.n >= 500_000 else "working set fits L2 (small run)"},
+        "roofline": None, "cpu_baseline": None, "e2e": None,
+        "gpu_launches": int(sim.kernel_launches - l0), "clocks": clocks,
+        "note": "not the headline workload: k_rod_force is a per-rod kernel, not yet tiled (DESIGN.md §9)",
     }
     print(json.dumps(line), flush=True)
     sim.close()

@@ -24,8 +24,13 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
     opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     n = args.cells_per_gpu
-    w = workloads.cell_sorting_slab(n, rank, world, args.density, n_threads=args.n_threads_ref)
-    cfg = w.config(capacity=int(n * 1.1) + 4096, device=local_rank)
+    if args.workload == "brownian_morse":
+        # configs[2]: ONE cube of n * world agents cut into slabs of whole planes
+        w = workloads.brownian_morse_slab(n * world, rank, world, n_threads=args.n_threads_ref)
+    else:
+        w = workloads.cell_sorting_slab(n, rank, world, args.density, n_threads=args.n_threads_ref)
+    n_rank = w.n
+    cfg = w.config(capacity=int(n_rank * 1.1) + 4096, device=local_rank)
     sim = SlabSimulation(cfg, device=local_rank, overlap=not args.no_overlap)
     sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
     sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
@@ -82,7 +87,8 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
     if not args.no_e2e:
         hp = torch.from_numpy(w.pos).pin_memory()
         hv = torch.from_numpy(w.vel).pin_memory()
-        hs = torch.from_numpy(w.species).pin_memory()
+        hs = torch.from_numpy(w.species).pin_memory() if w.species is not None else None
+        hs_ptr = hs.data_ptr() if hs is not None else None
         hi = torch.from_numpy(w.extra["ids"]).pin_memory()
         op = torch.empty_like(hp).pin_memory()
         ov = torch.empty_like(hv).pin_memory()
@@ -93,12 +99,12 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
                 torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
-            rc = lib.crb_set_agents(h, n, hp.data_ptr(), hv.data_ptr(), None, None, hs.data_ptr(), hi.data_ptr())
+            rc = lib.crb_set_agents(h, n_rank, hp.data_ptr(), hv.data_ptr(), None, None, hs_ptr, hi.data_ptr())
             if rc:
                 raise RuntimeError(lib.crb_last_error(h))
             sim.step(1)
             m = slab.n_agents
-            rc = lib.crb_get_agents(h, m, op.data_ptr() if m <= n else None, ov.data_ptr() if m <= n else None, None, None)
+            rc = lib.crb_get_agents(h, m, op.data_ptr() if m <= n_rank else None, ov.data_ptr() if m <= n_rank else None, None, None)
             if rc:
                 raise RuntimeError(lib.crb_last_error(h))
         torch.cuda.synchronize()
@@ -118,18 +124,18 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         pairs_per_launch = float(pr.item()) / world  # per GPU
         # the overlapped step splits the force pass into interior + boundary launches: time per STEP
         force_avg_ms = float(fm.item()) / max(args.steps, 1)
-        achieved_tf = pairs_per_launch * helpers.FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
+        achieved_tf = pairs_per_launch * helpers.flop_per_pair(args) / (force_avg_ms * 1e-3) / 1e12
         roofline = {
             "kernel": slab.force_kernel_name + " (per GPU, slowest rank)", "bound": "fp64", "achieved": achieved_tf,
             "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
             "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
             "traffic": None, "share_of_step": float(fm.item()) / ms_total,
-            "algorithmic_flop_per_pair": helpers.FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+            "algorithmic_flop_per_pair": helpers.flop_per_pair(args), "pairs_per_launch": pairs_per_launch,
             "pair_forces_per_s": pairs_per_launch * world / (force_avg_ms * 1e-3),
         }
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         reorder_avg_ms = reorder_ms / max(args.steps, 1)
-        reorder_gbs = n * helpers.REORDER_BYTES_PER_AGENT / (reorder_avg_ms * 1e-3) / 1e9
+        reorder_gbs = n_rank * helpers.REORDER_BYTES_PER_AGENT / (reorder_avg_ms * 1e-3) / 1e9
         roofline_hbm = {
             "kernel": "k_fill+k_reorder (rank 0)", "bound": "hbm", "achieved": reorder_gbs, "peak": hbm_peak,
             "unit": "GB/s", "frac": reorder_gbs / hbm_peak,

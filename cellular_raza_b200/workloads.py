@@ -214,6 +214,47 @@ def cell_sorting_slab(cells_per_rank: int, rank: int, world: int, density_per_vo
     return w
 
 
+def brownian_morse_scaled(n_cells: int, density_per_voxel: float = 4.0, **kw) -> Workload:
+    """C3 at constant density: L is a multiple of the 12-unit voxel edge (8 M cells in
+    L = 1,512 = 126 * 12 => rho ~ 4)."""
+    n_side = max(int(round((n_cells / density_per_voxel) ** (1.0 / 3.0))), 1)
+    return brownian_morse(n_cells, 12.0 * n_side, **kw)
+
+
+def brownian_morse_slab(cells_total: int, rank: int, world: int, density_per_voxel: float = 4.0, *,
+                        seed: int = 2, dt: float = 0.01, noise_mode: int = _abi.CRB_NOISE_PHILOX,
+                        n_threads: int = 1) -> Workload:
+    """BASELINE.json configs[2]: Brownian3D + MorsePotential, ``cells_total`` agents in ONE cube of
+    n_side^3 voxels (8 M: 126^3) cut into ``world`` slabs of whole planes (16,16,16,16,16,16,15,15 for 8
+    GPUs); only THIS rank's agents are generated, in proportion to its planes."""
+    from .slabs import slab_planes
+
+    n_side = max(int(round((cells_total / density_per_voxel) ** (1.0 / 3.0))), 1)
+    edge = 12.0 * n_side
+    first, count = slab_planes(n_side, world)[rank]
+    firsts = [f for f, _ in slab_planes(n_side, world)]
+    lo_id = int(round(cells_total * firsts[rank] / n_side))
+    hi_id = int(round(cells_total * (first + count) / n_side))
+    n = hi_id - lo_id
+    rng = np.random.default_rng([seed, rank])
+    pos = _uniform_positions(rng, n, 3, 0.0, edge)
+    x_lo, x_hi = first * 12.0, (first + count) * 12.0
+    pos[:, 0] = x_lo + (pos[:, 0] / edge) * (x_hi - x_lo)
+    np.clip(pos[:, 0], x_lo if rank else np.nextafter(0.0, 1.0), np.nextafter(x_hi, x_lo), out=pos[:, 0])
+    mn, mx = [0.0] * 3, [edge] * 3
+    nv, dx = _domain_from_interaction_range(mn, mx, 12.0)
+    cfg = dict(dim=3, mechanics_kind=_abi.CRB_MECH_BROWNIAN, interaction_kind=_abi.CRB_INT_MORSE,
+               domain_min=mn, domain_max=mx, n_voxels=nv, dx=dx, dt=dt, solver_order=2,
+               pair_weight_mode=_abi.CRB_WEIGHT_CHILI, ref_n_subdomains=n_threads, noise_mode=noise_mode,
+               rng_seed=seed)
+    w = Workload(name=f"brownian_morse_slab_{cells_total}/{world}", cfg_kwargs=cfg, pos=pos,
+                 vel=np.zeros((n, 3)), mech_params=np.tile([0.3, 0.3], (n, 1)),
+                 inter_params=np.tile([3.0, 0.5, 12.0, 0.01], (n, 1)), species=None)
+    w.extra["ids"] = np.arange(lo_id, hi_id, dtype=np.uint64)
+    w.extra["n_side"] = n_side
+    return w
+
+
 # ---------------------------------------------------------------------------------------------------
 MICRO_METRE = 1e-6
 MINUTE = 1.0
