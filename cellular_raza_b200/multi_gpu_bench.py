@@ -30,7 +30,10 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
     else:
         w = workloads.cell_sorting_slab(n, rank, world, args.density, n_threads=args.n_threads_ref)
     n_rank = w.n
-    cfg = w.config(capacity=int(n_rank * 1.1) + 4096, device=local_rank)
+    # the fixed-size halo / migration buffers are sized from the capacity: it must be the same on every rank
+    nmax = torch.tensor([n_rank], device="cuda", dtype=torch.int64)
+    dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+    cfg = w.config(capacity=int(int(nmax.item()) * 1.1) + 4096, device=local_rank)
     sim = SlabSimulation(cfg, device=local_rank, overlap=not args.no_overlap)
     sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
     sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])

@@ -285,6 +285,18 @@ class SlabSimulation:
         self.world = dist.get_world_size(group)
         device = torch.cuda.current_device() if device is None else device
         self.slab = SlabRank(cfg, self.rank, self.world, device, **caps)
+        # the exchange buffers have a fixed size derived from the capacities: a rank with another size
+        # would leave its neighbour waiting in ncclRecv forever, so compare before the first exchange
+        mine = torch.tensor([self.slab.halo_bytes, self.slab.mig_bytes], dtype=torch.int64,
+                            device=torch.device("cuda", device))
+        every = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        if any(not torch.equal(t, mine) for t in every):
+            sizes = [tuple(int(v) for v in t.tolist()) for t in every]
+            self.slab.close()
+            raise _abi.SimulationError(_abi.CRB_ERR_INVALID_ARG,
+                                       f"halo/migration buffer sizes differ between ranks {sizes}: create every "
+                                       "slab with the same capacity, ghost_capacity and migration_capacity")
         self.cfg = self.slab.cfg
         self.dim = self.slab.dim
 

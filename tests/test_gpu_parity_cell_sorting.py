@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from cellular_raza_b200 import _abi, workloads
+from cellular_raza_b200.device import DeviceSimulation
 
 import parity
 
@@ -160,3 +161,53 @@ def test_c2_one_million_cells(oracle_lib, crb_lib):
     md = set(zip(*[a.tolist() for a in dev.get_migrations()]))
     mo = set(zip(*[a.tolist() for a in ora.get_migrations()]))
     assert md == mo
+
+
+def test_full_size_8m_properties(crb_lib):
+    """BASELINE.json configs[4] per-GPU size (8 M cells, 104^3 voxels): the oracle needs minutes here, so
+    the bench-size run is checked through size-independent properties — voxel keys recomputed with IEEE
+    sub/div/trunc in numpy (bit-exact, A1), device order sorted by key, per-voxel counts = histogram of
+    the keys, candidate pairs = sum over voxels n_v * (agents of the clipped 3^3 box) - N (A2), the net
+    force of a symmetric potential vanishes in physical weight mode, agents are conserved and stay
+    inside the domain, identifiers stay a permutation."""
+    n = 8_000_000
+    w = workloads.cell_sorting_scaled(n, 7.1, n_threads=1, pair_weight_mode=_abi.CRB_WEIGHT_PHYSICAL)
+    dev = DeviceSimulation(w.config())
+    dev.set_uniform_params(w.mech_params[0], w.inter_params[0])
+    dev.set_agents(w.pos, w.vel, None, None, w.species)
+    nv = np.asarray(w.cfg_kwargs["n_voxels"], dtype=np.int64)
+    dx = np.asarray(w.cfg_kwargs["dx"], dtype=np.float64)
+    mn = np.asarray(w.cfg_kwargs["domain_min"], dtype=np.float64)
+    mx = np.asarray(w.cfg_kwargs["domain_max"], dtype=np.float64)
+
+    def check_state():
+        pos, vel, ids, vox = dev.get_agents()
+        assert len(ids) == n
+        idx = np.trunc((pos - mn) / dx).astype(np.int64)  # cartesian_cuboid_n.rs:469-490
+        plain = (idx[:, 0] * nv[1] + idx[:, 1]) * nv[2] + idx[:, 2]
+        assert np.array_equal(plain.astype(np.uint64), vox), "voxel keys are not bit-exact"
+        assert (np.diff(vox.astype(np.int64)) >= 0).all(), "device order is not sorted by voxel"
+        counts = np.bincount(plain, minlength=int(nv.prod()))
+        assert np.array_equal(counts.astype(np.uint32), dev.get_voxel_counts())
+        assert (pos >= mn).all() and (pos <= mx).all()
+        s = np.sort(ids)
+        assert np.array_equal(s, np.arange(n, dtype=np.uint64))
+        return counts.reshape(nv)
+
+    c = check_state()
+    # ordered candidate pairs from the histogram alone
+    pad = np.pad(c, 1)
+    box = np.zeros_like(c)
+    for a in range(3):
+        for b in range(3):
+            for d in range(3):
+                box += pad[a:a + nv[0], b:b + nv[1], d:d + nv[2]]
+    assert dev.count_candidate_pairs() == int((c * box).sum() - n)
+    f = dev.debug_forces()
+    assert np.isfinite(f).all()
+    net = np.abs(f.sum(axis=0)).max()
+    assert net <= 1e-9 * np.abs(f).sum(), f"net force {net:.3e}"
+    dev.step(5)
+    check_state()
+    assert dev.force_kernel_name.startswith("k_force_tile2")
+    dev.close()
