@@ -63,3 +63,53 @@ def test_tile_kernel_dense_voxels_fall_back(crb_lib, monkeypatch):
     fa = _forces(w, "agent", monkeypatch)
     for kernel in ("tile", "tile2"):
         assert np.array_equal(fa, _forces(w, kernel, monkeypatch)), kernel
+
+
+def _box_workload(n_voxels, density, seed, n_threads, clustered=False):
+    """cell_sorting population in a NON-cubic box of n_voxels voxels of edge 18 (ragged tiles: odd
+    plane / row counts, single-voxel axes) at `density` agents per voxel; `clustered` piles a tenth of
+    the agents into one voxel so that a staging window overflows."""
+    base = workloads.cell_sorting(n_cells=8, domain_size=36.0, n_threads=n_threads)
+    nv = np.asarray(n_voxels, dtype=np.uint64)
+    n = max(int(density * float(nv.prod())), 2)
+    rng = np.random.default_rng(seed)
+    mx = 18.0 * nv.astype(np.float64)
+    pos = rng.uniform(1e-9, 1.0, (n, 3)) * (mx - 2e-9)
+    if clustered:
+        k = n // 10
+        pos[:k] = rng.uniform(0.05, 0.95, (k, 3)) * 18.0 + 18.0 * (nv // 2).astype(np.float64)
+    cfg = dict(base.cfg_kwargs)
+    cfg.update(domain_max=mx.tolist(), n_voxels=nv, dx=np.full(3, 18.0))
+    return workloads.Workload(
+        name="box", cfg_kwargs=cfg, pos=pos, vel=np.zeros((n, 3)), mech_params=np.tile([2.0, 1.0], (n, 1)),
+        inter_params=np.tile([6.0, 2.0, 1.5], (n, 1)), species=(rng.random(n) < 0.5).astype(np.uint8))
+
+
+@pytest.mark.parametrize("n_voxels,density,n_threads,clustered", [
+    ((1, 1, 1), 9.0, 1, False),       # a single voxel: every tile row but one is invalid
+    ((7, 1, 2), 6.0, 2, False),       # the rods example's shape: single-voxel axis 1 (SURVEY.md §7 vii)
+    ((3, 5, 11), 7.1, 3, False),      # odd plane and row counts: half-empty 2 x 2 tiles on two faces
+    ((5, 4, 37), 2.5, 1, False),      # long fastest axis, benchmark density: several chunks per tile
+    ((4, 6, 9), 31.0, 4, False),      # dense: candidates exceed the staging capacity => z-windows
+    ((6, 6, 6), 7.1, 1, True),        # one overfull voxel: per-agent path inside the tile kernels
+    ((9, 2, 64), 0.3, 5, False),      # nearly empty voxels, most tiles without targets
+])
+def test_tile_kernels_ragged_geometries(crb_lib, monkeypatch, n_voxels, density, n_threads, clustered):
+    """k_force_tile2 / k_force_tile == k_force_integrate BITWISE on ragged grids, and the same again
+    after steps (reflection at the walls, migration, cell-list rebuild feed the next force pass)."""
+    w = _box_workload(n_voxels, density, seed=11, n_threads=n_threads, clustered=clustered)
+    fa = _forces(w, "agent", monkeypatch)
+    for kernel in ("tile", "tile2"):
+        assert np.array_equal(fa, _forces(w, kernel, monkeypatch)), kernel
+    states = []
+    for kernel in ("agent", "tile2"):
+        monkeypatch.setenv("CRB_FORCE_KERNEL", kernel)
+        sim = DeviceSimulation(w.config())
+        sim.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+        sim.step(3 if (clustered or density > 20) else 12)
+        pos, vel, ids, vox = sim.get_agents()
+        o = np.argsort(ids)
+        states.append((pos[o], vel[o], vox[o]))
+        sim.close()
+    for a, b in zip(*states):
+        assert np.array_equal(a, b)
