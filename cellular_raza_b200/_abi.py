@@ -150,6 +150,7 @@ SYMBOLS = [
     ("crb_slab_compute_interior", C.c_int, [_vp, C.c_int]),
     ("crb_slab_compute_boundary", C.c_int, [_vp]),
     ("crb_slab_migration_export", C.c_int, [_vp, _vp, _vp, _u64p]),
+    ("crb_slab_migration_counts", C.c_int, [_vp, _u64p]),
     ("crb_slab_migration_import", C.c_int, [_vp, _vp, _vp, _u64p]),
     ("crb_slab_finish", C.c_int, [_vp, C.c_int]),
     ("crb_debug_forces", C.c_int, [_vp, C.c_uint64, _vp]),

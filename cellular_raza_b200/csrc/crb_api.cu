@@ -49,6 +49,8 @@ struct crb_sim {
     HaloLayout hl;
     MigLayout ml;
     bool step_open = false;  // crb_slab_compute done, crb_slab_finish pending
+    bool mig_counts_pending = false;  // export enqueued without reading its counts back (n_out == NULL)
+    u64 mig_out[2] = {0, 0};          // agents exported in the open step (lo, hi)
     u64 n_src = 0;           // unsorted sources of the open step (owned + arrivals)
     u64 n_gone = 0;          // agents exported in the open step
     cudaStream_t stream = nullptr;
@@ -1453,10 +1455,12 @@ int crb_slab_compute_boundary(crb_sim* s) {
 }
 
 int crb_slab_migration_export(crb_sim* s, void* lo_buf, void* hi_buf, uint64_t n_out[2]) {
-    if (!s || !n_out) return CRB_ERR_INVALID_ARG;
+    if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_compute first");
     CU(s, cudaSetDevice((int)s->cfg.device));
-    n_out[0] = n_out[1] = 0;
+    if (n_out) n_out[0] = n_out[1] = 0;
+    s->mig_out[0] = s->mig_out[1] = 0;
+    s->mig_counts_pending = false;
     if (s->world == 1) return 0;
     const u64 plane = s->hl.plane;
     CU(s, cudaMemsetAsync(s->scratch_u64, 0, 2 * sizeof(u64), s->stream));
@@ -1493,15 +1497,30 @@ int crb_slab_migration_export(crb_sim* s, void* lo_buf, void* hi_buf, uint64_t n
     if (s->has_lo) CU(s, cudaMemcpyAsync(lo_buf, s->scratch_u64, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
     if (s->has_hi) CU(s, cudaMemcpyAsync(hi_buf, s->scratch_u64 + 1, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
     stage_end(s, 4, nl);
+    CU(s, cudaGetLastError());
+    if (!n_out) {
+        // asynchronous form: the counts are read back by crb_slab_migration_import together with the
+        // arrival counts (ONE host synchronisation per step instead of two)
+        s->mig_counts_pending = true;
+        return 0;
+    }
     u64 cnt[2] = {0, 0};
     CU(s, cudaMemcpyAsync(cnt, s->scratch_u64, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
-    CU(s, cudaGetLastError());
     if (cnt[0] > s->mcap || cnt[1] > s->mcap)
         return fail(s, CRB_ERR_CAPACITY, "more migrating agents than migration_capacity");
     n_out[0] = cnt[0];
     n_out[1] = cnt[1];
+    s->mig_out[0] = cnt[0];
+    s->mig_out[1] = cnt[1];
     s->n_gone = cnt[0] + cnt[1];
+    return 0;
+}
+
+int crb_slab_migration_counts(const crb_sim* s, uint64_t n_out[2]) {
+    if (!s || !n_out) return CRB_ERR_INVALID_ARG;
+    n_out[0] = s->mig_out[0];
+    n_out[1] = s->mig_out[1];
     return 0;
 }
 
@@ -1510,6 +1529,7 @@ int crb_slab_migration_import(crb_sim* s, const void* lo_buf, const void* hi_buf
     if (!s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_compute first");
     CU(s, cudaSetDevice((int)s->cfg.device));
     u64 cnt[2] = {0, 0};
+    u64 outc[2] = {0, 0};
     if (s->has_lo) {
         if (!lo_buf) return fail(s, CRB_ERR_INVALID_ARG, "lower migration buffer missing");
         CU(s, cudaMemcpyAsync(&cnt[0], lo_buf, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
@@ -1518,7 +1538,17 @@ int crb_slab_migration_import(crb_sim* s, const void* lo_buf, const void* hi_buf
         if (!hi_buf) return fail(s, CRB_ERR_INVALID_ARG, "upper migration buffer missing");
         CU(s, cudaMemcpyAsync(&cnt[1], hi_buf, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     }
+    if (s->mig_counts_pending)
+        CU(s, cudaMemcpyAsync(outc, s->scratch_u64, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
+    if (s->mig_counts_pending) {
+        s->mig_counts_pending = false;
+        if (outc[0] > s->mcap || outc[1] > s->mcap)
+            return fail(s, CRB_ERR_CAPACITY, "more migrating agents than migration_capacity");
+        s->mig_out[0] = outc[0];
+        s->mig_out[1] = outc[1];
+        s->n_gone = outc[0] + outc[1];
+    }
     if (cnt[0] > s->mcap || cnt[1] > s->mcap)
         return fail(s, CRB_ERR_CAPACITY, "more arriving agents than migration_capacity");
     if (s->n_src + cnt[0] + cnt[1] > s->cap + 2 * s->mcap)

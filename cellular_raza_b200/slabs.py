@@ -131,6 +131,15 @@ class SlabRank(DeviceSimulation):
         self._check(self._lib.crb_slab_migration_export(self._h, self._p(self.mig_out[0]), self._p(self.mig_out[1]), n))
         return int(n[0]), int(n[1])
 
+    def migration_export_async(self):
+        """enqueue only: the counts come back with the arrival counts (one host sync per step)"""
+        self._check(self._lib.crb_slab_migration_export(self._h, self._p(self.mig_out[0]), self._p(self.mig_out[1]), None))
+
+    def migration_out_counts(self):
+        n = (C.c_uint64 * 2)()
+        self._check(self._lib.crb_slab_migration_counts(self._h, n))
+        return int(n[0]), int(n[1])
+
     def migration_import(self):
         n = (C.c_uint64 * 2)()
         self._check(self._lib.crb_slab_migration_import(self._h, self._p(self.mig_in[0]), self._p(self.mig_in[1]), n))
@@ -227,9 +236,11 @@ class LocalSlabGroup:
                 self.halo_exchange()
                 for rk in self.ranks:
                     rk.compute(last)
-            outs = [rk.migration_export() for rk in self.ranks]
+            for rk in self.ranks:
+                rk.migration_export_async()
             self._exchange("mig_out", "mig_in")
             ins = [rk.migration_import() for rk in self.ranks]
+            outs = [rk.migration_out_counts() for rk in self.ranks]
             for rk, o, i in zip(self.ranks, outs, ins):
                 rk.last_migration = (*o, *i)
                 rk.finish(last)
@@ -336,9 +347,12 @@ class SlabSimulation:
             else:
                 self.halo_exchange()
                 s.compute(last)
-            out = s.migration_export()
+            # export, ncclSend/ncclRecv of the fixed-size buffers and the count read-back are all enqueued
+            # while the force pass still runs: ONE host synchronisation per step (in migration_import)
+            s.migration_export_async()
             self._exchange(s.mig_out, s.mig_in)
             inn = s.migration_import()
+            out = s.migration_out_counts()
             s.last_migration = (*out, *inn)
             s.finish(last)
 

@@ -248,7 +248,11 @@ int crb_slab_halo_import(crb_sim* sim, const void* lo_buf, const void* hi_buf);
 int crb_slab_compute(crb_sim* sim, int save_prev);
 int crb_slab_compute_interior(crb_sim* sim, int save_prev);
 int crb_slab_compute_boundary(crb_sim* sim);
+/* n_out == NULL: the export is only enqueued; its counts are read back by crb_slab_migration_import in
+ * the same host synchronisation as the arrival counts and are available from crb_slab_migration_counts
+ * afterwards (the buffers have a fixed size, so the transfer does not need the counts). */
 int crb_slab_migration_export(crb_sim* sim, void* lo_buf, void* hi_buf, uint64_t n_out[2]);
+int crb_slab_migration_counts(const crb_sim* sim, uint64_t n_out[2]);
 int crb_slab_migration_import(crb_sim* sim, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]);
 int crb_slab_finish(crb_sim* sim, int save_prev);
 

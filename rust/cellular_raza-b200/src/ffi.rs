@@ -104,6 +104,7 @@ extern "C" {
     pub fn crb_slab_compute_interior(sim: *mut crb_sim, save_prev: c_int) -> c_int;
     pub fn crb_slab_compute_boundary(sim: *mut crb_sim) -> c_int;
     pub fn crb_slab_migration_export(sim: *mut crb_sim, lo_buf: *mut c_void, hi_buf: *mut c_void, n_out: *mut u64) -> c_int;
+    pub fn crb_slab_migration_counts(sim: *const crb_sim, n_out: *mut u64) -> c_int;
     pub fn crb_slab_migration_import(sim: *mut crb_sim, lo_buf: *const c_void, hi_buf: *const c_void, n_in: *mut u64) -> c_int;
     pub fn crb_slab_finish(sim: *mut crb_sim, save_prev: c_int) -> c_int;
     // parity taps
