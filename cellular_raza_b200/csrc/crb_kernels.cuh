@@ -673,36 +673,60 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
     if (tp >= R.n) return;
     const u64 p = R.first + tp;
     const u32 i = R.tmp_idx[p];
-    const u32 v = R.newkey[i];
-    const u32 sb = R.start_new[v], se = R.start_new[v + 1];
-    const u64 my = R.sortkey[i];
+    // ---- every load of the agent's state is issued BEFORE the rank loop and before any store: the
+    // kernel is latency bound (one long-scoreboard stall per load otherwise), so the bytes in flight per
+    // thread decide the bandwidth (12-18 independent 8-byte loads instead of one at a time)
+    double bp[3], bv[3], bx[3], bw[3], b0x[3], b0v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c < R.D) {
+            bp[c] = __ldg(&R.B.pos[c][i]);
+            bv[c] = __ldg(&R.B.vel[c][i]);
+            bx[c] = __ldg(&R.B.h1x[c][i]);
+            bw[c] = __ldg(&R.B.h1v[c][i]);
+            if (R.save_prev) {
+                b0x[c] = __ldg(&R.B.h0x[c][i]);
+                b0v[c] = __ldg(&R.B.h0v[c][i]);
+            }
+        }
+    }
+    const u8 hl = __ldg(&R.B.hlen[i]);
+    const u64 id = __ldg(&R.A.id[i]);
+    const u8 sp = R.has_species ? __ldg(&R.A.species[i]) : (u8)0;
+    const u32 v = __ldg(&R.newkey[i]);
+    const u64 my = __ldg(&R.sortkey[i]);
+    const u32 sb = __ldg(&R.start_new[v]), se = __ldg(&R.start_new[v + 1]);
+    // stable rank inside the voxel's segment
     u32 rank = 0;
-    for (u32 q = sb; q < se; ++q) rank += (R.sortkey[R.tmp_idx[q]] < my) ? 1u : 0u;
+    for (u32 q = sb; q < se; ++q) rank += (__ldg(&R.sortkey[__ldg(&R.tmp_idx[q])]) < my) ? 1u : 0u;
     const u64 d = (u64)sb + rank;
     R.key_out[d] = v;
     if (R.slot_of_src) R.slot_of_src[i] = (u32)d;
-    for (int c = 0; c < R.D; ++c) {
-        R.Y.pos[c][d] = R.B.pos[c][i];
-        R.Y.vel[c][d] = R.B.vel[c][i];
-        R.Y.h1x[c][d] = R.B.h1x[c][i];
-        R.Y.h1v[c][d] = R.B.h1v[c][i];
-        if (R.save_prev) {
-            R.Y.h0x[c][d] = R.B.h0x[c][i];
-            R.Y.h0v[c][d] = R.B.h0v[c][i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c < R.D) {
+            R.Y.pos[c][d] = bp[c];
+            R.Y.vel[c][d] = bv[c];
+            R.Y.h1x[c][d] = bx[c];
+            R.Y.h1v[c][d] = bw[c];
+            if (R.save_prev) {
+                R.Y.h0x[c][d] = b0x[c];
+                R.Y.h0v[c][d] = b0v[c];
+            }
         }
     }
     {
-        const double p0 = R.B.pos[0][i], p1 = R.B.pos[1][i];
-        const double p2 = R.D == 3 ? R.B.pos[2][i] : R.mn[2];
+        const double p0 = bp[0], p1 = bp[1];
+        const double p2 = R.D == 3 ? bp[2] : R.mn[2];
         R.Y.posf[d] = make_float4((float)(p0 - R.mn[0]), (float)(p1 - R.mn[1]), (float)(p2 - R.mn[2]),
                                   __uint_as_float(v));
-        // species | (voxel index along the fastest axis & 0xff) << 8: what the drain of k_force_tile
+        // species | (voxel index along the fastest axis & 0xff) << 8: what the drain of the tile kernels
         // needs besides the voxel index (one 4-byte word per staged candidate)
-        R.Y.meta[d] = (u32)(R.has_species ? R.A.species[i] : 0) | (((v % R.n2) & 0xffu) << 8);
+        R.Y.meta[d] = (u32)sp | (((v % R.n2) & 0xffu) << 8);
     }
-    R.Y.hlen[d] = R.B.hlen[i];
-    R.Y.id[d] = R.A.id[i];
-    if (R.has_species) R.Y.species[d] = R.A.species[i];
+    R.Y.hlen[d] = hl;
+    R.Y.id[d] = id;
+    if (R.has_species) R.Y.species[d] = sp;
     for (int k = 0; k < R.n_mp; ++k) R.Y.mp[k][d] = R.A.mp[k][i];
     for (int k = 0; k < R.n_ip; ++k) R.Y.ip[k][d] = R.A.ip[k][i];
 }
