@@ -654,13 +654,34 @@ __global__ void __launch_bounds__(256) k_rod_reorder(const RodReorderParams R) {
     for (u32 q = sb; q < se; ++q) rank += (R.sortkey[R.tmp_idx[q]] < my) ? 1u : 0u;
     const u64 d = (u64)sb + rank;
     R.key_out[d] = v;
-    for (int w = 0; w < R.W; ++w) {
-        const u64 oi = (u64)w * R.cap + i, od = (u64)w * R.cap + d;
-        R.Y.pos[od] = R.B.pos[oi];
-        R.Y.vel[od] = R.B.vel[oi];
-        R.Y.h1x[od] = R.B.h1x[oi];
-        R.Y.h1v[od] = R.B.h1v[oi];
-        if (R.save_prev) {
+    // latency-bound gather: groups of 6 planes x 4 arrays = 24 independent loads in flight per thread
+    // before the first store (one long-scoreboard stall per group instead of one per load)
+    for (int w0 = 0; w0 < R.W; w0 += 6) {
+        double a[6], b[6], c[6], e[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (w0 + k < R.W) {
+                const u64 oi = (u64)(w0 + k) * R.cap + i;
+                a[k] = __ldg(&R.B.pos[oi]);
+                b[k] = __ldg(&R.B.vel[oi]);
+                c[k] = __ldg(&R.B.h1x[oi]);
+                e[k] = __ldg(&R.B.h1v[oi]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (w0 + k < R.W) {
+                const u64 od = (u64)(w0 + k) * R.cap + d;
+                R.Y.pos[od] = a[k];
+                R.Y.vel[od] = b[k];
+                R.Y.h1x[od] = c[k];
+                R.Y.h1v[od] = e[k];
+            }
+        }
+    }
+    if (R.save_prev) {
+        for (int w = 0; w < R.W; ++w) {
+            const u64 oi = (u64)w * R.cap + i, od = (u64)w * R.cap + d;
             R.Y.h0x[od] = R.B.h0x[oi];
             R.Y.h0v[od] = R.B.h0v[oi];
         }
