@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-CRB_ABI_VERSION = 3
+CRB_ABI_VERSION = 4
 CRB_MAX_DIM = 3
 
 # crb_status
@@ -37,6 +37,9 @@ CRB_INT_CELL_SORTING_BENCH = 1
 CRB_INT_MORSE = 2
 CRB_INT_BOUND_LJ = 3
 CRB_INT_MIE = 4
+CRB_INT_NONE = 5
+CRB_DOMAIN_FORCE_NONE = 0
+CRB_DOMAIN_FORCE_SPRING = 1
 # crb_pair_weight_mode
 CRB_WEIGHT_CHILI = 0
 CRB_WEIGHT_PHYSICAL = 1
@@ -52,6 +55,7 @@ N_INTER_PARAMS = {
     CRB_INT_MORSE: 4,
     CRB_INT_BOUND_LJ: 4,
     CRB_INT_MIE: 6,
+    CRB_INT_NONE: 0,
 }
 
 
@@ -80,6 +84,10 @@ class CrbConfig(C.Structure):
         ("capacity", C.c_uint64),
         ("ghost_capacity", C.c_uint64),
         ("migration_capacity", C.c_uint64),
+        ("domain_force_kind", C.c_uint32),
+        ("reserved0", C.c_uint32),
+        ("domain_force_strength", C.c_double * CRB_MAX_DIM),
+        ("domain_force_anchor", C.c_double * CRB_MAX_DIM),
     ]
 
 

@@ -191,7 +191,17 @@ class Agent:
     is in the reference (cell_sorting/src/main.rs:99-105)."""
 
     mechanics: _Mechanics
-    interaction: object
+    interaction: object = None  # None: an agent without the Interaction aspect (domain_force_spring.rs:70-75)
+
+
+@dataclass
+class SpringDomainForce:
+    """``SubDomainForce::calculate_custom_force`` of cellular_raza/tests/domain_force_spring.rs:56-68, one
+    strength and anchor per axis: ``force[c] = -strength[c] * (pos[c] - anchor[c])``.  The reference lets
+    the user write any force law; the device offers this closed form (include/crb.h crb_domain_force_kind)."""
+
+    strength: Sequence[float]
+    anchor: Sequence[float] | None = None
 
 
 # ---- time (cellular_raza-core/src/time.rs) ---------------------------------------------------------
@@ -290,13 +300,13 @@ def _pack(agents: Sequence[Agent], dim: int):
     if n == 0:
         raise ValueError("no agents")
     mk = {type(a.mechanics).KIND for a in agents}
-    ik = {type(a.interaction).KIND for a in agents}
+    ik = {(_abi.CRB_INT_NONE if a.interaction is None else type(a.interaction).KIND) for a in agents}
     if len(mk) != 1 or len(ik) != 1:
         raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "all agents must use the same mechanics and interaction types")
     pos = np.array([a.mechanics.pos for a in agents], dtype=np.float64).reshape(n, dim)
     vel = np.array([a.mechanics.velocity() for a in agents], dtype=np.float64).reshape(n, dim)
     mp = np.array([a.mechanics.row() for a in agents], dtype=np.float64)
-    ip = np.array([a.interaction.row() for a in agents], dtype=np.float64)
+    ip = np.array([([] if a.interaction is None else a.interaction.row()) for a in agents], dtype=np.float64).reshape(n, -1)
     sp = np.array([getattr(a.interaction, "species", 0) for a in agents], dtype=np.uint8)
     return mk.pop(), ik.pop(), pos, vel, mp, ip, sp
 
@@ -305,15 +315,22 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
                    aspects: Sequence[str] = ("Mechanics", "Interaction"), *,
                    mechanics_solver_order: int = 2, determinism: bool = True,
                    pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI, noise_mode: int | None = None,
-                   noise_table: np.ndarray | None = None, device: int = 0) -> StorageAccess:
+                   noise_table: np.ndarray | None = None, device: int = 0,
+                   domain_force: SpringDomainForce | None = None) -> StorageAccess:
     """``run_simulation!`` of the B200 backend.  ``settings.n_threads`` is chili's subdomain count: it
     does not create threads here, it selects the pair weights chili applies for that decomposition
     (SURVEY.md finding 2); ``pair_weight_mode=CRB_WEIGHT_PHYSICAL`` applies both halves everywhere."""
-    unsupported = set(aspects) - {"Mechanics", "Interaction"}
-    if unsupported:
+    unsupported = set(aspects) - {"Mechanics", "Interaction", "DomainForce"}
+    if unsupported or "Mechanics" not in aspects:
         raise SimulationError(_abi.CRB_ERR_INVALID_ARG, f"aspects {sorted(unsupported)} are outside the hot path (SURVEY.md §8)")
+    if ("DomainForce" in aspects) != (domain_force is not None):
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "aspect DomainForce needs domain_force=SpringDomainForce(...) and vice versa")
     dim = domain.dim
+    if "Interaction" not in aspects:
+        agents = [Agent(a.mechanics, None) for a in agents]
     mk, ik, pos, vel, mp, ip, sp = _pack(agents, dim)
+    if ("Interaction" in aspects) == (ik == _abi.CRB_INT_NONE):
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "aspect Interaction needs agents with an interaction")
     if noise_mode is None:
         noise_mode = _abi.CRB_NOISE_NONE if mk == _abi.CRB_MECH_NEWTON_DAMPED else (
             _abi.CRB_NOISE_TABLE if noise_table is not None else _abi.CRB_NOISE_PHILOX)
@@ -321,7 +338,10 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
                       n_voxels=domain.n_voxels, dx=domain.dx, dt=settings.time.dt, capacity=len(agents),
                       solver_order=mechanics_solver_order, pair_weight_mode=pair_weight_mode,
                       ref_n_subdomains=max(settings.n_threads, 1), noise_mode=noise_mode,
-                      rng_seed=domain.rng_seed, device=device)
+                      rng_seed=domain.rng_seed, device=device,
+                      domain_force_kind=_abi.CRB_DOMAIN_FORCE_SPRING if domain_force is not None else _abi.CRB_DOMAIN_FORCE_NONE,
+                      domain_force_strength=None if domain_force is None else domain_force.strength,
+                      domain_force_anchor=None if domain_force is None else domain_force.anchor)
     sim = DeviceSimulation(cfg)
     try:
         sim.set_agents(pos, vel, mp, ip, sp)

@@ -229,6 +229,11 @@ KParams make_params(crb_sim* s) {
     P.weight_mode = (int)s->cfg.pair_weight_mode;
     P.noise_mode = (int)s->cfg.noise_mode;
     P.save_prev = 0;
+    P.dforce = (int)s->cfg.domain_force_kind;
+    for (int d = 0; d < 3; ++d) {
+        P.dk[d] = d < s->D ? s->cfg.domain_force_strength[d] : 0.0;
+        P.dx0[d] = d < s->D ? s->cfg.domain_force_anchor[d] : 0.0;
+    }
     return P;
 }
 
@@ -260,6 +265,7 @@ void launch_force_d(crb_sim* s, const KParams& P, bool force_only) {
         case CRB_INT_MORSE: launch_force_u<D, CRB_INT_MORSE>(s, P, force_only); break;
         case CRB_INT_BOUND_LJ: launch_force_u<D, CRB_INT_BOUND_LJ>(s, P, force_only); break;
         case CRB_INT_MIE: launch_force_u<D, CRB_INT_MIE>(s, P, force_only); break;
+        case CRB_INT_NONE: launch_force_u<D, CRB_INT_NONE>(s, P, force_only); break;
     }
 }
 
@@ -282,6 +288,7 @@ void plan_tile(crb_sim* s) {
     s->tile_ok = false;
     s->tile2_ok = false;
     if (!s->uniform || s->n == 0 || s->kernel_choice == 1) return;
+    if (s->cfg.interaction_kind == CRB_INT_NONE) return;  // no pair forces: the per-agent kernel integrates
     // the tile kernel evaluates the species potential without its upper clamp (acts only for R1 + R2 < 0)
     if ((s->cfg.interaction_kind == CRB_INT_CELL_SORTING || s->cfg.interaction_kind == CRB_INT_CELL_SORTING_BENCH) &&
         s->uni.ip[0] < 0.0)
@@ -606,6 +613,7 @@ uint32_t crb_n_inter_params(uint32_t kind) {
         case CRB_INT_MORSE: return 4;
         case CRB_INT_BOUND_LJ: return 4;
         case CRB_INT_MIE: return 6;
+        case CRB_INT_NONE: return 0;
     }
     return 0;
 }
@@ -686,8 +694,12 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         if (cfg->noise_mode != CRB_NOISE_NONE)
             return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: only CRB_NOISE_NONE (diffusion_constant 0)");
     }
-    if (cfg->interaction_kind > CRB_INT_MIE)
+    if (cfg->interaction_kind > CRB_INT_NONE)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
+    if (cfg->domain_force_kind > CRB_DOMAIN_FORCE_SPRING)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown domain_force_kind");
+    if (rods && cfg->domain_force_kind != CRB_DOMAIN_FORCE_NONE)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: the DomainForce aspect is not implemented");
     if (cfg->solver_order > 2)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "solver_order must be 0, 1 or 2");
     if (cfg->world_size == 0 || cfg->rank >= cfg->world_size)

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
                     }
                     force_from_global<D, INTER>(P, i, v, X + a, Y + b, z, xi, acc);
                     if constexpr (FORCE_ONLY) {
+                        add_domain_force<D>(P, xi, acc);
 #pragma unroll
                         for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
                     } else {
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
             if (valid) {
                 if (t.calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
                 if constexpr (FORCE_ONLY) {
+                    add_domain_force<D>(P, t.x, t.acc);
 #pragma unroll
                     for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = t.acc[c];
                 } else {

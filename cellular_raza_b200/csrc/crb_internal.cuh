@@ -103,6 +103,9 @@ struct KParams {
     int* err;         // [0] status, [1] latch flag, [2..3] agent id
     double dt;
     int mech, inter, order, weight_mode, noise_mode, save_prev;
+    // DomainForce aspect (crb_domain_force_kind): linear spring -dk[c] * (pos[c] - dx0[c])
+    int dforce;
+    double dk[3], dx0[3];
 };
 
 // ---- slab exchange buffers ----------------------------------------------------------

@@ -213,6 +213,26 @@ struct Pot<CRB_INT_MIE> {
     }
 };
 
+// aspects without Interaction: no pair forces (the neighbour loops are skipped at compile time)
+template <>
+struct Pot<CRB_INT_NONE> {
+    static constexpr int NI = 0;
+    static constexpr bool kUsesSpecies = false;
+    __device__ __forceinline__ void init(const double*) {}
+    __device__ __forceinline__ double coef(double, double, bool, int*) const { return 0.0; }
+};
+
+// SubDomainBox::calculate_custom_domain_force (chili/update_mechanics.rs:248-274): the force of the
+// subdomain on one agent is ADDED to the pair forces accumulated so far (AuxStorage::add_force).
+// CRB_DOMAIN_FORCE_SPRING = cellular_raza/tests/domain_force_spring.rs:56-68, same operation order.
+template <int D>
+__device__ __forceinline__ void add_domain_force(const KParams& P, const double* x, double* f) {
+    if (P.dforce == CRB_DOMAIN_FORCE_SPRING) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) f[c] = __dadd_rn(f[c], __dmul_rn(-P.dk[c], __dsub_rn(x[c], P.dx0[c])));
+    }
+}
+
 // coefficient as the tile kernel evaluates it (same arithmetic; cell sorting without the upper clamp)
 template <int INTER>
 __device__ __forceinline__ double coef_tile(const Pot<INTER>& p, double r2, double ext_radius,
@@ -309,9 +329,13 @@ __device__ __forceinline__ AgentDyn<D> load_agent_dyn(const KParams& P, const u6
 template <int D, bool UNIFORM>
 __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, const u32 v,
                                                 const u32 own_lo, const int i0, const int i1,
-                                                const int i2, const double* xi, const double* acc,
+                                                const int i2, const double* xi, const double* acc_pairs,
                                                 const AgentDyn<D>& dyn) {
     const Grid& g = P.g;
+    double acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = acc_pairs[c];
+    add_domain_force<D>(P, xi, acc);  // aspect DomainForce (no-op when dforce == NONE)
     const int n1 = g.ng[1], n2 = g.ng[2];
     // ---- A7: Mechanics::calculate_increment / get_random_contribution ---------------------------
     double mp[CRB_MAX_MECH_PARAMS];
@@ -502,6 +526,7 @@ __global__ void __launch_bounds__(kForceThreads)
     const int z_lo = i2 > 0 ? i2 - 1 : 0;
     const int z_hi = i2 + 1 < n2 ? i2 + 1 : n2 - 1;
     for (int d0 = -1; d0 <= 1; ++d0) {
+        if (INTER == CRB_INT_NONE) break;  // aspects without Interaction
         const int X = i0 + d0;
         if (X < 0 || X >= g.L0) continue;
         for (int d1 = -1; d1 <= 1; ++d1) {
@@ -547,6 +572,7 @@ __global__ void __launch_bounds__(kForceThreads)
     if (calc_flag) latch_error(P.err, CRB_ERR_CALC, P.A.id[i]);
 
     if constexpr (FORCE_ONLY) {
+        add_domain_force<D>(P, xi, acc);
 #pragma unroll
         for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = acc[c];
     } else {

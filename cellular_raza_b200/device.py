@@ -41,6 +41,9 @@ def make_config(
     rng_seed: int = 0,
     device: int = 0,
     rod_n_vertices: int = 0,
+    domain_force_kind: int = _abi.CRB_DOMAIN_FORCE_NONE,
+    domain_force_strength=None,
+    domain_force_anchor=None,
 ) -> CrbConfig:
     cfg = CrbConfig()
     cfg.abi_version = _abi.CRB_ABI_VERSION
@@ -63,6 +66,10 @@ def make_config(
     cfg.dt = float(dt)
     cfg.rng_seed = rng_seed
     cfg.capacity = int(capacity)
+    cfg.domain_force_kind = domain_force_kind
+    for i in range(dim):
+        cfg.domain_force_strength[i] = float(domain_force_strength[i]) if domain_force_strength is not None else 0.0
+        cfg.domain_force_anchor[i] = float(domain_force_anchor[i]) if domain_force_anchor is not None else 0.0
     return cfg
 
 

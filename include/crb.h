@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 3
+#define CRB_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------------------------- */
 typedef enum crb_status {
@@ -74,8 +74,21 @@ typedef enum crb_interaction_kind {
                                        cellular_raza-benchmarks/src/cell_sorting.rs:79-86        */
     CRB_INT_MORSE = 2,              /* [radius, potential_stiffness, cutoff, strength]  :151-260 */
     CRB_INT_BOUND_LJ = 3,           /* [epsilon, sigma, bound, cutoff]                  :122-138 */
-    CRB_INT_MIE = 4                 /* [radius, strength, bound, cutoff, en, em]        :345-389 */
+    CRB_INT_MIE = 4,                /* [radius, strength, bound, cutoff, en, em]        :345-389 */
+    CRB_INT_NONE = 5                /* aspects without Interaction (e.g. [Mechanics, DomainForce]): no
+                                       pair forces, no parameters                                 */
 } crb_interaction_kind;
+
+/* DomainForce aspect: SubDomainBox::calculate_custom_domain_force (chili/update_mechanics.rs:248-274)
+ * adds SubDomainForce::calculate_custom_force(pos, vel, info) of the subdomain to every agent's force in
+ * step 1 (run_sim.rs:276-278).  That function is user code in the reference; the closed device set
+ * offers the linear spring of the reference's own known-answer test
+ * (cellular_raza/tests/domain_force_spring.rs:56-68):
+ *     force[c] = -domain_force_strength[c] * (pos[c] - domain_force_anchor[c]). */
+typedef enum crb_domain_force_kind {
+    CRB_DOMAIN_FORCE_NONE = 0,
+    CRB_DOMAIN_FORCE_SPRING = 1
+} crb_domain_force_kind;
 
 /* How the two half-forces of a pair are weighted (SURVEY.md finding 2).
  * CHILI reproduces cellular_raza-core/src/backend/chili/update_mechanics.rs:206-234 as written:
@@ -126,6 +139,10 @@ typedef struct crb_config {
     uint64_t capacity;              /* max number of OWNED agents resident on this device        */
     uint64_t ghost_capacity;        /* slabs: max agents of one boundary plane (0 = 1.5 x mean)  */
     uint64_t migration_capacity;    /* slabs: max agents crossing one slab face per step (0=auto)*/
+    uint32_t domain_force_kind;     /* crb_domain_force_kind (aspect DomainForce)                */
+    uint32_t reserved0;
+    double domain_force_strength[CRB_MAX_DIM];
+    double domain_force_anchor[CRB_MAX_DIM];
 } crb_config;
 
 typedef struct crb_sim crb_sim; /* opaque */

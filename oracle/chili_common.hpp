@@ -45,6 +45,7 @@ inline uint32_t n_inter_params(uint32_t kind) {
         case CRB_INT_MORSE: return 4;
         case CRB_INT_BOUND_LJ: return 4;
         case CRB_INT_MIE: return 6;
+        case CRB_INT_NONE: return 0;
     }
     return 0;
 }

@@ -614,13 +614,33 @@ void sort_step_2(Oracle& o, uint64_t s) {
     }
 }
 
+// SubDomainBox::calculate_custom_domain_force (chili/update_mechanics.rs:248-274), appended to step 1
+// by the DomainForce aspect (run_sim.rs:276-278): every cell of the subdomain, voxels ascending, gets
+// SubDomainForce::calculate_custom_force(pos, vel, info) added to its force.  The force law is user code
+// in the reference; CRB_DOMAIN_FORCE_SPRING restates cellular_raza/tests/domain_force_spring.rs:56-68
+// (force_x = -spring_strength * (pos.x - 0.0), one strength and anchor per axis here).
+void domain_force_step(Oracle& o, uint64_t s) {
+    if (o.cfg.domain_force_kind != CRB_DOMAIN_FORCE_SPRING) return;
+    const uint64_t v_lo = o.smap.first_voxel(s), v_hi = o.smap.first_voxel(s + 1);
+    for (uint64_t v = v_lo; v < v_hi; ++v)
+        for (Cell& c : o.vox[v])
+            for (int i = 0; i < o.D; ++i) {
+                const double f = -o.cfg.domain_force_strength[i] * (c.pos[i] - o.cfg.domain_force_anchor[i]);
+                c.force[i] += f;
+                c.abs_sum += std::fabs(f);
+            }
+}
+
 bool run_forces(Oracle& o) {
     const int64_t S = (int64_t)o.smap.n_sub;
     std::atomic<int> ok{1};
+    const bool pairs = o.cfg.interaction_kind != CRB_INT_NONE;  // aspects without Interaction
     parallel_for(S, o.n_threads, [&](int64_t s) {
-        if (!step_1(o, (uint64_t)s)) ok = 0;
+        if (pairs && !step_1(o, (uint64_t)s)) ok = 0;
+        domain_force_step(o, (uint64_t)s);
     });
     if (!ok) return false;
+    if (!pairs) return true;
     parallel_for(S, o.n_threads, [&](int64_t s) {
         if (!step_2(o, (uint64_t)s)) ok = 0;
     });

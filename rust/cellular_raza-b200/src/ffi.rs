@@ -1,9 +1,9 @@
-//! `extern "C"` block mirroring include/crb.h 1:1 (ABI version 3).  Replaces the shape of
+//! `extern "C"` block mirroring include/crb.h 1:1 (ABI version 4).  Replaces the shape of
 //! cellular_raza-core/src/backend/cara/mod.rs:5-62 (`#[repr(C)] Runner` + `extern "C"`).
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const CRB_ABI_VERSION: u32 = 3;
+pub const CRB_ABI_VERSION: u32 = 4;
 
 pub const CRB_OK: c_int = 0;
 pub const CRB_ERR_CALC: c_int = -1;
@@ -26,6 +26,10 @@ pub const CRB_INT_CELL_SORTING_BENCH: u32 = 1;
 pub const CRB_INT_MORSE: u32 = 2;
 pub const CRB_INT_BOUND_LJ: u32 = 3;
 pub const CRB_INT_MIE: u32 = 4;
+pub const CRB_INT_NONE: u32 = 5;
+
+pub const CRB_DOMAIN_FORCE_NONE: u32 = 0;
+pub const CRB_DOMAIN_FORCE_SPRING: u32 = 1;
 
 pub const CRB_WEIGHT_CHILI: u32 = 0;
 pub const CRB_WEIGHT_PHYSICAL: u32 = 1;
@@ -58,6 +62,10 @@ pub struct crb_config {
     pub capacity: u64,
     pub ghost_capacity: u64,
     pub migration_capacity: u64,
+    pub domain_force_kind: u32,
+    pub reserved0: u32,
+    pub domain_force_strength: [f64; 3],
+    pub domain_force_anchor: [f64; 3],
 }
 
 #[repr(C)]

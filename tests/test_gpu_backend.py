@@ -83,3 +83,23 @@ def test_snapshot_async_equals_blocking_download(crb_lib):
     with pytest.raises(cr.SimulationError):
         sim.snapshot_wait(t1)
     sim.close()
+
+
+def test_domain_force_spring_like_reference_test(crb_lib):
+    """cellular_raza/tests/domain_force_spring.rs:76-117 through run_simulation with aspects
+    [Mechanics, DomainForce]: x(t) = x0 cos(omega t) within 1e-3 at every saved iteration."""
+    k, mass, dt, x0 = 0.0032, 0.5, 0.001, 10.0
+    domain = cr.CartesianCuboid.from_boundaries_and_n_voxels([-77.0] * 2, [77.0] * 2, [3, 3])
+    settings = cr.Settings(1, cr.FixedStepsize.from_partial_save_interval(0.0, dt, 10.0, 0.1),
+                           cr.StorageBuilder(priority=["Memory"]))
+    agents = [cr.Agent(cr.NewtonDamped2D([x0, 0.0], [0.0, 0.0], 0.0, mass))]
+    acc = cr.run_simulation(domain, agents, settings, aspects=["Mechanics", "DomainForce"],
+                            domain_force=cr.SpringDomainForce([k, 0.0]))
+    hist = acc.cells.load_all_elements()
+    assert len(hist) == 101
+    omega = np.sqrt(k / mass)
+    for it, cells in hist.items():
+        (c,) = cells.values()
+        assert abs(c["pos"][0] - x0 * np.cos(omega * it * dt)) < 1e-3
+    with pytest.raises(cr.SimulationError):
+        cr.run_simulation(domain, agents, settings, aspects=["Mechanics", "DomainForce"])

@@ -188,3 +188,44 @@ def test_empty_population_and_empty_voxels(crb_lib):
     dev.step(2)
     assert dev.n_agents == 0 and dev.get_agents()[0].shape == (0, 3)
     dev.close()
+
+
+@pytest.mark.parametrize("n_threads", [1, 4])
+def test_domain_force_with_interaction(oracle_lib, crb_lib, n_threads):
+    """aspects [Mechanics, Interaction, DomainForce]: the spring of domain_force_spring.rs:56-68 (per-axis
+    strengths, anchor at the domain centre) on top of the cell_sorting pair forces — forces 1e-12 (the
+    tile kernels add it in their fused epilogue), 100-step trajectory 1e-9, cell lists bit-exact."""
+    w = workloads.cell_sorting(n_threads=n_threads)
+    kw = dict(domain_force_kind=_abi.CRB_DOMAIN_FORCE_SPRING, domain_force_strength=[0.02, 0.0, 0.035],
+              domain_force_anchor=[55.0, 55.0, 55.0])
+    dev, ora = parity.make_pair(w, n_threads_oracle=n_threads, **kw)
+    err, fd, fo = parity.force_errors(dev, ora)
+    assert err.max() <= FORCE_TOL
+    plain, _ = parity.make_pair(w, n_threads_oracle=n_threads)[0], None
+    f0 = plain.debug_forces()[np.argsort(plain.get_agents()[2])]
+    assert np.abs(fd - f0).max() > 1e-3, "the domain force did not act"
+    plain.close()
+    dev.step(100)
+    ora.step(100)
+    perr, _, key_diff = parity.state_errors(dev, ora, 110.0)
+    assert perr <= 1e-9 and not key_diff.any()
+    parity.assert_same_membership(dev, ora)
+    dev.close()
+    ora.close()
+
+
+def test_no_interaction_aspect(oracle_lib, crb_lib):
+    """CRB_INT_NONE + spring: several free particles oscillate independently; device == oracle to 1e-12."""
+    from test_oracle_known_answers import _spring_workload
+
+    w = _spring_workload(n_extra=7)
+    dev, ora = parity.make_pair(w)
+    assert dev.force_kernel_name == "k_force_integrate"
+    assert np.array_equal(dev.debug_forces()[np.argsort(dev.get_agents()[2])],
+                          ora.forces()[0][np.argsort(ora.get_agents()[2])])
+    dev.step(500)
+    ora.step(500)
+    perr, verr, key_diff = parity.state_errors(dev, ora, 154.0)
+    assert perr <= 1e-13 and verr <= 1e-13 and not key_diff.any()
+    dev.close()
+    ora.close()

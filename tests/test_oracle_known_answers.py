@@ -306,3 +306,34 @@ def test_potentials_known_values(oracle_lib):
     # benchmark copy has the opposite sign (cellular_raza-benchmarks/src/cell_sorting.rs:79-86)
     fe_, _ = oracle_lib.pair_force(_abi.CRB_INT_CELL_SORTING_BENCH, [0, 0, 0.0], [0, 0, 15.0], [6.0, 2.0, 1.5], 0, 6.0, 0)
     np.testing.assert_array_equal(fe_, -fa)
+
+
+def _spring_workload(n_extra: int = 0):
+    """cellular_raza/tests/domain_force_spring.rs:76-117: ONE NewtonDamped2D particle (damping 0, mass 0.5)
+    at x0 = 10 in [-77, 77]^2 with 3 x 3 voxels, dt 1e-3, aspects [Mechanics, DomainForce] with
+    force_x = -0.0032 * (pos.x - 0)."""
+    from cellular_raza_b200.workloads import Workload
+
+    n = 1 + n_extra
+    pos = np.zeros((n, 2))
+    pos[:, 0] = 10.0 + 3.0 * np.arange(n)
+    cfg = dict(dim=2, mechanics_kind=_abi.CRB_MECH_NEWTON_DAMPED, interaction_kind=_abi.CRB_INT_NONE,
+               domain_min=[-77.0] * 2, domain_max=[77.0] * 2, n_voxels=[3] * 2, dx=[154.0 / 3.0] * 2, dt=1e-3,
+               ref_n_subdomains=1, solver_order=2, domain_force_kind=_abi.CRB_DOMAIN_FORCE_SPRING,
+               domain_force_strength=[0.0032, 0.0], domain_force_anchor=[0.0, 0.0])
+    return Workload("spring", cfg, pos, np.zeros((n, 2)), np.tile([0.0, 0.5], (n, 1)), np.zeros((n, 0)))
+
+
+def test_domain_force_spring(oracle_lib):
+    # domain_force_spring.rs:107-116: |x(t) - x0 cos(omega t)| < 1e-3 at every saved iteration (every 100
+    # steps) over 10,000 steps, omega = sqrt(k / m)
+    w = _spring_workload()
+    o = oracle_lib.ChiliOracle(w.config())
+    o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    omega = np.sqrt(0.0032 / 0.5)
+    f, _ = o.forces()
+    assert f[0, 0] == -0.0032 * 10.0 and f[0, 1] == 0.0
+    for it in range(100, 10_001, 100):
+        o.step(100)
+        x = o.get_agents()[0][0, 0]
+        assert abs(x - 10.0 * np.cos(omega * it * 1e-3)) < 1e-3
