@@ -43,19 +43,26 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells-per-gpu", type=int, default=8_000_000)
+    ap.add_argument("--cells-per-gpu", type=int, default=None,
+                    help="agents per GPU (default 8 M; bacterial_rods 2 M = configs[3]; as-shipped 1,600)")
     ap.add_argument("--density", type=float, default=7.1, help="agents per voxel")
     ap.add_argument("--n-threads-ref", type=int, default=1,
                     help="chili n_threads whose pair weights are reproduced (CRB_WEIGHT_CHILI)")
     ap.add_argument("--cpu-sample-cells", type=int, default=1_000_000)
-    ap.add_argument("--workload", default="cell_sorting", choices=["cell_sorting", "brownian_morse", "bacterial_rods"],
+    ap.add_argument("--cpu-sample-seconds", type=float, default=12.0,
+                    help="cpu_baseline: CPU work of the bounded sample (steps chosen from one probe step)")
+    ap.add_argument("--workload", default="cell_sorting", choices=["cell_sorting", "brownian_morse", "bacterial_rods", "cell_sorting_as_shipped"],
                     help="cell_sorting = the headline (BASELINE.json configs[1]/[4]); brownian_morse = configs[2] "
-                         "(N > 1: ONE cube of cells-per-gpu x N agents cut into slabs); bacterial_rods = configs[3] (1 GPU)")
+                         "(N > 1: ONE cube of cells-per-gpu x N agents cut into slabs); bacterial_rods = configs[3] (1 GPU); "
+                         "cell_sorting_as_shipped = configs[0] (1,600 cells, latency-bound, 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: halo exchange before the force pass instead of behind its interior planes")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.cells_per_gpu is None:
+        args.cells_per_gpu = {"bacterial_rods": 2_000_000, "cell_sorting_as_shipped": 1600}.get(args.workload, 8_000_000)
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -137,25 +144,49 @@ def ncu_traffic(cells: int, kernel: str):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps: int, warmup: int, sample_cells: int):
+def cpu_reference_run(args, steps: int, warmup: int, sample_cells: int, target_s: float | None = None):
     """Times the CPU restatement of chili (oracle/) on the host cores: one emulated chili subdomain
     per core, `sample_cells` agents at the workload's density.  The Rust reference itself cannot be
-    built in this image, so kind = "port"."""
+    built in this image, so kind = "port".  With `target_s` the number of timed steps is chosen from
+    one probe step so that the sample is about that many seconds of CPU work (bounded sample)."""
     from cellular_raza_b200 import workloads
-    from oracle.chili_oracle import ChiliOracle
 
     cores = host_cores()
-    w = workloads.cell_sorting_scaled(sample_cells, args.density, n_threads=cores)
-    o = ChiliOracle(w.config(), n_threads=cores)
-    o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+    if args.workload == "bacterial_rods":
+        from oracle.rods_oracle import RodsOracle
+
+        side = max(int(round((sample_cells / 5) ** 0.5)), 1)
+        w = workloads.bacterial_rods(side, side, rods_per_tile=5, n_threads=cores, spring_length_range=(4.0, 6.0))
+        o = RodsOracle(w.config(), n_threads=cores)
+        o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+        shape = f"{w.n} rods ({side}x{side} tiles, same density)"
+    else:
+        from oracle.chili_oracle import ChiliOracle
+
+        if args.workload == "brownian_morse":
+            w = workloads.brownian_morse_scaled(sample_cells, 4.0, n_threads=cores, noise_mode=0)
+        elif args.workload == "cell_sorting_as_shipped":
+            cores = min(cores, 4)  # main.rs:22 ships n_threads = 4
+            w = workloads.cell_sorting(n_threads=cores)
+        else:
+            w = workloads.cell_sorting_scaled(sample_cells, args.density, n_threads=cores)
+        o = ChiliOracle(w.config(), n_threads=cores)
+        o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+        shape = f"{w.n} cells ({w.cfg_kwargs['n_voxels'][0]}^3 voxels, same density)"
     if warmup:
         o.step(warmup)
+    if target_s is not None:
+        t0 = time.perf_counter()
+        o.step(1)
+        probe = max(time.perf_counter() - t0, 1e-6)
+        steps = int(min(max(round(target_s / probe), 2), 20000))
+    n_before = w.n if not hasattr(o, "n_agents") else o.n_agents
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
-    val = w.n * steps / dt
-    sample = (f"{w.n} cells ({w.cfg_kwargs['n_voxels'][0]}^3 voxels, same density) x {steps} steps, "
-              f"{cores} threads = {cores} emulated chili subdomains, {dt:.1f} s")
+    n_after = w.n if not hasattr(o, "n_agents") else o.n_agents
+    val = 0.5 * (n_before + n_after) * steps / dt
+    sample = (f"{shape} x {steps} steps, {cores} threads = {cores} emulated chili subdomains, {dt:.1f} s")
     o.close()
     return val, cores, sample, dt / steps * 1e3
 
@@ -165,7 +196,11 @@ def run_reference(args):
     if rank != 0:
         return
     total = args.steps + args.warmup
+    # bounded sample: every step of this arm is one pass over `sample_cells` agents of the same workload
+    # (about 1 s on 16 host threads at 1 M cells), so that --steps K --warmup W ends within minutes
     sample_cells = args.cpu_sample_cells if total <= 30 else max(args.cpu_sample_cells // 4, 50_000)
+    if args.workload == "bacterial_rods":
+        sample_cells = min(sample_cells, 200_000)
     val, cores, sample, ms = cpu_reference_run(args, args.steps, args.warmup, sample_cells)
     line = {
         "impl": "reference",
@@ -190,6 +225,8 @@ def make_workload(args, n: int):
 
     if args.workload == "brownian_morse":
         return workloads.brownian_morse_scaled(n, 4.0, n_threads=args.n_threads_ref, noise_mode=_abi.CRB_NOISE_PHILOX)
+    if args.workload == "cell_sorting_as_shipped":
+        return workloads.cell_sorting(n_threads=max(args.n_threads_ref, 4))  # main.rs:22 ships n_threads = 4
     return workloads.cell_sorting_scaled(n, args.density, n_threads=args.n_threads_ref)
 
 
@@ -204,6 +241,18 @@ def workload_config(args) -> dict:
             "pair_weights": f"chili-as-written(n_threads={args.n_threads_ref})", "dt": 0.01,
             "l2_policy": "working set larger than L2", "decomposition": f"slab{args.gpus}" if args.gpus > 1 else "single",
         }
+    if args.workload == "cell_sorting_as_shipped":
+        return {
+            "workload": "cell_sorting as shipped (BASELINE.json configs[0]: 1,600 cells, 6^3 voxels; latency-bound)",
+            "cells_per_gpu": 1600, "cells_total": 1600, "agents_per_voxel": 7.4, "mechanics": "NewtonDamped3D",
+            "interaction": "cell_sorting species potential", "solver": "AB3 (order 2)",
+            "pair_weights": f"chili-as-written(n_threads={max(args.n_threads_ref, 4)})", "dt": 0.2,
+            "l2_policy": "working set fits L2 by construction (1,600 agents): launch-latency bound, reported not tuned",
+            "decomposition": "single",
+        }
+    if args.workload == "bacterial_rods":
+        return {"workload": "bacterial_rods (BASELINE.json configs[3])", "rods_initial": args.cells_per_gpu, "vertices": 5,
+                "aspects": "Mechanics, Interaction, Cycle, NeighborSensing", "dt_min": 0.1}
     return {
         "workload": "cell_sorting_3d_weak_scaling (BASELINE.json configs[4]; configs[1] with --cells-per-gpu 1000000)",
         "cells_per_gpu": args.cells_per_gpu, "cells_total": n_total, "agents_per_voxel": args.density,
@@ -240,6 +289,7 @@ def run_b200(args):
     if args.workload == "bacterial_rods":
         return run_rods(args, dev_id)
     w = make_workload(args, n)
+    n = w.n
     sim = DeviceSimulation(w.config(device=dev_id))
     sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
     sim.set_agents(w.pos, w.vel, None, None, w.species)
@@ -330,7 +380,7 @@ def run_b200(args):
     # ---- CPU baseline (oracle, bounded sample) ----------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference_run(args, 1, 0, min(args.cpu_sample_cells, n))
+        v, cores, sample, _ = cpu_reference_run(args, 1, 0, min(args.cpu_sample_cells, n), target_s=args.cpu_sample_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     line = {
@@ -347,6 +397,11 @@ def run_b200(args):
     sim.close()
 
 
+# per ordered candidate rod pair, 20 vertex-segment evaluations x (Morse 30 flop + nearest
+# point ~25 flop) + 25 neighbour-sensing distance checks x 9 flop (the exp is not counted)
+ROD_FLOP_PER_PAIR = 20 * (30.0 + 25.0) + 25 * 9.0
+
+
 def run_rods(args, dev_id: int):
     """BASELINE.json configs[3]: bacterial_rods (RodMechanics + RodInteraction, growth / division => the rod
     count changes inside the timed region; agent-steps = sum over steps of the current count, here
@@ -354,6 +409,7 @@ def run_rods(args, dev_id: int):
     import torch
 
     from cellular_raza_b200 import workloads
+    from cellular_raza_b200.device import measure_fp64_peak
     from cellular_raza_b200.rods import RodSimulation
 
     n = args.cells_per_gpu
@@ -366,9 +422,13 @@ def run_rods(args, dev_id: int):
     sim.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
     stream = torch.cuda.ExternalStream(sim.stream, device=dev_id)
     sim.step(max(args.warmup, 3))
+    fp64_peak, _ = measure_fp64_peak(dev_id)
+    pairs0 = sim.count_candidate_pairs()
     sampler = ClockSampler(dev_id)
     sampler.start()
     time.sleep(0.3)
+    sim.enable_timers(True)
+    sim.reset_timers()
     l0, n0 = sim.kernel_launches, sim.n_agents
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -378,8 +438,68 @@ def run_rods(args, dev_id: int):
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     n1 = sim.n_agents
+    launches = int(sim.kernel_launches - l0)
+    force_ms, force_launches = sim.stage_time_ms(0)
+    scan_ms, _ = sim.stage_time_ms(1)
+    reorder_ms, _ = sim.stage_time_ms(2)
+    divide_ms, _ = sim.stage_time_ms(4)
+    sim.enable_timers(False)
     clocks = sampler.stop()
+    pairs1 = sim.count_candidate_pairs()
     value = 0.5 * (n0 + n1) * args.steps / (ms_total * 1e-3)
+    pairs_per_launch = 0.5 * (pairs0 + pairs1)
+    force_avg_ms = force_ms / max(force_launches, 1)
+    achieved_tf = pairs_per_launch * ROD_FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "k_rod_force<5 vertices> (one thread per rod)", "bound": "fp64", "achieved": achieved_tf,
+        "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+        "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+        "traffic": ncu_traffic(n, "rod_force"), "share_of_step": force_ms / ms_total,
+        "algorithmic_flop_per_pair": ROD_FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+        "pair_forces_per_s": pairs_per_launch / (force_avg_ms * 1e-3),
+        "note": "the shipped rod density is 0.31 rods per voxel (~2 candidate rods per rod): the kernel is "
+                "dominated by the per-rod spring/curvature mechanics and by divergence, not by pair flops",
+    }
+
+    # ---- e2e: host buffers in, host buffers out, every step (the rod count is pinned by re-uploading the
+    # same n rods; positions/velocities of the previous step's first n rods are fed back) ---------------
+    e2e = None
+    if not args.no_e2e:
+        nn = w.n
+        V = 5
+        hp = torch.from_numpy(np.ascontiguousarray(w.pos)).pin_memory()
+        hv = torch.from_numpy(np.ascontiguousarray(w.vel)).pin_memory()
+        hm = torch.from_numpy(np.ascontiguousarray(w.mech_params)).pin_memory()
+        hi = torch.from_numpy(np.ascontiguousarray(w.inter_params)).pin_memory()
+        cap_out = int(nn * 1.2) + 16
+        op = torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()
+        ov = torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()
+        lib, h = sim._lib, sim._h
+        e2e_steps = args.steps
+        for k in range(2 + e2e_steps):
+            if k == 2:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            rc = lib.crb_set_agents(h, nn, hp.data_ptr(), hv.data_ptr(), hm.data_ptr(), hi.data_ptr(), None, None)
+            rc = rc or lib.crb_step(h, 1)
+            rc = rc or lib.crb_get_agents(h, cap_out, op.data_ptr(), ov.data_ptr(), None, None)
+            if rc:
+                raise RuntimeError(lib.crb_last_error(h))
+        torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t0
+        e2e = {
+            "value": nn * e2e_steps / dt_e2e, "unit": UNIT,
+            "h2d_bytes_per_step": int(nn * (2 * V * 24 + 8 * 8 + 4 * 8)), "d2h_bytes_per_step": int(nn * 2 * V * 24),
+            "ms_per_step": dt_e2e / e2e_steps * 1e3,
+            "what": "crb_set_agents(pinned host pos, vel, mech, inter rows) + crb_step(1) + crb_get_agents(host pos, vel) per step",
+        }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_run(args, 1, 0, min(args.cpu_sample_cells, 200_000, n),
+                                                target_s=args.cpu_sample_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -388,8 +508,10 @@ def run_rods(args, dev_id: int):
                    "rods_after": n1, "vertices": 5, "tiles": [side, side],
                    "aspects": "Mechanics, Interaction, Cycle, NeighborSensing", "dt_min": 0.1,
                    "l2_policy": "working set larger than L2" if w.n >= 500_000 else "working set fits L2 (small run)"},
-        "roofline": None, "cpu_baseline": None, "e2e": None,
-        "gpu_launches": int(sim.kernel_launches - l0), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks,
+        "stage_ms_per_step": {"force_integrate": force_ms / args.steps, "divide": divide_ms / args.steps,
+                              "scan": scan_ms / args.steps, "reorder": reorder_ms / args.steps},
         "note": "not the headline workload: k_rod_force is a per-rod kernel, not yet tiled (DESIGN.md §9)",
     }
     print(json.dumps(line), flush=True)

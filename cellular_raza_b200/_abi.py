@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-CRB_ABI_VERSION = 4
+CRB_ABI_VERSION = 5
 CRB_MAX_DIM = 3
 
 # crb_status
@@ -40,6 +40,7 @@ CRB_INT_MIE = 4
 CRB_INT_NONE = 5
 CRB_DOMAIN_FORCE_NONE = 0
 CRB_DOMAIN_FORCE_SPRING = 1
+CRB_DOMAIN_FORCE_ROD_GEL = 2
 # crb_pair_weight_mode
 CRB_WEIGHT_CHILI = 0
 CRB_WEIGHT_PHYSICAL = 1

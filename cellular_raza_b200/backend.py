@@ -101,6 +101,10 @@ class NewtonDamped2D(NewtonDamped3D):
     pass
 
 
+class NewtonDamped1D(NewtonDamped3D):
+    pass
+
+
 @dataclass
 class Brownian3D(_Mechanics):  # :336-357
     diffusion_constant: float = 0.0
@@ -112,6 +116,10 @@ class Brownian3D(_Mechanics):  # :336-357
 
 
 class Brownian2D(Brownian3D):
+    pass
+
+
+class Brownian1D(Brownian3D):  # used by the reference's tests/brownian_diffusion_constant_approx.rs:230-258
     pass
 
 
@@ -128,6 +136,10 @@ class Langevin3D(_Mechanics):  # :434-463
 
 
 class Langevin2D(Langevin3D):
+    pass
+
+
+class Langevin1D(Langevin3D):
     pass
 
 

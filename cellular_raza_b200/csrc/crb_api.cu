@@ -288,6 +288,7 @@ void plan_tile(crb_sim* s) {
     s->tile_ok = false;
     s->tile2_ok = false;
     if (!s->uniform || s->n == 0 || s->kernel_choice == 1) return;
+    if (s->D < 2) return;  // 1-D domains: 3 neighbour voxels, the per-agent kernel is the path
     if (s->cfg.interaction_kind == CRB_INT_NONE) return;  // no pair forces: the per-agent kernel integrates
     // the tile kernel evaluates the species potential without its upper clamp (acts only for R1 + R2 < 0)
     if ((s->cfg.interaction_kind == CRB_INT_CELL_SORTING || s->cfg.interaction_kind == CRB_INT_CELL_SORTING_BENCH) &&
@@ -479,8 +480,10 @@ int launch_force(crb_sim* s, const KParams& P, bool force_only, const PlaneRange
         return s->D == 3 ? launch_tile_d<3>(s, P, force_only, pr) : launch_tile_d<2>(s, P, force_only, pr);
     if (s->D == 3)
         launch_force_d<3>(s, P, force_only);
-    else
+    else if (s->D == 2)
         launch_force_d<2>(s, P, force_only);
+    else
+        launch_force_d<1>(s, P, force_only);  // 1-D (Brownian1D, Langevin1D, NewtonDamped1D): per-agent kernel
     return 0;
 }
 
@@ -678,8 +681,8 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     *out = nullptr;
     if (cfg->abi_version != CRB_ABI_VERSION)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "abi_version mismatch");
-    if (cfg->dim != 2 && cfg->dim != 3)
-        return fail(nullptr, CRB_ERR_INVALID_ARG, "dim must be 2 or 3");
+    if (cfg->dim < 1 || cfg->dim > 3)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "dim must be 1, 2 or 3");
     if (cfg->mechanics_kind > CRB_MECH_ROD)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown mechanics_kind");
     const bool rods = cfg->mechanics_kind == CRB_MECH_ROD;
@@ -696,10 +699,12 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     }
     if (cfg->interaction_kind > CRB_INT_NONE)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
-    if (cfg->domain_force_kind > CRB_DOMAIN_FORCE_SPRING)
+    if (cfg->domain_force_kind > CRB_DOMAIN_FORCE_ROD_GEL)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown domain_force_kind");
-    if (rods && cfg->domain_force_kind != CRB_DOMAIN_FORCE_NONE)
-        return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: the DomainForce aspect is not implemented");
+    if (rods && cfg->domain_force_kind == CRB_DOMAIN_FORCE_SPRING)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: DomainForce is CRB_DOMAIN_FORCE_ROD_GEL (CartesianSubDomainRods)");
+    if (!rods && cfg->domain_force_kind == CRB_DOMAIN_FORCE_ROD_GEL)
+        return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_DOMAIN_FORCE_ROD_GEL needs mechanics_kind CRB_MECH_ROD");
     if (cfg->solver_order > 2)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "solver_order must be 0, 1 or 2");
     if (cfg->world_size == 0 || cfg->rank >= cfg->world_size)
@@ -734,10 +739,10 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
     g.D = D;
     g.ng[0] = (int)cfg->n_voxels[0];
     g.ng[1] = D == 3 ? (int)cfg->n_voxels[1] : 1;
-    g.ng[2] = (int)cfg->n_voxels[D - 1];
+    g.ng[2] = D >= 2 ? (int)cfg->n_voxels[D - 1] : 1;  // 1-D: the only axis is the slab axis a0
     g.cax[0] = 0;
     g.cax[1] = D == 3 ? 1 : -1;
-    g.cax[2] = D - 1;
+    g.cax[2] = D >= 2 ? D - 1 : -1;
     {
         // slab of whole voxel planes along axis 0: ranks below `rem` own one plane more; one ghost
         // plane towards every neighbour
@@ -974,8 +979,10 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
     if (n) {
         if (D == 3)
             k_ingest_keys<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(P);
-        else
+        else if (D == 2)
             k_ingest_keys<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(P);
+        else
+            k_ingest_keys<1><<<blocks_for(n, 256), 256, 0, s->stream>>>(P);
         s->launches++;
     }
     if ((rc = check_latch(s))) {

@@ -40,12 +40,14 @@ __device__ __forceinline__ bool voxel_axis_index(double p, double mn, double dx,
 template <int D>
 __device__ __forceinline__ bool voxel_of(const Grid& g, const double* p, int* i0, int* i1,
                                          int* i2) {
-    u64 a0, a1 = 0, a2;
+    u64 a0, a1 = 0, a2 = 0;
     if (!voxel_axis_index(p[0], g.mn[0], g.dx[0], &a0)) return false;
     if (D == 3) {
         if (!voxel_axis_index(p[1], g.mn[1], g.dx[1], &a1)) return false;
     }
-    if (!voxel_axis_index(p[D - 1], g.mn[D - 1], g.dx[D - 1], &a2)) return false;
+    if (D >= 2) {
+        if (!voxel_axis_index(p[D - 1], g.mn[D - 1], g.dx[D - 1], &a2)) return false;
+    }
     if (a0 >= (u64)g.ng[0] || a1 >= (u64)g.ng[1] || a2 >= (u64)g.ng[2]) return false;
     *i0 = (int)a0;
     *i1 = (int)a1;
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
         }
     }
     {
-        const double p0 = bp[0], p1 = bp[1];
+        const double p0 = bp[0], p1 = R.D >= 2 ? bp[1] : R.mn[1];
         const double p2 = R.D == 3 ? bp[2] : R.mn[2];
         R.Y.posf[d] = make_float4((float)(p0 - R.mn[0]), (float)(p1 - R.mn[1]), (float)(p2 - R.mn[2]),
                                   __uint_as_float(v));

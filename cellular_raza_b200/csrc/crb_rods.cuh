@@ -56,6 +56,9 @@ struct RodParams {
     double reject;      // conservative centre-distance bound: max(cutoff, 2 radius) with slack
     double nb_thresh2;  // smallest s with sqrt_rn(s) >= 2 radius: (norm < 2 radius) <=> (s < nb_thresh2)
     int order, weight_mode, save_prev;
+    // aspect DomainForce (CRB_DOMAIN_FORCE_ROD_GEL): CartesianSubDomainRods (bacterial_rods.rs:433-477)
+    int dforce;
+    double gel_pressure, surface_friction, surface_friction_distance;
 };
 
 // ---- exact-order helpers (nalgebra dot / norm of a 3-vector: (x*x + y*y) + z*z, no fma) -----------
@@ -92,6 +95,36 @@ __device__ __forceinline__ void rod_eval(const RodPot& M, const double* p, const
 #pragma unroll
     for (int c = 0; c < 3; ++c) f[c] = z[c] * cf;
     *t_out = t;
+}
+
+// ---- SubDomainForce of CartesianSubDomainRods (bacterial_rods.rs:433-477), added to the force of step 1
+// (SubDomainBox::calculate_custom_domain_force, chili/update_mechanics.rs:248-274): every vertex feels
+// (0, 0, -gel_pressure); a moving vertex within surface_friction_distance of a wall of the domain
+// additionally -vel/|vel| * gel_pressure * surface_friction.  Reference operation order.
+template <int V>
+__device__ __forceinline__ void rod_domain_force(const RodParams& P, const double (*pos)[3], const double (*vel)[3],
+                                                 double (*acc)[3]) {
+    if (P.dforce != CRB_DOMAIN_FORCE_ROD_GEL) return;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        double f[3] = {0.0, 0.0, -P.gel_pressure};
+        bool near = false;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            near |= fabs(__dsub_rn(pos[v][c], P.g.mn[c])) <= P.surface_friction_distance;
+            near |= fabs(__dsub_rn(pos[v][c], P.g.mx[c])) <= P.surface_friction_distance;
+        }
+        const double q = norm3_rn(vel[v]);
+        if (q != 0.0 && near) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double dir = __ddiv_rn(vel[v][c], q);
+                f[c] = __dadd_rn(f[c], __dmul_rn(__dmul_rn(-dir, P.gel_pressure), P.surface_friction));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[v][c] = __dadd_rn(acc[v][c], f[c]);
+    }
 }
 
 // ---- boundary + voxel key + bookkeeping shared by k_rod_force and k_rod_divide ----------------------
@@ -351,6 +384,14 @@ __global__ void __launch_bounds__(kRodThreads) k_rod_force(const RodParams P) {
     if (!valid) return;
 
     if constexpr (FORCE_ONLY) {
+        if (P.dforce == CRB_DOMAIN_FORCE_ROD_GEL) {
+            double vel[V][3];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) vel[v][c] = P.A.vel[(u64)(v * 3 + c) * cap + i];
+            rod_domain_force<V>(P, own, vel, acc);
+        }
 #pragma unroll
         for (int v = 0; v < V; ++v)
 #pragma unroll
@@ -364,6 +405,7 @@ __global__ void __launch_bounds__(kRodThreads) k_rod_force(const RodParams P) {
         for (int v = 0; v < V; ++v)
 #pragma unroll
             for (int c = 0; c < 3; ++c) vel[v][c] = P.A.vel[(u64)(v * 3 + c) * cap + i];
+        rod_domain_force<V>(P, own, vel, acc);  // aspect DomainForce (no-op unless CRB_DOMAIN_FORCE_ROD_GEL)
         double len = P.A.len[i];
         double dist[V - 1][3], nrm[V - 1];
 #pragma unroll

@@ -84,6 +84,10 @@ RodParams rods_params(crb_sim* s) {
     P.order = (int)s->cfg.solver_order;
     P.weight_mode = (int)s->cfg.pair_weight_mode;
     P.save_prev = 0;
+    P.dforce = (int)s->cfg.domain_force_kind;
+    P.gel_pressure = s->cfg.domain_force_strength[0];
+    P.surface_friction = s->cfg.domain_force_strength[1];
+    P.surface_friction_distance = s->cfg.domain_force_strength[2];
     return P;
 }
 

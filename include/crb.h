@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 4
+#define CRB_ABI_VERSION 5
 
 /* ---- status codes ------------------------------------------------------------------------- */
 typedef enum crb_status {
@@ -87,7 +87,14 @@ typedef enum crb_interaction_kind {
  *     force[c] = -domain_force_strength[c] * (pos[c] - domain_force_anchor[c]). */
 typedef enum crb_domain_force_kind {
     CRB_DOMAIN_FORCE_NONE = 0,
-    CRB_DOMAIN_FORCE_SPRING = 1
+    CRB_DOMAIN_FORCE_SPRING = 1,
+    /* CRB_MECH_ROD only: SubDomainForce of CartesianSubDomainRods (bacterial_rods.rs:433-477): every vertex
+     * feels (0, 0, -gel_pressure); a moving vertex within surface_friction_distance of any wall of the
+     * DOMAIN additionally feels -vel/|vel| * gel_pressure * surface_friction.
+     * domain_force_strength = {gel_pressure, surface_friction, surface_friction_distance}
+     * (CartesianCuboidRods::create_subdomains passes surface_friction as the distance, :406 — the host
+     * decides which value to send); domain_force_anchor is unused. */
+    CRB_DOMAIN_FORCE_ROD_GEL = 2
 } crb_domain_force_kind;
 
 /* How the two half-forces of a pair are weighted (SURVEY.md finding 2).
@@ -115,7 +122,7 @@ typedef enum crb_noise_mode {
 /* ---- configuration ------------------------------------------------------------------------ */
 typedef struct crb_config {
     uint32_t abi_version;      /* CRB_ABI_VERSION                                                */
-    uint32_t dim;              /* 2 or 3                                                         */
+    uint32_t dim;              /* 1, 2 or 3 (1-D runs on the per-agent kernel; rods need 3)     */
     uint32_t mechanics_kind;   /* crb_mechanics_kind                                             */
     uint32_t interaction_kind; /* crb_interaction_kind                                           */
     uint32_t solver_order;     /* `mechanics_solver_order` kwarg of run_simulation!: N in

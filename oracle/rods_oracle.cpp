@@ -358,9 +358,46 @@ void step_3(Oracle& o, uint64_t s) {
     }
 }
 
+// SubDomainBox::calculate_custom_domain_force (chili/update_mechanics.rs:248-274), appended to step 1 when
+// the aspects contain DomainForce (run_sim.rs:277-278), with the SubDomainForce of CartesianSubDomainRods
+// (bacterial_rods.rs:433-477): force = rows (0, 0, -gel_pressure); for every vertex with |v| != 0 that lies
+// within surface_friction_distance of domain_min or domain_max in ANY component:
+// row += -(v / |v|) * gel_pressure * surface_friction; then aux.add_force(force).
+// cfg.domain_force_strength = {gel_pressure, surface_friction, surface_friction_distance}.
+void domain_force_step(Oracle& o, uint64_t s) {
+    if (o.cfg.domain_force_kind != CRB_DOMAIN_FORCE_ROD_GEL) return;
+    const double gel = o.cfg.domain_force_strength[0], fric = o.cfg.domain_force_strength[1],
+                 dist = o.cfg.domain_force_strength[2];
+    const uint64_t v_lo = o.smap.first_voxel(s), v_hi = o.smap.first_voxel(s + 1);
+    for (uint64_t v = v_lo; v < v_hi; ++v)
+        for (Rod& r : o.vox[v]) {
+            Mat f;
+            for (int a = 0; a < o.V; ++a) {
+                for (int c = 0; c < o.D; ++c) f.m[a][c] = (c == 2) ? -gel : 0.0;
+                bool near = false;
+                for (int c = 0; c < o.D; ++c) {
+                    near = near || std::fabs(r.pos.m[a][c] - o.cfg.domain_min[c]) <= dist;
+                    near = near || std::fabs(r.pos.m[a][c] - o.cfg.domain_max[c]) <= dist;
+                }
+                const double q = normD(r.vel.m[a], o.D);
+                if (q != 0.0 && near)
+                    for (int c = 0; c < o.D; ++c) {
+                        const double dir = r.vel.m[a][c] / q;
+                        f.m[a][c] += ((-dir) * gel) * fric;
+                    }
+            }
+            for (int a = 0; a < o.V; ++a)
+                for (int c = 0; c < o.D; ++c) r.force.m[a][c] += f.m[a][c];
+            r.abs_sum += mat_absmax(f, o.V, o.D);
+        }
+}
+
 void run_forces(Oracle& o) {
     const int64_t S = (int64_t)o.smap.n_sub;
-    parallel_for(S, o.n_threads, [&](int64_t s) { step_1(o, (uint64_t)s); });
+    parallel_for(S, o.n_threads, [&](int64_t s) {
+        step_1(o, (uint64_t)s);
+        domain_force_step(o, (uint64_t)s);
+    });
     parallel_for(S, o.n_threads, [&](int64_t s) { step_2(o, (uint64_t)s); });
     parallel_for(S, o.n_threads, [&](int64_t s) { step_3(o, (uint64_t)s); });
 }

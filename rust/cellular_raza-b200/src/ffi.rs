@@ -3,7 +3,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const CRB_ABI_VERSION: u32 = 4;
+pub const CRB_ABI_VERSION: u32 = 5;
 
 pub const CRB_OK: c_int = 0;
 pub const CRB_ERR_CALC: c_int = -1;
@@ -30,6 +30,7 @@ pub const CRB_INT_NONE: u32 = 5;
 
 pub const CRB_DOMAIN_FORCE_NONE: u32 = 0;
 pub const CRB_DOMAIN_FORCE_SPRING: u32 = 1;
+pub const CRB_DOMAIN_FORCE_ROD_GEL: u32 = 2;
 
 pub const CRB_WEIGHT_CHILI: u32 = 0;
 pub const CRB_WEIGHT_PHYSICAL: u32 = 1;

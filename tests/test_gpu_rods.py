@@ -187,3 +187,39 @@ def test_error_paths(crb_lib):
     d.close()
     with pytest.raises(SimulationError):
         RodSimulation(w.config(dim=2))
+
+
+@pytest.mark.parametrize("n_threads", [1, 8])
+def test_domain_force_gel_pressure_and_surface_friction(crb_lib, n_threads):
+    """aspect DomainForce for rods (CRB_DOMAIN_FORCE_ROD_GEL = SubDomainForce of CartesianSubDomainRods,
+    bacterial_rods.rs:433-477): gel pressure on every vertex, friction on moving vertices near a wall."""
+    w = workloads.bacterial_rods(4, 4, rods_per_tile=24, n_threads=n_threads)
+    um = workloads.MICRO_METRE
+    w.vel = np.random.default_rng(8).normal(0.0, 0.3 * um, w.vel.shape)
+    w.vel[::3] = 0.0  # rods at rest feel no friction
+    over = dict(domain_force_kind=_abi.CRB_DOMAIN_FORCE_ROD_GEL,
+                domain_force_strength=[0.02 * um, 0.4, 2.0 * um])
+    dev, ora = make_pair(w, **over)
+    plain = RodSimulation(w.config())
+    plain.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    diff = dev.debug_forces() - plain.debug_forces()
+    plain.close()
+    assert np.abs(diff[..., 2]).min() > 0                       # every vertex is pushed down
+    assert (np.abs(diff[..., 0]) > 0).any() and (diff[..., 0] == 0).any()  # friction only for some
+    assert_same_population(dev, ora)
+    err, _ = force_check(dev, ora)
+    assert err <= FORCE_TOL, err
+    dev.step(60)
+    ora.step(60)
+    pd, vd, po, vo = assert_same_population(dev, ora)
+    L = max(w.cfg_kwargs["domain_max"])
+    assert np.abs(pd - po).max() / L <= TRAJ_TOL
+    assert np.abs(vd - vo).max() <= 1e-8 * np.abs(vo).max()
+    dev.close()
+    ora.close()
+
+
+def test_domain_force_kind_mismatch_is_rejected(crb_lib):
+    w = workloads.bacterial_rods(1, 1)
+    with pytest.raises(SimulationError):
+        RodSimulation(w.config(domain_force_kind=_abi.CRB_DOMAIN_FORCE_SPRING))

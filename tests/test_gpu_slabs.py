@@ -162,3 +162,27 @@ def test_overlapped_step_equals_plain_step(crb_lib):
     rk.compute_boundary()
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_1d_slabs_equal_single_handle(crb_lib, world):
+    """1-D domain (NewtonDamped1D + Morse): the only axis is the slab axis, a halo 'plane' is ONE voxel."""
+    n, L = 1400, 12.0 * 400
+    w = workloads.brownian_morse(n, L, dim=1, n_threads=3, noise_mode=_abi.CRB_NOISE_NONE)
+    w.cfg_kwargs["mechanics_kind"] = _abi.CRB_MECH_NEWTON_DAMPED
+    w.mech_params = np.tile([0.1, 1.0], (n, 1))
+    w.vel = np.random.default_rng(3).normal(0.0, 8.0, size=(n, 1))  # fast enough to cross slab faces
+    one, grp = _single(w), _group(w, world, ghost_capacity=256, migration_capacity=256)
+    f1 = one.debug_forces()[np.argsort(one.get_agents()[2])]
+    fg = grp.debug_forces()[np.argsort(grp.get_agents()[2])]
+    assert np.array_equal(f1, fg)
+    migrated = 0
+    for _ in range(5):
+        one.step(20)
+        grp.step(20)
+        migrated += sum(sum(rk.last_migration) for rk in grp.ranks)
+        for a, b in zip(_by_id(one), _by_id(grp)):
+            assert np.array_equal(a, b)
+    assert migrated > 0
+    one.close()
+    grp.close()

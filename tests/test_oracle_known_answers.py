@@ -144,7 +144,8 @@ def test_free_motion(oracle_lib):
             assert np.abs(pos[:, 0] - calc).max() < 1e-5
 
 
-@pytest.mark.parametrize("dim,diff,seed", [(3, 1.0, 1), (3, 0.5, 2), (3, 0.25, 3), (2, 1.0, 4), (2, 0.5, 5)])
+@pytest.mark.parametrize("dim,diff,seed", [(3, 1.0, 1), (3, 0.5, 2), (3, 0.25, 3), (2, 1.0, 4), (2, 0.5, 5), (2, 0.25, 6),
+                                           (1, 1.0, 7), (1, 0.5, 8), (1, 0.25, 9)])
 def test_brownian_msd(oracle_lib, dim, diff, seed):
     # tests/brownian_diffusion_constant_approx.rs:8-36, 110-124: 160 particles from the domain
     # centre, dt 1e-3, 200 steps, MSD = 2 dim D t within 3.5 sigma.  Noise comes from the table
@@ -166,6 +167,37 @@ def test_brownian_msd(oracle_lib, dim, diff, seed):
         p = o.get_agents()[0]
         sq = ((p - L / 2.0) ** 2).sum(axis=1)
         assert abs(2.0 * dim * diff * it * dt - sq.mean()) <= 3.5 * sq.std()
+
+
+@pytest.mark.parametrize("dim,diff,damping,seed", [(3, 80.0, 10.0, 1), (3, 40.0, 10.0, 2), (3, 20.0, 10.0, 3),
+                                                   (3, 40.0, 1.0, 4), (3, 40.0, 0.1, 5), (2, 80.0, 10.0, 6),
+                                                   (2, 40.0, 10.0, 7), (2, 20.0, 10.0, 8)])
+def test_langevin_msd(oracle_lib, dim, diff, damping, seed):
+    # tests/brownian_diffusion_constant_approx.rs:260-340 (test_langevin!, diffusion_constant_langevin_*):
+    # mass 1, kT = D * damping * mass, v(0) = 0, 160 particles, dt 1e-3, 200 steps; for iteration > 1
+    # MSD = -dim kT/m/g^2 (1 - e^{-g t})(3 - e^{-g t}) + 2 dim kT/m t/g within 3.5 sigma
+    n, L, dt, steps = 160, 200.0, 1e-3, 200
+    from cellular_raza_b200.workloads import Workload
+
+    kT = diff * damping * 1.0
+    pos = np.full((n, dim), L / 2.0)
+    cfg = dict(dim=dim, mechanics_kind=_abi.CRB_MECH_LANGEVIN, interaction_kind=_abi.CRB_INT_MORSE,
+               domain_min=[0.0] * dim, domain_max=[L] * dim, n_voxels=[3] * dim, dx=[L / 3.0] * dim, dt=dt,
+               ref_n_subdomains=1, noise_mode=_abi.CRB_NOISE_TABLE)
+    w = Workload("msd_langevin", cfg, pos, np.zeros((n, dim)), np.tile([1.0, damping, kT], (n, 1)),
+                 np.tile([1.0, 1.0, 0.0, 0.0], (n, 1)))
+    o = oracle_lib.ChiliOracle(w.config())
+    o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    o.set_noise(workloads.noise_table(steps, n, dim, seed))
+    for it in range(1, steps + 1):
+        o.step(1)
+        if it > 1:
+            p = o.get_agents()[0]
+            sq = ((p - L / 2.0) ** 2).sum(axis=1)
+            t = it * dt
+            e = np.exp(-damping * t)
+            expected = -dim * kT / damping ** 2 * (1.0 - e) * (3.0 - e) + 2.0 * dim * kT * t / damping
+            assert abs(expected - sq.mean()) <= 3.5 * sq.std()
 
 
 def test_determinism(oracle_lib):

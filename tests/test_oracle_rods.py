@@ -160,3 +160,40 @@ def test_neighbor_counts_symmetric_for_equal_radii():
     o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
     f, a, nb = o.forces()
     assert nb.sum() % 2 == 0 and nb.sum() > 0
+
+
+def test_domain_force_gel_pressure_and_surface_friction():
+    """SubDomainForce of CartesianSubDomainRods (bacterial_rods.rs:433-477): every vertex feels
+    (0, 0, -gel_pressure); a MOVING vertex within surface_friction_distance of a domain wall additionally
+    feels -v/|v| * gel_pressure * surface_friction.  Straight relaxed rods without neighbours in range, so
+    the step-1 force is the domain force alone."""
+    from cellular_raza_b200 import _abi
+
+    um = workloads.MICRO_METRE
+    w = workloads.bacterial_rods(1, 1, rods_per_tile=3)
+    V = 5
+    seg = 3.0 * um
+    pos = np.zeros((3, V, 3))
+    vel = np.zeros((3, V, 3))
+    for k, (x0, y0, z0) in enumerate([(20 * um, 7 * um, 20 * um), (100 * um, 0.5 * um, 20 * um), (150 * um, 7 * um, 20 * um)]):
+        pos[k, :, 0] = x0 + seg * np.arange(V)
+        pos[k, :, 1] = y0
+        pos[k, :, 2] = z0
+    vel[1, :, 0] = 3.0   # rod 1 lies 0.5 um from the y = 0 wall and moves along (3, 0, 4) / 5
+    vel[1, :, 2] = 4.0
+    vel[2, :, 1] = 1.0   # rod 2 moves but is far from every wall
+    gel, fric, dist = 0.25, 0.5, 1.0 * um
+    cfg = w.config(domain_force_kind=_abi.CRB_DOMAIN_FORCE_ROD_GEL, domain_force_strength=[gel, fric, dist])
+    o = ro.RodsOracle(cfg, n_threads=2)
+    o.set_agents(pos, vel, w.mech_params[:3], w.inter_params[:3])
+    f, _, _ = o.forces()
+    order = np.argsort(o.get_agents()[2][:, 1])  # Initial(n) identifiers -> input order
+    f = f[order]
+    np.testing.assert_array_equal(f[0], np.tile([0.0, 0.0, -gel], (V, 1)))
+    np.testing.assert_array_equal(f[2], np.tile([0.0, 0.0, -gel], (V, 1)))
+    expect = np.array([-(3.0 / 5.0) * gel * fric, 0.0, -gel - (4.0 / 5.0) * gel * fric])
+    np.testing.assert_allclose(f[1], np.tile(expect, (V, 1)), rtol=1e-15, atol=0)
+    # without the aspect the same rods feel nothing
+    o2 = ro.RodsOracle(w.config(), n_threads=2)
+    o2.set_agents(pos, vel, w.mech_params[:3], w.inter_params[:3])
+    assert np.abs(o2.forces()[0]).max() == 0.0
