@@ -248,6 +248,7 @@ def workload_config(args) -> dict:
             "interaction": "cell_sorting species potential", "solver": "AB3 (order 2)",
             "pair_weights": f"chili-as-written(n_threads={max(args.n_threads_ref, 4)})", "dt": 0.2,
             "l2_policy": "working set fits L2 by construction (1,600 agents): launch-latency bound, reported not tuned",
+            "stepping": "crb_step(K) replays CUDA graphs of two steps each; stage times from a second, event-instrumented pass",
             "decomposition": "single",
         }
     if args.workload == "bacterial_rods":
@@ -303,7 +304,11 @@ def run_b200(args):
     sampler = ClockSampler(dev_id)
     sampler.start()
     time.sleep(0.3)
-    sim.enable_timers(True)
+    # the per-stage CUDA events live inside the timed region, except for the launch-bound as-shipped case:
+    # six extra event records per 60-us step would be a large part of what is measured there (and the library
+    # replays CUDA graphs only while its timers are off), so its stage times come from a second pass
+    split_timers = args.workload == "cell_sorting_as_shipped"
+    sim.enable_timers(not split_timers)
     sim.reset_timers()
     l0 = sim.kernel_launches
     torch.cuda.synchronize()
@@ -314,6 +319,17 @@ def run_b200(args):
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     launches = sim.kernel_launches - l0
+    ms_stage_total = ms_total
+    if split_timers:
+        sim.enable_timers(True)
+        sim.reset_timers()
+        torch.cuda.synchronize()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        sim.step(args.steps)
+        e3.record(stream)
+        torch.cuda.synchronize()
+        ms_stage_total = e2.elapsed_time(e3)
     force_ms, force_launches = sim.stage_time_ms(0)
     scan_ms, _ = sim.stage_time_ms(1)
     reorder_ms, reorder_launches = sim.stage_time_ms(2)
@@ -331,7 +347,7 @@ def run_b200(args):
         "kernel": sim.force_kernel_name, "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
         "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-        "traffic": ncu_traffic(n, "force"), "share_of_step": force_ms / ms_total,
+        "traffic": ncu_traffic(n, "force"), "share_of_step": force_ms / ms_stage_total,
         "algorithmic_flop_per_pair": flop_per_pair(args), "pairs_per_launch": pairs_per_launch,
         "pair_forces_per_s": pairs_per_launch / (force_avg_ms * 1e-3),
     }
@@ -342,7 +358,7 @@ def run_b200(args):
         "kernel": "k_fill+k_reorder (cell-list rebuild / migration scatter)", "bound": "hbm",
         "achieved": reorder_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": reorder_gbs / hbm_peak,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-        "traffic": ncu_traffic(n, "reorder"), "share_of_step": reorder_ms / ms_total, "scan_share_of_step": scan_ms / ms_total,
+        "traffic": ncu_traffic(n, "reorder"), "share_of_step": reorder_ms / ms_stage_total, "scan_share_of_step": scan_ms / ms_stage_total,
         "algorithmic_bytes_per_agent": REORDER_BYTES_PER_AGENT,
     }
 

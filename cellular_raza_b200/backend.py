@@ -206,6 +206,63 @@ class Agent:
     interaction: object = None  # None: an agent without the Interaction aspect (domain_force_spring.rs:70-75)
 
 
+# ---- bacterial rods (cell_building_blocks/bacterial_rods.rs; examples/bacterial_rods/src/main.rs) -----
+MICRO_METRE = 1e-6
+MINUTE = 1.0
+GROWTH_BASE_RATE = 0.1 * MICRO_METRE / MINUTE  # examples/bacterial_rods/src/main.rs:12
+
+
+@dataclass
+class RodMechanics:  # bacterial_rods.rs:82-107
+    pos: Sequence[Sequence[float]]  # nrows x 3 (one row per vertex, like nalgebra::MatrixXx3)
+    vel: Sequence[Sequence[float]]
+    diffusion_constant: float = 0.0
+    spring_tension: float = 0.0
+    rigidity: float = 0.0
+    spring_length: float = 0.0
+    damping: float = 0.0
+    KIND = _abi.CRB_MECH_ROD
+
+
+@dataclass
+class RodInteraction:  # bacterial_rods.rs:272-290: newtype around a point potential
+    potential: MorsePotential
+    KIND = _abi.CRB_INT_MORSE
+
+    def row(self):
+        return self.potential.row()
+
+
+@dataclass
+class RodAgent:
+    """``Agent`` of cellular_raza-examples/bacterial_rods/src/main.rs:14-109: RodMechanics +
+    RodInteraction<MorsePotential> + the Cycle / NeighborSensing fields and rules of the example
+    (growth_rate <- GROWTH_BASE_RATE * max(8 - neighbours, 0) / 8, division above the threshold)."""
+
+    mechanics: RodMechanics
+    interaction: RodInteraction
+    growth_rate: float = GROWTH_BASE_RATE
+    spring_length_threshold: float = 6.0 * MICRO_METRE
+    growth_base_rate: float = GROWTH_BASE_RATE
+
+    def mech_row(self):  # CRB_MECH_ROD row of include/crb.h
+        m = self.mechanics
+        return [m.diffusion_constant, m.spring_tension, m.rigidity, m.spring_length, m.damping,
+                self.growth_rate, self.spring_length_threshold, self.growth_base_rate]
+
+
+@dataclass
+class CartesianCuboidRods:  # bacterial_rods.rs:338-411
+    domain: CartesianCuboid
+    gel_pressure: float = 0.0
+    surface_friction: float = 0.0
+    surface_friction_distance: float = 0.0  # create_subdomains passes surface_friction instead (:406)
+
+    @property
+    def dim(self) -> int:
+        return self.domain.dim
+
+
 @dataclass
 class SpringDomainForce:
     """``SubDomainForce::calculate_custom_force`` of cellular_raza/tests/domain_force_spring.rs:56-68, one
@@ -328,10 +385,14 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
                    mechanics_solver_order: int = 2, determinism: bool = True,
                    pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI, noise_mode: int | None = None,
                    noise_table: np.ndarray | None = None, device: int = 0,
-                   domain_force: SpringDomainForce | None = None) -> StorageAccess:
+                   domain_force: SpringDomainForce | None = None, capacity: int | None = None) -> StorageAccess:
     """``run_simulation!`` of the B200 backend.  ``settings.n_threads`` is chili's subdomain count: it
     does not create threads here, it selects the pair weights chili applies for that decomposition
     (SURVEY.md finding 2); ``pair_weight_mode=CRB_WEIGHT_PHYSICAL`` applies both halves everywhere."""
+    agents = list(agents)
+    if agents and isinstance(agents[0], RodAgent):
+        return _run_rods(domain, agents, settings, aspects, mechanics_solver_order=mechanics_solver_order,
+                         pair_weight_mode=pair_weight_mode, device=device, capacity=capacity)
     unsupported = set(aspects) - {"Mechanics", "Interaction", "DomainForce"}
     if unsupported or "Mechanics" not in aspects:
         raise SimulationError(_abi.CRB_ERR_INVALID_ARG, f"aspects {sorted(unsupported)} are outside the hot path (SURVEY.md §8)")
@@ -469,3 +530,132 @@ def _store(state, params, cells: StorageManager, iteration: int, sb: StorageBuil
                 ],
             })
         (d / f"batch_{0:020d}_{k:020d}.json").write_text(json.dumps({"data": data}, indent=2))
+
+
+# ---- bacterial rods: aspects [Mechanics, Interaction, Cycle, NeighborSensing] (+ DomainForce) ------------
+_IDENT_NAMES = {0: "Division", 1: "Initial", 2: "Inserted"}  # CellIdentifier, concepts/src/cell.rs:18-25
+
+
+def _ident(t):
+    kind, a, b = int(t[0]), int(t[1]), int(t[2])
+    if kind == 1:
+        return ("Initial", a)
+    return (_IDENT_NAMES[kind], a, b)
+
+
+def _ident_json(key):
+    return {key[0]: key[1]} if key[0] == "Initial" else {key[0]: [key[1], key[2]]}
+
+
+def _matrix_json(m: np.ndarray):
+    """nalgebra 0.34 serde of Matrix<f64, Dyn, Const<3>, VecStorage>: the storage as the tuple
+    (data column-major, nrows, ncols) with the Const dimension as unit (un-vendored dependency; layout
+    restated from its published source, not pinned by any reference fixture)."""
+    return [np.asarray(m).T.reshape(-1).tolist(), int(m.shape[0]), None]
+
+
+def _run_rods(domain, agents: Sequence[RodAgent], settings: Settings, aspects, *, mechanics_solver_order: int,
+              pair_weight_mode: int, device: int, capacity: int | None = None) -> StorageAccess:
+    """``run_simulation!(domain, agents, settings, aspects: [Mechanics, Interaction, Cycle, NeighborSensing],
+    zero_force_default: |c| MatrixXx3::zeros(nrows))`` of examples/bacterial_rods/src/main.rs:202-210.
+    The rod count changes when rods divide (``CycleEvent::Division``), identifiers follow
+    chili/update_cycle.rs:33-66; snapshots are taken after the step of every save point."""
+    from .rods import RodSimulation
+
+    need = {"Mechanics", "Interaction", "Cycle", "NeighborSensing"}
+    aspects = set(aspects)
+    if not need <= aspects or aspects - need - {"DomainForce"}:
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG,
+                              "rod agents run aspects [Mechanics, Interaction, Cycle, NeighborSensing] (+ DomainForce)")
+    gel = domain if isinstance(domain, CartesianCuboidRods) else None
+    cub = gel.domain if gel is not None else domain
+    if ("DomainForce" in aspects) and gel is None:
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "aspect DomainForce needs a CartesianCuboidRods domain")
+    if cub.dim != 3:
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "RodMechanics<f64, 3> needs a 3-D domain")
+    n = len(agents)
+    pos = np.array([a.mechanics.pos for a in agents], dtype=np.float64)
+    vel = np.array([a.mechanics.vel for a in agents], dtype=np.float64)
+    if pos.ndim != 3 or pos.shape[2] != 3 or vel.shape != pos.shape:
+        raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "all rods need the same nrows x 3 position/velocity matrices")
+    V = pos.shape[1]
+    mp = np.array([a.mech_row() for a in agents], dtype=np.float64)
+    ip = np.array([a.interaction.row() for a in agents], dtype=np.float64)
+    ts = settings.time
+    save_its = sorted(set(ts.save_iterations))
+    # device capacity (the reference grows its Vecs; the device needs a bound): head room for three
+    # doublings unless the caller passes `capacity`; exceeding it is a CapacityError, never a silent drop
+    capacity = int(capacity or max(8 * n, 1024))
+    use_force = "DomainForce" in aspects
+    cfg = make_config(dim=3, mechanics_kind=_abi.CRB_MECH_ROD, interaction_kind=_abi.CRB_INT_MORSE,
+                      domain_min=cub.min, domain_max=cub.max, n_voxels=cub.n_voxels, dx=cub.dx, dt=ts.dt,
+                      capacity=capacity, solver_order=mechanics_solver_order, pair_weight_mode=pair_weight_mode,
+                      ref_n_subdomains=max(settings.n_threads, 1), rng_seed=cub.rng_seed, device=device,
+                      rod_n_vertices=V,
+                      domain_force_kind=_abi.CRB_DOMAIN_FORCE_ROD_GEL if use_force else _abi.CRB_DOMAIN_FORCE_NONE,
+                      # create_subdomains hands surface_friction to surface_friction_distance (bacterial_rods.rs:406)
+                      domain_force_strength=[gel.gel_pressure, gel.surface_friction, gel.surface_friction] if use_force else None)
+    sim = RodSimulation(cfg)
+    try:
+        sim.set_agents(pos, vel, mp, ip)
+        sb = settings.storage
+        root = None
+        if "SerdeJson" in sb.priority:
+            root = Path(sb.location)
+            if sb.add_date:
+                root = root / _time.strftime("%Y-%m-%d-T%H-%M-%S")
+            if sb.suffix:
+                root = root / sb.suffix
+        cells = StorageManager(None if root is None else root / "cells" / "json")
+        subdomains = StorageManager(None if root is None else root / "subdomains" / "json")
+        inter_row = ip[0].tolist()
+
+        def save(iteration):
+            p, v, ident, parent, vox = sim.get_agents()
+            m = sim.get_params()
+            hx, hv, hl = sim.get_aux()
+            keys = [_ident(t) for t in ident]
+            if "Memory" in sb.priority:
+                cells.memory[iteration] = {
+                    k: {"pos": p[a], "vel": v[a], "voxel": int(vox[a]), "spring_length": float(m[a, 3]),
+                        "growth_rate": float(m[a, 5]),
+                        "parent": None if int(parent[a, 0]) > 2 else _ident(parent[a]),
+                        "aux": {"positions": hx[a, : hl[a]], "velocities": hv[a, : hl[a]]}}
+                    for a, k in enumerate(keys)
+                }
+            if cells.json_dir is not None:
+                d = cells.json_dir / f"{iteration:020d}"
+                d.mkdir(parents=True, exist_ok=True)
+                data = []
+                zero = _matrix_json(np.zeros((V, 3)))
+                for a, k in enumerate(keys):
+                    ident_j = _ident_json(k)
+                    par = None if int(parent[a, 0]) > 2 else _ident_json(_ident(parent[a]))
+                    cell = {"mechanics": {"pos": _matrix_json(p[a]), "vel": _matrix_json(v[a]),
+                                          "diffusion_constant": float(m[a, 0]), "spring_tension": float(m[a, 1]),
+                                          "rigidity": float(m[a, 2]), "spring_length": float(m[a, 3]),
+                                          "damping": float(m[a, 4])},
+                            "interaction": {"radius": inter_row[0], "potential_stiffness": inter_row[1],
+                                            "cutoff": inter_row[2], "strength": inter_row[3]},
+                            "growth_rate": float(m[a, 5]), "spring_length_threshold": float(m[a, 6])}
+                    aux = {"cycle": {"cycle_events": []},
+                           "mechanics": {"positions": [_matrix_json(x) for x in hx[a, : hl[a]]],
+                                         "velocities": [_matrix_json(x) for x in hv[a, : hl[a]]],
+                                         "current_force": zero, "zero_force": zero},
+                           "neighbor_sensing": {"accumulator": 0}}
+                    data.append({"identifier": ident_j,
+                                 "element": [{"identifier": ident_j, "parent": par, "cell": cell}, aux]})
+                (d / f"batch_{0:020d}_{0:020d}.json").write_text(json.dumps({"data": data}, indent=2))
+
+        if save_its and save_its[0] == 0:
+            save(0)
+        it = 0
+        for target in [x for x in save_its if x > 0]:
+            sim.step(target - it)
+            it = target
+            save(it)
+        if it < ts.maximum_iterations:
+            sim.step(ts.maximum_iterations - it)
+        return StorageAccess(cells, subdomains, root)
+    finally:
+        sim.close()

@@ -102,6 +102,12 @@ struct crb_sim {
     int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 k_force_tile, 3 k_force_tile2 (env CRB_FORCE_KERNEL)
     bool timers_on = false;
     StageTimer timers[kNumStages];
+    // CUDA graphs of TWO consecutive steps (the X/Y, key, start buffers swap every step, so the pointer set
+    // repeats with period 2), one per buffer orientation; see crb_step
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+    const void* step_graph_key[2] = {nullptr, nullptr};
+    u64 step_graph_launches = 0;  // kernels inside one graph (two steps)
+    bool graphs_off = false;      // env CRB_NO_GRAPH
     // bacterial rods (CRB_MECH_ROD): own state layout, see crb_rods.cuh
     bool rods = false;
     RodState RX, RT, RY;
@@ -539,6 +545,16 @@ int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool inges
     return 0;
 }
 
+// the captured kernel parameters (pointers, agent count, tile plan, uniform parameter rows) are baked into
+// the graph nodes: any call that changes one of them drops the graphs
+void graphs_invalidate(crb_sim* s) {
+    for (int k = 0; k < 2; ++k) {
+        if (s->step_graph[k]) cudaGraphExecDestroy(s->step_graph[k]);
+        s->step_graph[k] = nullptr;
+        s->step_graph_key[k] = nullptr;
+    }
+}
+
 int check_latch(crb_sim* s) {
     CU(s, cudaMemcpyAsync(s->err_host, s->err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
@@ -825,6 +841,7 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         M.off_sp = take(M.mcap);
         M.bytes = off;
     }
+    s->graphs_off = std::getenv("CRB_NO_GRAPH") != nullptr;
     if (const char* kc = std::getenv("CRB_FORCE_KERNEL")) {
         if (!std::strcmp(kc, "agent")) s->kernel_choice = 1;
         if (!std::strcmp(kc, "tile")) s->kernel_choice = 2;
@@ -892,6 +909,7 @@ void crb_destroy(crb_sim* s) {
     if (s->stream2) cudaStreamSynchronize(s->stream2);
     if (s->stream) cudaStreamSynchronize(s->stream);
     timers_resolve(s);
+    graphs_invalidate(s);
     for (void* p : s->allocs) cudaFree(p);
     if (s->err_host) cudaFreeHost(s->err_host);
     if (s->snap_pending) cudaEventSynchronize(s->ev_snap_done);
@@ -923,6 +941,7 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
                    const double* mech_params, const double* inter_params, const uint8_t* species,
                    const uint64_t* ids) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    graphs_invalidate(s);
     if (n > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
     if (n && !pos) return fail(s, CRB_ERR_INVALID_ARG, "pos is required");
     CU(s, cudaSetDevice((int)s->cfg.device));
@@ -1002,6 +1021,7 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
 
 int crb_set_uniform_params(crb_sim* s, const double* mech_row, const double* inter_row) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    graphs_invalidate(s);
     if (!mech_row && !inter_row) {
         s->uniform_declared = false;
         return 0;
@@ -1304,6 +1324,64 @@ int step_finish(crb_sim* s, bool save_prev) {
 }
 }  // namespace
 
+// Launch-bound populations (the reference's own examples hold 10^3..10^5 agents: one step is seven launches
+// of a few microseconds each) run batches of steps as CUDA graphs.  One graph = TWO consecutive steps: the
+// sorted/target state buffers swap after every step, so the pointer set repeats with period two.  Eligible:
+// one device, point agents, no per-step host input (the noise-table cursor and the Philox iteration counter
+// travel by value in the kernel parameters => deterministic mechanics or CRB_NOISE_NONE only), timers off.
+// The last step of a batch always runs outside the graph (it alone writes the older ring-buffer entry,
+// save_prev).  Same kernels in the same order => bit-identical to the plain loop (tested).
+static bool graph_eligible(const crb_sim* s) {
+    if (s->graphs_off || s->timers_on || s->world > 1 || s->rods || !s->n) return false;
+    const bool stochastic = s->cfg.noise_mode != CRB_NOISE_NONE && s->cfg.mechanics_kind != CRB_MECH_NEWTON_DAMPED;
+    return !stochastic;
+}
+
+static int plain_step(crb_sim* s, bool last) {
+    int rc;
+    if ((rc = step_compute(s, last))) return rc;
+    return step_finish(s, last);
+}
+
+static int graph_for_orientation(crb_sim* s, cudaGraphExec_t* out) {
+    const void* key = (const void*)s->X.pos[0];
+    for (int k = 0; k < 2; ++k)
+        if (s->step_graph[k] && s->step_graph_key[k] == key) {
+            *out = s->step_graph[k];
+            return 0;
+        }
+    const int slot = s->step_graph[0] ? 1 : 0;
+    if (s->step_graph[slot]) {
+        cudaGraphExecDestroy(s->step_graph[slot]);
+        s->step_graph[slot] = nullptr;
+    }
+    const u64 it0 = s->iteration, nc0 = s->noise_cursor, l0 = s->launches;
+    CU(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeRelaxed));
+    int rc = plain_step(s, false);
+    if (!rc) rc = plain_step(s, false);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+    // nothing ran: the host-side bookkeeping of the two captured steps is rolled back (the buffer
+    // orientation is back where it was after two swaps)
+    s->step_graph_launches = s->launches - l0;
+    s->iteration = it0;
+    s->noise_cursor = nc0;
+    s->launches = l0;
+    if (rc || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc ? rc : fail(s, CRB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+    }
+    cudaGraphExec_t ge = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) return fail(s, CRB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ie));
+    s->step_graph[slot] = ge;
+    s->step_graph_key[slot] = key;
+    *out = ge;
+    return 0;
+}
+
 int crb_step(crb_sim* s, uint64_t n_steps) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "crb_step before crb_set_agents");
@@ -1312,12 +1390,21 @@ int crb_step(crb_sim* s, uint64_t n_steps) {
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->aux_settable = false;
     if (s->rods) return rods_step(s, n_steps);
-    for (u64 it = 0; it < n_steps; ++it) {
-        const bool last = it + 1 == n_steps;
-        int rc;
-        if ((rc = step_compute(s, last))) return rc;
-        if ((rc = step_finish(s, last))) return rc;
+    u64 it = 0;
+    int rc;
+    if (n_steps >= 4 && graph_eligible(s)) {
+        const u64 pairs = (n_steps - 1) / 2;  // the last step stays outside
+        cudaGraphExec_t ge = nullptr;
+        if ((rc = graph_for_orientation(s, &ge))) return rc;
+        for (u64 k = 0; k < pairs; ++k) CU(s, cudaGraphLaunch(ge, s->stream));
+        s->iteration += 2 * pairs;
+        s->noise_cursor += 2 * pairs;
+        s->launches += pairs * s->step_graph_launches;
+        step_mark(s);
+        it = 2 * pairs;
     }
+    for (; it < n_steps; ++it)
+        if ((rc = plain_step(s, it + 1 == n_steps))) return rc;
     return check_latch(s);
 }
 

@@ -40,12 +40,14 @@ __device__ __forceinline__ bool voxel_axis_index(double p, double mn, double dx,
 template <int D>
 __device__ __forceinline__ bool voxel_of(const Grid& g, const double* p, int* i0, int* i1,
                                          int* i2) {
-    u64 a0, a1 = 0, a2 = 0;
+    u64 a0, a1 = 0, a2;
     if (!voxel_axis_index(p[0], g.mn[0], g.dx[0], &a0)) return false;
     if (D == 3) {
         if (!voxel_axis_index(p[1], g.mn[1], g.dx[1], &a1)) return false;
     }
-    if (D >= 2) {
+    if constexpr (D == 1) {
+        a2 = 0;  // 1-D: the only axis is the slab axis a0
+    } else {
         if (!voxel_axis_index(p[D - 1], g.mn[D - 1], g.dx[D - 1], &a2)) return false;
     }
     if (a0 >= (u64)g.ng[0] || a1 >= (u64)g.ng[1] || a2 >= (u64)g.ng[2]) return false;

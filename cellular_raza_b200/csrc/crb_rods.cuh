@@ -372,6 +372,8 @@ __global__ void __launch_bounds__(kRodThreads) k_rod_force(const RodParams P) {
                              dz = cz - __ldg(&P.A.cen[2 * cap + jj]);
                 const double lim = hi_r + __ldg(&P.A.cen[3 * cap + jj]);
                 if (fma(dz, dz, fma(dy, dy, dx * dx)) <= lim * lim) {
+                    // (a second-level test on the 25 vertex-vertex distances was measured: it rejects too few
+                    //  of these candidates to pay for its 15 gathered loads, 4.21 ms vs 3.71 ms at 2 M rods)
                     s_list[cnt * kRodThreads + tid] = jj;
                     ++cnt;
                 }

@@ -52,3 +52,19 @@ def test_unsupported_aspects_are_rejected():
     a = [cr.Agent(cr.NewtonDamped3D([1.0, 1.0, 1.0]), cr.MorsePotential(1.0, 1.0, 2.0, 0.1))]
     with pytest.raises(cr.SimulationError):
         cr.run_simulation(d, a, s, aspects=["Mechanics", "Reactions"])
+
+
+def test_rod_agent_packing_and_aspects():
+    # Agent of cellular_raza-examples/bacterial_rods/src/main.rs:14-25, 120-138
+    um = cr.MICRO_METRE
+    mech = cr.RodMechanics(np.zeros((5, 3)).tolist(), np.zeros((5, 3)).tolist(), 0.0, 10.0, 1.0 * um, 2.0 * um, 1.5)
+    a = cr.RodAgent(mech, cr.RodInteraction(cr.MorsePotential(3.0 * um, 0.5 / um, 5.0 * um, 0.1 * um ** 2)))
+    assert a.mech_row() == [0.0, 10.0, 1.0 * um, 2.0 * um, 1.5, cr.GROWTH_BASE_RATE, 6.0 * um, cr.GROWTH_BASE_RATE]
+    assert a.interaction.row() == [3.0 * um, 0.5 / um, 5.0 * um, 0.1 * um ** 2]
+    d = cr.CartesianCuboidRods(cr.CartesianCuboid.from_boundaries_and_n_voxels([0.0] * 3, [200 * um, 15 * um, 45 * um], [8, 1, 2]))
+    s = cr.Settings(8, cr.FixedStepsize.from_partial_save_steps(0.0, 0.1, 2, 1))
+    with pytest.raises(cr.SimulationError):  # the rod agent needs all four aspects of main.rs:206
+        cr.run_simulation(d, [a], s, aspects=["Mechanics", "Interaction"])
+    assert cr._ident((1, 7, 0)) == ("Initial", 7) and cr._ident_json(("Division", 3, 2)) == {"Division": [3, 2]}
+    m = cr._matrix_json(np.arange(6.0).reshape(2, 3))
+    assert m == [[0.0, 3.0, 1.0, 4.0, 2.0, 5.0], 2, None]  # column-major data, nrows, Const<3> as unit

@@ -103,3 +103,50 @@ def test_domain_force_spring_like_reference_test(crb_lib):
         assert abs(c["pos"][0] - x0 * np.cos(omega * it * dt)) < 1e-3
     with pytest.raises(cr.SimulationError):
         cr.run_simulation(domain, agents, settings, aspects=["Mechanics", "DomainForce"])
+
+
+def test_bacterial_rods_example_through_run_simulation(crb_lib, tmp_path):
+    """cellular_raza-examples/bacterial_rods/src/main.rs:111-212, shortened: rod agents with the four aspects
+    of the example through the reference-shaped entry point; rods grow and divide (dynamic agent count,
+    Division identifiers with parents), snapshots equal the oracle's state at the same iterations."""
+    from cellular_raza_b200 import workloads
+    from oracle.rods_oracle import RodsOracle
+
+    w = workloads.bacterial_rods(2, 2, rods_per_tile=6, spring_length_range=(5.5, 5.99))
+    um = cr.MICRO_METRE
+    agents = []
+    for k in range(w.n):
+        mp, ip = w.mech_params[k], w.inter_params[k]
+        mech = cr.RodMechanics(w.pos[k].tolist(), w.vel[k].tolist(), mp[0], mp[1], mp[2], mp[3], mp[4])
+        agents.append(cr.RodAgent(mech, cr.RodInteraction(cr.MorsePotential(ip[0], ip[1], ip[2], ip[3])),
+                                  growth_rate=mp[5], spring_length_threshold=mp[6], growth_base_rate=mp[7]))
+    kw = w.cfg_kwargs
+    domain = cr.CartesianCuboidRods(cr.CartesianCuboid.from_boundaries_and_n_voxels(
+        kw["domain_min"], kw["domain_max"], [int(x) for x in kw["n_voxels"]]))
+    settings = cr.Settings(8, cr.FixedStepsize.from_partial_save_steps(0.0, kw["dt"], 120, 40),
+                           cr.StorageBuilder(location=str(tmp_path), priority=["SerdeJson", "Memory"]))
+    acc = cr.run_simulation(domain, agents, settings, aspects=["Mechanics", "Interaction", "Cycle", "NeighborSensing"])
+    assert acc.cells.get_all_iterations() == [0, 40, 80, 120]
+    ora = RodsOracle(w.config(), n_threads=4)
+    ora.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    L = max(kw["domain_max"])
+    for it in (40, 80, 120):
+        ora.step(40)
+        po, vo, ido, pao, xo = ora.get_agents()
+        mem = acc.cells.memory[it]
+        assert len(mem) == len(ido)
+        for a in range(len(ido)):
+            c = mem[cr._ident(ido[a])]
+            assert np.abs(c["pos"] - po[a]).max() / L <= 1e-9
+            assert c["voxel"] == int(xo[a])
+            assert c["parent"] == (None if int(pao[a, 0]) > 2 else cr._ident(pao[a]))
+    last = acc.cells.memory[120]
+    assert len(last) > w.n and any(k[0] == "Division" for k in last)  # rods divided
+    f = acc.path / "cells" / "json" / f"{120:020d}" / f"batch_{0:020d}_{0:020d}.json"
+    body = json.loads(f.read_text())
+    e = next(x for x in body["data"] if "Division" in x["identifier"])
+    cbox, aux = e["element"]
+    assert set(cbox) == {"identifier", "parent", "cell"} and cbox["parent"] is not None
+    assert set(cbox["cell"]) == {"mechanics", "interaction", "growth_rate", "spring_length_threshold"}
+    assert cbox["cell"]["mechanics"]["pos"][1:] == [5, None] and len(cbox["cell"]["mechanics"]["pos"][0]) == 15
+    assert set(aux) == {"cycle", "mechanics", "neighbor_sensing"}

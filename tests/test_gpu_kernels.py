@@ -113,3 +113,36 @@ def test_tile_kernels_ragged_geometries(crb_lib, monkeypatch, n_voxels, density,
         sim.close()
     for a, b in zip(*states):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n_steps", [4, 5, 21, 40])
+def test_graph_batches_equal_plain_loop(crb_lib, monkeypatch, n_steps):
+    """crb_step(n) replays CUDA graphs of two steps each for deterministic mechanics (csrc/crb_api.cu
+    crb_step); the same kernels in the same order must give the bits of the plain launch loop, for even and
+    odd batch lengths (both buffer orientations) and across consecutive batches."""
+    w = workloads.cell_sorting(n_threads=4)
+
+    def run(no_graph):
+        if no_graph:
+            monkeypatch.setenv("CRB_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("CRB_NO_GRAPH", raising=False)
+        d = DeviceSimulation(w.config())
+        d.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+        l0 = d.kernel_launches
+        d.step(n_steps)
+        launches = d.kernel_launches - l0
+        d.step(3)          # below the graph threshold: plain
+        d.step(n_steps)    # second batch, possibly on the other buffer orientation
+        out = d.get_agents() + d.get_aux() + (d.get_migrations(),)
+        d.close()
+        return out, launches
+
+    a, la = run(False)
+    b, lb = run(True)
+    assert la == lb == 6 * n_steps  # the launch counter counts the kernels inside the graphs
+    for x, y in zip(a[:7], b[:7]):
+        np.testing.assert_array_equal(x, y)
+    oa, ob = np.argsort(a[7][0]), np.argsort(b[7][0])  # the migration tap is unordered
+    for x, y in zip(a[7], b[7]):
+        np.testing.assert_array_equal(x[oa], y[ob])

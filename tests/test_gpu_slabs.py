@@ -171,7 +171,7 @@ def test_1d_slabs_equal_single_handle(crb_lib, world):
     w = workloads.brownian_morse(n, L, dim=1, n_threads=3, noise_mode=_abi.CRB_NOISE_NONE)
     w.cfg_kwargs["mechanics_kind"] = _abi.CRB_MECH_NEWTON_DAMPED
     w.mech_params = np.tile([0.1, 1.0], (n, 1))
-    w.vel = np.random.default_rng(3).normal(0.0, 8.0, size=(n, 1))  # fast enough to cross slab faces
+    w.vel = np.random.default_rng(3).normal(0.0, 60.0, size=(n, 1))  # fast enough to cross slab faces
     one, grp = _single(w), _group(w, world, ghost_capacity=256, migration_capacity=256)
     f1 = one.debug_forces()[np.argsort(one.get_agents()[2])]
     fg = grp.debug_forces()[np.argsort(grp.get_agents()[2])]
