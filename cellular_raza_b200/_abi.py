@@ -173,6 +173,7 @@ SYMBOLS = [
     ("crb_stream", C.c_void_p, [_vp]),
     ("crb_measure_fp64_peak", C.c_int, [C.c_uint32, _f64p, _f64p]),
     ("crb_debug_rsqrt", C.c_int, [C.c_uint32, _vp, _vp, C.c_uint64]),
+    ("crb_debug_exp", C.c_int, [C.c_uint32, _vp, _vp, C.c_uint64]),
     ("crb_decomp_res", C.c_int, [C.c_uint64, C.c_uint64, _u64p, _u64p, _u64p]),
     ("crb_domain_from_interaction_range", C.c_int, [C.c_uint32, _f64p, _f64p, C.c_double, _u64p, _f64p]),
     ("crb_domain_from_n_voxels", C.c_int, [C.c_uint32, _f64p, _f64p, _u64p, _f64p]),

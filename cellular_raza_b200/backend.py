@@ -385,10 +385,14 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
                    mechanics_solver_order: int = 2, determinism: bool = True,
                    pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI, noise_mode: int | None = None,
                    noise_table: np.ndarray | None = None, device: int = 0,
-                   domain_force: SpringDomainForce | None = None, capacity: int | None = None) -> StorageAccess:
+                   domain_force: SpringDomainForce | None = None, capacity: int | None = None,
+                   devices: Sequence[int] | None = None) -> StorageAccess:
     """``run_simulation!`` of the B200 backend.  ``settings.n_threads`` is chili's subdomain count: it
     does not create threads here, it selects the pair weights chili applies for that decomposition
-    (SURVEY.md finding 2); ``pair_weight_mode=CRB_WEIGHT_PHYSICAL`` applies both halves everywhere."""
+    (SURVEY.md finding 2); ``pair_weight_mode=CRB_WEIGHT_PHYSICAL`` applies both halves everywhere.
+    ``devices=[0, 1, ...]`` cuts the domain into one slab of voxel planes per listed GPU (one
+    host thread drives all of them, halo and migration buffers travel by peer copies); the results are
+    bit-identical to the single-device run.  A device may be listed several times (several slabs on it)."""
     agents = list(agents)
     if agents and isinstance(agents[0], RodAgent):
         return _run_rods(domain, agents, settings, aspects, mechanics_solver_order=mechanics_solver_order,
@@ -415,6 +419,10 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
                       domain_force_kind=_abi.CRB_DOMAIN_FORCE_SPRING if domain_force is not None else _abi.CRB_DOMAIN_FORCE_NONE,
                       domain_force_strength=None if domain_force is None else domain_force.strength,
                       domain_force_anchor=None if domain_force is None else domain_force.anchor)
+    if devices is not None and len(devices) > 1:
+        if domain_force is not None:
+            raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "devices=[...] with DomainForce: use one device")
+        return _run_slabs(cfg, list(devices), agents, settings, pos, vel, mp, ip, sp, noise_table)
     sim = DeviceSimulation(cfg)
     try:
         sim.set_agents(pos, vel, mp, ip, sp)
@@ -490,6 +498,52 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
         return StorageAccess(cells, subdomains, root)
     finally:
         sim.close()
+
+
+def _run_slabs(cfg, devices, agents, settings: Settings, pos, vel, mp, ip, sp, noise_table) -> StorageAccess:
+    """one slab per entry of ``devices`` driven by this host thread (``slabs.LocalSlabGroup``); snapshots are
+    gathered slab by slab at the save points."""
+    import copy
+
+    from .slabs import LocalSlabGroup
+
+    cfg.capacity = max(len(agents), 1)  # every slab can hold the whole population (clustering over time)
+    grp = LocalSlabGroup(lambda: copy.copy(cfg), len(devices), devices=devices)
+    try:
+        grp.set_agents(pos, vel, mp, ip, sp)
+        if noise_table is not None:
+            grp.set_noise(noise_table)
+        sb = settings.storage
+        root = None
+        if "SerdeJson" in sb.priority:
+            root = Path(sb.location)
+            if sb.add_date:
+                root = root / _time.strftime("%Y-%m-%d-T%H-%M-%S")
+            if sb.suffix:
+                root = root / sb.suffix
+        cells = StorageManager(None if root is None else root / "cells" / "json")
+        subdomains = StorageManager(None if root is None else root / "subdomains" / "json")
+        names = {"mech": type(agents[0].mechanics).__name__, "inter": type(agents[0].interaction).__name__}
+        ts = settings.time
+        save_its = sorted(set(ts.save_iterations))
+
+        def save(iteration):
+            state = (*grp.get_agents(), *grp.get_aux())
+            k = state[2].astype(np.int64)  # identifiers are the input indices (CellIdentifier::Initial(n))
+            _store(state, (mp[k], ip[k], sp[k]), cells, iteration, sb, names)
+
+        if save_its and save_its[0] == 0:
+            save(0)
+        it = 0
+        for target in [x for x in save_its if x > 0]:
+            grp.step(target - it)
+            it = target
+            save(it)
+        if it < ts.maximum_iterations:
+            grp.step(ts.maximum_iterations - it)
+        return StorageAccess(cells, subdomains, root)
+    finally:
+        grp.close()
 
 
 def _save(sim: DeviceSimulation, cells: StorageManager, iteration: int, sb: StorageBuilder, names: dict):

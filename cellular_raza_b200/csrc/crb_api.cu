@@ -963,6 +963,14 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
                 if (inter_params[i * s->n_ip + k] != s->uni.ip[k]) s->uniform = false;
         }
     }
+    // the uniform-parameter kernels evaluate the Morse exponential without overflow handling (exp_bounded): its
+    // largest argument, potential_stiffness * (R1 + R2) at distance 0, must stay below 700; such a parameter row
+    // (physically meaningless: a force of 1e304) takes the per-agent-parameter kernels with CUDA's exp() instead
+    if (s->uniform && s->cfg.interaction_kind == CRB_INT_MORSE && !(s->uni.ip[1] * (s->uni.ip[0] + s->uni.ip[0]) < 700.0)) {
+        if (s->uniform_declared || !inter_params)
+            return fail(s, CRB_ERR_CALC, "CalcError: MorsePotential potential_stiffness * 2 radius >= 700 overflows exp in f64");
+        s->uniform = false;
+    }
     int rc;
     if ((rc = upload_rows(s, pos, D, s->T.pos, n))) return rc;
     if (vel && s->cfg.mechanics_kind != CRB_MECH_BROWNIAN) {
@@ -1077,6 +1085,23 @@ int crb_debug_rsqrt(uint32_t device, const double* x, double* y, uint64_t n) {
     }
     cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice);
     k_rsqrt_test<<<blocks_for(n, 256), 256>>>(dx, dy, n);
+    cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    return cudaGetLastError() == cudaSuccess ? 0 : CRB_ERR_CUDA;
+}
+
+int crb_debug_exp(uint32_t device, const double* x, double* y, uint64_t n) {
+    if (!x || !y) return CRB_ERR_INVALID_ARG;
+    if (cudaSetDevice((int)device) != cudaSuccess) return CRB_ERR_CUDA;
+    double *dx = nullptr, *dy = nullptr;
+    if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess) return CRB_ERR_CUDA;
+    if (cudaMalloc(&dy, n * sizeof(double)) != cudaSuccess) {
+        cudaFree(dx);
+        return CRB_ERR_CUDA;
+    }
+    cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    k_exp_test<<<blocks_for(n, 256), 256>>>(dx, dy, n);
     cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(dx);
     cudaFree(dy);

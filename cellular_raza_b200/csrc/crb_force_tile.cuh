@@ -170,7 +170,7 @@ __device__ __forceinline__ void force_from_global(const KParams& P, const u64 i,
                 const bool same_sub = (j >= sub_lo) & (j < sub_hi);
                 const bool keep = same_voxel | !same_sub;
                 const u8 spj = Pot<INTER>::kUsesSpecies ? __ldg(&P.A.species[j]) : 0;
-                double cf = own.coef(r2, P.u.ip[0], spi == spj, &calc_flag);
+                double cf = coef_uniform<INTER>(own, r2, P.u.ip[0], spi == spj, &calc_flag);
                 cf = keep ? cf : 0.5 * cf;
 #pragma unroll
                 for (int c = 0; c < D; ++c) acc[c] = fma(z[c], cf, acc[c]);

@@ -81,6 +81,35 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
     return y;
 }
 
+// exp(x) for |x| < 700 without the special-case handling of CUDA's exp() (overflow / underflow / NaN paths):
+// k = round(x / ln 2) by the 1.5 * 2^52 shift, r = x - k ln 2 in two steps (|r| <= 0.3466), Taylor polynomial
+// of degree 13 (remainder r^14 / 14! < 5e-18), exponent add.  Relative error < 2.3e-16 (checked on the device
+// by tests/test_gpu_kernels.py::test_exp_bounded_accuracy).  Used by the Morse potential, whose argument is
+// clamped from below in the kernels and bounded from above by a host-side check (a * (R1 + R2) < 700).
+__device__ __forceinline__ double exp_bounded(double x) {
+    const double shift = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma(x, 1.4426950408889634074, shift);
+    const int k = __double2loint(t);
+    const double kd = t - shift;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;          // 1/13!
+    p = fma(p, r, 2.0876756987868100e-09);      // 1/12!
+    p = fma(p, r, 2.5052108385441720e-08);      // 1/11!
+    p = fma(p, r, 2.7557319223985888e-07);      // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);      // 1/9!
+    p = fma(p, r, 2.4801587301587302e-05);      // 1/8!
+    p = fma(p, r, 1.9841269841269841e-04);      // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);      // 1/6!
+    p = fma(p, r, 8.3333333333333332e-03);      // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);      // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);      // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 template <int INTER>
 struct Pot;
 
@@ -155,6 +184,18 @@ struct Pot<CRB_INT_MORSE> {
         const double e = exp(-a * (dist - (radius + ext_radius)));
         const double c = m2sa * e * (1.0 - e) * rinv;
         return (r2 == 0.0 || dist > cutoff) ? 0.0 : c;  // (:158-162) zero beyond the cutoff / at r = 0
+    }
+    // tile kernels (uniform parameters): branch-free lean exponential.  The argument is at most
+    // a * (R1 + R2) < 700 (plan_tile checks it, otherwise the per-agent kernel with coef() runs); below -700
+    // the true value is < 1e-304 and the clamp changes the coefficient by less than that.
+    __device__ __forceinline__ double coef_bounded(double r2, double ext_radius) const {
+        const double rinv = rsqrt_nr(r2);
+        const double dist = r2 * rinv;
+        double x = -a * (dist - (radius + ext_radius));
+        x = x < -700.0 ? -700.0 : x;
+        const double e = exp_bounded(x);
+        const double c = m2sa * e * (1.0 - e) * rinv;
+        return (r2 == 0.0 || dist > cutoff) ? 0.0 : c;
     }
 };
 
@@ -243,6 +284,20 @@ __device__ __forceinline__ double coef_tile(const Pot<INTER>& p, double r2, doub
                                             bool same_species, int* flag) {
     if constexpr (INTER == CRB_INT_CELL_SORTING || INTER == CRB_INT_CELL_SORTING_BENCH)
         return p.template coef_t<false>(r2, ext_radius, same_species);
+    else if constexpr (INTER == CRB_INT_MORSE)
+        return p.coef_bounded(r2, ext_radius);
+    else
+        return p.coef(r2, ext_radius, same_species, flag);
+}
+
+// coefficient of a pair under UNIFORM parameters outside the tile kernels (k_force_integrate<UNIFORM>, the dense
+// voxel fall-back of the tile kernels): Morse takes the same bounded exponential as the tile kernels, so that every
+// uniform-parameter path gives the same bits (tile == per-agent kernel, slabs == single handle)
+template <int INTER>
+__device__ __forceinline__ double coef_uniform(const Pot<INTER>& p, double r2, double ext_radius,
+                                               bool same_species, int* flag) {
+    if constexpr (INTER == CRB_INT_MORSE)
+        return p.coef_bounded(r2, ext_radius);
     else
         return p.coef(r2, ext_radius, same_species, flag);
 }
@@ -554,7 +609,7 @@ __global__ void __launch_bounds__(kForceThreads)
                 double cf;
                 if (UNIFORM) {
                     const double ext_radius = ipi[0];
-                    cf = own.coef(r2, ext_radius, spi == spj, &calc_flag);
+                    cf = coef_uniform<INTER>(own, r2, ext_radius, spi == spj, &calc_flag);
                     cf = keep ? cf : 0.5 * cf;
                 } else {
                     double ipj[CRB_MAX_INTER_PARAMS];
@@ -1046,6 +1101,10 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 __global__ void k_rsqrt_test(const double* x, double* y, u64 n) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = rsqrt_nr(x[i]);
+}
+__global__ void k_exp_test(const double* x, double* y, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = exp_bounded(x[i]);
 }
 __global__ void k_iota_u64(u64* a, u64 n) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;

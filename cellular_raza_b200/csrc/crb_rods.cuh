@@ -80,7 +80,8 @@ __device__ __forceinline__ void rod_eval(const RodPot& M, const double* p, const
                                          double* t_out) {
     const double ap0 = p[0] - a[0], ap1 = p[1] - a[1], ap2 = p[2] - a[2];
     double t = fma(ab[2], ap2, fma(ab[1], ap1, ab[0] * ap0)) * inv_ab2;
-    t = fmin(fmax(t, 0.0), 1.0);
+    t = !(t > 0.0) ? 0.0 : t;  // clamp(t, 0, 1) as compare-selects (NaN -> 0 like fmax): fmin/fmax on f64
+    t = t > 1.0 ? 1.0 : t;     // cost 15 instructions per evaluation (ncu), this costs 6
     const double omt = __dsub_rn(1.0, t);
     double z[3];
 #pragma unroll
@@ -89,7 +90,12 @@ __device__ __forceinline__ void rod_eval(const RodPot& M, const double* p, const
     const double d2 = fma(z[2], z[2], fma(z[1], z[1], z[0] * z[0]));
     const double rinv = rsqrt_nr(d2);
     const double dist = d2 * rinv;
-    const double e = exp(-M.stiffness * (dist - M.rsum));
+    // branch-free (a branch here stops the compiler from interleaving the five evaluations of a segment:
+    // measured 3.7 -> 4.9 ms).  x <= stiffness * rsum < 700 is checked on the host (rods_set_agents); below
+    // -700 the true value is < 1e-304 and the clamp changes the force by less than that.
+    double x = -M.stiffness * (dist - M.rsum);
+    x = x < -700.0 ? -700.0 : x;
+    const double e = exp_bounded(x);
     double cf = M.m2sa * e * (1.0 - e) * rinv;
     cf = (d2 == 0.0 || dist > M.cutoff) ? 0.0 : cf;
 #pragma unroll

@@ -91,16 +91,26 @@ RodParams rods_params(crb_sim* s) {
     return P;
 }
 
+inline size_t rods_smem_pad() {
+    if (const char* e = std::getenv("CRB_ROD_SMEM_PAD")) return (size_t)std::atol(e);
+    return 0;
+}
+
 template <int V>
 void rods_launch_force_v(crb_sim* s, const RodParams& P, bool force_only) {
     const u32 grid = blocks_for(P.n, kRodThreads);
     if (!grid) return;
     // (register caps of 168 / 128 for 3 / 4 resident CTAs were measured: 4.27 / 4.63 ms against 3.7 ms at
     // 2 M rods — the spills cost more than the occupancy gives)
-    if (force_only)
+    if (force_only) {
         k_rod_force<V, true><<<grid, kRodThreads, 0, s->stream>>>(P);
-    else
-        k_rod_force<V, false><<<grid, kRodThreads, 0, s->stream>>>(P);
+        return;
+    }
+    // resident CTAs per SM are capped through an unused dynamic shared-memory request (see rods_smem_pad)
+    static const size_t pad = rods_smem_pad();
+    auto k = k_rod_force<V, false>;
+    if (pad) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    k<<<grid, kRodThreads, pad, s->stream>>>(P);
 }
 template <int V>
 void rods_launch_divide_v(crb_sim* s, const RodParams& P) {
@@ -225,6 +235,10 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
             growth[i] = mech_params[i * 8 + RMP_GROWTH];
         }
     }
+    // the device evaluates the Morse exponential without overflow handling (exp_bounded): its largest
+    // argument, potential_stiffness * (R1 + R2) at distance 0, must stay below the f64 overflow of exp
+    if (n && !(s->uni.ip[1] * (s->uni.ip[0] + s->uni.ip[0]) < 700.0))
+        return fail(s, CRB_ERR_CALC, "CalcError: MorsePotential potential_stiffness * 2 radius >= 700 overflows exp in f64");
     if (s->uni.mp[RMP_DIFF] != 0.0)
         return fail(s, CRB_ERR_INVALID_ARG,
                     "rods: diffusion_constant != 0 is not supported (the example ships 0; noise contract A7 "

@@ -329,6 +329,8 @@ int crb_measure_fp64_peak(uint32_t device, double* tflops, double* ms);
 
 /* parity tap of the device reciprocal square root used by every potential (y[i] = 1/sqrt(x[i])). */
 int crb_debug_rsqrt(uint32_t device, const double* x, double* y, uint64_t n);
+/* parity tap of the bounded-argument exponential of the Morse potential (y[i] = exp(x[i]), |x| < 700). */
+int crb_debug_exp(uint32_t device, const double* x, double* y, uint64_t n);
 
 /* ---- helpers that restate reference setup arithmetic on the host -------------------------- */
 /* get_decomp_res (cartesian_cuboid_n.rs:19-59): returns 0 and (n, m, average_len) or

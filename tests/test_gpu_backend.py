@@ -150,3 +150,29 @@ def test_bacterial_rods_example_through_run_simulation(crb_lib, tmp_path):
     assert set(cbox["cell"]) == {"mechanics", "interaction", "growth_rate", "spring_length_threshold"}
     assert cbox["cell"]["mechanics"]["pos"][1:] == [5, None] and len(cbox["cell"]["mechanics"]["pos"][0]) == 15
     assert set(aux) == {"cycle", "mechanics", "neighbor_sensing"}
+
+
+def test_run_simulation_over_slabs_equals_single_device(crb_lib):
+    """``devices=[...]``: the reference-shaped entry point cut into slabs (three slabs on this one GPU)
+    stores exactly the snapshots of the single-device run (slabs are bit-identical)."""
+    rng = np.random.default_rng(2)
+    n = 900
+    pos = rng.uniform(0.5, 107.0, (n, 3))
+    agents = [cr.Agent(cr.NewtonDamped3D(pos[k].tolist(), [0.0] * 3, 2.0, 1.0),
+                       cr.CellSpecificInteraction(int(k <= n // 2), 6.0, 2.0, 1.5)) for k in range(n)]
+    domain = cr.CartesianCuboid.from_boundaries_and_interaction_range([0.0] * 3, [108.0] * 3, 18.0)
+
+    def run(**kw):
+        settings = cr.Settings(4, cr.FixedStepsize.from_partial_save_steps(0.0, 0.2, 60, 20),
+                               cr.StorageBuilder(priority=["Memory"]))
+        return cr.run_simulation(domain, agents, settings, **kw).cells.load_all_elements()
+
+    one, many = run(), run(devices=[0, 0, 0])
+    assert sorted(one) == sorted(many) == [0, 20, 40, 60]
+    for it in one:
+        assert one[it].keys() == many[it].keys()
+        for key, c in one[it].items():
+            d = many[it][key]
+            assert np.array_equal(c["pos"], d["pos"]) and np.array_equal(c["vel"], d["vel"])
+            assert c["voxel"] == d["voxel"]
+            assert np.array_equal(c["aux"]["positions"], d["aux"]["positions"])

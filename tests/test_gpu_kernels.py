@@ -146,3 +146,18 @@ def test_graph_batches_equal_plain_loop(crb_lib, monkeypatch, n_steps):
     oa, ob = np.argsort(a[7][0]), np.argsort(b[7][0])  # the migration tap is unordered
     for x, y in zip(a[7], b[7]):
         np.testing.assert_array_equal(x[oa], y[ob])
+
+
+def test_exp_bounded_accuracy(crb_lib):
+    """the lean exponential of the Morse potential (csrc/crb_kernels.cuh exp_bounded) against long double:
+    relative error below 2.3e-16 over the whole admitted range |x| < 700."""
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.uniform(-700.0, 700.0, 300_000), rng.uniform(-5.0, 5.0, 300_000),
+                        np.array([0.0, 1.0, -1.0, 0.5, 3.0, -3.0, 1e-300, -1e-17, 699.9, -699.9,
+                                  0.34657359027997264, -0.34657359027997264])])
+    y = np.empty_like(x)
+    rc = crb_lib.crb_debug_exp(0, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), x.size)
+    assert rc == 0
+    ref = np.exp(x.astype(np.longdouble))
+    rel = np.abs((y.astype(np.longdouble) - ref) / ref).astype(np.float64)
+    assert rel.max() <= 2.3e-16, f"max rel err {rel.max():.3e} at x={x[rel.argmax()]!r}"
