@@ -201,6 +201,128 @@ __device__ __forceinline__ void rod_finish(const RodParams& P, const u64 slot, d
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-rod epilogue of a step, given the complete step-1 force `acc` and the neighbour count `nb`:
+// RodMechanics::calculate_increment (bacterial_rods.rs:157-213), AB wrapper (chili/solvers.rs:156-300),
+// react_to_neighbors (main.rs:66-73), update_cycle (:87-98); rods without a Division event finish here
+// (rod_finish), the others are completed by k_rod_divide.  Shared by the fused kernel (k_rod_force) and the
+// split pair (k_rod_force<FORCE_ONLY> + k_rod_update); ADD_DOMAIN = false when `acc` already holds the
+// DomainForce contribution.
+// ------------------------------------------------------------------------------------------------
+template <int V, bool ADD_DOMAIN>
+__device__ __forceinline__ void rod_epilogue(const RodParams& P, const u64 i, double (*own)[3], double (*acc)[3],
+                                             const u32 nb, const u32 vk, const u32 own_lo) {
+    const u64 cap = P.cap;
+    // ---- RodMechanics::calculate_increment (bacterial_rods.rs:157-213), reference op order ----
+    double vel[V][3];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vel[v][c] = P.A.vel[(u64)(v * 3 + c) * cap + i];
+    if (ADD_DOMAIN) rod_domain_force<V>(P, own, vel, acc);  // aspect DomainForce (no-op unless CRB_DOMAIN_FORCE_ROD_GEL)
+    double len = P.A.len[i];
+    double dist[V - 1][3], nrm[V - 1];
+#pragma unroll
+    for (int s = 0; s + 1 < V; ++s) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dist[s][c] = __dsub_rn(own[s][c], own[s + 1][c]);
+        nrm[s] = norm3_rn(dist[s]);
+    }
+#pragma unroll
+    for (int s = 0; s + 1 < V; ++s) {
+        if (nrm[s] != 0.0) {
+            const double stretch = __dsub_rn(nrm[s], len);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double dir = __ddiv_rn(dist[s][c], nrm[s]);
+                const double fi = __dmul_rn(__dmul_rn(-dir, P.tension), stretch);
+                acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(fi, 0.5));
+                acc[s + 1][c] = __dadd_rn(acc[s + 1][c], __dmul_rn(-fi, 0.5));
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s + 2 < V; ++s) {
+        const double prod = dot3_rn(dist[s], dist[s + 1]);
+        double angle = 0.0;
+        if (!(nrm[s] == 0.0 || nrm[s + 1] == 0.0)) {
+            double cang = __ddiv_rn(prod, __dmul_rn(nrm[s], nrm[s + 1]));
+            cang = cang < -1.0 ? -1.0 : cang;
+            cang = cang > 1.0 ? 1.0 : cang;
+            angle = acos(cang);
+        }
+        double fd[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) fd[c] = __dsub_rn(dist[s][c], dist[s + 1][c]);
+        const double nfd = norm3_rn(fd);
+        const double tn = tan(__dmul_rn(0.5, angle));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double dir = nfd != 0.0 ? __ddiv_rn(fd[c], nfd) : fd[c];
+            const double f = __dmul_rn(__dmul_rn(__dmul_rn(dir, 2.0), P.rigidity), tn);
+            acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(-f, 0.5));
+            acc[s + 1][c] = __dadd_rn(acc[s + 1][c], f);
+            acc[s + 2][c] = __dadd_rn(acc[s + 2][c], __dmul_rn(-f, 0.5));
+        }
+    }
+    // ---- AB wrapper (chili/solvers.rs:156-300): dx = vel, dv = total force - vel * damping -------
+    const int N = P.order;
+    const int hlen = P.A.hlen[i];
+    const int n_prev = N == 0 ? 0 : (hlen + 1 < N ? hlen + 1 : N);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const u64 o = (u64)(v * 3 + c) * cap + i;
+            const double dxv = vel[v][c];
+            const double dvv = __dsub_rn(acc[v][c], __dmul_rn(vel[v][c], P.damping));
+            const double oldx = P.A.h1x[o], oldv = P.A.h1v[o];
+            double pn, wn;
+            if (N == 2 && n_prev == 2) {
+                pn = helper_ab3(own[v][c], dxv, oldx, dxv, P.dt, 0.0);
+                wn = helper_ab3(vel[v][c], dvv, oldv, dvv, P.dt, 0.0);
+            } else if (n_prev == 1) {
+                pn = helper_ab2(own[v][c], dxv, dxv, P.dt, 0.0);
+                wn = helper_ab2(vel[v][c], dvv, dvv, P.dt, 0.0);
+            } else {
+                pn = helper_euler(own[v][c], dxv, P.dt, 0.0);
+                wn = helper_euler(vel[v][c], dvv, P.dt, 0.0);
+            }
+            own[v][c] = pn;
+            vel[v][c] = wn;
+            P.B.h1x[o] = N >= 1 ? dxv : oldx;
+            P.B.h1v[o] = N >= 1 ? dvv : oldv;
+            if (P.save_prev) {
+                P.B.h0x[o] = oldx;
+                P.B.h0v[o] = oldv;
+            }
+        }
+    P.B.hlen[i] = (u8)n_prev;
+    // ---- react_to_neighbors (main.rs:66-73) and update_cycle (:87-98) ---------------------------
+    double growth;
+    if (nb > 0)
+        growth = fmax(__ddiv_rn(__dmul_rn(P.growth_base, __dsub_rn(8.0, (double)nb)), 8.0), 0.0);
+    else
+        growth = P.growth_base;
+    len = __dadd_rn(len, __dmul_rn(growth, P.dt));
+    P.B.growth[i] = growth;
+    P.B.len[i] = len;
+    const bool divide = len > P.threshold;
+    P.div_flag[i] = divide ? 1 : 0;
+    if (divide) {
+        // completed by k_rod_divide (geometry changes before boundary and voxel key)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                P.B.pos[(u64)(v * 3 + c) * cap + i] = own[v][c];
+                P.B.vel[(u64)(v * 3 + c) * cap + i] = vel[v][c];
+            }
+    } else {
+        rod_finish<V>(P, i, own, vel, vk, i - own_lo, P.A.ident[cap + i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_rod_force: one thread per rod of A (sorted by voxel).
 //
 // Phase 1 (filter): the thread walks the <= 9 contiguous candidate ranges of its 3^D neighbourhood and
@@ -407,115 +529,28 @@ __global__ void __launch_bounds__(kRodThreads) k_rod_force(const RodParams P) {
         P.nb_out[i] = nb;
         return;
     } else {
-        // ---- RodMechanics::calculate_increment (bacterial_rods.rs:157-213), reference op order ----
-        double vel[V][3];
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) vel[v][c] = P.A.vel[(u64)(v * 3 + c) * cap + i];
-        rod_domain_force<V>(P, own, vel, acc);  // aspect DomainForce (no-op unless CRB_DOMAIN_FORCE_ROD_GEL)
-        double len = P.A.len[i];
-        double dist[V - 1][3], nrm[V - 1];
-#pragma unroll
-        for (int s = 0; s + 1 < V; ++s) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) dist[s][c] = __dsub_rn(own[s][c], own[s + 1][c]);
-            nrm[s] = norm3_rn(dist[s]);
-        }
-#pragma unroll
-        for (int s = 0; s + 1 < V; ++s) {
-            if (nrm[s] != 0.0) {
-                const double stretch = __dsub_rn(nrm[s], len);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const double dir = __ddiv_rn(dist[s][c], nrm[s]);
-                    const double fi = __dmul_rn(__dmul_rn(-dir, P.tension), stretch);
-                    acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(fi, 0.5));
-                    acc[s + 1][c] = __dadd_rn(acc[s + 1][c], __dmul_rn(-fi, 0.5));
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s + 2 < V; ++s) {
-            const double prod = dot3_rn(dist[s], dist[s + 1]);
-            double angle = 0.0;
-            if (!(nrm[s] == 0.0 || nrm[s + 1] == 0.0)) {
-                double cang = __ddiv_rn(prod, __dmul_rn(nrm[s], nrm[s + 1]));
-                cang = cang < -1.0 ? -1.0 : cang;
-                cang = cang > 1.0 ? 1.0 : cang;
-                angle = acos(cang);
-            }
-            double fd[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) fd[c] = __dsub_rn(dist[s][c], dist[s + 1][c]);
-            const double nfd = norm3_rn(fd);
-            const double tn = tan(__dmul_rn(0.5, angle));
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double dir = nfd != 0.0 ? __ddiv_rn(fd[c], nfd) : fd[c];
-                const double f = __dmul_rn(__dmul_rn(__dmul_rn(dir, 2.0), P.rigidity), tn);
-                acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(-f, 0.5));
-                acc[s + 1][c] = __dadd_rn(acc[s + 1][c], f);
-                acc[s + 2][c] = __dadd_rn(acc[s + 2][c], __dmul_rn(-f, 0.5));
-            }
-        }
-        // ---- AB wrapper (chili/solvers.rs:156-300): dx = vel, dv = total force - vel * damping -------
-        const int N = P.order;
-        const int hlen = P.A.hlen[i];
-        const int n_prev = N == 0 ? 0 : (hlen + 1 < N ? hlen + 1 : N);
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const u64 o = (u64)(v * 3 + c) * cap + i;
-                const double dxv = vel[v][c];
-                const double dvv = __dsub_rn(acc[v][c], __dmul_rn(vel[v][c], P.damping));
-                const double oldx = P.A.h1x[o], oldv = P.A.h1v[o];
-                double pn, wn;
-                if (N == 2 && n_prev == 2) {
-                    pn = helper_ab3(own[v][c], dxv, oldx, dxv, P.dt, 0.0);
-                    wn = helper_ab3(vel[v][c], dvv, oldv, dvv, P.dt, 0.0);
-                } else if (n_prev == 1) {
-                    pn = helper_ab2(own[v][c], dxv, dxv, P.dt, 0.0);
-                    wn = helper_ab2(vel[v][c], dvv, dvv, P.dt, 0.0);
-                } else {
-                    pn = helper_euler(own[v][c], dxv, P.dt, 0.0);
-                    wn = helper_euler(vel[v][c], dvv, P.dt, 0.0);
-                }
-                own[v][c] = pn;
-                vel[v][c] = wn;
-                P.B.h1x[o] = N >= 1 ? dxv : oldx;
-                P.B.h1v[o] = N >= 1 ? dvv : oldv;
-                if (P.save_prev) {
-                    P.B.h0x[o] = oldx;
-                    P.B.h0v[o] = oldv;
-                }
-            }
-        P.B.hlen[i] = (u8)n_prev;
-        // ---- react_to_neighbors (main.rs:66-73) and update_cycle (:87-98) ---------------------------
-        double growth;
-        if (nb > 0)
-            growth = fmax(__ddiv_rn(__dmul_rn(P.growth_base, __dsub_rn(8.0, (double)nb)), 8.0), 0.0);
-        else
-            growth = P.growth_base;
-        len = __dadd_rn(len, __dmul_rn(growth, P.dt));
-        P.B.growth[i] = growth;
-        P.B.len[i] = len;
-        const bool divide = len > P.threshold;
-        P.div_flag[i] = divide ? 1 : 0;
-        if (divide) {
-            // completed by k_rod_divide (geometry changes before boundary and voxel key)
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    P.B.pos[(u64)(v * 3 + c) * cap + i] = own[v][c];
-                    P.B.vel[(u64)(v * 3 + c) * cap + i] = vel[v][c];
-                }
-        } else {
-            rod_finish<V>(P, i, own, vel, vk, i - own_lo, P.A.ident[cap + i]);
-        }
+        rod_epilogue<V, true>(P, i, own, acc, nb, vk, own_lo);
     }
+}
+
+// split variant: k_rod_force<V, true> writes force_out / nb_out, this kernel runs the epilogue at full
+// occupancy (the fused kernel holds 8 warps per SM at 239 registers and pays the cold instruction fetches of
+// this once-per-rod code in full)
+template <int V>
+__global__ void __launch_bounds__(128, 4) k_rod_update(const RodParams P) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const u64 cap = P.cap;
+    double own[V][3], acc[V][3];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            own[v][c] = P.A.pos[(u64)(v * 3 + c) * cap + i];
+            acc[v][c] = P.force_out[(u64)(v * 3 + c) * cap + i];
+        }
+    const u32 vk = P.key[i];
+    rod_epilogue<V, false>(P, i, own, acc, (u32)P.nb_out[i], vk, P.start[vk]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -113,6 +113,11 @@ void rods_launch_force_v(crb_sim* s, const RodParams& P, bool force_only) {
     k<<<grid, kRodThreads, pad, s->stream>>>(P);
 }
 template <int V>
+void rods_launch_update_v(crb_sim* s, const RodParams& P) {
+    const u32 grid = blocks_for(P.n, 128);
+    if (grid) k_rod_update<V><<<grid, 128, 0, s->stream>>>(P);
+}
+template <int V>
 void rods_launch_divide_v(crb_sim* s, const RodParams& P) {
     const u32 grid = blocks_for(P.n, 128);
     if (grid) k_rod_divide<V><<<grid, 128, 0, s->stream>>>(P);
@@ -133,6 +138,16 @@ void rods_launch_ingest_v(crb_sim* s, const RodParams& P) {
         case 8: CALL(8); break;                       \
     }
 
+void rods_launch_update(crb_sim* s, const RodParams& P) {
+#define CALL(VV) rods_launch_update_v<VV>(s, P)
+    RODS_DISPATCH_V(s, CALL);
+#undef CALL
+}
+// split step: pair forces (FORCE_ONLY kernel -> force_out / nb_out) and the per-rod epilogue as two kernels
+inline bool rods_split() {
+    static const bool v = !(std::getenv("CRB_ROD_SPLIT") && std::atoi(std::getenv("CRB_ROD_SPLIT")) == 0);
+    return v;
+}
 void rods_launch_force(crb_sim* s, const RodParams& P, bool force_only) {
 #define CALL(VV) rods_launch_force_v<VV>(s, P, force_only)
     RODS_DISPATCH_V(s, CALL)
@@ -298,8 +313,19 @@ int rods_step(crb_sim* s, u64 n_steps) {
         RodParams P = rods_params(s);
         P.save_prev = last ? 1 : 0;
         stage_begin(s, 0);
-        rods_launch_force(s, P, false);
-        stage_end(s, 0, s->n ? 1 : 0);
+        if (rods_split()) {
+            int rc0;
+            if (!s->force_out && (rc0 = dalloc(s, &s->force_out, s->cap_total * 3 * s->V))) return rc0;
+            if (!s->nb_out && (rc0 = dalloc(s, &s->nb_out, s->cap_total))) return rc0;
+            P.force_out = s->force_out;
+            P.nb_out = s->nb_out;
+            rods_launch_force(s, P, true);
+            rods_launch_update(s, P);
+            stage_end(s, 0, s->n ? 2 : 0);
+        } else {
+            rods_launch_force(s, P, false);
+            stage_end(s, 0, s->n ? 1 : 0);
+        }
         stage_begin(s, 4);
         rods_launch_divide(s, P);
         if (s->n)
