@@ -280,6 +280,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     if args.gpus > 1:
+        if args.workload in ("bacterial_rods", "cell_sorting_as_shipped"):
+            raise SystemExit(f"--workload {args.workload} is a single-GPU line (rods are not slab-decomposed; "
+                             "1,600 cells do not fill one GPU): run it with --gpus 1")
         from cellular_raza_b200 import multi_gpu_bench
 
         return multi_gpu_bench.run(args, rank, world, local_rank, sys.modules[__name__])
