@@ -91,26 +91,16 @@ RodParams rods_params(crb_sim* s) {
     return P;
 }
 
-inline size_t rods_smem_pad() {
-    if (const char* e = std::getenv("CRB_ROD_SMEM_PAD")) return (size_t)std::atol(e);
-    return 0;
-}
-
 template <int V>
 void rods_launch_force_v(crb_sim* s, const RodParams& P, bool force_only) {
     const u32 grid = blocks_for(P.n, kRodThreads);
     if (!grid) return;
     // (register caps of 168 / 128 for 3 / 4 resident CTAs were measured: 4.27 / 4.63 ms against 3.7 ms at
     // 2 M rods — the spills cost more than the occupancy gives)
-    if (force_only) {
+    if (force_only)
         k_rod_force<V, true><<<grid, kRodThreads, 0, s->stream>>>(P);
-        return;
-    }
-    // resident CTAs per SM are capped through an unused dynamic shared-memory request (see rods_smem_pad)
-    static const size_t pad = rods_smem_pad();
-    auto k = k_rod_force<V, false>;
-    if (pad) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-    k<<<grid, kRodThreads, pad, s->stream>>>(P);
+    else
+        k_rod_force<V, false><<<grid, kRodThreads, 0, s->stream>>>(P);
 }
 template <int V>
 void rods_launch_update_v(crb_sim* s, const RodParams& P) {
