@@ -161,3 +161,34 @@ def test_exp_bounded_accuracy(crb_lib):
     ref = np.exp(x.astype(np.longdouble))
     rel = np.abs((y.astype(np.longdouble) - ref) / ref).astype(np.float64)
     assert rel.max() <= 2.3e-16, f"max rel err {rel.max():.3e} at x={x[rel.argmax()]!r}"
+
+
+def test_graphs_are_dropped_when_the_population_changes(crb_lib, monkeypatch):
+    """the kernel parameters baked into the step graphs (agent count, tile plan, uniform rows) change with
+    crb_set_agents: a second population on the same handle must not replay the first one's graphs."""
+    w1 = workloads.cell_sorting(n_threads=1)
+    w2 = workloads.cell_sorting(n_cells=700, domain_size=72.0, seed=4, n_threads=1)
+
+    def run(no_graph):
+        if no_graph:
+            monkeypatch.setenv("CRB_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("CRB_NO_GRAPH", raising=False)
+        d = DeviceSimulation(w1.config())
+        outs = []
+        for w in (w1, w2, w1):
+            if w is w2:
+                # a different domain needs its own handle in general; same handle is legal when the grid is the
+                # same, so w2 reuses w1's domain with fewer agents
+                pos = w2.pos / 72.0 * 110.0
+                d.set_agents(pos, w2.vel, w2.mech_params * [1.0, 1.5], w2.inter_params, w2.species)
+            else:
+                d.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, w.species)
+            d.step(9)
+            outs.append(d.get_agents())
+        d.close()
+        return outs
+
+    for a, b in zip(run(False), run(True)):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
