@@ -509,12 +509,17 @@ int launch_force(crb_sim* s, const KParams& P, bool force_only, const PlaneRange
 int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool ingest) {
     const u64 nv = s->nvox;
     stage_begin(s, 1);
-    k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt,
-                                                            s->tile_sums, nv);
-    k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv,
-                                                    (u32)s->G);
-    k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
-    stage_end(s, 1, 3);
+    if (s->n_tiles == 1) {
+        k_scan_single<<<1, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, nv, (u32)s->G);
+        stage_end(s, 1, 1);
+    } else {
+        k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt,
+                                                                s->tile_sums, nv);
+        k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv,
+                                                        (u32)s->G);
+        k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
+        stage_end(s, 1, 3);
+    }
     stage_begin(s, 2);
     int nl = 0;
     if (n_src) {

@@ -696,6 +696,28 @@ __global__ void __launch_bounds__(kScanThreads)
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
+// the whole scan in one launch when the histogram fits one tile (n <= kScanTile voxels: every example the
+// reference ships): out[k] = base + sum(in[0..k)), out[n] = base + total, like the three passes together
+__global__ void __launch_bounds__(kScanThreads)
+    k_scan_single(const u32* __restrict__ in, u32* __restrict__ out, u64 n, u32 base) {
+    __shared__ u32 tot;
+    const u64 b = (u64)threadIdx.x * kScanItems;
+    u32 v[kScanItems];
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = b + k < n ? in[b + k] : 0u;
+        s += v[k];
+    }
+    u32 off = block_exclusive_scan(s, &tot) + base;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (b + k < n) out[b + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) out[n] = tot + base;
+}
+
 __global__ void __launch_bounds__(kScanThreads)
     k_scan_sums(u32* __restrict__ tile_sums, u32 n_tiles, u32* __restrict__ grand_total, u32 base) {
     __shared__ u32 tot;

@@ -158,10 +158,15 @@ void rods_launch_ingest(crb_sim* s, const RodParams& P) {
 int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev) {
     const u64 nv = s->nvox;
     stage_begin(s, 1);
-    k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, s->tile_sums, nv);
-    k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv, 0u);
-    k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
-    stage_end(s, 1, 3);
+    if (s->n_tiles == 1) {
+        k_scan_single<<<1, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, nv, 0u);
+        stage_end(s, 1, 1);
+    } else {
+        k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, s->tile_sums, nv);
+        k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv, 0u);
+        k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
+        stage_end(s, 1, 3);
+    }
     stage_begin(s, 2);
     int nl = 0;
     if (n_src) {

@@ -140,7 +140,9 @@ def test_graph_batches_equal_plain_loop(crb_lib, monkeypatch, n_steps):
 
     a, la = run(False)
     b, lb = run(True)
-    assert la == lb == 6 * n_steps  # the launch counter counts the kernels inside the graphs
+    # the launch counter counts the kernels inside the graphs: force + scan (one launch: 216 voxels fit one
+    # scan tile) + fill + reorder per step
+    assert la == lb == 4 * n_steps
     for x, y in zip(a[:7], b[:7]):
         np.testing.assert_array_equal(x, y)
     oa, ob = np.argsort(a[7][0]), np.argsort(b[7][0])  # the migration tap is unordered
