@@ -15,7 +15,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libcrb200.so"
-SOURCES = [CSRC / "crb_api.cu"]
+SOURCES = [CSRC / "crb_api.cu", CSRC / "crb_tile.cu", CSRC / "crb_tile2.cu", CSRC / "crb_tile3.cu"]
+OBJ_DIR = PKG / "build"
 HEADERS = [p for p in CSRC.glob("*.cuh")] + [PKG.parent / "include" / "crb.h"]
 
 NVCC_FLAGS = [
@@ -45,19 +46,38 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> Path:
+    """one object per translation unit, compiled in parallel (the tile kernel families dominate the compile time),
+    then one link step"""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
+
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, *(extra or []), "-o", str(LIB), *map(str, SOURCES)]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), flush=True)
+    OBJ_DIR.mkdir(exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+
+    def compile_one(src: Path):
+        obj = OBJ_DIR / (src.stem + ".o")
+        cmd = [nvcc_path(), *flags, *(extra or []), "-c", "-o", str(obj), str(src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"nvcc failed compiling {src.name}")
+        if verbose:
+            print(f"==== {src.name}\n" + res.stdout + res.stderr)
+    cmd = [nvcc_path(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
+           *[str(o) for _, o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libcrb200.so")
-    if verbose:
-        print(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libcrb200.so")
     return LIB
 
 

@@ -13,6 +13,8 @@
 
 #include "crb_force_tile.cuh"
 #include "crb_force_tile2.cuh"
+#include "crb_force_tile3.cuh"
+#include "crb_launch.cuh"
 #include "crb_rods.cuh"
 
 using namespace crb;
@@ -20,6 +22,8 @@ using namespace crb;
 namespace {
 
 thread_local std::string g_create_error;
+const char* const kOpenStepMsg =
+    "a slab step is open (crb_slab_compute .. crb_slab_finish): the state is partly updated, read it after crb_slab_finish";
 
 struct StageTimer {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
@@ -99,7 +103,12 @@ struct crb_sim {
     bool tile2_ok = false;
     size_t tile2_smem = 0;
     int tile2_threads = kTileThreads;
-    int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 k_force_tile, 3 k_force_tile2 (env CRB_FORCE_KERNEL)
+    // k_force_tile3 geometry (2 x 2-row tiles, tensor-core distance filter)
+    TileLaunch tile3;
+    bool tile3_ok = false;
+    size_t tile3_smem = 0;
+    int tile3_threads = kTileThreads;
+    int kernel_choice = 0;  // 0 auto, 1 per-agent kernel, 2 k_force_tile, 3 k_force_tile2, 4 k_force_tile3 (env CRB_FORCE_KERNEL)
     bool timers_on = false;
     StageTimer timers[kNumStages];
     // CUDA graphs of TWO consecutive steps (the X/Y, key, start buffers swap every step, so the pointer set
@@ -173,6 +182,26 @@ int alloc_state(crb_sim* s, State& st, bool dynamic, bool stat) {
             if ((rc = dalloc(s, &st.ip[k], s->cap_total))) return rc;
     }
     return 0;
+}
+
+// parameter mode word of the exchange headers: 0 = per-agent parameter columns, otherwise an FNV-1a hash of the
+// uniform rows with the lowest bit set
+u64 param_mode(const crb_sim* s) {
+    if (!s->uniform) return 0;
+    u64 h = 1469598103934665603ull;
+    auto mix = [&](const double* p, int n) {
+        for (int k = 0; k < n; ++k) {
+            u64 b;
+            std::memcpy(&b, &p[k], 8);
+            for (int i = 0; i < 8; ++i) {
+                h ^= (b >> (8 * i)) & 0xff;
+                h *= 1099511628211ull;
+            }
+        }
+    };
+    mix(s->uni.mp, s->n_mp);
+    mix(s->uni.ip, s->n_ip);
+    return h | 1ull;
 }
 
 inline u32 blocks_for(u64 n, u32 threads) { return (u32)((n + threads - 1) / threads); }
@@ -293,6 +322,7 @@ double uniform_cutoff(const crb_sim* s) {
 void plan_tile(crb_sim* s) {
     s->tile_ok = false;
     s->tile2_ok = false;
+    s->tile3_ok = false;
     if (!s->uniform || s->n == 0 || s->kernel_choice == 1) return;
     if (s->D < 2) return;  // 1-D domains: 3 neighbour voxels, the per-agent kernel is the path
     if (s->cfg.interaction_kind == CRB_INT_NONE) return;  // no pair forces: the per-agent kernel integrates
@@ -406,6 +436,89 @@ void plan_tile(crb_sim* s) {
         const long tiles = (long)((T.x_count + 1) / 2) * ((g.ng[1] + 1) / 2) * s->tile2.nchunks;
         if (tiles < sms) s->tile2_ok = false;
     }
+    // ---- k_force_tile3: the same 2 x 2-row tiles with the tensor-core distance filter ---------------------
+    // 52 B per staged candidate (exact record 32 B + five FP32 filter arrays), no sentinels, target rows padded
+    // to multiples of 16 slots (a half-warp = one MMA tile of targets lies in one row)
+    s->tile3_ok = false;
+    if (s->kernel_choice == 0 || s->kernel_choice == 4) {
+        const size_t per_cand3 = sizeof(TileCand) + 5 * sizeof(float);
+        const double halo3 = srows * 2.0 * rho * 1.05;
+        double best3 = 0, fill3 = 0;
+        const char* forced3 = std::getenv("CRB_TILE3_THREADS");
+        for (int nt : {256, 128}) {
+            if (forced3 && std::atoi(forced3) != nt) continue;
+            const int ctas = 512 / nt;
+            const size_t budget3 = (size_t)227 * 1024 / ctas - 1024;
+            const double lanes = nt - trows * 8.0 - 4.0;  // expected padding of a row to 16 slots: 7.5
+            for (int nchunks = 1; nchunks <= n2; ++nchunks) {
+                const int chunk_len = (n2 + nchunks - 1) / nchunks;
+                if (chunk_len > 61 && nchunks < n2) continue;
+                if (nchunks > 1 && (n2 + nchunks - 2) / (nchunks - 1) == chunk_len) continue;
+                const int kmax = chunk_len + 2;
+                const size_t fixed3 = (size_t)(kT3Queue + 1) * nt * 6 + (size_t)kT2Rows * (kmax + 1) * sizeof(u32) + 64 +
+                                      64 * per_cand3 + 128 + 1024 /* static */;
+                if (budget3 <= fixed3) continue;
+                const u32 cap3 = (u32)std::min<size_t>(((budget3 - fixed3) / per_cand3) / 32 * 32, 60000);
+                const double ts = std::min(((double)cap3 - halo3) / per_t, lanes);
+                if (ts < 8.0) continue;
+                const double Rc = chunk_len * col;
+                const int mseg = std::max(1, (int)std::ceil(Rc * 1.05 / ts));
+                const double fill = Rc / mseg;
+                const double score = fill * ctas;
+                if (score <= best3 * 1.001) continue;
+                best3 = score;
+                TileLaunch& U = s->tile3;
+                U = T;
+                U.chunk_len = chunk_len;
+                U.nchunks = (n2 + chunk_len - 1) / chunk_len;
+                U.kmax = kmax;
+                U.tseg = (u32)ts;
+                U.cap = cap3;
+                U.nseg = mseg + 1;
+                s->tile3_threads = nt;
+                s->tile3_smem = tile3_smem_bytes(U.cap, U.kmax, nt);
+                s->tile3_ok = s->tile3_smem <= budget3 + 1024 && tile3_c32(U.cap) < 65536;
+                fill3 = fill;
+            }
+        }
+        if (s->tile3_ok) {
+            // conservative cutoff^2 of the TF32 filter.  Filter coordinates are relative to the centre of the
+            // staged window: |c0|, |c1| <= 2 voxels, |c2| <= (kmax + 1) / 2 voxels (+ 1 % for agents that sit on
+            // a face).  Rounding to TF32 (cvt.rna, 10 explicit mantissa bits) moves a coordinate by at most
+            // 2^-11 of its magnitude; the FP32 filter copy and the origin subtraction add <= 2 ext 2^-22 as in
+            // the FP32 filter; the FP32 accumulation of the eight products and the TF32 split of |b|^2 are
+            // covered by 2^-17 of the largest squared norm.
+            TileLaunch& U = s->tile3;
+            const int ax0 = 0, ax1 = s->D == 3 ? 1 : -1, ax2 = s->D - 1;
+            double m0 = 2.02 * g.dx[ax0], m1 = ax1 >= 0 ? 2.02 * g.dx[ax1] : 0.0;
+            double m2 = (0.5 * (U.kmax + 1) + 0.02) * g.dx[ax2];
+            const double e0 = m0 * std::ldexp(1.0, -11), e1 = m1 * std::ldexp(1.0, -11), e2 = m2 * std::ldexp(1.0, -11);
+            const double delta = std::sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+            const double r2max = m0 * m0 + m1 * m1 + m2 * m2;
+            float cut2m = INFINITY;
+            if (std::isfinite(cutoff) && cutoff > 0) {
+                const double c = (cutoff + 2.0 * delta + 2.0 * ext * std::ldexp(1.0, -22)) * (1.0 + std::ldexp(1.0, -19));
+                const double c2 = c * c + r2max * std::ldexp(1.0, -17);
+                cut2m = (float)c2;
+                if ((double)cut2m < c2) cut2m = std::nextafterf(cut2m, INFINITY);
+            }
+            U.cut2m = cut2m;
+            if (!std::isfinite(cut2m)) s->tile3_ok = false;  // no cutoff: nothing to filter
+        }
+        if (s->tile3_ok && s->tile_ok && s->kernel_choice == 0) {
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, (int)s->cfg.device);
+            const long tiles = (long)((T.x_count + 1) / 2) * ((g.ng[1] + 1) / 2) * s->tile3.nchunks;
+            if (tiles < sms) s->tile3_ok = false;
+        }
+        if (s->tile3_ok && std::getenv("CRB_DEBUG_PLAN")) {
+            const TileLaunch& U = s->tile3;
+            std::fprintf(stderr, "[crb] tile3 plan: threads %d smem %zu cap %u tseg %u nseg %d chunk %d x %d "
+                                 "rho %.2f expected targets/CTA %.0f cut2m %.4f\n",
+                         s->tile3_threads, s->tile3_smem, U.cap, U.tseg, U.nseg, U.chunk_len, U.nchunks, rho, fill3,
+                         (double)U.cut2m);
+        }
+    }
     if (s->tile2_ok && std::getenv("CRB_DEBUG_PLAN")) {
         const TileLaunch& U = s->tile2;
         std::fprintf(stderr, "[crb] tile2 plan: threads %d smem %zu cap %u tseg %u nseg %d chunk %d x %d "
@@ -420,80 +533,36 @@ struct PlaneRange {
     cudaStream_t st = nullptr;
 };
 
-template <int D, int INTER>
-int launch_tile_t(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
-    TileLaunch T = s->tile;
+// the tile kernels are compiled in their own translation units (crb_tile.cu, crb_tile2.cu, crb_tile3.cu: the library
+// builds in parallel); crb_launch.cuh declares their launchers
+int launch_tile_family(crb_sim* s, int which, const KParams& P, bool force_only, const PlaneRange& pr) {
+    TileLaunch T = which == 3 ? s->tile3 : which == 2 ? s->tile2 : s->tile;
     if (pr.x_count >= 0) {
         T.x_begin = pr.x_begin;
         T.x_count = pr.x_count;
     }
     cudaStream_t st = pr.st ? pr.st : s->stream;
-    const u32 grid = (u32)T.x_count * (u32)s->g.ng[1] * (u32)T.nseg * (u32)T.nchunks;
-    if (!grid) return 0;
-    if (force_only) {
-        auto k = k_force_tile<D, INTER, true>;
-        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile_smem));
-        k<<<grid, s->tile_threads, s->tile_smem, st>>>(P, T);
+    const int inter = (int)s->cfg.interaction_kind;
+    cudaError_t e;
+    if (which == 1) {
+        const u32 grid = (u32)T.x_count * (u32)s->g.ng[1] * (u32)T.nseg * (u32)T.nchunks;
+        if (!grid) return 0;
+        e = launch_k_force_tile(s->D, inter, force_only, P, T, grid, s->tile_threads, s->tile_smem, st);
     } else {
-        auto k = k_force_tile<D, INTER, false>;
-        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile_smem));
-        k<<<grid, s->tile_threads, s->tile_smem, st>>>(P, T);
+        const u32 nx2 = (u32)(T.x_count + 1) / 2, ny2 = (u32)(s->g.ng[1] + 1) / 2;
+        const u32 grid = nx2 * ny2 * (u32)T.nseg * (u32)T.nchunks;
+        if (!grid) return 0;
+        e = which == 3 ? launch_k_force_tile3(s->D, inter, force_only, P, T, grid, s->tile3_threads, s->tile3_smem, st)
+                       : launch_k_force_tile2(s->D, inter, force_only, P, T, grid, s->tile2_threads, s->tile2_smem, st);
     }
-    return 0;
-}
-
-template <int D, int INTER>
-int launch_tile2_t(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
-    TileLaunch T = s->tile2;
-    if (pr.x_count >= 0) {
-        T.x_begin = pr.x_begin;
-        T.x_count = pr.x_count;
-    }
-    cudaStream_t st = pr.st ? pr.st : s->stream;
-    const u32 nx2 = (u32)(T.x_count + 1) / 2, ny2 = (u32)(s->g.ng[1] + 1) / 2;
-    const u32 grid = nx2 * ny2 * (u32)T.nseg * (u32)T.nchunks;
-    if (!grid) return 0;
-    auto go = [&](auto k) -> int {
-        CU(s, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->tile2_smem));
-        k<<<grid, s->tile2_threads, s->tile2_smem, st>>>(P, T);
-        return 0;
-    };
-    if (s->tile2_threads == 256)
-        return force_only ? go(k_force_tile2<D, INTER, true, 256>) : go(k_force_tile2<D, INTER, false, 256>);
-    return force_only ? go(k_force_tile2<D, INTER, true, 128>) : go(k_force_tile2<D, INTER, false, 128>);
-}
-
-template <int D>
-int launch_tile2_d(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
-    switch (s->cfg.interaction_kind) {
-        case CRB_INT_CELL_SORTING: return launch_tile2_t<D, CRB_INT_CELL_SORTING>(s, P, force_only, pr);
-        case CRB_INT_CELL_SORTING_BENCH:
-            return launch_tile2_t<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only, pr);
-        case CRB_INT_MORSE: return launch_tile2_t<D, CRB_INT_MORSE>(s, P, force_only, pr);
-        case CRB_INT_BOUND_LJ: return launch_tile2_t<D, CRB_INT_BOUND_LJ>(s, P, force_only, pr);
-        case CRB_INT_MIE: return launch_tile2_t<D, CRB_INT_MIE>(s, P, force_only, pr);
-    }
-    return 0;
-}
-
-template <int D>
-int launch_tile_d(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr) {
-    switch (s->cfg.interaction_kind) {
-        case CRB_INT_CELL_SORTING: return launch_tile_t<D, CRB_INT_CELL_SORTING>(s, P, force_only, pr);
-        case CRB_INT_CELL_SORTING_BENCH:
-            return launch_tile_t<D, CRB_INT_CELL_SORTING_BENCH>(s, P, force_only, pr);
-        case CRB_INT_MORSE: return launch_tile_t<D, CRB_INT_MORSE>(s, P, force_only, pr);
-        case CRB_INT_BOUND_LJ: return launch_tile_t<D, CRB_INT_BOUND_LJ>(s, P, force_only, pr);
-        case CRB_INT_MIE: return launch_tile_t<D, CRB_INT_MIE>(s, P, force_only, pr);
-    }
+    if (e != cudaSuccess) return fail(s, CRB_ERR_CUDA, std::string("tile kernel launch: ") + cudaGetErrorString(e));
     return 0;
 }
 
 int launch_force(crb_sim* s, const KParams& P, bool force_only, const PlaneRange& pr = PlaneRange()) {
-    if (s->tile2_ok)
-        return s->D == 3 ? launch_tile2_d<3>(s, P, force_only, pr) : launch_tile2_d<2>(s, P, force_only, pr);
-    if (s->tile_ok)
-        return s->D == 3 ? launch_tile_d<3>(s, P, force_only, pr) : launch_tile_d<2>(s, P, force_only, pr);
+    if (s->tile3_ok) return launch_tile_family(s, 3, P, force_only, pr);
+    if (s->tile2_ok) return launch_tile_family(s, 2, P, force_only, pr);
+    if (s->tile_ok) return launch_tile_family(s, 1, P, force_only, pr);
     if (s->D == 3)
         launch_force_d<3>(s, P, force_only);
     else if (s->D == 2)
@@ -587,8 +656,12 @@ int check_latch(crb_sim* s) {
                 return fail(s, code, "BoundaryError: Particle is out of domain (agent id " +
                                          std::to_string(id) + ")");
             case CRB_ERR_INDEX:
-                return fail(s, code, "IndexError: could not find voxel index (agent " +
+                return fail(s, code, "IndexError: could not find voxel index, or agent id beyond the noise table (agent " +
                                          std::to_string(id) + ")");
+            case CRB_ERR_STATE:
+                return fail(s, code, "slab exchange: the neighbouring slab uses another parameter mode (uniform row vs "
+                                     "per-agent columns, or a different uniform row): declare the same row with "
+                                     "crb_set_uniform_params on every rank, or on none");
             default: return fail(s, code, "device error " + std::to_string(code));
         }
     }
@@ -861,6 +934,7 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         if (!std::strcmp(kc, "agent")) s->kernel_choice = 1;
         if (!std::strcmp(kc, "tile")) s->kernel_choice = 2;
         if (!std::strcmp(kc, "tile2")) s->kernel_choice = 3;
+        if (!std::strcmp(kc, "tile3")) s->kernel_choice = 4;
     }
 
     auto bail = [&](int rc) {
@@ -947,6 +1021,7 @@ uint64_t crb_kernel_launches(const crb_sim* s) { return s ? s->launches : 0; }
 const char* crb_force_kernel_name(const crb_sim* s) {
     if (!s) return "";
     if (s->rods) return "k_rod_force";
+    if (s->tile3_ok) return s->tile3_threads == 256 ? "k_force_tile3<256 threads, 2 CTAs/SM, tf32 mma filter>" : "k_force_tile3<128 threads, 4 CTAs/SM, tf32 mma filter>";
     if (s->tile2_ok) return s->tile2_threads == 256 ? "k_force_tile2<256 threads, 2 CTAs/SM>" : "k_force_tile2<128 threads, 4 CTAs/SM>";
     if (s->tile_ok) return "k_force_tile";
     return "k_force_integrate";
@@ -965,6 +1040,18 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
     // uniform-parameter fast path: all agents share one parameter row
     if (s->uniform_declared) {
         s->uniform = true;
+    } else if (s->world > 1) {
+        // slabs: whether ALL agents share one parameter row is a property of the whole population, not of the
+        // subset this rank was handed (a slab that starts empty, or one whose own agents happen to agree, must not
+        // take the uniform path while a neighbour ships per-agent columns).  Without a declaration
+        // (crb_set_uniform_params on EVERY rank) a slab keeps per-agent parameter columns.
+        if (n && (!mech_params || !inter_params))
+            return fail(s, CRB_ERR_INVALID_ARG,
+                        "slab handle: mech_params and inter_params are required unless crb_set_uniform_params "
+                        "declared one row on every rank");
+        s->uniform = false;
+        for (int k = 0; k < s->n_mp; ++k) s->uni.mp[k] = 0.0;
+        for (int k = 0; k < s->n_ip; ++k) s->uni.ip[k] = 0.0;
     } else {
         if (n && (!mech_params || !inter_params))
             return fail(s, CRB_ERR_INVALID_ARG, "mech_params and inter_params are required");
@@ -1126,6 +1213,7 @@ int crb_debug_exp(uint32_t device, const double* x, double* y, uint64_t n) {
 int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t* ids,
                    uint64_t* voxel) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_agents(s, cap, pos, vel, (u64*)ids, (u64*)voxel);
@@ -1157,6 +1245,7 @@ int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t*
 int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_params,
                    uint8_t* species) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_params(s, cap, mech_params, inter_params, species);
@@ -1188,6 +1277,7 @@ int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_
 
 int crb_get_aux(crb_sim* s, uint64_t cap, double* hist_dx, double* hist_dv, uint32_t* hist_len) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_aux(s, cap, hist_dx, hist_dv, hist_len);
@@ -1474,6 +1564,7 @@ int crb_slab_halo_export(crb_sim* s, void* lo_buf, void* hi_buf) {
     const u32 grid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
     HaloLayout L = s->hl;
     if (s->uniform) L.n_ip = 0;
+    L.mode = param_mode(s);
     stage_begin(s, 3);
     int nl = 0;
     if (s->has_lo && lo_buf) {
@@ -1500,6 +1591,7 @@ int crb_slab_halo_import(crb_sim* s, const void* lo_buf, const void* hi_buf) {
     const u32 grid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
     HaloLayout L = s->hl;
     if (s->uniform) L.n_ip = 0;
+    L.mode = param_mode(s);
     stage_begin(s, 3);
     int nl = 0;
     if (s->has_lo) {
@@ -1554,7 +1646,7 @@ int crb_slab_compute_interior(crb_sim* s, int save_prev) {
     int b, e;
     interior_planes(s, &b, &e);
     // the per-agent kernel (non-uniform parameters) is not split: everything runs in the boundary call
-    if (!(s->tile_ok || s->tile2_ok) || e <= b || !s->n) return 0;
+    if (!(s->tile_ok || s->tile2_ok || s->tile3_ok) || e <= b || !s->n) return 0;
     // the interior pass starts once the sorted state X of the previous step and the cleared histogram exist
     CU(s, cudaEventRecord(s->ev_ready, s->stream));
     CU(s, cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));
@@ -1625,6 +1717,7 @@ int crb_slab_migration_export(crb_sim* s, void* lo_buf, void* hi_buf, uint64_t n
         M.hi_begin = s->has_hi ? (u32)((s->g.L0 - 1) * plane) : 0xffffffffu;
         M.vox_base = (u64)s->g.p0 * plane;
         M.L = s->ml;
+        M.L.mode = param_mode(s);
         M.buf[0] = (unsigned char*)lo_buf;
         M.buf[1] = (unsigned char*)hi_buf;
         M.counter = s->scratch_u64;
@@ -1717,6 +1810,7 @@ int crb_slab_migration_import(crb_sim* s, const void* lo_buf, const void* hi_buf
         M.vox_base = (u64)s->g.p0 * plane;
         M.nvox = s->nvox;
         M.L = s->ml;
+        M.L.mode = param_mode(s);
         M.buf = (const unsigned char*)(side == 0 ? lo_buf : hi_buf);
         M.err = s->err;
         M.uniform = s->uniform ? 1 : 0;
@@ -1880,6 +1974,7 @@ int crb_sync(crb_sim* s) {
 
 int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
     if (!s || !force) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
@@ -1898,6 +1993,7 @@ int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
 
 int crb_get_identifiers(crb_sim* s, uint64_t cap, uint64_t* ident, uint64_t* parent) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_identifiers(s, cap, (u64*)ident, (u64*)parent);
@@ -1964,6 +2060,7 @@ int crb_get_migrations(crb_sim* s, uint64_t cap, uint64_t* ids, uint64_t* old_vo
 
 int crb_get_voxel_counts(crb_sim* s, uint64_t cap, uint32_t* counts) {
     if (!s || !counts) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     const u64 plane = (u64)s->g.ng[1] * s->g.ng[2];
     const u64 first = (u64)s->g.own_lo * plane, last = (u64)s->g.own_hi * plane;
     if (cap < last - first) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
@@ -1978,6 +2075,7 @@ int crb_get_voxel_counts(crb_sim* s, uint64_t cap, uint32_t* counts) {
 
 int crb_count_candidate_pairs(crb_sim* s, uint64_t* n_pairs) {
     if (!s || !n_pairs) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
     CU(s, cudaSetDevice((int)s->cfg.device));
     *n_pairs = 0;
     if (!s->n) return 0;

@@ -49,6 +49,7 @@ struct TileLaunch {
     u32 cap;        // staged-candidate capacity (incl. sentinels)
     int kmax;       // max voxels of a window + 1 (row stride of the wst table)
     float cut2f;    // conservative FP32 cutoff^2 of the filter
+    float cut2m;    // conservative cutoff^2 of the TF32 tensor-core filter (k_force_tile3)
 };
 
 // exact data of one staged candidate: one address computation and two LDS.128 per evaluated pair

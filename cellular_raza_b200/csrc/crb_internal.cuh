@@ -73,11 +73,14 @@ struct Uniform {
     double ip[CRB_MAX_INTER_PARAMS];
 };
 
-// sortkey layout: bit 63 = moved this step; bits 20..62 = previous global VoxelPlainIndex;
-// bits 0..19 = previous rank inside that voxel.  Ascending sortkey inside a voxel reproduces
-// chili's order: stayers in place, then movers by (source voxel, in-voxel order)
-// (chili/update_mechanics.rs:427-476).
+// sortkey layout: bit 63 = moved this step; bit 62 = moved in from ANOTHER chili subdomain; bits 20..61 =
+// previous global VoxelPlainIndex; bits 0..19 = previous rank inside that voxel.  Ascending sortkey inside a
+// voxel reproduces chili's order: stayers in place, then the movers of the voxel's own subdomain by (source
+// voxel, in-voxel order) — appended by sort_cells_in_voxels_step_1 — then the movers received from other
+// subdomains, sorted by source voxel — appended by step_2 (chili/update_mechanics.rs:427-476, 492-511).
 #define CRB_SK_MOVED (1ull << 63)
+#define CRB_SK_REMOTE (1ull << 62)
+#define CRB_SK_VOXEL(sk) (((sk) & ~(CRB_SK_MOVED | CRB_SK_REMOTE)) >> CRB_SK_RANK_BITS)
 #define CRB_SK_RANK_BITS 20
 #define CRB_SK_RANK_MASK ((1ull << CRB_SK_RANK_BITS) - 1)
 
@@ -121,7 +124,8 @@ struct HaloLayout {
     u64 off_sp;       // u8
     u64 off_ip[CRB_MAX_INTER_PARAMS];
     u64 bytes;
-    // header: u64 n at byte 0
+    u64 mode;  // parameter mode of the sender: 0 = per-agent columns, else hash of the uniform row | 1
+    // header: u64 n at byte 0, u64 mode at byte 8
 };
 // One migration buffer carries complete agents (dynamic + static state) that changed slab.
 struct MigLayout {
@@ -132,7 +136,8 @@ struct MigLayout {
     u64 off_id, off_sortkey, off_gvox;  // u64
     u64 off_hlen, off_sp;               // u8
     u64 bytes;
-    // header: u64 n at byte 0
+    u64 mode;  // as HaloLayout::mode
+    // header: u64 n at byte 0, u64 mode at byte 8
 };
 
 #define CRB_KEY_GONE 0xffffffffu  // newkey of an agent that left this slab (skipped by the reorder)

@@ -436,8 +436,12 @@ __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, c
         double zn[4];
         const u64 id = P.A.id[i];
         if (P.noise_mode == CRB_NOISE_TABLE) {
+            // the table is indexed by the caller's agent id: an id beyond its rows is an IndexError, not a read
+            // past the allocation
+            const bool ok = id < P.noise_ids;
+            if (!ok) latch_error(P.err, CRB_ERR_INDEX, id);
 #pragma unroll
-            for (int c = 0; c < D; ++c) zn[c] = P.noise[(P.noise_cursor * P.noise_ids + id) * D + c];
+            for (int c = 0; c < D; ++c) zn[c] = ok ? P.noise[(P.noise_cursor * P.noise_ids + id) * D + c] : 0.0;
         } else {
             philox_normal4(P.seed, id, P.iteration, 0, zn);
         }
@@ -502,16 +506,26 @@ __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, c
     // ---- A1/A10: new voxel, migration flag, histogram --------------------------------------------
     int q0, q1, q2;
     u32 nk = v;
+    const u64 gp_old = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
+    u64 gp_new = gp_old;
     if (voxel_of<D>(g, p_new, &q0, &q1, &q2)) {
         const int l0 = q0 - g.p0;
-        if (l0 >= 0 && l0 < g.L0) nk = ((u32)l0 * (u32)n1 + (u32)q1) * (u32)n2 + (u32)q2;
+        if (l0 >= 0 && l0 < g.L0) {
+            nk = ((u32)l0 * (u32)n1 + (u32)q1) * (u32)n2 + (u32)q2;
+            gp_new = ((u64)q0 * n1 + q1) * n2 + q2;
+        }
         // (a target plane outside the local planes cannot happen on one device; the multi-GPU
         //  path handles it before this point is reached)
     }
-    const u64 gp_old = ((u64)(i0 + g.p0) * n1 + i1) * n2 + i2;
     u64 rank_old = i - own_lo;
     if (rank_old > CRB_SK_RANK_MASK) rank_old = CRB_SK_RANK_MASK;
-    P.sortkey[i] = (nk != v ? CRB_SK_MOVED : 0ull) | (gp_old << CRB_SK_RANK_BITS) | rank_old;
+    u64 sk = (gp_old << CRB_SK_RANK_BITS) | rank_old;
+    if (nk != v) {
+        sk |= CRB_SK_MOVED;
+        // a mover that changes chili subdomain travels as SendCell and is appended after the local movers
+        if (g.sm_nsub > 1 && g.sub_of(gp_old) != g.sub_of(gp_new)) sk |= CRB_SK_REMOTE;
+    }
+    P.sortkey[i] = sk;
     P.newkey[i] = nk;
     P.rank_arb[i] = atomicAdd(&P.count_new[nk], 1u);
 
@@ -639,6 +653,9 @@ __global__ void __launch_bounds__(kForceThreads)
     }
 }
 
+// the kernels below are not templates: only the translation unit of the C ABI (crb_api.cu) defines them; the tile
+// kernel translation units (crb_tile*.cu) set CRB_TILE_TU
+#ifndef CRB_TILE_TU
 // ------------------------------------------------------------------------------------------------
 // exclusive scan of count_new[0..n) -> start_new[0..n], start_new[n] = total.
 // three passes: per-block scan (4096 items), scan of block sums (one block), add.
@@ -934,7 +951,7 @@ __global__ void k_collect_migrations(const u64* __restrict__ sortkey, const u32*
     const u64 slot = atomicAdd(counter, 1ull);
     if (slot >= cap) return;
     ids[slot] = id_old[i];
-    oldv[slot] = (sk & ~CRB_SK_MOVED) >> CRB_SK_RANK_BITS;
+    oldv[slot] = CRB_SK_VOXEL(sk);
     newv[slot] = (u64)newkey[i] + (u64)g.p0 * g.ng[1] * g.ng[2];
 }
 
@@ -950,7 +967,8 @@ __global__ void k_halo_export(const State A, const u32* __restrict__ start, u32 
     const u32 a = start[v0], b = start[v0 + (u32)L.plane];
     const u64 n = b - a;
     if (t == 0) {
-        *reinterpret_cast<u64*>(buf) = n;
+        reinterpret_cast<u64*>(buf)[0] = n;
+        reinterpret_cast<u64*>(buf)[1] = L.mode;
         if (n > L.gcap) latch_error(err, CRB_ERR_CAPACITY, n);
     }
     if (t <= L.plane) reinterpret_cast<u32*>(buf + L.off_rel)[t] = start[v0 + (u32)t] - a;
@@ -970,9 +988,15 @@ __global__ void k_halo_export(const State A, const u32* __restrict__ start, u32 
 __global__ void k_halo_import(State A, u32* __restrict__ start, u32 v0, u64 edge, int lower, HaloLayout L,
                               const unsigned char* __restrict__ buf, int* err) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 n = *reinterpret_cast<const u64*>(buf);
+    const u64 n = reinterpret_cast<const u64*>(buf)[0];
     if (n > L.gcap) {
         if (t == 0) latch_error(err, CRB_ERR_CAPACITY, n);
+        return;
+    }
+    // both sides of a face must agree on uniform vs per-agent parameters (and on the uniform row): the columns a
+    // uniform sender leaves out would be read as stale memory by a per-agent receiver
+    if (reinterpret_cast<const u64*>(buf)[1] != L.mode) {
+        if (t == 0) latch_error(err, CRB_ERR_STATE, reinterpret_cast<const u64*>(buf)[1]);
         return;
     }
     const u64 base = lower ? edge - n : edge;
@@ -1016,6 +1040,10 @@ struct MigExportParams {
 };
 __global__ void k_mig_export(const MigExportParams M) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {  // parameter mode word of the headers (the counts at byte 0 are copied in by the host code)
+        if (M.buf[0]) reinterpret_cast<u64*>(M.buf[0])[1] = M.L.mode;
+        if (M.buf[1]) reinterpret_cast<u64*>(M.buf[1])[1] = M.L.mode;
+    }
     if (t >= M.n) return;
     const u64 i = M.first + t;
     const u32 k = M.newkey[i];
@@ -1067,6 +1095,11 @@ struct MigImportParams {
 __global__ void k_mig_import(const MigImportParams M) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= M.n) return;
+    if (reinterpret_cast<const u64*>(M.buf)[1] != M.L.mode) {
+        if (t == 0) latch_error(M.err, CRB_ERR_STATE, reinterpret_cast<const u64*>(M.buf)[1]);
+        M.newkey[M.dst + t] = CRB_KEY_GONE;
+        return;
+    }
     const u64 i = M.dst + t;
     const MigLayout& L = M.L;
     const unsigned char* buf = M.buf;
@@ -1140,5 +1173,7 @@ __global__ void k_global_keys(const u32* key, u64* out, u64 base, u64 n) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (u64)key[i] + base;
 }
+
+#endif  // CRB_TILE_TU
 
 }  // namespace crb

@@ -185,7 +185,13 @@ __device__ __forceinline__ void rod_finish(const RodParams& P, const u64 slot, d
     }
     const u64 gp_old = (u64)v_old + (u64)g.p0 * n1 * n2;
     const u64 rk = rank_old > CRB_SK_RANK_MASK ? CRB_SK_RANK_MASK : rank_old;
-    P.sortkey[slot] = (nk != v_old ? CRB_SK_MOVED : 0ull) | (gp_old << CRB_SK_RANK_BITS) | rk;
+    u64 sk = (gp_old << CRB_SK_RANK_BITS) | rk;
+    if (nk != v_old) {
+        sk |= CRB_SK_MOVED;
+        // a rod that changes chili subdomain is appended after the local movers (crb_internal.cuh)
+        if (g.sm_nsub > 1 && g.sub_of(gp_old) != g.sub_of((u64)nk + (u64)g.p0 * n1 * n2)) sk |= CRB_SK_REMOTE;
+    }
+    P.sortkey[slot] = sk;
     P.newkey[slot] = nk;
     P.rank_arb[slot] = atomicAdd(&P.count_new[nk], 1u);
 #pragma unroll

@@ -152,6 +152,16 @@ class SlabRank(DeviceSimulation):
         raise RuntimeError("a slab is stepped by its group (LocalSlabGroup.step / SlabSimulation.step)")
 
 
+def uniform_row(mp, ip):
+    """(mech_row, inter_row) when every agent shares one parameter row, else None (also None for an empty
+    population or missing arrays)"""
+    if mp is None or ip is None or len(mp) == 0:
+        return None
+    if (mp == mp[0]).all() and (ip == ip[0]).all():
+        return np.array(mp[0], dtype=np.float64), np.array(ip[0], dtype=np.float64)
+    return None
+
+
 def split_agents_by_slab(cfg: _abi.CrbConfig, world: int, pos: np.ndarray) -> np.ndarray:
     return rank_of_position(pos[:, 0], cfg.domain_min[0], cfg.dx[0], int(cfg.n_voxels[0]), world)
 
@@ -188,10 +198,29 @@ class LocalSlabGroup:
                 a = np.broadcast_to(a, (n, width))
             return np.ascontiguousarray(a[m])
 
+        # uniform vs per-agent parameters is decided on the WHOLE population and declared on every slab: a slab that
+        # starts empty, or whose own agents happen to share one row, must not differ from its neighbours (the halo /
+        # migration buffers of a uniform slab carry no parameter columns; crb_slab_*_import checks the mode word)
+        rk0 = self.ranks[0]
+        mp = None if mech_params is None else np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, rk0.n_mech))
+        ip = None if inter_params is None else np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, rk0.n_inter))
+        row = uniform_row(mp, ip)
         for r, rk in enumerate(self.ranks):
             m = owner == r
-            rk.set_agents(pos[m], sel(vel, m), sel(mech_params, m, rk.n_mech), sel(inter_params, m, rk.n_inter),
-                          sel(species, m), ids[m])
+            if row is not None:
+                rk.set_uniform_params(*row)
+                rk.set_agents(pos[m], sel(vel, m), None, None, sel(species, m), ids[m])
+            elif mp is None or ip is None:
+                # rows declared earlier with set_uniform_params on every rank
+                rk.set_agents(pos[m], sel(vel, m), None, None, sel(species, m), ids[m])
+            else:
+                rk.set_uniform_params(None, None)
+                rk.set_agents(pos[m], sel(vel, m), np.ascontiguousarray(mp[m]), np.ascontiguousarray(ip[m]),
+                              sel(species, m), ids[m])
+
+    def set_uniform_params(self, mech_row=None, inter_row=None):
+        for rk in self.ranks:
+            rk.set_uniform_params(mech_row, inter_row)
 
     def set_noise(self, z):
         for rk in self.ranks:
@@ -310,15 +339,43 @@ class SlabSimulation:
                                        "slab with the same capacity, ghost_capacity and migration_capacity")
         self.cfg = self.slab.cfg
         self.dim = self.slab.dim
+        self._declared = False
 
     def close(self):
         self.slab.close()
 
     def set_agents(self, pos, vel, mech_params, inter_params, species=None, ids=None):
-        """``pos`` … are THIS rank's agents (axis-0 coordinate inside the slab)."""
+        """``pos`` … are THIS rank's agents (axis-0 coordinate inside the slab).  When parameter arrays are given,
+        whether all agents of ALL ranks share one row is agreed on with one all_gather: every rank then declares
+        that row (or none does) — a rank never decides from its own subset (an empty slab has no row at all)."""
+        if mech_params is not None and inter_params is not None and not self._declared:
+            n = len(pos)
+            mp = np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, self.slab.n_mech))
+            ip = np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, self.slab.n_inter))
+            row = uniform_row(mp, ip)
+            if n == 0:
+                mine = ("empty",)
+            elif row is None:
+                mine = ("mixed",)
+            else:
+                mine = ("row", row[0].tolist(), row[1].tolist())
+            every = [None] * self.world
+            self.dist.all_gather_object(every, mine, group=self.group)
+            rows = [e for e in every if e[0] == "row"]
+            mixed = any(e[0] == "mixed" for e in every)
+            same = bool(rows) and all(r[1:] == rows[0][1:] for r in rows)
+            if same and not mixed:
+                self.slab.set_uniform_params(np.array(rows[0][1]), np.array(rows[0][2]))
+                self.slab.set_agents(pos, vel, None, None, species, ids)
+            else:
+                self.slab.set_uniform_params(None, None)
+                self.slab.set_agents(pos, vel, np.ascontiguousarray(mp), np.ascontiguousarray(ip), species, ids)
+            return
         self.slab.set_agents(pos, vel, mech_params, inter_params, species, ids)
 
     def set_uniform_params(self, mech_row=None, inter_row=None):
+        """must be called with the same rows on every rank"""
+        self._declared = mech_row is not None or inter_row is not None
         self.slab.set_uniform_params(mech_row, inter_row)
 
     def _exchange(self, outs, ins):

@@ -50,7 +50,7 @@ def test_tile_kernel_equals_agent_kernel(crb_lib, monkeypatch, make):
     w = make()
     fa = _forces(w, "agent", monkeypatch)
     scale = np.abs(fa).max()
-    for kernel in ("tile", "tile2"):
+    for kernel in ("tile", "tile2", "tile3"):
         ft = _forces(w, kernel, monkeypatch)
         assert np.abs(fa - ft).max() <= 1e-14 * scale, kernel
         assert np.array_equal(fa, ft), f"{kernel} and per-agent kernels should agree bitwise"
@@ -61,7 +61,7 @@ def test_tile_kernel_dense_voxels_fall_back(crb_lib, monkeypatch):
     inside k_force_tile; results must not change."""
     w = workloads.cell_sorting(n_cells=6000, domain_size=54.0)  # 3^3 voxels, 222 agents per voxel
     fa = _forces(w, "agent", monkeypatch)
-    for kernel in ("tile", "tile2"):
+    for kernel in ("tile", "tile2", "tile3"):
         assert np.array_equal(fa, _forces(w, kernel, monkeypatch)), kernel
 
 
@@ -99,7 +99,7 @@ def test_tile_kernels_ragged_geometries(crb_lib, monkeypatch, n_voxels, density,
     after steps (reflection at the walls, migration, cell-list rebuild feed the next force pass)."""
     w = _box_workload(n_voxels, density, seed=11, n_threads=n_threads, clustered=clustered)
     fa = _forces(w, "agent", monkeypatch)
-    for kernel in ("tile", "tile2"):
+    for kernel in ("tile", "tile2", "tile3"):
         assert np.array_equal(fa, _forces(w, kernel, monkeypatch)), kernel
     states = []
     for kernel in ("agent", "tile2"):
@@ -111,8 +111,9 @@ def test_tile_kernels_ragged_geometries(crb_lib, monkeypatch, n_voxels, density,
         o = np.argsort(ids)
         states.append((pos[o], vel[o], vox[o]))
         sim.close()
-    for a, b in zip(*states):
-        assert np.array_equal(a, b)
+    for other in states[1:]:
+        for a, b in zip(states[0], other):
+            assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("n_steps", [4, 5, 21, 40])

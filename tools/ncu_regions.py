@@ -10,11 +10,20 @@ hi = next(k for k, r in enumerate(rows) if "Source" in r and len(r) > 5)
 hh = rows[hi]
 ii, st = hh.index("Instructions Executed"), hh.index("Warp Stall Sampling (All Samples)")
 D = "cellular_raza_b200/csrc/"
-files = {f: open(D + f).read().splitlines() for f in ("crb_force_tile.cuh", "crb_force_tile2.cuh", "crb_kernels.cuh")}
-main = files["crb_force_tile2.cuh" if which == "tile2" else "crb_force_tile.cuh"]
+files = {f: open(D + f).read().splitlines() for f in ("crb_force_tile.cuh", "crb_force_tile2.cuh", "crb_force_tile3.cuh", "crb_kernels.cuh")}
+mainname = {"tile2": "crb_force_tile2.cuh", "tile3": "crb_force_tile3.cuh"}.get(which, "crb_force_tile.cuh")
+main = files[mainname]
 def find(pat):
     return next(i + 1 for i, l in enumerate(main) if pat in l)
-marks = [("prologue", find("const KParams P, const TileLaunch T)")), ("window_search", find("window size: largest kc")),
+if which == "tile3":
+    marks = [("prologue", find("const KParams P, const TileLaunch T)")), ("window_search", find("window size: largest kc")),
+             ("row_ranges", find("---- row ranges")), ("staging", find("---- stage the candidates")),
+             ("target_setup", find("---- targets:")), ("filter_setup(A frags)", find("---- filter phase")),
+             ("filter_rows", find("while (r < 9 && !full)")), ("filter_mma", find("for (int s = 0; s < 4; ++s)")),
+             ("filter_reduce_push", find("// OR over the quad")), ("drain_ctl", find("---- drain (FP64, exact)")),
+             ("epilogue", find("if (valid) {"))]
+else:
+    marks = [("prologue", find("const KParams P, const TileLaunch T)")), ("window_search", find("window size: largest kc")),
          ("row_ranges", find("---- row ranges")), ("staging", find("---- stage the candidates")),
          ("target_setup", find("---- targets:")), ("drain_ctl", find("auto drain = [&]()")),
          ("filter", find("for (int r = 0; r < 9; ++r)" if which == "tile2" else "for (int r = 0; r < kTileRows; ++r) {")), ("epilogue", find("if (valid) {"))]
@@ -23,15 +32,16 @@ def at(f, ln, t):
     return 0 < ln <= len(L) and L[ln - 1].strip() == t
 def region(ln, text):
     t = text.strip()
-    mainf = "crb_force_tile2.cuh" if which == "tile2" else "crb_force_tile.cuh"
-    if at(mainf, ln, t) and not at("crb_kernels.cuh", ln, t) and not (which == "tile2" and at("crb_force_tile.cuh", ln, t) and 60 < ln < 135):
+    mainf = mainname
+    if at(mainf, ln, t) and not at("crb_kernels.cuh", ln, t) and not (which in ("tile2", "tile3") and at("crb_force_tile.cuh", ln, t) and 60 < ln < 135):
         if ln < marks[0][1]:
+            if which == "tile3": return "filter_mma"
             return "eval(tile_eval)" if (which != "tile2" and ln > 60) else "other"
         r = "prologue"
         for name, start in marks:
             if ln >= start: r = name
         return r
-    if which == "tile2" and at("crb_force_tile.cuh", ln, t) and ln < 200:
+    if which in ("tile2", "tile3") and at("crb_force_tile.cuh", ln, t) and ln < 200:
         return "eval(tile_eval)"
     if at("crb_kernels.cuh", ln, t):
         return "eval(coef/rsqrt)" if ln < 260 else "epilogue(integrate)"
