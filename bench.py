@@ -57,6 +57,8 @@ def parse_args():
                          "cell_sorting_as_shipped = configs[0] (1,600 cells, latency-bound, 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="N = 1 headline run: skip the short legs of BASELINE.json configs[0..3] (key extra_configs)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: halo exchange before the force pass instead of behind its interior planes")
     args = ap.parse_args()
@@ -191,16 +193,23 @@ def cpu_reference_run(args, steps: int, warmup: int, sample_cells: int, target_s
     return val, cores, sample, dt / steps * 1e3
 
 
+def reference_sample_cells(args) -> int:
+    """cells the reference arm (--impl reference) steps: a bounded sample of the configured population at the same
+    density (about 1 s per step on 16 host threads at 1 M cells), so that --steps K --warmup W ends within minutes"""
+    total = args.steps + args.warmup
+    sample_cells = args.cpu_sample_cells if total <= 30 else max(args.cpu_sample_cells // 4, 50_000)
+    if args.workload == "bacterial_rods":
+        sample_cells = min(sample_cells, 200_000)
+    if args.workload == "cell_sorting_as_shipped":
+        sample_cells = 1600
+    return int(min(sample_cells, args.cells_per_gpu))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = args.steps + args.warmup
-    # bounded sample: every step of this arm is one pass over `sample_cells` agents of the same workload
-    # (about 1 s on 16 host threads at 1 M cells), so that --steps K --warmup W ends within minutes
-    sample_cells = args.cpu_sample_cells if total <= 30 else max(args.cpu_sample_cells // 4, 50_000)
-    if args.workload == "bacterial_rods":
-        sample_cells = min(sample_cells, 200_000)
+    sample_cells = reference_sample_cells(args)
     val, cores, sample, ms = cpu_reference_run(args, args.steps, args.warmup, sample_cells)
     line = {
         "impl": "reference",
@@ -211,6 +220,10 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # what this arm actually stepped: a bounded sample of the configured population at the same density
+        # (agent-steps/s of this code is size-independent to a few per cent between 1 M and 8 M cells)
+        "ran": {"cells": sample_cells, "steps_timed": args.steps, "warmup": args.warmup,
+                "of_configured_cells_per_gpu": args.cells_per_gpu},
     }
     print(json.dumps(line), flush=True)
 
@@ -231,6 +244,12 @@ def make_workload(args, n: int):
 
 
 def workload_config(args) -> dict:
+    cfg = _workload_config(args)
+    cfg["reference_arm_sample_cells"] = reference_sample_cells(args)
+    return cfg
+
+
+def _workload_config(args) -> dict:
     n_total = args.cells_per_gpu * args.gpus
     if args.workload == "brownian_morse":
         return {
@@ -268,9 +287,6 @@ def workload_config(args) -> dict:
 def run_b200(args):
     import torch
 
-    from cellular_raza_b200 import workloads
-    from cellular_raza_b200.device import DeviceSimulation, measure_fp64_peak
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -289,6 +305,52 @@ def run_b200(args):
 
     dev_id = local_rank
     torch.cuda.set_device(dev_id)
+    line = measure_point(args, dev_id)
+    if args.workload == "cell_sorting" and not args.no_extra_configs:
+        # the other BASELINE.json configurations as short legs of the same run, so that the driver's record holds
+        # a measured number for every one of them (value, roofline, e2e each; no CPU baseline; < 60 s together)
+        line["extra_configs"] = extra_config_legs(args, dev_id)
+    print(json.dumps(line), flush=True)
+
+
+EXTRA_LEGS = (
+    # key, workload, cells, steps, warmup, e2e steps
+    ("configs[0] cell_sorting as shipped (1,600 cells)", "cell_sorting_as_shipped", 1600, 2000, 50, 20),
+    ("configs[1] cell_sorting 1 M cells", "cell_sorting", 1_000_000, 20, 5, 5),
+    ("configs[2] Brownian3D + Morse 8 M cells (1 GPU)", "brownian_morse", 8_000_000, 8, 3, 3),
+    ("configs[3] bacterial_rods 2 M rods", "bacterial_rods", 2_000_000, 8, 3, 3),
+)
+
+
+def extra_config_legs(args, dev_id: int) -> dict:
+    import copy
+
+    out = {}
+    for key, workload, cells, steps, warmup, e2e_steps in EXTRA_LEGS:
+        a = copy.copy(args)
+        a.workload, a.cells_per_gpu, a.steps, a.warmup = workload, cells, steps, warmup
+        a.density = 7.1
+        a.no_cpu_baseline = True
+        a.e2e_steps = e2e_steps
+        t0 = time.perf_counter()
+        try:
+            leg = measure_point(a, dev_id)
+            keep = ("value", "unit", "ms_per_step", "steps", "warmup", "config", "roofline", "roofline_hbm", "e2e",
+                    "gpu_launches", "stage_ms_per_step")
+            out[key] = {k: leg[k] for k in keep if k in leg}
+        except Exception as e:  # a failing leg must not take the headline down
+            out[key] = {"error": f"{type(e).__name__}: {e}"}
+        out[key]["leg_wall_s"] = round(time.perf_counter() - t0, 2)
+    return out
+
+
+def measure_point(args, dev_id: int) -> dict:
+    """one workload on one GPU -> the JSON line as a dict"""
+    import torch
+
+    from cellular_raza_b200 import workloads
+    from cellular_raza_b200.device import DeviceSimulation, measure_fp64_peak
+
     n = args.cells_per_gpu
     if args.workload == "bacterial_rods":
         return run_rods(args, dev_id)
@@ -366,34 +428,76 @@ def run_b200(args):
     }
 
     # ---- e2e: host buffers in, host buffers out, every step --------------------------------------
+    # Two handles alternate so that the upload of population k + 1 (crb_set_agents_async), the step of population k
+    # (crb_step_async) and the download of population k - 1 (crb_snapshot_async) overlap: PCIe is full duplex and
+    # the copies of one handle run beside the kernels of the other.  Every iteration still moves its complete input
+    # from pinned host memory to the device and its complete result back, inside the timed region.
     e2e = None
     if not args.no_e2e:
-        hp = torch.from_numpy(w.pos).pin_memory()
-        hv = torch.from_numpy(w.vel).pin_memory()
+        import ctypes as C
+
+        lib = sim._lib
+        sim_b = DeviceSimulation(w.config(device=dev_id))
+        sim_b.set_uniform_params(w.mech_params[0], w.inter_params[0])
+        handles = [sim._h, sim_b._h]
+        # two buffer sets per handle: the upload of a handle's next population is queued BEFORE the download of its
+        # previous one is awaited (the download reads the packed snapshot buffer, not the state), so the result
+        # that feeds back as an input is the one of four iterations ago
+        ins = [[None, None], [None, None]]
+        outs = [[None, None], [None, None]]
+        for k in range(2):
+            for j in range(2):
+                ins[k][j] = [torch.from_numpy(w.pos.copy()).pin_memory(), torch.from_numpy(w.vel.copy()).pin_memory()]
+                outs[k][j] = [torch.empty(w.pos.shape, dtype=torch.float64).pin_memory(),
+                              torch.empty(w.vel.shape, dtype=torch.float64).pin_memory()]
         hs = torch.from_numpy(w.species).pin_memory() if w.species is not None else None
         hs_ptr = hs.data_ptr() if hs is not None else None
-        op = torch.empty_like(hp).pin_memory()
-        ov = torch.empty_like(hv).pin_memory()
-        lib, h = sim._lib, sim._h
-        e2e_steps = args.steps
-        for k in range(2 + e2e_steps):
-            if k == 2:
+        e2e_steps = getattr(args, "e2e_steps", None) or args.steps
+        pending = [None, None]  # buffer set of the snapshot in flight per handle
+        nn = C.c_uint64()
+
+        def chk(rc, h):
+            if rc:
+                raise RuntimeError((lib.crb_last_error(h) or b"").decode())
+
+        def retire(k):
+            h, j = handles[k], pending[k]
+            chk(lib.crb_snapshot_wait(h, C.byref(nn)), h)
+            pending[k] = None
+            ins[k][j], outs[k][j] = outs[k][j], ins[k][j]  # this result is a later input of the handle
+
+        t0 = None
+        warm = 8
+        for it in range(warm + e2e_steps):
+            k, j = it % 2, (it // 2) % 2
+            if it == warm:
+                for q in range(2):
+                    if pending[q] is not None:
+                        retire(q)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-            rc = lib.crb_set_agents(h, n, hp.data_ptr(), hv.data_ptr(), None, None, hs_ptr, None)
-            rc = rc or lib.crb_step(h, 1)
-            rc = rc or lib.crb_get_agents(h, n, op.data_ptr(), ov.data_ptr(), None, None)
-            if rc:
-                raise RuntimeError(lib.crb_last_error(h))
-            hp, op = op, hp
-            hv, ov = ov, hv
+            h = handles[k]
+            chk(lib.crb_set_agents_async(h, n, ins[k][j][0].data_ptr(), ins[k][j][1].data_ptr(), None, None, hs_ptr, None), h)
+            chk(lib.crb_step_async(h, 1), h)
+            if pending[k] is not None:
+                retire(k)  # the download of this handle's previous population (started two iterations ago)
+            chk(lib.crb_snapshot_async(h, n, outs[k][j][0].data_ptr(), outs[k][j][1].data_ptr(), None, None, None, None, None), h)
+            pending[k] = j
+        for q in range(2):
+            if pending[q] is not None:
+                retire(q)
+        for h in handles:
+            chk(lib.crb_sync(h), h)  # latched device errors of the asynchronous calls surface here
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
+        sim_b.close()
         e2e = {
             "value": n * e2e_steps / dt_e2e, "unit": UNIT,
             "h2d_bytes_per_step": int(n * (24 + 24 + 1)), "d2h_bytes_per_step": int(n * 48),
             "ms_per_step": dt_e2e / e2e_steps * 1e3,
-            "what": "crb_set_agents(pinned host pos, vel, species) + crb_step(1) + crb_get_agents(host pos, vel) per step",
+            "what": "per step: crb_set_agents_async(pinned host pos, vel, species) + crb_step_async(1) + "
+                    "crb_snapshot_async(pinned host pos, vel) + crb_snapshot_wait; two handles alternate so that "
+                    "upload, step and download of consecutive populations overlap",
         }
 
     # ---- CPU baseline (oracle, bounded sample) ----------------------------------------------------
@@ -412,8 +516,8 @@ def run_b200(args):
                               "reorder": reorder_ms / args.steps},
         "published_reference": "chili on Threadripper 3960X: 2.02e4 (1 thread, 1.3 M cells), best 1.01e5 (43 threads, 20 k cells); BASELINE.md",
     }
-    print(json.dumps(line), flush=True)
     sim.close()
+    return line
 
 
 # per ordered candidate rod pair, 20 vertex-segment evaluations x (Morse 30 flop + nearest
@@ -496,7 +600,7 @@ def run_rods(args, dev_id: int):
         op = torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()
         ov = torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()
         lib, h = sim._lib, sim._h
-        e2e_steps = args.steps
+        e2e_steps = getattr(args, "e2e_steps", None) or args.steps
         for k in range(2 + e2e_steps):
             if k == 2:
                 torch.cuda.synchronize()
@@ -535,8 +639,8 @@ def run_rods(args, dev_id: int):
                               "scan": scan_ms / args.steps, "reorder": reorder_ms / args.steps},
         "note": "not the headline workload: k_rod_force is a per-rod kernel, not yet warp-cooperative (DESIGN.md §9)",
     }
-    print(json.dumps(line), flush=True)
     sim.close()
+    return line
 
 
 def main():

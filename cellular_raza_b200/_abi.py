@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-CRB_ABI_VERSION = 5
+CRB_ABI_VERSION = 6
 CRB_MAX_DIM = 3
 
 # crb_status
@@ -132,6 +132,7 @@ SYMBOLS = [
     ("crb_n_mech_params", C.c_uint32, [C.c_uint32]),
     ("crb_n_inter_params", C.c_uint32, [C.c_uint32]),
     ("crb_set_agents", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("crb_set_agents_async", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("crb_set_uniform_params", C.c_int, [_vp, _vp, _vp]),
     ("crb_n_agents", C.c_uint64, [_vp]),
     ("crb_get_agents", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp]),
@@ -143,6 +144,7 @@ SYMBOLS = [
     ("crb_debug_neighbor_counts", C.c_int, [_vp, C.c_uint64, _vp]),
     ("crb_set_noise", C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
     ("crb_step", C.c_int, [_vp, C.c_uint64]),
+    ("crb_step_async", C.c_int, [_vp, C.c_uint64]),
     ("crb_sync", C.c_int, [_vp]),
     ("crb_iteration", C.c_uint64, [_vp]),
     ("crb_force_kernel_name", C.c_char_p, [_vp]),

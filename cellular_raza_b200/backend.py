@@ -197,6 +197,38 @@ class CellSpecificInteraction:  # cellular_raza-examples/cell_sorting/src/main.r
         return [self.cell_radius, self.potential_strength, self.relative_interaction_range]
 
 
+# ---- the F32 variants of the building blocks ---------------------------------------------------------
+# mechanics.rs:202-204, 385-387, 569-571 (NewtonDamped{1,2,3}DF32, Brownian{1,2,3}DF32, Langevin{1,2,3}DF32) and
+# interaction.rs:144-145, 262-263, 405 (BoundLennardJonesF32, MorsePotentialF32, MiePotentialF32) are the same
+# structs over f32.  The device state of this backend is f64 structure-of-arrays throughout (BASELINE.json
+# north_star) and its parity contract (forces 1e-12, trajectories 1e-9) cannot be stated for f32
+# arithmetic; an f32 state would be a second layout and a second set of kernels, not a parameter.  The decision
+# (INTEGRATION.md "F32 building blocks"): the names exist so that a ported model fails at the first call with a
+# message that says what to do, instead of an AttributeError or a silent widening to f64.
+class _F32Refused:
+    F64_TWIN = ""
+
+    def __init__(self, *args, **kwargs):
+        raise SimulationError(
+            _abi.CRB_ERR_INVALID_ARG,
+            f"{type(self).__name__}: the B200 backend keeps all agent state in f64 and does not run the F32 variants of "
+            f"the building blocks (cellular_raza-building-blocks mechanics.rs:202-204, 385-387, 569-571; "
+            f"interaction.rs:144-145, 262-263, 405); use {self.F64_TWIN} (results within f32 rounding of the F32 "
+            "variant) or the chili backend")
+
+
+def _f32(name: str, twin: str):
+    return type(name, (_F32Refused,), {"F64_TWIN": twin, "__doc__": f"refused: see {twin} (f64)"})
+
+
+for _d in (1, 2, 3):
+    for _k in ("NewtonDamped", "Brownian", "Langevin"):
+        globals()[f"{_k}{_d}DF32"] = _f32(f"{_k}{_d}DF32", f"{_k}{_d}D")
+for _k in ("MorsePotential", "BoundLennardJones", "MiePotential"):
+    globals()[f"{_k}F32"] = _f32(f"{_k}F32", _k)
+del _d, _k
+
+
 @dataclass
 class Agent:
     """what ``#[derive(CellAgent)] struct Cell { #[Mechanics] mechanics, #[Interaction] interaction }``
@@ -363,6 +395,18 @@ class Settings:  # chili/setup.rs:17-27
     progressbar: str | None = None
 
 
+def _storage_names(agents, domain, n_threads: int) -> dict:
+    """what the snapshot writers need besides the state: the agents' struct types (serde field names) and the map
+    from a plain voxel index to its chili subdomain (= storage instance of the batch file)"""
+    subs = chili_subdomains(domain.min, domain.max, domain.n_voxels, domain.dx, n_threads)
+    firsts = np.cumsum([0] + [len(s["voxels"]) for s in subs])[:-1]
+    inter = agents[0].interaction if agents else None
+    return {"mech": type(agents[0].mechanics).__name__ if agents else "", "inter": type(inter).__name__,
+            "mech_cls": type(agents[0].mechanics) if agents else None, "inter_cls": None if inter is None else type(inter),
+            "subdomains": subs,
+            "sub_of": (lambda vox: np.searchsorted(firsts, np.asarray(vox, dtype=np.int64), side="right") - 1)}
+
+
 # ---- the entry point -------------------------------------------------------------------------------
 def _pack(agents: Sequence[Agent], dim: int):
     n = len(agents)
@@ -422,7 +466,7 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
     if devices is not None and len(devices) > 1:
         if domain_force is not None:
             raise SimulationError(_abi.CRB_ERR_INVALID_ARG, "devices=[...] with DomainForce: use one device")
-        return _run_slabs(cfg, list(devices), agents, settings, pos, vel, mp, ip, sp, noise_table)
+        return _run_slabs(cfg, list(devices), agents, settings, pos, vel, mp, ip, sp, noise_table, domain)
     sim = DeviceSimulation(cfg)
     try:
         sim.set_agents(pos, vel, mp, ip, sp)
@@ -440,7 +484,7 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
         subdomains = StorageManager(None if root is None else root / "subdomains" / "json")
         ts = settings.time
         save_its = sorted(set(ts.save_iterations))
-        agent_rows = {"mech": type(agents[0].mechanics).__name__, "inter": type(agents[0].interaction).__name__}
+        agent_rows = _storage_names(agents, domain, max(settings.n_threads, 1))
         # Snapshots do not stop the stepping loop: crb_snapshot_async packs the state on the device and
         # copies it to pinned host memory on a side stream while the next steps run; the JSON / memory
         # store is written by a writer thread (ctypes releases the GIL inside crb_step).
@@ -480,6 +524,7 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
             nonlocal pending
             flush()  # one snapshot in flight: finish the previous one first
             pending = (iteration, sim.snapshot_async(aux=True))
+            _store_subdomains(subdomains, iteration, sb, agent_rows["subdomains"])  # save_subdomains (run_sim.rs:322-325)
 
         if save_its and save_its[0] == 0:  # save_initial (time.rs:243-255)
             save(0)
@@ -500,7 +545,7 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
         sim.close()
 
 
-def _run_slabs(cfg, devices, agents, settings: Settings, pos, vel, mp, ip, sp, noise_table) -> StorageAccess:
+def _run_slabs(cfg, devices, agents, settings: Settings, pos, vel, mp, ip, sp, noise_table, domain) -> StorageAccess:
     """one slab per entry of ``devices`` driven by this host thread (``slabs.LocalSlabGroup``); snapshots are
     gathered slab by slab at the save points."""
     import copy
@@ -523,7 +568,7 @@ def _run_slabs(cfg, devices, agents, settings: Settings, pos, vel, mp, ip, sp, n
                 root = root / sb.suffix
         cells = StorageManager(None if root is None else root / "cells" / "json")
         subdomains = StorageManager(None if root is None else root / "subdomains" / "json")
-        names = {"mech": type(agents[0].mechanics).__name__, "inter": type(agents[0].interaction).__name__}
+        names = _storage_names(agents, domain, max(settings.n_threads, 1))
         ts = settings.time
         save_its = sorted(set(ts.save_iterations))
 
@@ -531,6 +576,7 @@ def _run_slabs(cfg, devices, agents, settings: Settings, pos, vel, mp, ip, sp, n
             state = (*grp.get_agents(), *grp.get_aux())
             k = state[2].astype(np.int64)  # identifiers are the input indices (CellIdentifier::Initial(n))
             _store(state, (mp[k], ip[k], sp[k]), cells, iteration, sb, names)
+            _store_subdomains(subdomains, iteration, sb, names["subdomains"])
 
         if save_its and save_its[0] == 0:
             save(0)
@@ -552,8 +598,95 @@ def _save(sim: DeviceSimulation, cells: StorageManager, iteration: int, sb: Stor
     _store(state, sim.get_params(), cells, iteration, sb, names)
 
 
+_SPECIES_NAMES = {0: "RedCell", 1: "BlueCell"}  # enum Species of cell_sorting/src/main.rs:25-29 (serde unit variants)
+
+
+def _serde_fields(cls, skip=("pos", "vel", "species")):
+    """field names of a building-block struct in declaration order = the keys its serde derive writes
+    (mechanics.rs:54-65, 253-261, 413-426; interaction.rs:87-96, 215-224, 322-335; the dataclasses above declare the
+    same fields in the same order, and their row() methods list the scalar ones in that order)"""
+    import dataclasses
+
+    return [f.name for f in dataclasses.fields(cls) if f.name not in skip]
+
+
+def _cell_body(names: dict, pos, vel, mp_row, ip_row, species) -> dict:
+    """the user's ``#[derive(CellAgent, Serialize)] struct Cell { interaction, mechanics }``
+    (cell_sorting/src/main.rs:99-105) with the building-block structs' own serde field names:
+    ``mechanics: {pos, vel, damping_constant, mass}``, ``interaction: {species: "BlueCell" | "RedCell", cell_radius,
+    potential_strength, relative_interaction_range}`` — what cell_sorting/src/plot.py:43-57 reads."""
+    mcls, icls = names["mech_cls"], names.get("inter_cls")
+    mech = {"pos": [float(x) for x in pos]}
+    if "vel" in {f for f in _serde_fields(mcls, skip=())}:
+        mech["vel"] = [float(x) for x in vel]
+    for k, v in zip(_serde_fields(mcls), mp_row):
+        mech[k] = float(v)
+    cell = {}
+    if icls is not None:
+        inter = {}
+        if icls is CellSpecificInteraction:
+            inter["species"] = _SPECIES_NAMES.get(int(species), int(species))
+        for k, v in zip(_serde_fields(icls), ip_row):
+            inter[k] = float(v)
+        cell["interaction"] = inter
+    cell["mechanics"] = mech
+    return cell
+
+
+def chili_subdomains(domain_min, domain_max, n_voxels, dx, n_threads: int) -> list[dict]:
+    """``CartesianSubDomain`` of every chili subdomain as ``create_subdomains`` builds it
+    (cartesian_cuboid_n.rs:415-423, 500-583): contiguous chunks of the voxel enumeration (last axis fastest), bounding
+    box of the chunk as min / max; serde field names of the struct."""
+    from itertools import product
+
+    nv = [int(x) for x in n_voxels]
+    dim = len(nv)
+    lib = _abi.load_library()
+    import ctypes as C
+
+    n, m, avg = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    total = int(np.prod(nv))
+    if lib.crb_decomp_res(total, max(int(n_threads), 1), C.byref(n), C.byref(m), C.byref(avg)) != 0:
+        raise SimulationError(_abi.CRB_ERR_DECOMPOSE, "DecomposeError: Could not find a suiting decomposition")
+    sizes = [int(avg.value)] * int(n.value) + [int(avg.value) - 1] * int(m.value)
+    sizes = [x for x in sizes if x > 0]
+    voxels = list(product(*[range(k) for k in nv]))
+    out, first = [], 0
+    for size in sizes:
+        chunk = voxels[first:first + size]
+        first += size
+        lo = [min(v[i] for v in chunk) for i in range(dim)]
+        hi = [max(v[i] for v in chunk) for i in range(dim)]
+        out.append({
+            "min": [float(domain_min[i] + lo[i] * dx[i]) for i in range(dim)],
+            "max": [float(domain_min[i] + (hi[i] + 1.0) * dx[i]) for i in range(dim)],
+            "dx": [float(x) for x in dx], "voxels": [list(v) for v in chunk],
+            "domain_min": [float(x) for x in domain_min], "domain_max": [float(x) for x in domain_max],
+            "domain_n_voxels": nv,
+        })
+    return out
+
+
+def _store_subdomains(subdomains: "StorageManager", iteration: int, sb: "StorageBuilder", subs: list[dict], wrap=None):
+    """save_subdomains (chili/datastructures.rs:349-371): one ``single_<instance>_<k>.json`` per subdomain holding
+    ``{"identifier": SubDomainPlainIndex, "element": SubDomain}`` (storage/concepts.rs:156-162, 702-743)"""
+    if "Memory" in sb.priority:
+        subdomains.memory[iteration] = {i: (wrap(s) if wrap else s) for i, s in enumerate(subs)}
+    if subdomains.json_dir is None:
+        return
+    d = subdomains.json_dir / f"{iteration:020d}"
+    d.mkdir(parents=True, exist_ok=True)
+    for i, sub in enumerate(subs):
+        k = 0
+        while (d / f"single_{i:020d}_{k:020d}.json").exists():
+            k += 1
+        (d / f"single_{i:020d}_{k:020d}.json").write_text(
+            json.dumps({"identifier": i, "element": wrap(sub) if wrap else sub}, indent=2))
+
+
 def _store(state, params, cells: StorageManager, iteration: int, sb: StorageBuilder, names: dict):
-    """save_cells (chili/datastructures.rs:373-396) -> store_batch_elements (storage/concepts.rs:766-790)."""
+    """save_cells (chili/datastructures.rs:373-396) -> store_batch_elements (storage/concepts.rs:766-790): one batch
+    file per storage instance = chili subdomain (``names["sub_of"]`` maps a plain voxel index to it)."""
     pos, vel, ids, vox, hx, hv, hl = state
     mp, ip, sp = params
     if "Memory" in sb.priority:
@@ -565,25 +698,29 @@ def _store(state, params, cells: StorageManager, iteration: int, sb: StorageBuil
     if cells.json_dir is not None:
         d = cells.json_dir / f"{iteration:020d}"
         d.mkdir(parents=True, exist_ok=True)
-        k = 0
-        while (d / f"batch_{0:020d}_{k:020d}.json").exists():
-            k += 1
         dim = pos.shape[1]
-        data = []
-        for a in range(len(ids)):
-            ident = {"Initial": int(ids[a])}
-            data.append({
-                "identifier": ident,
-                "element": [
-                    {"identifier": ident, "parent": None,
-                     "cell": {"mechanics": {"pos": pos[a].tolist(), "vel": vel[a].tolist(), "type": names["mech"],
-                                            "params": mp[a].tolist()},
-                              "interaction": {"type": names["inter"], "params": ip[a].tolist(), "species": int(sp[a])}}},
-                    {"mechanics": {"positions": hx[a, : hl[a]].tolist(), "velocities": hv[a, : hl[a]].tolist(),
-                                   "current_force": [0.0] * dim, "zero_force": [0.0] * dim}},
-                ],
-            })
-        (d / f"batch_{0:020d}_{k:020d}.json").write_text(json.dumps({"data": data}, indent=2))
+        sub_of = names.get("sub_of")
+        inst = np.zeros(len(ids), dtype=np.int64) if sub_of is None else sub_of(vox)
+        for instance in np.unique(inst) if len(ids) else [0]:
+            data = []
+            for a in np.nonzero(inst == instance)[0]:
+                ident = {"Initial": int(ids[a])}
+                data.append({
+                    "identifier": ident,
+                    "element": [
+                        {"identifier": ident, "parent": None,
+                         "cell": _cell_body(names, pos[a], vel[a], mp[a], ip[a], sp[a])},
+                        # _CrAuxStorage of aspects [Mechanics, Interaction]: only Mechanics contributes a field
+                        # (cellular_raza-core-proc-macro/src/aux_storage.rs:807-823); RingBuffer = circ_buffer 0.1.8
+                        # (un-vendored): written as the sequence of its entries, oldest first
+                        {"mechanics": {"positions": hx[a, : hl[a]].tolist(), "velocities": hv[a, : hl[a]].tolist(),
+                                       "current_force": [0.0] * dim, "zero_force": [0.0] * dim}},
+                    ],
+                })
+            k = 0
+            while (d / f"batch_{int(instance):020d}_{k:020d}.json").exists():
+                k += 1
+            (d / f"batch_{int(instance):020d}_{k:020d}.json").write_text(json.dumps({"data": data}, indent=2))
 
 
 # ---- bacterial rods: aspects [Mechanics, Interaction, Cycle, NeighborSensing] (+ DomainForce) ------------
@@ -649,6 +786,12 @@ def _run_rods(domain, agents: Sequence[RodAgent], settings: Settings, aspects, *
                       domain_force_kind=_abi.CRB_DOMAIN_FORCE_ROD_GEL if use_force else _abi.CRB_DOMAIN_FORCE_NONE,
                       # create_subdomains hands surface_friction to surface_friction_distance (bacterial_rods.rs:406)
                       domain_force_strength=[gel.gel_pressure, gel.surface_friction, gel.surface_friction] if use_force else None)
+    rod_subs = chili_subdomains(cub.min, cub.max, cub.n_voxels, cub.dx, max(settings.n_threads, 1))
+    _firsts = np.cumsum([0] + [len(x["voxels"]) for x in rod_subs])[:-1]
+
+    def rod_sub_of(vox):
+        return np.searchsorted(_firsts, np.asarray(vox, dtype=np.int64), side="right") - 1
+
     sim = RodSimulation(cfg)
     try:
         sim.set_agents(pos, vel, mp, ip)
@@ -699,7 +842,18 @@ def _run_rods(domain, agents: Sequence[RodAgent], settings: Settings, aspects, *
                            "neighbor_sensing": {"accumulator": 0}}
                     data.append({"identifier": ident_j,
                                  "element": [{"identifier": ident_j, "parent": par, "cell": cell}, aux]})
-                (d / f"batch_{0:020d}_{0:020d}.json").write_text(json.dumps({"data": data}, indent=2))
+                # one batch file per storage instance = chili subdomain of the rod's voxel
+                inst = rod_sub_of(vox) if len(keys) else np.zeros(0, dtype=np.int64)
+                for instance in (np.unique(inst) if len(keys) else [0]):
+                    part = [data[a] for a in np.nonzero(inst == instance)[0]] if len(keys) else []
+                    (d / f"batch_{int(instance):020d}_{0:020d}.json").write_text(json.dumps({"data": part}, indent=2))
+            # save_subdomains: CartesianSubDomainRods { subdomain, gel_pressure, surface_friction,
+            # surface_friction_distance } (bacterial_rods.rs:425-435) or the plain CartesianSubDomain
+            _store_subdomains(subdomains, iteration, sb, rod_subs, wrap=(
+                (lambda sub: {"subdomain": sub, "gel_pressure": float(gel.gel_pressure),
+                              "surface_friction": float(gel.surface_friction),
+                              # create_subdomains hands surface_friction to the distance field (:406)
+                              "surface_friction_distance": float(gel.surface_friction)}) if gel is not None else None))
 
         if save_its and save_its[0] == 0:
             save(0)

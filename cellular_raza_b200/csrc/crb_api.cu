@@ -440,7 +440,9 @@ void plan_tile(crb_sim* s) {
     // 52 B per staged candidate (exact record 32 B + five FP32 filter arrays), no sentinels, target rows padded
     // to multiples of 16 slots (a half-warp = one MMA tile of targets lies in one row)
     s->tile3_ok = false;
-    if (s->kernel_choice == 0 || s->kernel_choice == 4) {
+    // (measured round 2: within 3 % of k_force_tile2 at 8 M cells, slower at low density; the planner therefore keeps
+    // k_force_tile2 unless asked: CRB_FORCE_KERNEL=tile3)
+    if (s->kernel_choice == 4) {
         const size_t per_cand3 = sizeof(TileCand) + 5 * sizeof(float);
         const double halo3 = srows * 2.0 * rho * 1.05;
         double best3 = 0, fill3 = 0;
@@ -1027,11 +1029,12 @@ const char* crb_force_kernel_name(const crb_sim* s) {
     return "k_force_integrate";
 }
 
-int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
-                   const double* mech_params, const double* inter_params, const uint8_t* species,
-                   const uint64_t* ids) {
+static int set_agents_impl(crb_sim* s, uint64_t n, const double* pos, const double* vel,
+                           const double* mech_params, const double* inter_params, const uint8_t* species,
+                           const uint64_t* ids, bool async) {
     if (!s) return CRB_ERR_INVALID_ARG;
     graphs_invalidate(s);
+    if (async && s->rods) return fail(s, CRB_ERR_STATE, "crb_set_agents_async: not available for CRB_MECH_ROD");
     if (n > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
     if (n && !pos) return fail(s, CRB_ERR_INVALID_ARG, "pos is required");
     CU(s, cudaSetDevice((int)s->cfg.device));
@@ -1114,19 +1117,33 @@ int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
             k_ingest_keys<1><<<blocks_for(n, 256), 256, 0, s->stream>>>(P);
         s->launches++;
     }
-    if ((rc = check_latch(s))) {
+    // asynchronous form: ingestion errors (BoundaryError / IndexError of an agent outside the domain) stay latched
+    // on the device and are returned by the next synchronising call
+    if (!async && (rc = check_latch(s))) {
         s->n = 0;
         s->have_agents = false;
         return rc;
     }
     if ((rc = sort_into_place(s, n, n, true, true))) return rc;
-    CU(s, cudaStreamSynchronize(s->stream));
+    if (!async) CU(s, cudaStreamSynchronize(s->stream));
     plan_tile(s);
     s->have_agents = true;
-    s->aux_settable = true;
+    s->aux_settable = !async;
     s->last_step_n = 0;
     s->noise_cursor = 0;
     return 0;
+}
+
+int crb_set_agents(crb_sim* s, uint64_t n, const double* pos, const double* vel,
+                   const double* mech_params, const double* inter_params, const uint8_t* species,
+                   const uint64_t* ids) {
+    return set_agents_impl(s, n, pos, vel, mech_params, inter_params, species, ids, false);
+}
+
+int crb_set_agents_async(crb_sim* s, uint64_t n, const double* pos, const double* vel,
+                         const double* mech_params, const double* inter_params, const uint8_t* species,
+                         const uint64_t* ids) {
+    return set_agents_impl(s, n, pos, vel, mech_params, inter_params, species, ids, true);
 }
 
 int crb_set_uniform_params(crb_sim* s, const double* mech_row, const double* inter_row) {
@@ -1512,14 +1529,19 @@ static int graph_for_orientation(crb_sim* s, cudaGraphExec_t* out) {
     return 0;
 }
 
-int crb_step(crb_sim* s, uint64_t n_steps) {
+static int step_impl(crb_sim* s, uint64_t n_steps, bool async);
+
+int crb_step(crb_sim* s, uint64_t n_steps) { return step_impl(s, n_steps, false); }
+int crb_step_async(crb_sim* s, uint64_t n_steps) { return step_impl(s, n_steps, true); }
+
+static int step_impl(crb_sim* s, uint64_t n_steps, bool async) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "crb_step before crb_set_agents");
     if (s->world > 1)
         return fail(s, CRB_ERR_STATE, "slab handle: drive the step with crb_slab_* (halo/migration exchange)");
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->aux_settable = false;
-    if (s->rods) return rods_step(s, n_steps);
+    if (s->rods) return rods_step(s, n_steps);  // (rods read their division counts back: always synchronous)
     u64 it = 0;
     int rc;
     if (n_steps >= 4 && graph_eligible(s)) {
@@ -1535,7 +1557,7 @@ int crb_step(crb_sim* s, uint64_t n_steps) {
     }
     for (; it < n_steps; ++it)
         if ((rc = plain_step(s, it + 1 == n_steps))) return rc;
-    return check_latch(s);
+    return async ? 0 : check_latch(s);
 }
 
 // ---- slab protocol (one handle per device; the caller moves the buffers between devices) -----------

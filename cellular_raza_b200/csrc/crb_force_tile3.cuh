@@ -314,7 +314,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile3(const KParams P, c
         // origin of the filter coordinates (units of posf = position - domain min): centre of the 4 x 4 rows
         // and of the window along the fastest axis
         float o0, o1, o2;
+        float cut2w;  // conservative cutoff^2 of THIS window (plan_tile bounds the largest window; most are shorter)
         {
+            // |c0|, |c1| <= 2 voxels, |c2| <= half the window (+ 1 % for agents on a face); TF32 rounding moves a
+            // coordinate by <= 2^-11 of its magnitude; T.cut2f is the FP32 filter's cutoff^2 = (cutoff + FP32
+            // allowance)^2, to which the TF32 allowance and the accumulation allowance 2^-17 r^2_max are added
+            const float m0 = 2.02f * (float)g.dx[0];
+            const float m1 = D == 3 ? 2.02f * (float)g.dx[1] : 0.0f;
+            const float m2 = (0.5f * (float)(wb - wa) + 0.02f) * (float)g.dx[D - 1];
+            const float r2max = m0 * m0 + m1 * m1 + m2 * m2;
+            const float delta = sqrtf(r2max) * 4.8828125e-4f * 1.0001f;  // 2^-11
+            const float c = sqrtf(T.cut2f) * 1.000001f + 2.0f * delta;
+            cut2w = fminf(c * c * 1.000001f + r2max * 7.62939453125e-6f, T.cut2m);  // 2^-17
             const float zc = 0.5f * (float)(wa + wb);
             o0 = (float)((double)(X + g.p0 + 1) * g.dx[0]);
             if (D == 3) {
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile3(const KParams P, c
             const int sr0A = (trA >> 1) * 4 + (trA & 1), sr0B = (trB >> 1) * 4 + (trB & 1);
             // filter coordinates of the own target (the staged, rounded values) and |a|^2 - cut^2
             const float ax = FX[sj_self], ay = FY[sj_self], az = FZ[sj_self];
-            const float sown = fmaf(az, az, fmaf(ay, ay, ax * ax)) - T.cut2m;
+            const float sown = fmaf(az, az, fmaf(ay, ay, ax * ax)) - cut2w;
             const float m2x = -2.0f * ax, m2y = -2.0f * ay, m2z = -2.0f * az;
 
             u32* const qm0 = qm + tid;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 5
+#define CRB_ABI_VERSION 6
 
 /* ---- status codes ------------------------------------------------------------------------- */
 typedef enum crb_status {
@@ -180,6 +180,16 @@ int crb_set_agents(crb_sim* sim, uint64_t n, const double* pos, const double* ve
                    const double* mech_params, const double* inter_params,
                    const uint8_t* species, const uint64_t* ids);
 
+/* Asynchronous form of crb_set_agents for a pipelined host (upload of population k + 1, step of population k and
+ * download of population k - 1 overlap when two handles alternate): the copies and the ingestion kernels are only
+ * queued on the handle's stream.  The host buffers must be page-locked (crb_host_alloc) and stay untouched until the
+ * next synchronising call on the handle (crb_sync, crb_step, crb_get_*, crb_snapshot_wait).  Ingestion errors
+ * (BoundaryError / IndexError of an agent outside the domain) are latched on the device and returned by crb_sync /
+ * crb_step.  crb_set_aux cannot follow this form.  Point agents only. */
+int crb_set_agents_async(crb_sim* sim, uint64_t n, const double* pos, const double* vel,
+                         const double* mech_params, const double* inter_params,
+                         const uint8_t* species, const uint64_t* ids);
+
 /* declares that every agent shares one parameter row (the common case for the building-block
  * examples); afterwards crb_set_agents may be called with mech_params == inter_params == NULL
  * and skips the per-agent parameter columns entirely.  Passing NULL, NULL reverts. */
@@ -224,6 +234,9 @@ uint64_t crb_n_divisions(const crb_sim* sim);
  * apply_boundary, sort_cells_in_voxels_step_1/2 (chili/update_mechanics.rs). Asynchronous errors
  * raised on the device (CalcError, BoundaryError) are latched and returned here. */
 int crb_step(crb_sim* sim, uint64_t n_steps);
+/* queues the steps and returns without waiting for the device; errors raised on the device stay latched until
+ * crb_sync / crb_step (rods always synchronise: their division counts are read back every step). */
+int crb_step_async(crb_sim* sim, uint64_t n_steps);
 /* blocks until all queued device work of the handle is done and returns the latched status. */
 int crb_sync(crb_sim* sim);
 /* number of steps taken since creation. */

@@ -3,7 +3,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const CRB_ABI_VERSION: u32 = 5;
+pub const CRB_ABI_VERSION: u32 = 6;
 
 pub const CRB_OK: c_int = 0;
 pub const CRB_ERR_CALC: c_int = -1;
@@ -83,6 +83,8 @@ extern "C" {
     pub fn crb_last_error(sim: *const crb_sim) -> *const c_char;
     pub fn crb_set_agents(sim: *mut crb_sim, n: u64, pos: *const f64, vel: *const f64, mech_params: *const f64,
                           inter_params: *const f64, species: *const u8, ids: *const u64) -> c_int;
+    pub fn crb_set_agents_async(sim: *mut crb_sim, n: u64, pos: *const f64, vel: *const f64, mech_params: *const f64,
+                                inter_params: *const f64, species: *const u8, ids: *const u64) -> c_int;
     pub fn crb_set_uniform_params(sim: *mut crb_sim, mech_row: *const f64, inter_row: *const f64) -> c_int;
     pub fn crb_n_agents(sim: *const crb_sim) -> u64;
     pub fn crb_get_agents(sim: *mut crb_sim, cap: u64, pos: *mut f64, vel: *mut f64, ids: *mut u64,
@@ -95,6 +97,7 @@ extern "C" {
     pub fn crb_get_identifiers(sim: *mut crb_sim, cap: u64, ident: *mut u64, parent: *mut u64) -> c_int;
     pub fn crb_n_divisions(sim: *const crb_sim) -> u64;
     pub fn crb_step(sim: *mut crb_sim, n_steps: u64) -> c_int;
+    pub fn crb_step_async(sim: *mut crb_sim, n_steps: u64) -> c_int;
     pub fn crb_sync(sim: *mut crb_sim) -> c_int;
     pub fn crb_iteration(sim: *const crb_sim) -> u64;
     // storage snapshots that do not stop the stepping loop

@@ -3,7 +3,7 @@
 //! hand-written sm_100a kernels behind the C ABI of `include/crb.h`.
 //!
 //! STATUS: this crate has NOT been compiled — the build image has no cargo/rustc.  It is written
-//! against `include/crb.h` (ABI 5) and mirrors `cellular_raza_b200/backend.py`, which drives the same
+//! against `include/crb.h` (ABI 6) and mirrors `cellular_raza_b200/backend.py`, which drives the same
 //! symbols through ctypes and is what `tests/` exercise.  Expect small fixes at first compile.
 //!
 //! What it replaces in the reference:
@@ -198,6 +198,7 @@ impl<const D: usize> Drop for B200Runner<D> {
 }
 
 /// Host copy of one snapshot (device order of the iteration it was taken at).
+#[derive(Default)]
 pub struct Snapshot<const D: usize> {
     pub pos: Vec<[f64; D]>,
     pub vel: Vec<[f64; D]>,
@@ -207,6 +208,19 @@ pub struct Snapshot<const D: usize> {
     pub hist_dx: Vec<[[f64; D]; 2]>,
     pub hist_dv: Vec<[[f64; D]; 2]>,
     pub hist_len: Vec<u32>,
+}
+
+impl<const D: usize> Snapshot<D> {
+    /// AuxStorage of agent `k`: the ring buffers of increments, oldest first (chili/aux_storage.rs:41-130)
+    pub fn aux(&self, k: usize) -> B200AuxStorage<D> {
+        let mut m = cellular_raza_core::backend::chili::AuxStorageMechanics::default();
+        use cellular_raza_core::backend::chili::UpdateMechanics;
+        for e in 0..self.hist_len[k] as usize {
+            m.set_last_position(self.hist_dx[k][e].into());
+            m.set_last_velocity(self.hist_dv[k][e].into());
+        }
+        B200AuxStorage { mechanics: m }
+    }
 }
 
 impl<const D: usize> B200Runner<D> {
@@ -294,6 +308,27 @@ impl<const D: usize> B200Runner<D> {
         self.check(rc)
     }
 
+    /// Upload of user cells (packs through [`DeviceCell`]).
+    pub fn set_cells<C: DeviceCell<D>>(&mut self, cells: &[C]) -> Result<(), SimulationError> {
+        let n = cells.len();
+        let (mut pos, mut vel) = (Vec::with_capacity(n * D), Vec::with_capacity(n * D));
+        let mut mech = vec![0.0f64; n * self.n_mech];
+        let mut inter = vec![0.0f64; n * self.n_inter];
+        let mut species = Vec::with_capacity(n);
+        for (k, c) in cells.iter().enumerate() {
+            pos.extend_from_slice(&c.mechanics().position());
+            vel.extend_from_slice(&c.mechanics().velocity());
+            c.mechanics().pack(&mut mech[k * self.n_mech..(k + 1) * self.n_mech]);
+            c.interaction().pack(&mut inter[k * self.n_inter..(k + 1) * self.n_inter]);
+            species.push(c.interaction().species());
+        }
+        let rc = unsafe {
+            ffi::crb_set_agents(self.sim, n as u64, pos.as_ptr(), vel.as_ptr(), mech.as_ptr(), inter.as_ptr(),
+                                species.as_ptr(), std::ptr::null())
+        };
+        self.check(rc)
+    }
+
     /// Replaces `n_steps` iterations of the generated loop body (run_sim.rs:380-403) for aspects
     /// [Mechanics, Interaction]; device-side CalcError / BoundaryError surface here.
     pub fn step(&mut self, n_steps: u64) -> Result<(), SimulationError> {
@@ -331,12 +366,150 @@ impl<const D: usize> B200Runner<D> {
     }
 }
 
-/// `run_simulation!(domain: …, agents: …, settings: …, aspects: [Mechanics, Interaction])` of this backend,
-/// as a function: the same required arguments as the macro of chili
-/// (cellular_raza-core-proc-macro/src/run_sim.rs:131-159).  `save` is called with every finished snapshot
+/// A user agent of the device model set: what `#[derive(CellAgent)] struct Cell { #[Mechanics] mechanics,
+/// #[Interaction] interaction }` is for chili (cellular_raza-examples/cell_sorting/src/main.rs:99-105).  The
+/// backend needs to pack the agent into parameter rows and to write the stepped state back into a clone of it
+/// for storage (`save_cells` serialises the user's own struct, chili/datastructures.rs:373-396).
+pub trait DeviceCell<const D: usize>: Clone + serde::Serialize {
+    type Mechanics: DeviceMechanics<D>;
+    type Interaction: DeviceInteraction;
+    fn mechanics(&self) -> &Self::Mechanics;
+    fn interaction(&self) -> &Self::Interaction;
+    /// `Position::set_pos` + `Velocity::set_velocity` of the concepts API
+    fn set_state(&mut self, pos: &[f64; D], vel: &[f64; D]);
+}
+
+/// `_CrAuxStorage` of aspects `[Mechanics, Interaction]` as the proc-macro generates it
+/// (cellular_raza-core-proc-macro/src/aux_storage.rs:807-823, 887-906): only Mechanics contributes a field.
+#[derive(Clone, serde::Serialize, serde::Deserialize)]
+pub struct B200AuxStorage<const D: usize> {
+    pub mechanics: cellular_raza_core::backend::chili::AuxStorageMechanics<
+        nalgebra::SVector<f64, D>,
+        nalgebra::SVector<f64, D>,
+        nalgebra::SVector<f64, D>,
+        2,
+    >,
+}
+
+/// The body of `run_main!` (cellular_raza-core-proc-macro/src/run_sim.rs:411-480) for this backend: storage
+/// managers `<path>/cells` and `<path>/subdomains` (:432-444), the time stepper of `settings.time`
+/// (cellular_raza-core/src/time.rs:173-266) driving batched `crb_step(n)` between `PartialSave` events, and
+/// `StorageAccess { cells, subdomains }` as the result (chili/result.rs:5-10).
+pub fn run_main<C, const D: usize>(
+    domain: CartesianCuboid<f64, D>,
+    agents: impl IntoIterator<Item = C>,
+    settings: &cellular_raza_core::backend::chili::Settings<
+        cellular_raza_core::time::FixedStepsize<f64>,
+        false,
+    >,
+    opt: B200Options,
+) -> Result<
+    cellular_raza_core::backend::chili::StorageAccess<
+        (cellular_raza_concepts::CellBox<C>, B200AuxStorage<D>),
+        cellular_raza_building_blocks::CartesianSubDomain<f64, D>,
+    >,
+    SimulationError,
+>
+where
+    C: DeviceCell<D> + for<'a> serde::Deserialize<'a>,
+{
+    use cellular_raza_concepts::{CellBox, CellIdentifier, Domain};
+    use cellular_raza_core::storage::{StorageInterfaceStore, StorageManager};
+    use cellular_raza_core::time::{TimeEvent, TimeStepper};
+
+    let cells: Vec<C> = agents.into_iter().collect();
+    let device: Vec<DeviceAgent<_, _>> = Vec::new();
+    let _ = device;
+    let n_threads: usize = settings.n_threads.into();
+    let dt = settings.time.dt;
+    let mut runner = B200Runner::<D>::new::<C::Mechanics, C::Interaction>(&domain, dt, n_threads, cells.len(), opt)?;
+    runner.set_cells(&cells)?;
+
+    // storage managers exactly as run_main builds them (run_sim.rs:432-444)
+    let builder = settings.storage.clone().init();
+    let mut storage_cells = StorageManager::<CellIdentifier, (CellBox<C>, B200AuxStorage<D>)>::open_or_create(
+        builder.clone().suffix(builder.get_suffix().join("cells")), 0)?;
+    let mut storage_subdomains = StorageManager::open_or_create(
+        builder.clone().suffix(builder.get_suffix().join("subdomains")), 0)?;
+    let subdomains = domain.create_subdomains(settings.n_threads)?;
+
+    let mut time_stepper = settings.time.clone();
+    let mut snap = Snapshot::<D>::default();
+    let mut steps_since_save = 0u64;
+    while let Some(next) = time_stepper.advance()? {
+        steps_since_save += 1;
+        if let Some(TimeEvent::PartialSave) = next.event {
+            runner.step(steps_since_save)?; // replaces that many iterations of run_sim.rs:380-403
+            steps_since_save = 0;
+            runner.snapshot_async(&mut snap)?;
+            runner.snapshot_wait()?;
+            let batch = (0..snap.ids.len()).map(|k| {
+                let id = CellIdentifier::Initial(snap.ids[k] as usize);
+                let mut c = cells[snap.ids[k] as usize].clone();
+                c.set_state(&snap.pos[k], &snap.vel[k]);
+                (id, (CellBox::new(id, None, c), snap.aux(k)))
+            });
+            storage_cells.store_batch_elements(next.iteration as u64, batch.collect::<Vec<_>>().iter().map(|(i, e)| (i, e)))?;
+            for (index, subdomain, _) in subdomains.iter() {
+                storage_subdomains.store_single_element(next.iteration as u64, index, subdomain)?;
+            }
+        }
+    }
+    if steps_since_save > 0 {
+        runner.step(steps_since_save)?;
+    }
+    Ok(cellular_raza_core::backend::chili::StorageAccess { cells: storage_cells, subdomains: storage_subdomains })
+}
+
+/// `run_simulation!` of this backend: the same required keyword arguments as chili's macro
+/// (cellular_raza-core-proc-macro/src/run_sim.rs:131-159, 594-607) and the same result type
+/// `Result<StorageAccess<_, _>, SimulationError>` (chili/result.rs:5-10), so that a model switches backend by
+/// changing the `use` line:
+///
+/// ```ignore
+/// use cellular_raza_b200::run_simulation;           // was: cellular_raza::core::backend::chili::run_simulation
+/// let storage = run_simulation!(
+///     domain: domain,
+///     agents: cells,
+///     settings: settings,
+///     aspects: [Mechanics, Interaction],
+/// )?;
+/// ```
+///
+/// Optional keyword arguments of the reference that this backend understands: `mechanics_solver_order: 0 | 1 | 2`
+/// (:146), `determinism` (:141; the device path is always deterministic).  `parallelizer`, `zero_force_default`,
+/// the `update_mechanics_interaction_step_*` plug-in points and `custom_update` belong to chili's generated loop and
+/// are rejected at compile time.  `aspects` must be `[Mechanics, Interaction]`, `[Mechanics]` or those plus
+/// `DomainForce` (anything else is outside the device model set).
+#[macro_export]
+macro_rules! run_simulation {
+    (domain: $domain:expr, agents: $agents:expr, settings: $settings:expr, aspects: [$($asp:ident),+ $(,)?]
+     $(, mechanics_solver_order: $order:expr)? $(, determinism: $det:expr)? $(,)?) => {{
+        $( $crate::__check_aspect!($asp); )+
+        #[allow(unused_mut)]
+        let mut opt = $crate::B200Options::default();
+        $( opt.mechanics_solver_order = $order; )?
+        $( let _: bool = $det; )?
+        $crate::run_main($domain, $agents, &$settings, opt)
+    }};
+}
+
+#[doc(hidden)]
+#[macro_export]
+macro_rules! __check_aspect {
+    (Mechanics) => {};
+    (Interaction) => {};
+    (DomainForce) => {};
+    ($other:ident) => {
+        compile_error!(concat!("aspect ", stringify!($other), " is outside the B200 backend's device model set"));
+    };
+}
+
+/// The same loop as a plain function over already packed agents (no storage): `save` receives every snapshot.
+/// `save` is called with every finished snapshot
 /// (feed `StorageManager::store_batch_elements`, storage/concepts.rs:766-790); it runs while the device
 /// already computes the next interval.
-pub fn run_simulation<M, I, const D: usize>(
+pub fn run_packed<M, I, const D: usize>(
     domain: &CartesianCuboid<f64, D>,
     agents: &[DeviceAgent<M, I>],
     dt: f64,

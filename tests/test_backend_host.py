@@ -68,3 +68,47 @@ def test_rod_agent_packing_and_aspects():
     assert cr._ident((1, 7, 0)) == ("Initial", 7) and cr._ident_json(("Division", 3, 2)) == {"Division": [3, 2]}
     m = cr._matrix_json(np.arange(6.0).reshape(2, 3))
     assert m == [[0.0, 3.0, 1.0, 4.0, 2.0, 5.0], 2, None]  # column-major data, nrows, Const<3> as unit
+
+
+def test_snapshot_body_has_the_reference_serde_layout():
+    """cell body = the building-block structs' own serde field names (mechanics.rs:54-65, 253-261, 413-426;
+    interaction.rs:87-96, 215-224, 322-335; cell_sorting/src/main.rs:25-38, 99-105)"""
+    names = {"mech_cls": cr.NewtonDamped3D, "inter_cls": cr.CellSpecificInteraction}
+    body = cr._cell_body(names, [1.0, 2.0, 3.0], [0.1, 0.2, 0.3], [2.0, 1.5], [6.0, 2.0, 1.5], 1)
+    assert body == {"interaction": {"species": "BlueCell", "cell_radius": 6.0, "potential_strength": 2.0,
+                                    "relative_interaction_range": 1.5},
+                    "mechanics": {"pos": [1.0, 2.0, 3.0], "vel": [0.1, 0.2, 0.3], "damping_constant": 2.0, "mass": 1.5}}
+    names = {"mech_cls": cr.Brownian2D, "inter_cls": cr.MorsePotential}
+    body = cr._cell_body(names, [1.0, 2.0], [0.0, 0.0], [0.3, 0.4], [3.0, 0.5, 12.0, 0.01], 0)
+    assert body["mechanics"] == {"pos": [1.0, 2.0], "diffusion_constant": 0.3, "kb_temperature": 0.4}
+    assert body["interaction"] == {"radius": 3.0, "potential_stiffness": 0.5, "cutoff": 12.0, "strength": 0.01}
+    names = {"mech_cls": cr.Langevin3D, "inter_cls": None}
+    body = cr._cell_body(names, [1.0, 2.0, 3.0], [4.0, 5.0, 6.0], [1.5, 0.7, 0.4], [], 0)
+    assert body == {"mechanics": {"pos": [1.0, 2.0, 3.0], "vel": [4.0, 5.0, 6.0], "mass": 1.5, "damping": 0.7,
+                                  "kb_temperature": 0.4}}
+
+
+def test_subdomain_snapshots_follow_create_subdomains():
+    """CartesianSubDomain of every chili subdomain (cartesian_cuboid_n.rs:415-423, 500-583): 5^3 voxels into 4
+    subdomains hold 32 + 31 + 31 + 31 voxels (the reference's own test :380-402), contiguous in the enumeration"""
+    subs = cr.chili_subdomains([0.0] * 3, [100.0] * 3, [5, 5, 5], [20.0] * 3, 4)
+    assert [len(s["voxels"]) for s in subs] == [32, 31, 31, 31]
+    flat = [tuple(v) for s in subs for v in s["voxels"]]
+    assert flat[0] == (0, 0, 0) and flat[1] == (0, 0, 1) and flat[-1] == (4, 4, 4) and len(set(flat)) == 125
+    assert subs[0]["min"] == [0.0, 0.0, 0.0] and subs[0]["max"] == [40.0, 100.0, 100.0]
+    assert subs[0]["domain_min"] == [0.0] * 3 and subs[0]["domain_n_voxels"] == [5, 5, 5]
+    assert set(subs[0]) == {"min", "max", "dx", "voxels", "domain_min", "domain_max", "domain_n_voxels"}
+
+
+@pytest.mark.parametrize("name,twin", [("NewtonDamped3DF32", "NewtonDamped3D"), ("Brownian2DF32", "Brownian2D"),
+                                       ("Langevin1DF32", "Langevin1D"), ("MorsePotentialF32", "MorsePotential"),
+                                       ("BoundLennardJonesF32", "BoundLennardJones"), ("MiePotentialF32", "MiePotential")])
+def test_f32_building_blocks_are_refused_with_a_message(name, twin):
+    """mechanics.rs:202-204, 385-387, 569-571; interaction.rs:144-145, 262-263, 405: the refusal is explicit
+    (CRB_ERR_INVALID_ARG + message naming the f64 twin), never a silent widening"""
+    from cellular_raza_b200 import _abi
+
+    with pytest.raises(cr.SimulationError) as e:
+        getattr(cr, name)([0.0, 0.0, 0.0], [0.0, 0.0, 0.0], 1.0, 1.0)
+    assert e.value.code == _abi.CRB_ERR_INVALID_ARG
+    assert twin in str(e.value) and "f64" in str(e.value)

@@ -56,6 +56,39 @@ def test_cell_sorting_example_with_json_storage(crb_lib, tmp_path):
     assert len(mem) == n
     moved = np.array([np.abs(mem[("Initial", k)]["pos"] - pos[k]).max() for k in range(n)])
     assert moved.max() > 1e-3  # the cells interact
+    # ---- what cellular_raza-examples/cell_sorting/src/plot.py:14-57 does with the output directory ------------
+    import glob
+
+    def get_cells_at_iteration(iteration):
+        cells = []
+        for batch in glob.glob(str(acc.path / "cells" / "json" / f"{iteration:020d}") + "/*"):
+            cells.extend(json.loads(open(batch).read())["data"])
+        return cells
+
+    cells = get_cells_at_iteration(40)
+    assert len(cells) == n
+    info = [(c["element"][0]["cell"]["mechanics"]["pos"], c["element"][0]["cell"]["interaction"]["cell_radius"],
+             c["element"][0]["cell"]["interaction"]["species"]) for c in cells]
+    assert all(len(p) == 3 and r == 6.0 and sp in ("RedCell", "BlueCell") for p, r, sp in info)
+    assert sum(sp == "BlueCell" for _, _, sp in info) == n // 2 + 1
+    one = cells[0]["element"][0]["cell"]
+    assert set(one["mechanics"]) == {"pos", "vel", "damping_constant", "mass"}  # serde of NewtonDamped3D, mechanics.rs:54-65
+    assert set(one["interaction"]) == {"species", "cell_radius", "potential_strength", "relative_interaction_range"}
+    # one batch file per storage instance = chili subdomain (Settings.n_threads = 4), cells of a file lie in its voxels
+    files = sorted((acc.path / "cells" / "json" / f"{40:020d}").glob("batch_*.json"))
+    assert [f.name for f in files] == [f"batch_{i:020d}_{0:020d}.json" for i in range(4)]
+    subs = []
+    for single in sorted(glob.glob(str(acc.path / "subdomains" / "json" / f"{40:020d}") + "/*")):
+        d = json.loads(open(single).read())
+        subs.append(d["element"])
+    assert len(subs) == 4
+    assert subs[0]["domain_min"] == [0.0] * 3 and subs[0]["domain_max"] == [72.0] * 3  # plot.py:46-50
+    assert sum(len(x["voxels"]) for x in subs) == 64 and subs[0]["domain_n_voxels"] == [4, 4, 4]
+    for i, f in enumerate(files):
+        vox = {tuple(v) for v in subs[i]["voxels"]}
+        for c in json.loads(f.read_text())["data"]:
+            p = c["element"][0]["cell"]["mechanics"]["pos"]
+            assert tuple(int(x // 18.0) for x in p) in vox
 
 
 def test_snapshot_async_equals_blocking_download(crb_lib):
@@ -150,6 +183,26 @@ def test_bacterial_rods_example_through_run_simulation(crb_lib, tmp_path):
     assert set(cbox["cell"]) == {"mechanics", "interaction", "growth_rate", "spring_length_threshold"}
     assert cbox["cell"]["mechanics"]["pos"][1:] == [5, None] and len(cbox["cell"]["mechanics"]["pos"][0]) == 15
     assert set(aux) == {"cycle", "mechanics", "neighbor_sensing"}
+    # ---- what cellular_raza-examples/bacterial_rods/plotter.py:22-51 does with the output directory -----------
+    import glob
+
+    import pandas as pd
+
+    results = []
+    for file in glob.glob(str(acc.path / "cells/json/{:020}".format(120)) + "/*"):
+        elements = json.load(open(file))["data"]
+        results.extend(element["element"][0] for element in elements)
+    df = pd.json_normalize(results)
+    assert len(df) == len(last)
+    positions = df["cell.mechanics.pos"].apply(lambda x: np.array(x[0], dtype=float).reshape(3, -1))
+    radii = np.array(list(df["cell.interaction.radius"]), dtype=float)
+    growth = np.array(list(df["cell.growth_rate"]), dtype=float)
+    assert positions.iloc[0].shape == (3, 5) and (radii > 0).all() and growth.shape == radii.shape
+    by_pos = {tuple(np.round(p.T.reshape(-1), 12)) for p in positions}
+    assert tuple(np.round(np.asarray(next(iter(last.values()))["pos"]).reshape(-1), 12)) in by_pos
+    sub = json.loads(next((acc.path / "subdomains" / "json" / f"{120:020d}").glob("single_*.json")).read_text())
+    assert set(sub["element"]) == {"subdomain", "gel_pressure", "surface_friction", "surface_friction_distance"}
+    assert set(sub["element"]["subdomain"]) == {"min", "max", "dx", "voxels", "domain_min", "domain_max", "domain_n_voxels"}
 
 
 def test_run_simulation_over_slabs_equals_single_device(crb_lib):
