@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true",
                     help="N = 1 headline run: skip the short legs of BASELINE.json configs[0..3] (key extra_configs)")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: slab exchange through crb_slab_step (peer memory over NVLink, no host sync) or the "
+                         "six-phase protocol over ncclSend/ncclRecv")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: halo exchange before the force pass instead of behind its interior planes")
     args = ap.parse_args()

@@ -25,6 +25,7 @@ CRB_ERR_INVALID_ARG = -16
 CRB_ERR_CAPACITY = -17
 CRB_ERR_CUDA = -18
 CRB_ERR_STATE = -19
+CRB_ERR_TIMEOUT = -20
 
 # crb_mechanics_kind
 CRB_MECH_NEWTON_DAMPED = 0
@@ -112,6 +113,7 @@ class SimulationError(RuntimeError):
             CRB_ERR_CAPACITY: "CapacityError",
             CRB_ERR_CUDA: "CudaError",
             CRB_ERR_STATE: "StateError",
+            CRB_ERR_TIMEOUT: "OtherThreadError",
         }.get(code, f"Error({code})")
 
 
@@ -164,6 +166,13 @@ SYMBOLS = [
     ("crb_slab_migration_counts", C.c_int, [_vp, _u64p]),
     ("crb_slab_migration_import", C.c_int, [_vp, _vp, _vp, _u64p]),
     ("crb_slab_finish", C.c_int, [_vp, C.c_int]),
+    ("crb_slab_arena_bytes", C.c_uint64, [_vp]),
+    ("crb_slab_arena", C.c_void_p, [_vp]),
+    ("crb_slab_ipc_handle", C.c_int, [_vp, _vp]),
+    ("crb_slab_connect", C.c_int, [_vp, _vp, _vp]),
+    ("crb_slab_connect_ipc", C.c_int, [_vp, _vp, _vp]),
+    ("crb_slab_step", C.c_int, [_vp, C.c_uint64]),
+    ("crb_slab_step_async", C.c_int, [_vp, C.c_uint64]),
     ("crb_debug_forces", C.c_int, [_vp, C.c_uint64, _vp]),
     ("crb_get_migrations", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _u64p]),
     ("crb_get_voxel_counts", C.c_int, [_vp, C.c_uint64, _vp]),

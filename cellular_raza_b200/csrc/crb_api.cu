@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "crb_force_tile.cuh"
 #include "crb_force_tile2.cuh"
 #include "crb_force_tile3.cuh"
@@ -22,6 +24,8 @@ using namespace crb;
 namespace {
 
 thread_local std::string g_create_error;
+const char* const kAsyncPendingMsg =
+    "asynchronous slab steps are queued (crb_slab_step_async): call crb_sync first";
 const char* const kOpenStepMsg =
     "a slab step is open (crb_slab_compute .. crb_slab_finish): the state is partly updated, read it after crb_slab_finish";
 
@@ -57,6 +61,17 @@ struct crb_sim {
     u64 mig_out[2] = {0, 0};          // agents exported in the open step (lo, hi)
     u64 n_src = 0;           // unsorted sources of the open step (owned + arrivals)
     u64 n_gone = 0;          // agents exported in the open step
+    // crb_slab_step: exchange arena (import buffers + flags) that the neighbours write into, their arenas mapped
+    // into this process, device-side agent counts and the exchange step counter
+    unsigned char* arena = nullptr;
+    u64 arena_bytes = 0, arena_halo = 0, arena_mig = 0;  // aligned sizes of one halo / migration buffer
+    unsigned char* peer_arena[2] = {nullptr, nullptr};
+    bool peer_ipc[2] = {false, false};
+    u64* cnt = nullptr;
+    u64* cnt_host = nullptr;  // pinned staging of the owned count
+    u64 slab_steps = 0;
+    bool slab_async_pending = false;  // crb_slab_step_async queued: s->n is stale until crb_sync
+    bool slab_preloaded = false;      // the kernels of crb_slab_step are loaded (lazy loading waits for an idle device)
     cudaStream_t stream = nullptr;
     // overlap of the halo exchange with interior force work: the interior planes run on `stream2`
     // (lowest priority) while the halo travels on `stream` (highest priority)
@@ -206,7 +221,20 @@ u64 param_mode(const crb_sim* s) {
 
 inline u32 blocks_for(u64 n, u32 threads) { return (u32)((n + threads - 1) / threads); }
 
+// NVTX ranges per stage (the reference's counterpart: `tracing` spans around every step function,
+// chili/update_mechanics.rs:152, 284, 343, 386, 417, 484), behind the environment flag CRB_NVTX=1: host-side ranges
+// around the launches of a stage, visible in Nsight Systems next to the kernels they enqueue
+const char* const kStageNames[] = {"crb:force+integrate (update_mechanics_interaction_step_1-3, local_mechanics_update, apply_boundary)",
+                                   "crb:scan (sort_cells_in_voxels: histogram prefix)",
+                                   "crb:reorder (sort_cells_in_voxels_step_1/2)", "crb:halo (PosInformation exchange)",
+                                   "crb:migration (SendCell exchange)"};
+bool nvtx_on() {
+    static const bool on = std::getenv("CRB_NVTX") != nullptr;
+    return on;
+}
+
 void stage_begin(crb_sim* s, int stage, cudaStream_t st = nullptr) {
+    if (nvtx_on()) nvtxRangePushA(kStageNames[stage]);
     if (!s->timers_on) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -216,6 +244,7 @@ void stage_begin(crb_sim* s, int stage, cudaStream_t st = nullptr) {
 }
 void stage_end(crb_sim* s, int stage, int n_launches, cudaStream_t st = nullptr) {
     s->launches += n_launches;
+    if (nvtx_on()) nvtxRangePop();
     if (!s->timers_on) return;
     cudaEventRecord(s->timers[stage].ev.back().second, st ? st : s->stream);
     s->timers[stage].launches += n_launches;
@@ -577,7 +606,9 @@ int launch_force(crb_sim* s, const KParams& P, bool force_only, const PlaneRange
 // scan count_new -> start_alt, fill, reorder T(+X static) -> Y, swap.
 // n_src: unsorted sources at [G, G + n_src) (owned agents of the step + arrivals, some of them marked
 // CRB_KEY_GONE); n_new: agents that remain = destination slots [G, G + n_new).
-int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool ingest) {
+// dev_counts: the numbers of sources / destinations live in s->cnt[1] / the scan total (crb_slab_step); n_src and
+// n_new then only bound the grids
+int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool ingest, bool dev_counts = false) {
     const u64 nv = s->nvox;
     stage_begin(s, 1);
     if (s->n_tiles == 1) {
@@ -595,7 +626,7 @@ int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool inges
     int nl = 0;
     if (n_src) {
         k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt,
-                                                             s->tmp_idx, s->G, n_src);
+                                                             s->tmp_idx, s->G, n_src, dev_counts ? s->cnt + 1 : nullptr);
         ++nl;
     }
     if (n_new) {
@@ -620,6 +651,7 @@ int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool inges
         R.has_species = 1;
         for (int d = 0; d < 3; ++d) R.mn[d] = d < s->D ? s->g.mn[d] : 0.0;
         R.n2 = (u32)s->g.ng[2];
+        R.nvox_dev = dev_counts ? nv : 0;
         k_reorder<<<blocks_for(n_new, 256), 256, 0, s->stream>>>(R);
         ++nl;
     }
@@ -658,8 +690,13 @@ int check_latch(crb_sim* s) {
                 return fail(s, code, "BoundaryError: Particle is out of domain (agent id " +
                                          std::to_string(id) + ")");
             case CRB_ERR_INDEX:
-                return fail(s, code, "IndexError: could not find voxel index, or agent id beyond the noise table (agent " +
+                return fail(s, code, "IndexError: could not find voxel index, agent id beyond the noise table, or an agent "
+                                     "crossed more than one voxel plane into a non-adjacent slab in one step (agent " +
                                          std::to_string(id) + ")");
+            case CRB_ERR_TIMEOUT:
+                return fail(s, code, "slab exchange: a neighbouring slab did not deliver its buffer of exchange step " +
+                                         std::to_string(id) + " in time (crb_slab_step must be called with the same "
+                                         "number of steps on every rank; a single host thread must interleave the ranks)");
             case CRB_ERR_STATE:
                 return fail(s, code, "slab exchange: the neighbouring slab uses another parameter mode (uniform row vs "
                                      "per-agent columns, or a different uniform row): declare the same row with "
@@ -699,6 +736,68 @@ int download_rows(crb_sim* s, double* host, int width, const double* const* cols
 }  // namespace
 
 #include "crb_rods_host.cuh"
+
+// loads every kernel crb_slab_step can launch on this handle (see crb_launch.cuh kPreloadOnly)
+template <int D>
+static void preload_agent_kernels(cudaError_t& e) {
+    cudaFuncAttributes at;
+    auto one = [&](auto k) {
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k);
+    };
+    one(k_force_integrate<D, CRB_INT_CELL_SORTING, true, false>);
+    one(k_force_integrate<D, CRB_INT_CELL_SORTING, false, false>);
+    one(k_force_integrate<D, CRB_INT_CELL_SORTING_BENCH, true, false>);
+    one(k_force_integrate<D, CRB_INT_CELL_SORTING_BENCH, false, false>);
+    one(k_force_integrate<D, CRB_INT_MORSE, true, false>);
+    one(k_force_integrate<D, CRB_INT_MORSE, false, false>);
+    one(k_force_integrate<D, CRB_INT_BOUND_LJ, true, false>);
+    one(k_force_integrate<D, CRB_INT_BOUND_LJ, false, false>);
+    one(k_force_integrate<D, CRB_INT_MIE, true, false>);
+    one(k_force_integrate<D, CRB_INT_MIE, false, false>);
+    one(k_force_integrate<D, CRB_INT_NONE, true, false>);
+    one(k_force_integrate<D, CRB_INT_NONE, false, false>);
+}
+
+static int slab_preload(crb_sim* s) {
+    if (s->slab_preloaded) return 0;
+    cudaError_t e = cudaSuccess;
+    cudaFuncAttributes at;
+    auto one = [&](auto k) {
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k);
+    };
+    one(k_set_u64);
+    one(k_zero_u32);
+    one(k_halo_export);
+    one(k_halo_import);
+    one(k_slab_publish);
+    one(k_slab_wait);
+    one(k_mig_export);
+    one(k_mig_import_dev);
+    one(k_slab_set_count);
+    one(k_scan_tiles);
+    one(k_scan_single);
+    one(k_scan_sums);
+    one(k_scan_add);
+    one(k_fill);
+    one(k_reorder);
+    if (s->D == 3) preload_agent_kernels<3>(e);
+    else if (s->D == 2) preload_agent_kernels<2>(e);
+    else preload_agent_kernels<1>(e);
+    if (s->D >= 2 && s->cfg.interaction_kind != CRB_INT_NONE) {
+        const int inter = (int)s->cfg.interaction_kind;
+        KParams P = make_params(s);
+        TileLaunch T = s->tile;
+        if (e == cudaSuccess) e = launch_k_force_tile(s->D, inter, false, P, T, kPreloadOnly, kTileThreads, 0, s->stream);
+        for (int nt : {128, 256}) {
+            if (e == cudaSuccess) e = launch_k_force_tile2(s->D, inter, false, P, T, kPreloadOnly, nt, 0, s->stream);
+            if (e == cudaSuccess) e = launch_k_force_tile3(s->D, inter, false, P, T, kPreloadOnly, nt, 0, s->stream);
+        }
+    }
+    if (e != cudaSuccess) return fail(s, CRB_ERR_CUDA, std::string("kernel preload: ") + cudaGetErrorString(e));
+    s->slab_preloaded = true;
+    return 0;
+}
+
 
 // =================================================================================================
 extern "C" {
@@ -978,7 +1077,21 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         (rc = dalloc(s, &s->tile_sums, s->n_tiles + 1)) || (rc = dalloc(s, &s->stage, s->cap_total * (rods ? 3 * s->V : 8))) ||
         (rc = dalloc(s, &s->err, 4)) || (rc = dalloc(s, &s->scratch_u64, 16)))
         return bail(rc);
+    if ((rc = dalloc(s, &s->cnt, 8))) return bail(rc);
+    if (s->world > 1 && !rods) {
+        s->arena_halo = (s->hl.bytes + 255) / 256 * 256;
+        s->arena_mig = (s->ml.bytes + 255) / 256 * 256;
+        s->arena_bytes = 256 + 4 * s->arena_halo + 4 * s->arena_mig;
+        // a plain cudaMalloc allocation of its own: cudaIpcGetMemHandle exports whole allocations
+        e = cudaMalloc((void**)&s->arena, s->arena_bytes);
+        if (e == cudaSuccess) e = cudaMemset(s->arena, 0, s->arena_bytes);
+        if (e != cudaSuccess) {
+            s->error = std::string("exchange arena: ") + cudaGetErrorString(e);
+            return bail(CRB_ERR_CUDA);
+        }
+    }
     e = cudaMallocHost((void**)&s->err_host, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->cnt_host, 8 * sizeof(u64));
     if (e != cudaSuccess) {
         s->error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
         return bail(CRB_ERR_CUDA);
@@ -1001,8 +1114,12 @@ void crb_destroy(crb_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     timers_resolve(s);
     graphs_invalidate(s);
+    for (int k = 0; k < 2; ++k)
+        if (s->peer_arena[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_arena[k]);
+    if (s->arena) cudaFree(s->arena);
     for (void* p : s->allocs) cudaFree(p);
     if (s->err_host) cudaFreeHost(s->err_host);
+    if (s->cnt_host) cudaFreeHost(s->cnt_host);
     if (s->snap_pending) cudaEventSynchronize(s->ev_snap_done);
     if (s->stream_io) cudaStreamSynchronize(s->stream_io);
     if (s->ev_snap_packed) cudaEventDestroy(s->ev_snap_packed);
@@ -1107,6 +1224,7 @@ static int set_agents_impl(crb_sim* s, uint64_t n, const double* pos, const doub
     }
     CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
     s->n = n;
+    s->slab_async_pending = false;  // the host-side count is authoritative again
     KParams P = make_params(s);
     if (n) {
         if (D == 3)
@@ -1231,6 +1349,7 @@ int crb_get_agents(crb_sim* s, uint64_t cap, double* pos, double* vel, uint64_t*
                    uint64_t* voxel) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_agents(s, cap, pos, vel, (u64*)ids, (u64*)voxel);
@@ -1263,6 +1382,7 @@ int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_
                    uint8_t* species) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_params(s, cap, mech_params, inter_params, species);
@@ -1295,6 +1415,7 @@ int crb_get_params(crb_sim* s, uint64_t cap, double* mech_params, double* inter_
 int crb_get_aux(crb_sim* s, uint64_t cap, double* hist_dx, double* hist_dv, uint32_t* hist_len) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_aux(s, cap, hist_dx, hist_dv, hist_len);
@@ -1427,12 +1548,17 @@ int crb_set_noise(crb_sim* s, const double* z, uint64_t n_steps, uint64_t n_ids)
 namespace {
 // stage A of one step: pair forces over the 3^D neighbourhood + fused integrate/boundary/new key for
 // the owned agents (ghost planes must hold the neighbours' boundary agents on a slab)
-int step_prepare(crb_sim* s) {
+int step_prepare(crb_sim* s, bool kernels_only = false) {
     const bool stochastic = s->cfg.noise_mode == CRB_NOISE_TABLE &&
                             s->cfg.mechanics_kind != CRB_MECH_NEWTON_DAMPED;
     if (stochastic && s->noise_cursor >= s->noise_steps)
         return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
-    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    if (kernels_only) {
+        k_zero_u32<<<blocks_for(s->nvox + 1, 256), 256, 0, s->stream>>>(s->count_new, s->nvox + 1, nullptr, 0, nullptr, 0);
+        s->launches++;
+    } else {
+        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    }
     return 0;
 }
 // force + integrate for the targets of a plane range (default: all owned planes) on pr.st
@@ -1443,6 +1569,21 @@ int step_launch(crb_sim* s, bool save_prev, const PlaneRange& pr) {
     int rc;
     if ((rc = launch_force(s, P, false, pr))) return rc;
     stage_end(s, 0, s->n ? 1 : 0, pr.st);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+// the whole force pass inside crb_slab_step: tile kernels take their targets from start[]; the per-agent kernel
+// (non-uniform parameters) gets the device-side count
+int step_launch_dev(crb_sim* s, bool save_prev) {
+    if (s->tile_ok || s->tile2_ok || s->tile3_ok) return step_launch(s, save_prev, PlaneRange());
+    KParams P = make_params(s);
+    P.save_prev = save_prev ? 1 : 0;
+    P.n = s->cap;
+    P.n_dev = s->cnt;
+    stage_begin(s, 0);
+    int rc;
+    if ((rc = launch_force(s, P, false, PlaneRange()))) return rc;
+    stage_end(s, 0, 1);
     CU(s, cudaGetLastError());
     return 0;
 }
@@ -1860,6 +2001,297 @@ int crb_slab_finish(crb_sim* s, int save_prev) {
     return 0;
 }
 
+// ---- crb_slab_step: the whole slab step behind ONE call, exchange over peer memory, no host synchronisation ------
+// arena layout (the same on every rank: the buffer sizes agree): 4 flags at byte 0 (halo from lo, halo from hi,
+// migration from lo, migration from hi), then halo_in[side][parity], then mig_in[side][parity]
+namespace {
+unsigned char* arena_halo_in(const crb_sim* s, unsigned char* base, int side, int parity) {
+    return base + 256 + (u64)(side * 2 + parity) * s->arena_halo;
+}
+unsigned char* arena_mig_in(const crb_sim* s, unsigned char* base, int side, int parity) {
+    return base + 256 + 4 * s->arena_halo + (u64)(side * 2 + parity) * s->arena_mig;
+}
+u64* arena_flag(unsigned char* base, int which) { return reinterpret_cast<u64*>(base) + which; }
+// a dead neighbour: 20 s (CRB_SLAB_TIMEOUT_MS), then CRB_ERR_TIMEOUT
+unsigned long long slab_timeout_ns() {
+    static const unsigned long long ns = [] {
+        const char* e = std::getenv("CRB_SLAB_TIMEOUT_MS");
+        return (e ? std::strtoull(e, nullptr, 10) : 20000ull) * 1000000ull;
+    }();
+    return ns;
+}
+}  // namespace
+
+uint64_t crb_slab_arena_bytes(const crb_sim* s) { return s ? s->arena_bytes : 0; }
+void* crb_slab_arena(crb_sim* s) { return s ? (void*)s->arena : nullptr; }
+
+int crb_slab_ipc_handle(crb_sim* s, void* handle64) {
+    if (!s || !handle64) return CRB_ERR_INVALID_ARG;
+    if (!s->arena) return fail(s, CRB_ERR_STATE, "no exchange arena (world_size == 1 or rods)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(s, cudaIpcGetMemHandle(&h, s->arena));
+    std::memcpy(handle64, &h, 64);
+    return 0;
+}
+
+static int connect_common(crb_sim* s) {
+    if (!s->arena) return fail(s, CRB_ERR_STATE, "no exchange arena (world_size == 1 or rods)");
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    for (int k = 0; k < 2; ++k) {
+        if (s->peer_arena[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer_arena[k]);
+        s->peer_arena[k] = nullptr;
+        s->peer_ipc[k] = false;
+    }
+    // flags restart with the connection (every rank connects before anyone steps: host-side barrier of the caller)
+    CU(s, cudaMemsetAsync(s->arena, 0, 256, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    s->slab_steps = 0;
+    return 0;
+}
+
+int crb_slab_connect(crb_sim* s, void* lo_arena, void* hi_arena) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    int rc;
+    if ((rc = connect_common(s))) return rc;
+    if ((s->has_lo && !lo_arena) || (s->has_hi && !hi_arena))
+        return fail(s, CRB_ERR_INVALID_ARG, "crb_slab_connect: a neighbour's arena is missing");
+    void* in[2] = {s->has_lo ? lo_arena : nullptr, s->has_hi ? hi_arena : nullptr};
+    for (int k = 0; k < 2; ++k) {
+        if (!in[k]) continue;
+        cudaPointerAttributes at;
+        CU(s, cudaPointerGetAttributes(&at, in[k]));
+        if (at.type != cudaMemoryTypeDevice) return fail(s, CRB_ERR_INVALID_ARG, "crb_slab_connect: not a device pointer");
+        if (at.device != (int)s->cfg.device) {
+            int can = 0;
+            CU(s, cudaDeviceCanAccessPeer(&can, (int)s->cfg.device, at.device));
+            if (!can) return fail(s, CRB_ERR_CUDA, "crb_slab_connect: no peer access to the neighbour's device");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(s, CRB_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        s->peer_arena[k] = (unsigned char*)in[k];
+    }
+    return 0;
+}
+
+int crb_slab_connect_ipc(crb_sim* s, const void* lo_handle64, const void* hi_handle64) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    int rc;
+    if ((rc = connect_common(s))) return rc;
+    if ((s->has_lo && !lo_handle64) || (s->has_hi && !hi_handle64))
+        return fail(s, CRB_ERR_INVALID_ARG, "crb_slab_connect_ipc: a neighbour's handle is missing");
+    const void* in[2] = {s->has_lo ? lo_handle64 : nullptr, s->has_hi ? hi_handle64 : nullptr};
+    for (int k = 0; k < 2; ++k) {
+        if (!in[k]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, in[k], 64);
+        void* p = nullptr;
+        CU(s, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_arena[k] = (unsigned char*)p;
+        s->peer_ipc[k] = true;
+    }
+    return 0;
+}
+
+static int slab_step_impl(crb_sim* s, uint64_t n_steps, bool async);
+// the host-side copy of the owned-agent count is refreshed from the device after asynchronous slab steps
+static int slab_finalize(crb_sim* s) {
+    if (!s->slab_async_pending) return 0;
+    u64 n_now = 0;
+    CU(s, cudaMemcpyAsync(&n_now, s->cnt, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    s->slab_async_pending = false;
+    s->last_step_n = 0;
+    s->n = std::min<u64>(n_now, s->cap);
+    s->n_src = s->n;
+    s->n_gone = 0;
+    plan_tile(s);
+    return 0;
+}
+
+int crb_slab_step(crb_sim* s, uint64_t n_steps) { return slab_step_impl(s, n_steps, false); }
+int crb_slab_step_async(crb_sim* s, uint64_t n_steps) { return slab_step_impl(s, n_steps, true); }
+
+static int slab_step_impl(crb_sim* s, uint64_t n_steps, bool async) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
+    if (s->rods) return fail(s, CRB_ERR_STATE, "rods are not slab-decomposed");
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, "a crb_slab_compute .. crb_slab_finish step is open");
+    if (s->world > 1 && ((s->has_lo && !s->peer_arena[0]) || (s->has_hi && !s->peer_arena[1])))
+        return fail(s, CRB_ERR_STATE, "crb_slab_step: connect the neighbours first (crb_slab_connect / crb_slab_connect_ipc)");
+    if (!n_steps) return 0;
+    CU(s, cudaSetDevice((int)s->cfg.device));
+    s->aux_settable = false;
+    const u64 plane = s->hl.plane;
+    const u32 threads = 256;
+    const u32 hgrid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
+    const u64 src_cap = s->cap + 2 * s->mcap;
+    int rc;
+    if ((rc = slab_preload(s))) return rc;
+    // the host knows the owned count here unless asynchronous steps are still queued; from now on it lives on the
+    // device
+    if (!s->slab_async_pending) {
+        k_set_u64<<<1, 32, 0, s->stream>>>(s->cnt, s->n);
+        s->launches++;
+    }
+    for (u64 it = 0; it < n_steps; ++it) {
+        const bool last = it + 1 == n_steps;
+        const u64 step_no = s->slab_steps;
+        const int par = (int)(step_no & 1);
+        if ((rc = step_prepare(s, true))) return rc;
+        // ---- interior planes on the second stream (needs no halo) ---------------------------------------------
+        int ib, ie;
+        interior_planes(s, &ib, &ie);
+        const bool split = (s->tile_ok || s->tile2_ok || s->tile3_ok) && ie > ib;
+        if (split) {
+            CU(s, cudaEventRecord(s->ev_ready, s->stream));
+            CU(s, cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));
+            PlaneRange pr;
+            pr.x_begin = ib;
+            pr.x_count = ie - ib;
+            pr.st = s->stream2;
+            if ((rc = step_launch(s, last, pr))) return rc;
+            CU(s, cudaEventRecord(s->ev_interior, s->stream2));
+        }
+        // ---- halo: boundary planes straight into the neighbours' import buffers, then their flags ----------------
+        HaloLayout L = s->hl;
+        if (s->uniform) L.n_ip = 0;
+        L.mode = param_mode(s);
+        stage_begin(s, 3);
+        int nl = 0;
+        if (s->has_lo) {  // my lowest owned plane is the neighbour's upper ghost plane: its side "hi"
+            k_halo_export<<<hgrid, threads, 0, s->stream>>>(s->X, s->start, (u32)(s->g.own_lo * plane), L,
+                                                           arena_halo_in(s, s->peer_arena[0], 1, par), s->err);
+            ++nl;
+        }
+        if (s->has_hi) {
+            k_halo_export<<<hgrid, threads, 0, s->stream>>>(s->X, s->start, (u32)((s->g.own_hi - 1) * plane), L,
+                                                           arena_halo_in(s, s->peer_arena[1], 0, par), s->err);
+            ++nl;
+        }
+        if (s->has_lo || s->has_hi) {
+            k_slab_publish<<<1, 32, 0, s->stream>>>(nullptr, nullptr, nullptr,
+                                                   s->has_lo ? arena_flag(s->peer_arena[0], 1) : nullptr,
+                                                   s->has_hi ? arena_flag(s->peer_arena[1], 0) : nullptr, step_no + 1, nullptr);
+            k_slab_wait<<<1, 32, 0, s->stream>>>(s->has_lo ? arena_flag(s->arena, 0) : nullptr,
+                                                s->has_hi ? arena_flag(s->arena, 1) : nullptr, step_no + 1,
+                                                slab_timeout_ns(), s->err);
+            nl += 2;
+        }
+        if (s->has_lo) {
+            k_halo_import<<<hgrid, threads, 0, s->stream>>>(s->X, s->start, 0u, s->G, 1, L,
+                                                           arena_halo_in(s, s->arena, 0, par), s->err, nullptr);
+            ++nl;
+        }
+        if (s->has_hi) {
+            k_halo_import<<<hgrid, threads, 0, s->stream>>>(s->X, s->start, (u32)((s->g.L0 - 1) * plane), s->G, 0, L,
+                                                           arena_halo_in(s, s->arena, 1, par), s->err, s->cnt);
+            ++nl;
+        }
+        stage_end(s, 3, nl);
+        // ---- boundary planes (or everything when the force pass is not split), then join the interior pass --------
+        if (!split) {
+            KParams P = make_params(s);
+            (void)P;
+            if ((rc = step_launch_dev(s, last))) return rc;
+        } else {
+            PlaneRange pr;
+            pr.st = s->stream;
+            if (ib > s->g.own_lo) {
+                pr.x_begin = s->g.own_lo;
+                pr.x_count = ib - s->g.own_lo;
+                if ((rc = step_launch(s, last, pr))) return rc;
+            }
+            if (s->g.own_hi > ie) {
+                pr.x_begin = ie;
+                pr.x_count = s->g.own_hi - ie;
+                if ((rc = step_launch(s, last, pr))) return rc;
+            }
+            CU(s, cudaStreamWaitEvent(s->stream, s->ev_interior, 0));
+        }
+        // ---- migration: leavers straight into the neighbours' buffers, counts + flags, arrivals ---------------------
+        stage_begin(s, 4);
+        nl = 0;
+        if (s->has_lo || s->has_hi) {
+            k_zero_u32<<<1, 32, 0, s->stream>>>(nullptr, 0, nullptr, 0, s->scratch_u64, 2);
+            MigExportParams M;
+            std::memset(&M, 0, sizeof(M));
+            M.A = s->X;
+            M.B = s->T;
+            M.newkey = s->newkey;
+            M.sortkey = s->sortkey;
+            M.first = s->G;
+            M.n = s->cap;
+            M.n_dev = s->cnt;
+            M.lo_end = s->has_lo ? (u32)plane : 0u;
+            M.hi_begin = s->has_hi ? (u32)((s->g.L0 - 1) * plane) : 0xffffffffu;
+            M.vox_base = (u64)s->g.p0 * plane;
+            M.L = s->ml;
+            M.L.mode = param_mode(s);
+            M.buf[0] = s->has_lo ? arena_mig_in(s, s->peer_arena[0], 1, par) : nullptr;
+            M.buf[1] = s->has_hi ? arena_mig_in(s, s->peer_arena[1], 0, par) : nullptr;
+            M.counter = s->scratch_u64;
+            M.err = s->err;
+            M.uniform = s->uniform ? 1 : 0;
+            k_mig_export<<<blocks_for(s->cap, 256), 256, 0, s->stream>>>(M);
+            // the leavers were counted in the histogram of the ghost planes: they take no slot here
+            k_zero_u32<<<blocks_for(plane, 256), 256, 0, s->stream>>>(
+                s->has_lo ? s->count_new : nullptr, s->has_lo ? plane : 0,
+                s->has_hi ? s->count_new + (s->g.L0 - 1) * plane : nullptr, s->has_hi ? plane : 0, nullptr, 0);
+            k_slab_publish<<<1, 32, 0, s->stream>>>(s->scratch_u64, M.buf[0], M.buf[1],
+                                                   s->has_lo ? arena_flag(s->peer_arena[0], 3) : nullptr,
+                                                   s->has_hi ? arena_flag(s->peer_arena[1], 2) : nullptr, step_no + 1,
+                                                   s->cnt + 4);
+            k_slab_wait<<<1, 32, 0, s->stream>>>(s->has_lo ? arena_flag(s->arena, 2) : nullptr,
+                                                s->has_hi ? arena_flag(s->arena, 3) : nullptr, step_no + 1,
+                                                slab_timeout_ns(), s->err);
+            nl += 5;
+        }
+        {
+            MigImportDevParams Q;
+            std::memset(&Q, 0, sizeof(Q));
+            Q.M.A = s->X;
+            Q.M.B = s->T;
+            Q.M.newkey = s->newkey;
+            Q.M.rank_arb = s->rank_arb;
+            Q.M.count_new = s->count_new;
+            Q.M.sortkey = s->sortkey;
+            Q.M.vox_base = (u64)s->g.p0 * plane;
+            Q.M.nvox = s->nvox;
+            Q.M.L = s->ml;
+            Q.M.L.mode = param_mode(s);
+            Q.M.err = s->err;
+            Q.M.uniform = s->uniform ? 1 : 0;
+            Q.buf[0] = s->has_lo ? arena_mig_in(s, s->arena, 0, par) : nullptr;
+            Q.buf[1] = s->has_hi ? arena_mig_in(s, s->arena, 1, par) : nullptr;
+            Q.first = s->G;
+            Q.src_cap = src_cap;
+            Q.cnt = s->cnt;
+            const dim3 grid(blocks_for(std::max<u64>(s->mcap, 1), 256), 2);
+            k_mig_import_dev<<<grid, 256, 0, s->stream>>>(Q);
+            ++nl;
+        }
+        stage_end(s, 4, nl);
+        CU(s, cudaGetLastError());
+        // ---- cell-list rebuild with device-side counts -----------------------------------------------------------------
+        if ((rc = sort_into_place(s, src_cap, s->cap, last, false, true))) return rc;
+        // (sort_into_place swapped start / start_alt: the totals of this step's scan are in s->start now)
+        k_slab_set_count<<<1, 32, 0, s->stream>>>(s->start, s->nvox, s->G, s->cap, s->cnt, s->err);
+        s->launches++;
+        s->iteration++;
+        s->noise_cursor++;
+        s->slab_steps++;
+    }
+    s->slab_async_pending = true;
+    if (async) return 0;
+    // ---- end of the batch: the only synchronisation -------------------------------------------------------------------
+    if ((rc = slab_finalize(s))) return rc;
+    return check_latch(s);
+}
+
 // ---- storage snapshots (save_cells at PartialSave iterations, chili/datastructures.rs:373-396) -----
 void* crb_host_alloc(uint64_t bytes) {
     void* p = nullptr;
@@ -1991,12 +2423,15 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
 int crb_sync(crb_sim* s) {
     if (!s) return CRB_ERR_INVALID_ARG;
     CU(s, cudaSetDevice((int)s->cfg.device));
+    int rc;
+    if ((rc = slab_finalize(s))) return rc;
     return check_latch(s);
 }
 
 int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
     if (!s || !force) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
@@ -2016,6 +2451,7 @@ int crb_debug_forces(crb_sim* s, uint64_t cap, double* force) {
 int crb_get_identifiers(crb_sim* s, uint64_t cap, uint64_t* ident, uint64_t* parent) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
     if (s->rods) return rods_get_identifiers(s, cap, (u64*)ident, (u64*)parent);
@@ -2083,6 +2519,7 @@ int crb_get_migrations(crb_sim* s, uint64_t cap, uint64_t* ids, uint64_t* old_vo
 int crb_get_voxel_counts(crb_sim* s, uint64_t cap, uint32_t* counts) {
     if (!s || !counts) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     const u64 plane = (u64)s->g.ng[1] * s->g.ng[2];
     const u64 first = (u64)s->g.own_lo * plane, last = (u64)s->g.own_hi * plane;
     if (cap < last - first) return fail(s, CRB_ERR_CAPACITY, "output buffer too small");
@@ -2098,6 +2535,7 @@ int crb_get_voxel_counts(crb_sim* s, uint64_t cap, uint32_t* counts) {
 int crb_count_candidate_pairs(crb_sim* s, uint64_t* n_pairs) {
     if (!s || !n_pairs) return CRB_ERR_INVALID_ARG;
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, kOpenStepMsg);
+    if (s->slab_async_pending) return fail(s, CRB_ERR_STATE, kAsyncPendingMsg);
     CU(s, cudaSetDevice((int)s->cfg.device));
     *n_pairs = 0;
     if (!s->n) return 0;

@@ -88,6 +88,7 @@ struct KParams {
     Grid g;
     State A, B;
     Uniform u;
+    const u64* n_dev;  // != nullptr: the owned-agent count lives on the device (crb_slab_step), n bounds the grid
     u64 n;            // owned agents in A
     u64 first;        // index of the first owned agent (ghost capacity G; 0 on a single device)
     u64 cap;          // allocated agents per array (owned capacity + 2 G)

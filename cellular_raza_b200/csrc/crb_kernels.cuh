@@ -513,9 +513,12 @@ __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, c
         if (l0 >= 0 && l0 < g.L0) {
             nk = ((u32)l0 * (u32)n1 + (u32)q1) * (u32)n2 + (u32)q2;
             gp_new = ((u64)q0 * n1 + q1) * n2 + q2;
+        } else {
+            // a voxel of the domain that is neither owned nor in a ghost plane: the agent crossed more than one
+            // plane of a neighbouring slab in ONE step (chili would move it anywhere; the slab protocol only
+            // exchanges with the adjacent slabs).  Never silently: IndexError.
+            latch_error(P.err, CRB_ERR_INDEX, P.A.id[i]);
         }
-        // (a target plane outside the local planes cannot happen on one device; the multi-GPU
-        //  path handles it before this point is reached)
     }
     u64 rank_old = i - own_lo;
     if (rank_old > CRB_SK_RANK_MASK) rank_old = CRB_SK_RANK_MASK;
@@ -556,7 +559,7 @@ template <int D, int INTER, bool UNIFORM, bool FORCE_ONLY>
 __global__ void __launch_bounds__(kForceThreads)
     k_force_integrate(const KParams P, const u64 first, const u64 count) {
     const u64 t = (u64)blockIdx.x * kForceThreads + threadIdx.x;
-    if (t >= count) return;
+    if (t >= (P.n_dev ? *P.n_dev : count)) return;
     const u64 i = first + t;
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
@@ -764,9 +767,13 @@ __global__ void __launch_bounds__(kScanThreads)
 // voxel's segment; k_reorder computes the stable rank inside the segment from the sortkeys and
 // moves the whole state B (dynamic fields) + A (static fields) -> Y.
 // ------------------------------------------------------------------------------------------------
+// n_dev != nullptr: the number of sources is read from device memory (crb_slab_step: the host never learns the
+// counts between steps; the grid is sized by the capacity)
 __global__ void k_fill(const u32* __restrict__ newkey, const u32* __restrict__ rank_arb,
-                       const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 first, u64 n) {
+                       const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 first, u64 n,
+                       const u64* __restrict__ n_dev = nullptr) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = *n_dev;
     if (t >= n) return;
     const u64 i = first + t;
     const u32 k = newkey[i];
@@ -790,11 +797,13 @@ struct ReorderParams {
     int has_species;
     double mn[3];  // CartesianCuboid::min (origin of the FP32 filter coordinates)
     u32 n2;        // voxels along the fastest axis
+    u64 nvox_dev;  // != 0: the number of destinations is start_new[nvox_dev] - first (device-side counts)
 };
 
 __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
     const u64 tp = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tp >= R.n) return;
+    const u64 n_dst = R.nvox_dev ? (u64)__ldg(&R.start_new[R.nvox_dev]) - R.first : R.n;
+    if (tp >= n_dst) return;
     const u64 p = R.first + tp;
     const u32 i = R.tmp_idx[p];
     // ---- every load of the agent's state is issued BEFORE the rank loop and before any store: the
@@ -986,8 +995,9 @@ __global__ void k_halo_export(const State A, const u32* __restrict__ start, u32 
 // agents begin at `edge` (= one past the last owned index).  posf.w is re-based to the local voxel
 // index of the ghost plane (the sender wrote its own local index).
 __global__ void k_halo_import(State A, u32* __restrict__ start, u32 v0, u64 edge, int lower, HaloLayout L,
-                              const unsigned char* __restrict__ buf, int* err) {
+                              const unsigned char* __restrict__ buf, int* err, const u64* __restrict__ n_dev = nullptr) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev && !lower) edge += *n_dev;  // upper ghost plane begins behind the owned agents: first + n
     const u64 n = reinterpret_cast<const u64*>(buf)[0];
     if (n > L.gcap) {
         if (t == 0) latch_error(err, CRB_ERR_CAPACITY, n);
@@ -1037,6 +1047,7 @@ struct MigExportParams {
     u64* counter;  // [2]
     int* err;
     int uniform;
+    const u64* n_dev;  // != nullptr: owned agents are counted on the device (crb_slab_step)
 };
 __global__ void k_mig_export(const MigExportParams M) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1044,7 +1055,7 @@ __global__ void k_mig_export(const MigExportParams M) {
         if (M.buf[0]) reinterpret_cast<u64*>(M.buf[0])[1] = M.L.mode;
         if (M.buf[1]) reinterpret_cast<u64*>(M.buf[1])[1] = M.L.mode;
     }
-    if (t >= M.n) return;
+    if (t >= (M.n_dev ? *M.n_dev : M.n)) return;
     const u64 i = M.first + t;
     const u32 k = M.newkey[i];
     int side;
@@ -1129,6 +1140,143 @@ __global__ void k_mig_import(const MigImportParams M) {
     const u32 nk = (u32)(gv - M.vox_base);
     M.newkey[i] = nk;
     M.rank_arb[i] = atomicAdd(&M.count_new[nk], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// crb_slab_step: exchange over peer memory without the host.  A sender's export kernels store
+// straight into the neighbour's import buffers (mapped peer memory: NVLink / NVSwitch, or the same device) and then
+// raise a step counter in the NEIGHBOUR's memory; the receiver's stream holds a one-thread kernel that spins on its
+// own, local counter.  Replaces the barrier between the exchange phases of chili
+// (cellular_raza-core/src/backend/chili/simulation_flow.rs:350-423) for two neighbours instead of all threads.
+// ------------------------------------------------------------------------------------------------
+// stores the migration counts into the headers of the neighbours' buffers, then publishes `value` to the flags;
+// runs after the export kernels of the same stream (their stores are complete: stream order), the system-scope
+// fence orders them before the flag for an observer on another device
+__global__ void k_slab_publish(const u64* __restrict__ counts, unsigned char* hdr_lo, unsigned char* hdr_hi,
+                               u64* flag_lo, u64* flag_hi, u64 value, u64* counts_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (counts) {
+        if (hdr_lo) *reinterpret_cast<u64*>(hdr_lo) = counts[0];
+        if (hdr_hi) *reinterpret_cast<u64*>(hdr_hi) = counts[1];
+        if (counts_out) {
+            counts_out[0] = counts[0];
+            counts_out[1] = counts[1];
+        }
+    }
+    __threadfence_system();
+    if (flag_lo) *reinterpret_cast<volatile u64*>(flag_lo) = value;
+    if (flag_hi) *reinterpret_cast<volatile u64*>(flag_hi) = value;
+}
+
+// spins until both local flags reached `value` (a neighbour that died would hang the stream: after `timeout_ns`
+// the kernel latches an error and lets the stream continue, the caller then fails at its next synchronisation)
+__global__ void k_slab_wait(const u64* flag_a, const u64* flag_b, u64 value, unsigned long long timeout_ns, int* err) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int k = 0; k < 2; ++k) {
+        const u64* f = k == 0 ? flag_a : flag_b;
+        if (!f) continue;
+        unsigned spins = 0;
+        while (true) {
+            u64 v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= value) break;
+            if ((++spins & 0x3ff) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > timeout_ns) {
+                    latch_error(err, CRB_ERR_TIMEOUT, value);
+                    return;
+                }
+            }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+
+// arrivals of both faces in one launch (blockIdx.y = side): counts come from the buffer headers, the destination
+// range behind the owned agents from the device-side count; thread (0, 0) of side 0 leaves the new number of sources
+struct MigImportDevParams {
+    MigImportParams M;        // buf / dst / n are filled in on the device
+    const unsigned char* buf[2];
+    u64 first;                // index of the first owned agent (G)
+    u64 src_cap;              // capacity of the unsorted source range (owned capacity + 2 migration capacities)
+    u64* cnt;                 // [0] owned agents, [1] out: sources = owned + arrivals, [2..3] out: arrivals per face
+};
+__global__ void k_mig_import_dev(const MigImportDevParams Q) {
+    const int side = blockIdx.y;
+    const unsigned char* buf = Q.buf[side];
+    const u64 n_own = Q.cnt[0];
+    const u64 n_lo = Q.buf[0] ? *reinterpret_cast<const u64*>(Q.buf[0]) : 0ull;
+    const u64 n_hi = Q.buf[1] ? *reinterpret_cast<const u64*>(Q.buf[1]) : 0ull;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool overflow = n_lo > Q.M.L.mcap || n_hi > Q.M.L.mcap || n_own + n_lo + n_hi > Q.src_cap;
+    if (t == 0 && side == 0) {
+        Q.cnt[1] = overflow ? n_own : n_own + n_lo + n_hi;
+        Q.cnt[2] = n_lo;
+        Q.cnt[3] = n_hi;
+        if (overflow) latch_error(Q.M.err, CRB_ERR_CAPACITY, n_lo + n_hi);
+    }
+    if (!buf || overflow) return;
+    const u64 n = side == 0 ? n_lo : n_hi;
+    if (t >= n) return;
+    if (reinterpret_cast<const u64*>(buf)[1] != Q.M.L.mode) {
+        if (t == 0) latch_error(Q.M.err, CRB_ERR_STATE, reinterpret_cast<const u64*>(buf)[1]);
+        Q.M.newkey[Q.first + n_own + (side ? n_lo : 0) + t] = CRB_KEY_GONE;
+        return;
+    }
+    const MigImportParams& M = Q.M;
+    const u64 i = Q.first + n_own + (side ? n_lo : 0) + t;
+    const MigLayout& L = M.L;
+    const int D = L.D;
+    for (int c = 0; c < D; ++c) {
+        M.B.pos[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[0 * D + c])[t];
+        M.B.vel[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[1 * D + c])[t];
+        M.B.h1x[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[2 * D + c])[t];
+        M.B.h1v[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[3 * D + c])[t];
+        M.B.h0x[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[4 * D + c])[t];
+        M.B.h0v[c][i] = reinterpret_cast<const double*>(buf + L.off_dyn[5 * D + c])[t];
+    }
+    if (!M.uniform) {
+        for (int q = 0; q < L.n_mp; ++q) M.A.mp[q][i] = reinterpret_cast<const double*>(buf + L.off_mp[q])[t];
+        for (int q = 0; q < L.n_ip; ++q) M.A.ip[q][i] = reinterpret_cast<const double*>(buf + L.off_ip[q])[t];
+    }
+    M.A.id[i] = reinterpret_cast<const u64*>(buf + L.off_id)[t];
+    M.sortkey[i] = reinterpret_cast<const u64*>(buf + L.off_sortkey)[t];
+    M.B.hlen[i] = (buf + L.off_hlen)[t];
+    M.A.species[i] = (buf + L.off_sp)[t];
+    const u64 gv = reinterpret_cast<const u64*>(buf + L.off_gvox)[t];
+    if (gv < M.vox_base || gv - M.vox_base >= M.nvox) {
+        latch_error(M.err, CRB_ERR_INDEX, M.A.id[i]);
+        M.newkey[i] = CRB_KEY_GONE;
+        return;
+    }
+    const u32 nk = (u32)(gv - M.vox_base);
+    M.newkey[i] = nk;
+    M.rank_arb[i] = atomicAdd(&M.count_new[nk], 1u);
+}
+
+// crb_slab_step queues kernels only (no copy-engine operations): a memset or copy of ANOTHER slab's stream can sit
+// behind one that waits for a spinning k_slab_wait in the copy engine's queue (observed: two slabs on one device
+// serialised completely), so the small clears and the count upload are kernels as well
+__global__ void k_zero_u32(u32* __restrict__ a, u64 n, u32* __restrict__ b, u64 nb, u64* __restrict__ c, u64 nc) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = 0u;
+    if (i < nb) b[i] = 0u;
+    if (i < nc) c[i] = 0ull;
+}
+__global__ void k_set_u64(u64* a, u64 v) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *a = v;
+}
+
+// after the reorder: the owned agents of the next step = grand total of the scan; capacity check
+__global__ void k_slab_set_count(const u32* __restrict__ start_new, u64 nvox, u64 first, u64 cap, u64* cnt, int* err) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const u64 n = (u64)start_new[nvox] - first;
+    cnt[0] = n;
+    if (n > cap) latch_error(err, CRB_ERR_CAPACITY, n);
 }
 
 // DFMA-only kernel: 8 independent chains per thread, 2 flop per fma.  Roofline denominator of the

@@ -3,13 +3,35 @@
 #include "crb_force_tile2.cuh"
 #include "crb_launch.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace crb {
 namespace {
 
+// cudaFuncSetAttribute is issued only when a kernel needs more dynamic shared memory than it was configured for
+// (per device): the call may wait for work in flight, which must not happen between the queued phases of
+// crb_slab_step (a device-side wait for a neighbouring slab may be pending in the stream)
 template <class K>
 cudaError_t go(K k, const KParams& P, const TileLaunch& T, u32 grid, int threads, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> configured;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (grid == kPreloadOnly) {  // force the lazy loading of this kernel now (crb_slab_step: see crb_launch.cuh)
+        cudaFuncAttributes at;
+        return cudaFuncGetAttributes(&at, k);
+    }
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& have = configured[{reinterpret_cast<const void*>(k), dev}];
+        if (have < smem) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            have = smem;
+        }
+    }
     k<<<grid, threads, smem, st>>>(P, T);
     return cudaGetLastError();
 }

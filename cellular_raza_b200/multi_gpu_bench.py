@@ -34,11 +34,49 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
     nmax = torch.tensor([n_rank], device="cuda", dtype=torch.int64)
     dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
     cfg = w.config(capacity=int(int(nmax.item()) * 1.1) + 4096, device=local_rank)
-    sim = SlabSimulation(cfg, device=local_rank, overlap=not args.no_overlap)
+    transport = getattr(args, "transport", "p2p")
+    sim = SlabSimulation(cfg, device=local_rank, overlap=not args.no_overlap, transport=transport)
     sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
     sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
     slab = sim.slab
     stream = slab.torch_stream
+
+    # ---- protocol check on the hardware the numbers come from: the same warm-up steps through crb_slab_step
+    # (peer-memory exchange, device-side counts) and through the six-phase protocol over ncclSend/ncclRecv must
+    # leave every rank with the same bits; the global agent count is conserved ---------------------------------
+    import hashlib
+
+    def state_hash():
+        pos, vel, ids, vox = slab.get_agents()
+        o = np.argsort(ids, kind="stable")
+        h = hashlib.blake2b(digest_size=16)
+        for a in (ids[o], vox[o], pos[o], vel[o]):
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.digest(), len(ids)
+
+    n_check = max(args.warmup, 3)
+    protocol_check = None
+    if transport == "p2p":
+        sim.step(n_check)
+        sim.sync()
+        h_p2p, n_p2p = state_hash()
+        sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
+        sim.transport = "nccl"
+        sim.step(n_check)
+        sim.sync()
+        h_nccl, n_nccl = state_hash()
+        sim.transport = "p2p"
+        same = torch.tensor([int(h_p2p == h_nccl), n_p2p, n_nccl], device="cuda", dtype=torch.int64)
+        allr = [torch.zeros_like(same) for _ in range(world)]
+        dist.all_gather(allr, same)
+        protocol_check = {
+            "p2p_equals_nccl_bitwise_on_every_rank": bool(all(int(t[0]) == 1 for t in allr)),
+            "steps": n_check, "agents_total_p2p": int(sum(int(t[1]) for t in allr)),
+            "agents_total_nccl": int(sum(int(t[2]) for t in allr)), "agents_expected": int(n * world),
+        }
+        if not protocol_check["p2p_equals_nccl_bitwise_on_every_rank"] or protocol_check["agents_total_p2p"] != n * world:
+            raise RuntimeError(f"slab protocol check failed: {protocol_check}")
+        sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
 
     sim.halo_exchange()
     pairs = slab.count_candidate_pairs()
@@ -86,30 +124,61 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
     value = n * world * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host buffers in / out every step (every rank its own slab) ---------------------------
+    # per rank: crb_set_agents_async (pinned host -> device) + the slab step + crb_snapshot_async (device -> pinned
+    # host); the download of step k overlaps the upload and the step of k + 1 (the snapshot reads its own packed
+    # buffer).  The pinned buffers are allocated after the process has been bound to the CPUs next to its GPU
+    # (NVML affinity: first-touch puts the pages on that NUMA node).
     e2e = None
     if not args.no_e2e:
-        hp = torch.from_numpy(w.pos).pin_memory()
-        hv = torch.from_numpy(w.vel).pin_memory()
+        import ctypes as C
+
+        numa = "not bound"
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            ncpu = os.cpu_count() or 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, (ncpu + 63) // 64)
+            cpus = [c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = f"bound to {len(cpus)} CPUs next to GPU {local_rank}"
+        except Exception as e:  # affinity is an optimisation, never a failure
+            numa = f"not bound ({type(e).__name__})"
+        lib, h = slab._lib, slab._h
+        ins = [[torch.from_numpy(w.pos.copy()).pin_memory(), torch.from_numpy(w.vel.copy()).pin_memory()] for _ in range(2)]
+        cap_out = int(cfg.capacity)
+        outs = [[torch.empty((cap_out, 3), dtype=torch.float64).pin_memory(),
+                 torch.empty((cap_out, 3), dtype=torch.float64).pin_memory()] for _ in range(2)]
         hs = torch.from_numpy(w.species).pin_memory() if w.species is not None else None
         hs_ptr = hs.data_ptr() if hs is not None else None
         hi = torch.from_numpy(w.extra["ids"]).pin_memory()
-        op = torch.empty_like(hp).pin_memory()
-        ov = torch.empty_like(hv).pin_memory()
-        lib, h = slab._lib, slab._h
         e2e_steps = max(args.steps // 2, 3)
-        for k in range(2 + e2e_steps):
-            if k == 2:
+        nn = C.c_uint64()
+        pending = False
+
+        def chk(rc):
+            if rc:
+                raise RuntimeError((lib.crb_last_error(h) or b"").decode())
+
+        for k in range(3 + e2e_steps):
+            j = k % 2
+            if k == 3:
+                if pending:
+                    chk(lib.crb_snapshot_wait(h, C.byref(nn)))
+                    pending = False
                 torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
-            rc = lib.crb_set_agents(h, n_rank, hp.data_ptr(), hv.data_ptr(), None, None, hs_ptr, hi.data_ptr())
-            if rc:
-                raise RuntimeError(lib.crb_last_error(h))
-            sim.step(1)
-            m = slab.n_agents
-            rc = lib.crb_get_agents(h, m, op.data_ptr() if m <= n_rank else None, ov.data_ptr() if m <= n_rank else None, None, None)
-            if rc:
-                raise RuntimeError(lib.crb_last_error(h))
+            chk(lib.crb_set_agents_async(h, n_rank, ins[j][0].data_ptr(), ins[j][1].data_ptr(), None, None, hs_ptr, hi.data_ptr()))
+            sim.step(1)  # halo + migration with the neighbours; synchronises this rank at its end
+            if pending:
+                chk(lib.crb_snapshot_wait(h, C.byref(nn)))
+            chk(lib.crb_snapshot_async(h, cap_out, outs[j][0].data_ptr(), outs[j][1].data_ptr(), None, None, None, None, None))
+            pending = True
+        if pending:
+            chk(lib.crb_snapshot_wait(h, C.byref(nn)))
         torch.cuda.synchronize()
         dist.barrier()
         dt_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
@@ -118,8 +187,10 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         e2e = {
             "value": n * world * e2e_steps / dt_e2e, "unit": helpers.UNIT,
             "h2d_bytes_per_step": int(world * n * (24 + 24 + 1 + 8)), "d2h_bytes_per_step": int(world * n * 48),
-            "ms_per_step": dt_e2e / e2e_steps * 1e3,
-            "what": "per rank: crb_set_agents(pinned host pos, vel, species, ids) + slab step (halo + migration over nccl) + crb_get_agents(host pos, vel)",
+            "ms_per_step": dt_e2e / e2e_steps * 1e3, "host_memory": numa,
+            "what": "per rank and step: crb_set_agents_async(pinned host pos, vel, species, ids) + slab step (halo + migration "
+                    "with the neighbours) + crb_snapshot_async(pinned host pos, vel); the download of a step overlaps the "
+                    "upload and the step of the next one",
         }
 
     if rank == 0:
@@ -148,7 +219,10 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         }
         cfgd = helpers.workload_config(args)
         cfgd.update({"halo_bytes_per_face": slab.halo_bytes, "migration_bytes_per_face": slab.mig_bytes,
-                     "exchange": "ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), 2 phases per step, no force return",
+                     "exchange": ("crb_slab_step: export kernels store into the neighbour's arena over NVLink (CUDA IPC), "
+                                  "device-side flags and counts, no host synchronisation inside the batch, no force return"
+                                  if transport == "p2p" else
+                                  "ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), 2 phases per step, no force return"),
                      "halo_overlap": "off" if args.no_overlap else "interior planes on a second stream while the halo travels"})
         line = {
             "metric": helpers.METRIC, "value": value, "unit": helpers.UNIT, "n_gpus": world, "steps": args.steps,
@@ -160,6 +234,7 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
                                   "reorder": reorder_ms / args.steps, "halo_pack_unpack": halo_ms / args.steps,
                                   "migration_pack_unpack": mig_ms / args.steps},
             "agents_after": float(n_now.item()),
+            "protocol_check": protocol_check,
         }
         print(json.dumps(line), flush=True)
     sim.close()

@@ -148,6 +148,34 @@ class SlabRank(DeviceSimulation):
     def finish(self, save_prev: bool = True):
         self._check(self._lib.crb_slab_finish(self._h, 1 if save_prev else 0))
 
+    # -- crb_slab_step: exchange over peer memory, no host synchronisation ------------------------------
+    @property
+    def arena(self) -> int:
+        return int(self._lib.crb_slab_arena(self._h) or 0)
+
+    def ipc_handle(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._check(self._lib.crb_slab_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, lo_arena: int | None, hi_arena: int | None):
+        """neighbours in THIS process: raw device pointers of their arenas"""
+        self._check(self._lib.crb_slab_connect(self._h, C.c_void_p(lo_arena) if lo_arena else None,
+                                               C.c_void_p(hi_arena) if hi_arena else None))
+
+    def connect_ipc(self, lo_handle: bytes | None, hi_handle: bytes | None):
+        """neighbours in other processes of the node: their CUDA IPC handles"""
+        lo = (C.c_ubyte * 64).from_buffer_copy(lo_handle) if lo_handle else None
+        hi = (C.c_ubyte * 64).from_buffer_copy(hi_handle) if hi_handle else None
+        self._check(self._lib.crb_slab_connect_ipc(self._h, lo, hi))
+
+    def slab_step(self, n_steps: int = 1):
+        self._check(self._lib.crb_slab_step(self._h, n_steps))
+
+    def slab_step_enqueue(self, n_steps: int = 1):
+        """queue only (crb_slab_step_async); :meth:`sync` completes the batch"""
+        self._check(self._lib.crb_slab_step_async(self._h, n_steps))
+
     def step(self, n_steps: int = 1):  # pragma: no cover - guarded in C as well
         raise RuntimeError("a slab is stepped by its group (LocalSlabGroup.step / SlabSimulation.step)")
 
@@ -171,13 +199,23 @@ class LocalSlabGroup:
     run several slabs on one GPU)."""
 
     def __init__(self, make_cfg, world: int, devices: Sequence[int] | None = None, overlap: bool = True,
-                 **caps):
+                 transport: str = "copy", **caps):
+        """``transport="copy"``: the six-phase protocol, buffers moved by device copies from this thread;
+        ``transport="p2p"``: ``crb_slab_step`` — the export kernels store into the neighbours' arenas and the
+        ranks synchronise through device-side flags (one step per rank, round robin: include/crb.h)."""
         devices = list(devices) if devices is not None else [0] * world
         self.world = world
         self.overlap = overlap
+        self.transport = transport
         self.ranks = [SlabRank(make_cfg(), r, world, devices[r], **caps) for r in range(world)]
         self.cfg = self.ranks[0].cfg
         self.dim = self.ranks[0].dim
+        if transport == "p2p":
+            for r, rk in enumerate(self.ranks):
+                rk.connect(self.ranks[r - 1].arena if r > 0 else None,
+                           self.ranks[r + 1].arena if r + 1 < world else None)
+        elif transport != "copy":
+            raise ValueError("transport must be 'copy' or 'p2p'")
 
     def close(self):
         for r in self.ranks:
@@ -252,6 +290,18 @@ class LocalSlabGroup:
             rk.halo_import()
 
     def step(self, n_steps: int = 1):
+        if self.transport == "p2p":
+            # one step per rank, round robin: a rank's queue waits (on the device) for exports of its neighbours,
+            # which this thread has to queue as well; nothing synchronises until every step of every rank is queued
+            for it in range(n_steps):
+                for rk in self.ranks:
+                    rk.slab_step_enqueue(1)
+                if it % 8 == 7:  # keep the launch queues short (a full queue would block this thread mid-round)
+                    for rk in self.ranks:
+                        rk.sync()
+            for rk in self.ranks:
+                rk.sync()
+            return
         for it in range(n_steps):
             last = it + 1 == n_steps
             if self.overlap:
@@ -314,13 +364,17 @@ class SlabSimulation:
     migration buffers travel with ncclSend/ncclRecv over NVLink."""
 
     def __init__(self, cfg: _abi.CrbConfig, device: int | None = None, group=None, overlap: bool = True,
-                 **caps):
+                 transport: str = "nccl", **caps):
+        """``transport="nccl"``: the six-phase protocol with ncclSend/ncclRecv between the phases (one host
+        synchronisation per step); ``transport="p2p"``: ``crb_slab_step`` — the neighbours' exchange arenas are mapped
+        through CUDA IPC and the export kernels store into them over NVLink, no host synchronisation inside a batch."""
         import torch
         import torch.distributed as dist
 
         self.dist = dist
         self.group = group
         self.overlap = overlap
+        self.transport = transport
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         device = torch.cuda.current_device() if device is None else device
@@ -340,6 +394,14 @@ class SlabSimulation:
         self.cfg = self.slab.cfg
         self.dim = self.slab.dim
         self._declared = False
+        if transport == "p2p":
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.slab.ipc_handle(), group=group)
+            self.slab.connect_ipc(handles[self.rank - 1] if self.rank > 0 else None,
+                                  handles[self.rank + 1] if self.rank + 1 < self.world else None)
+            dist.barrier(group=group)  # every rank has reset its flags before anyone steps
+        elif transport != "nccl":
+            raise ValueError("transport must be 'nccl' or 'p2p'")
 
     def close(self):
         self.slab.close()
@@ -393,6 +455,9 @@ class SlabSimulation:
 
     def step(self, n_steps: int = 1):
         s = self.slab
+        if self.transport == "p2p":
+            s.slab_step(n_steps)  # the whole batch behind one call of the C ABI
+            return
         for it in range(n_steps):
             last = it + 1 == n_steps
             if self.overlap:

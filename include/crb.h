@@ -42,7 +42,10 @@ typedef enum crb_status {
     CRB_ERR_INVALID_ARG = -16,
     CRB_ERR_CAPACITY = -17,   /* more agents than `capacity` (set_agents, division, migration)    */
     CRB_ERR_CUDA = -18,       /* CUDA runtime failure; message holds cudaGetErrorString           */
-    CRB_ERR_STATE = -19       /* call sequence violation (e.g. step before set_agents)            */
+    CRB_ERR_STATE = -19,      /* call sequence violation (e.g. step before set_agents)            */
+    CRB_ERR_TIMEOUT = -20     /* crb_slab_step: a neighbouring slab never delivered its halo / migration
+                                 buffer (the reference's counterpart: OtherThreadError at the barrier,
+                                 simulation_flow.rs:397-423)                                       */
 } crb_status;
 
 /* ---- model selection ---------------------------------------------------------------------- */
@@ -292,6 +295,33 @@ int crb_slab_migration_export(crb_sim* sim, void* lo_buf, void* hi_buf, uint64_t
 int crb_slab_migration_counts(const crb_sim* sim, uint64_t n_out[2]);
 int crb_slab_migration_import(crb_sim* sim, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]);
 int crb_slab_finish(crb_sim* sim, int save_prev);
+
+/* ---- the same step behind ONE call: exchange over peer memory, no host synchronisation ------------------------
+ * Every slab owns an "exchange arena" in device memory (import buffers for both faces, double-buffered by step
+ * parity, plus four step counters).  After the neighbours' arenas have been mapped (same process: the raw device
+ * pointer of crb_slab_arena, peer access is enabled when the devices differ; other processes of the node: the
+ * 64-byte CUDA IPC handle of crb_slab_ipc_handle, exchanged by any means — MPI, a file, torch.distributed)
+ *
+ *     crb_slab_step(sim, n)
+ *
+ * queues n complete steps: the halo and migration export kernels store straight into the neighbour's import
+ * buffers over NVLink / NVSwitch and then raise a counter in the NEIGHBOUR's arena; the receiver's stream holds a
+ * one-thread kernel that waits on its own, local counter.  Agent counts stay on the device (the grids are sized by
+ * the capacities), the interior planes overlap the halo exchange as in crb_slab_compute_interior, and the host
+ * synchronises ONCE, at the end of the batch (latched device errors are returned there).  Results are bit-identical
+ * to the six-phase protocol above and to a single handle.  Every rank of the decomposition must call crb_slab_step
+ * with the same n; a neighbour that never arrives turns into CRB_ERR_STATE after 20 s instead of a hang.
+ * A host that drives several slabs from ONE thread must interleave the ranks step by step (n = 1, round robin):
+ * a rank's queue would otherwise wait for exports that have not been queued yet. */
+uint64_t crb_slab_arena_bytes(const crb_sim* sim);
+void* crb_slab_arena(crb_sim* sim);
+int crb_slab_ipc_handle(crb_sim* sim, void* handle64);
+int crb_slab_connect(crb_sim* sim, void* lo_arena, void* hi_arena);
+int crb_slab_connect_ipc(crb_sim* sim, const void* lo_handle64, const void* hi_handle64);
+int crb_slab_step(crb_sim* sim, uint64_t n_steps);
+/* the same without the final synchronisation (for a host thread that drives several slabs: queue one step on every
+ * rank, then crb_sync every rank); the agent count and the getters are valid again after crb_sync. */
+int crb_slab_step_async(crb_sim* sim, uint64_t n_steps);
 
 /* ---- storage snapshots without stopping the stepping loop ---------------------------------------
  * Replaces the blocking save_cells of chili at PartialSave iterations (chili/datastructures.rs:373-396,

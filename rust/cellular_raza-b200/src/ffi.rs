@@ -15,6 +15,7 @@ pub const CRB_ERR_INVALID_ARG: c_int = -16;
 pub const CRB_ERR_CAPACITY: c_int = -17;
 pub const CRB_ERR_CUDA: c_int = -18;
 pub const CRB_ERR_STATE: c_int = -19;
+pub const CRB_ERR_TIMEOUT: c_int = -20;
 
 pub const CRB_MECH_NEWTON_DAMPED: u32 = 0;
 pub const CRB_MECH_BROWNIAN: u32 = 1;
@@ -119,6 +120,13 @@ extern "C" {
     pub fn crb_slab_migration_counts(sim: *const crb_sim, n_out: *mut u64) -> c_int;
     pub fn crb_slab_migration_import(sim: *mut crb_sim, lo_buf: *const c_void, hi_buf: *const c_void, n_in: *mut u64) -> c_int;
     pub fn crb_slab_finish(sim: *mut crb_sim, save_prev: c_int) -> c_int;
+    pub fn crb_slab_arena_bytes(sim: *const crb_sim) -> u64;
+    pub fn crb_slab_arena(sim: *mut crb_sim) -> *mut c_void;
+    pub fn crb_slab_ipc_handle(sim: *mut crb_sim, handle64: *mut c_void) -> c_int;
+    pub fn crb_slab_connect(sim: *mut crb_sim, lo_arena: *mut c_void, hi_arena: *mut c_void) -> c_int;
+    pub fn crb_slab_connect_ipc(sim: *mut crb_sim, lo_handle64: *const c_void, hi_handle64: *const c_void) -> c_int;
+    pub fn crb_slab_step(sim: *mut crb_sim, n_steps: u64) -> c_int;
+    pub fn crb_slab_step_async(sim: *mut crb_sim, n_steps: u64) -> c_int;
     // parity taps
     pub fn crb_debug_forces(sim: *mut crb_sim, cap: u64, force: *mut f64) -> c_int;
     pub fn crb_get_voxel_counts(sim: *mut crb_sim, cap: u64, counts: *mut u32) -> c_int;

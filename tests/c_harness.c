@@ -95,6 +95,8 @@ int main(int argc, char** argv) {
     uint64_t* ids = malloc(n * sizeof(uint64_t));
     uint64_t* vox = malloc(n * sizeof(uint64_t));
     CHECK(crb_get_agents(sim, n, p1, v1, ids, vox));
+    uint64_t n_pairs = 0;
+    CHECK(crb_count_candidate_pairs(sim, &n_pairs));
 
     /* storage snapshot on the side stream into page-locked buffers, while two more steps are queued */
     double* sp = crb_host_alloc(n * 3 * sizeof(double));
@@ -141,8 +143,6 @@ int main(int argc, char** argv) {
         sy += by_id[i * 3 + 1];
         sz += by_id[i * 3 + 2];
     }
-    uint64_t n_pairs = 0;
-    CHECK(crb_count_candidate_pairs(sim, &n_pairs));
     printf("C_HARNESS n=%" PRIu64 " steps=%" PRIu64 " ring=%" PRIu64 " pairs=%" PRIu64 " launches=%" PRIu64
            " kernel=\"%s\" checksum=%a,%a,%a\n",
            seen, steps, max_hl, n_pairs, crb_kernel_launches(sim), crb_force_kernel_name(sim), sx, sy, sz);

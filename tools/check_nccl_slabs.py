@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N tools/check_nccl_slabs.py : slabs over NCCL (one process per GPU) must
-reproduce the single-handle run on rank 0 bit for bit.  Prints 'NCCL_SLABS_OK' on success."""
+"""torchrun --nproc-per-node N tools/check_nccl_slabs.py [nccl|p2p] : slabs with one process per GPU — the
+six-phase protocol over ncclSend/ncclRecv, or crb_slab_step with the neighbours' arenas mapped through CUDA IPC —
+must reproduce the single-handle run on rank 0 bit for bit.  Prints 'NCCL_SLABS_OK' on success."""
 import os
 import sys
 
@@ -22,12 +23,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     steps = 24
+    transport = sys.argv[1] if len(sys.argv) > 1 else "nccl"
     w = workloads.cell_sorting_scaled(120_000, 7.1, n_threads=3)  # identical on every rank (seeded)
     cfg = w.config(device=local)
     owner = split_agents_by_slab(cfg, world, w.pos)
     m = owner == rank
     ids = np.arange(w.n, dtype=np.uint64)
-    sim = SlabSimulation(cfg, device=local)
+    sim = SlabSimulation(cfg, device=local, transport=transport)
     sim.set_agents(w.pos[m], w.vel[m], w.mech_params[m], w.inter_params[m], w.species[m], ids[m])
     crossed = 0
     for _ in range(3):
@@ -61,7 +63,7 @@ def main():
         o = np.argsort(i1)
         ok = (len(allp) == w.n and np.array_equal(allp[:, 0:3], p1[o]) and np.array_equal(allp[:, 3:6], v1[o])
               and np.array_equal(allp[:, 7].astype(np.uint64), x1[o]))
-        print(f"world {world}: agents {len(allp)}, crossed slabs (sampled steps) {int(cr.item())}, bitwise equal: {ok}")
+        print(f"world {world} transport {transport}: agents {len(allp)}, crossed slabs (sampled steps) {int(cr.item())}, bitwise equal: {ok}")
         if ok:
             print("NCCL_SLABS_OK")
     sim.close()
