@@ -899,8 +899,6 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
             return fail(nullptr, CRB_ERR_INVALID_ARG, "rod_n_vertices must be in [2, 8]");
         if (cfg->world_size != 1)
             return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: slab decomposition is not implemented yet");
-        if (cfg->noise_mode != CRB_NOISE_NONE)
-            return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: only CRB_NOISE_NONE (diffusion_constant 0)");
     }
     if (cfg->interaction_kind > CRB_INT_NONE)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
@@ -1529,7 +1527,7 @@ int crb_set_noise(crb_sim* s, const double* z, uint64_t n_steps, uint64_t n_ids)
     if (s->cfg.noise_mode != CRB_NOISE_TABLE)
         return fail(s, CRB_ERR_STATE, "crb_set_noise needs noise_mode == CRB_NOISE_TABLE");
     CU(s, cudaSetDevice((int)s->cfg.device));
-    const u64 count = n_steps * n_ids * s->D;
+    const u64 count = n_steps * n_ids * s->D * s->V;  // rods: one number per vertex and coordinate
     if (s->noise) {
         cudaFree(s->noise);
         s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)s->noise));

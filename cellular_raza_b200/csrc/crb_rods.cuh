@@ -56,10 +56,21 @@ struct RodParams {
     double reject;      // conservative centre-distance bound: max(cutoff, 2 radius) with slack
     double nb_thresh2;  // smallest s with sqrt_rn(s) >= 2 radius: (norm < 2 radius) <=> (s < nb_thresh2)
     int order, weight_mode, save_prev;
+    // RodMechanics::get_random_contribution (bacterial_rods.rs:215-240): dpos = N(0, sqrt(dt)) * 2^-2 * D / dt
+    int noise_mode;
+    const double* noise;  // CRB_NOISE_TABLE: z[(step * n_ids + row) * 3V + c * V + v] (column-major fill of the matrix)
+    u64 noise_ids, noise_cursor, iteration, seed;
+    double diffusion;
     // aspect DomainForce (CRB_DOMAIN_FORCE_ROD_GEL): CartesianSubDomainRods (bacterial_rods.rs:433-477)
     int dforce;
     double gel_pressure, surface_friction, surface_friction_distance;
 };
+
+// row of the noise table / Philox key of a rod: Initial(k) rods use k, rods born by division fold their
+// Division(voxel, counter) identifier (the oracle restates the same rule: both sides read the same numbers)
+__host__ __device__ inline u64 rod_noise_key(u64 kind, u64 a, u64 b) {
+    return kind == 1 ? a : ((a * 0x9E3779B97F4A7C15ull + b) * 0xBF58476D1CE4E5B9ull) >> 11;
+}
 
 // ---- exact-order helpers (nalgebra dot / norm of a 3-vector: (x*x + y*y) + z*z, no fma) -----------
 __device__ __forceinline__ double dot3_rn(const double* a, const double* b) {
@@ -270,27 +281,54 @@ __device__ __forceinline__ void rod_epilogue(const RodParams& P, const u64 i, do
             acc[s + 2][c] = __dadd_rn(acc[s + 2][c], __dmul_rn(-f, 0.5));
         }
     }
+    // ---- get_random_contribution (bacterial_rods.rs:215-240): dpos[v][c] = ((0 + sqrt(dt) z) * 2^-2 * D) / dt with
+    // the matrix filled column-major from the generator (the k-th number goes to row k % V, column k / V); dvel = 0.
+    // The update loop below runs in that order (coordinate outer, vertex inner), so only four numbers are live.
+    const int noise_mode = P.noise_mode;
+    u64 nkey = 0;
+    const double* zrow = nullptr;
+    double sd = 0.0;
+    if (noise_mode != CRB_NOISE_NONE) {
+        nkey = rod_noise_key(P.A.ident[i], P.A.ident[cap + i], P.A.ident[2 * cap + i]);
+        sd = sqrt(P.dt);
+        if (noise_mode == CRB_NOISE_TABLE)
+            zrow = P.noise + (P.noise_cursor * P.noise_ids + nkey % (P.noise_ids ? P.noise_ids : 1)) * (u64)(3 * V);
+    }
     // ---- AB wrapper (chili/solvers.rs:156-300): dx = vel, dv = total force - vel * damping -------
     const int N = P.order;
     const int hlen = P.A.hlen[i];
     const int n_prev = N == 0 ? 0 : (hlen + 1 < N ? hlen + 1 : N);
+    double zn[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int v = 0; v < V; ++v)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int v = 0; v < V; ++v) {
+            const int k = c * V + v;
+            double rxv = 0.0;
+            if (noise_mode != CRB_NOISE_NONE) {
+                double z;
+                if (noise_mode == CRB_NOISE_TABLE) {
+                    z = zrow[k];
+                } else {
+                    if ((k & 3) == 0) philox_normal4(P.seed, nkey, P.iteration, (u32)(k >> 2), zn);
+                    z = zn[k & 3];
+                }
+                const double m = __dadd_rn(0.0, __dmul_rn(sd, z));
+                rxv = __ddiv_rn(__dmul_rn(__dmul_rn(m, 0.25), P.diffusion), P.dt);
+            }
             const u64 o = (u64)(v * 3 + c) * cap + i;
             const double dxv = vel[v][c];
             const double dvv = __dsub_rn(acc[v][c], __dmul_rn(vel[v][c], P.damping));
             const double oldx = P.A.h1x[o], oldv = P.A.h1v[o];
             double pn, wn;
             if (N == 2 && n_prev == 2) {
-                pn = helper_ab3(own[v][c], dxv, oldx, dxv, P.dt, 0.0);
+                pn = helper_ab3(own[v][c], dxv, oldx, dxv, P.dt, rxv);
                 wn = helper_ab3(vel[v][c], dvv, oldv, dvv, P.dt, 0.0);
             } else if (n_prev == 1) {
-                pn = helper_ab2(own[v][c], dxv, dxv, P.dt, 0.0);
+                pn = helper_ab2(own[v][c], dxv, dxv, P.dt, rxv);
                 wn = helper_ab2(vel[v][c], dvv, dvv, P.dt, 0.0);
             } else {
-                pn = helper_euler(own[v][c], dxv, P.dt, 0.0);
+                pn = helper_euler(own[v][c], dxv, P.dt, rxv);
                 wn = helper_euler(vel[v][c], dvv, P.dt, 0.0);
             }
             own[v][c] = pn;

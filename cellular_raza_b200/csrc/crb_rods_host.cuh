@@ -84,6 +84,13 @@ RodParams rods_params(crb_sim* s) {
     P.order = (int)s->cfg.solver_order;
     P.weight_mode = (int)s->cfg.pair_weight_mode;
     P.save_prev = 0;
+    P.noise_mode = mp[RMP_DIFF] != 0.0 ? (int)s->cfg.noise_mode : CRB_NOISE_NONE;  // D == 0: dpos is exactly 0
+    P.noise = s->noise;
+    P.noise_ids = s->noise_ids;
+    P.noise_cursor = s->noise_cursor;
+    P.iteration = s->iteration;
+    P.seed = s->cfg.rng_seed;
+    P.diffusion = mp[RMP_DIFF];
     P.dforce = (int)s->cfg.domain_force_kind;
     P.gel_pressure = s->cfg.domain_force_strength[0];
     P.surface_friction = s->cfg.domain_force_strength[1];
@@ -249,10 +256,10 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
     // argument, potential_stiffness * (R1 + R2) at distance 0, must stay below the f64 overflow of exp
     if (n && !(s->uni.ip[1] * (s->uni.ip[0] + s->uni.ip[0]) < 700.0))
         return fail(s, CRB_ERR_CALC, "CalcError: MorsePotential potential_stiffness * 2 radius >= 700 overflows exp in f64");
-    if (s->uni.mp[RMP_DIFF] != 0.0)
+    if (s->uni.mp[RMP_DIFF] != 0.0 && s->cfg.noise_mode == CRB_NOISE_NONE)
         return fail(s, CRB_ERR_INVALID_ARG,
-                    "rods: diffusion_constant != 0 is not supported (the example ships 0; noise contract A7 "
-                    "covers point agents only)");
+                    "rods: diffusion_constant != 0 needs noise_mode CRB_NOISE_TABLE or CRB_NOISE_PHILOX "
+                    "(RodMechanics::get_random_contribution, bacterial_rods.rs:215-240)");
     s->uniform = true;
     int rc;
     if ((rc = rods_upload_planes(s, pos, W, s->RT.pos, n))) return rc;
@@ -297,12 +304,15 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
     s->aux_settable = false;
     s->last_step_n = 0;
     s->last_divisions = 0;
+    s->noise_cursor = 0;
     return 0;
 }
 
 int rods_step(crb_sim* s, u64 n_steps) {
     for (u64 it = 0; it < n_steps; ++it) {
         const bool last = it + 1 == n_steps;
+        if (s->cfg.noise_mode == CRB_NOISE_TABLE && s->uni.mp[RMP_DIFF] != 0.0 && s->noise_cursor >= s->noise_steps)
+            return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
         CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
         CU(s, cudaMemsetAsync(s->n_div_dev, 0, sizeof(u32), s->stream));
         RodParams P = rods_params(s);
@@ -341,6 +351,7 @@ int rods_step(crb_sim* s, u64 n_steps) {
         if ((rc = rods_sort_into_place(s, s->n + n_div, last))) return rc;
         s->n += n_div;
         s->iteration++;
+        s->noise_cursor++;
     }
     return check_latch(s);
 }

@@ -68,6 +68,16 @@ class RodSimulation(DeviceSimulation):
         self._check(self._lib.crb_get_aux(self._h, n, _ptr(hx), _ptr(hv), _ptr(hl)))
         return hx, hv, hl
 
+    def set_noise(self, z):
+        """z[n_steps, n_ids, 3 V] standard normal numbers, entry ``c * V + v`` of a row feeding coordinate c of vertex
+        v (nalgebra's ``from_distribution`` fills the V x 3 matrix column by column, bacterial_rods.rs:230-236).  The
+        row of a rod is its ``Initial(k)`` number k, a daughter's row is a fixed hash of ``Division(voxel, counter)``;
+        rows are taken modulo ``n_ids``."""
+        z = _f64(z)
+        if z.ndim != 3 or z.shape[2] != self.dim * self.V:
+            raise ValueError("noise must have shape (n_steps, n_ids, dim * V)")
+        self._check(self._lib.crb_set_noise(self._h, _ptr(z), z.shape[0], z.shape[1]))
+
     @property
     def n_divisions(self) -> int:
         """Division events carried out by the last step."""

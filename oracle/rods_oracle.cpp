@@ -94,6 +94,9 @@ struct Oracle {
     uint64_t iteration = 0;
     uint64_t n_divisions = 0;
     int n_threads = 1;
+    // shared noise table: z[(step * n_ids + row) * D V + c V + v] standard normal numbers
+    std::vector<double> noise;
+    uint64_t noise_steps = 0, noise_ids = 0, noise_cursor = 0;
     std::vector<std::vector<std::vector<PosInfo>>> q_pos;
     std::vector<std::vector<std::vector<ForceInfo>>> q_force;
     std::vector<std::vector<std::vector<SendCell>>> q_cell;
@@ -454,12 +457,32 @@ void rod_increment(int D, int V, const Mat& pos, const Mat& vel, const double* m
         }
 }
 
-// local_mechanics_update -> Adams-Bashforth wrapper (chili/solvers.rs:156-300); the random
-// contribution of RodMechanics (bacterial_rods.rs:215-240) is z * 2^-2 * D / dt with
-// diffusion_constant = 0 in the example: only noise_mode NONE is restated (dpos = dvel = 0).
+// row of the noise table of a rod: Initial(k) rods use k, rods born by division fold their Division(voxel, counter)
+// identifier (the same rule as rod_noise_key of the device code; a contract of the shared table, not of chili)
+uint64_t rod_noise_key(const Ident& id) {
+    return id.kind == 1 ? id.a : ((id.a * 0x9E3779B97F4A7C15ull + id.b) * 0xBF58476D1CE4E5B9ull) >> 11;
+}
+
+// local_mechanics_update -> Adams-Bashforth wrapper (chili/solvers.rs:156-300).  Random contribution of
+// RodMechanics (bacterial_rods.rs:215-240): dpos = Matrix::from_distribution(nrows, Normal(0, sqrt(dt)), rng)
+// * 2^-2 * diffusion_constant / dt, dvel = 0; nalgebra fills the matrix column-major, so the k-th number drawn goes
+// to row k % nrows, column k / nrows; Normal samples mean + std_dev * z.  The ChaCha8 stream is replaced by the shared
+// table (noise_mode TABLE); noise_mode NONE gives dpos = 0.
 void local_mechanics_update(const Oracle& o, Rod& r, double dt) {
     const int D = o.D, V = o.V;
     const uint32_t N = o.cfg.solver_order;
+    Mat rx;
+    std::memset(&rx, 0, sizeof(rx));
+    if (o.cfg.noise_mode == CRB_NOISE_TABLE && r.mp[MP_DIFF] != 0.0 && o.noise_ids) {
+        const uint64_t row = rod_noise_key(r.id) % o.noise_ids;
+        const double* z = o.noise.data() + (o.noise_cursor * o.noise_ids + row) * (uint64_t)(D * V);
+        const double sd = std::sqrt(dt);
+        for (int v = 0; v < V; ++v)
+            for (int c = 0; c < D; ++c) {
+                const double m = 0.0 + sd * z[c * V + v];
+                rx.m[v][c] = m * 0.25 * r.mp[MP_DIFF] / dt;
+            }
+    }
     const Mat force = r.force;
     std::memset(&r.force, 0, sizeof(Mat));
     r.abs_sum = 0;
@@ -486,13 +509,13 @@ void local_mechanics_update(const Oracle& o, Rod& r, double dt) {
             const double x = r.pos.m[v][c], w = r.vel.m[v][c];
             double nx, nw;
             if (N == 2 && n_prev == 2) {
-                nx = helper_ab3(x, dx.m[v][c], r.ring_dx[0].m[v][c], r.ring_dx[1].m[v][c], dt, 0.0);
+                nx = helper_ab3(x, dx.m[v][c], r.ring_dx[0].m[v][c], r.ring_dx[1].m[v][c], dt, rx.m[v][c]);
                 nw = helper_ab3(w, dv.m[v][c], r.ring_dv[0].m[v][c], r.ring_dv[1].m[v][c], dt, 0.0);
             } else if (n_prev == 1) {
-                nx = helper_ab2(x, dx.m[v][c], r.ring_dx[0].m[v][c], dt, 0.0);
+                nx = helper_ab2(x, dx.m[v][c], r.ring_dx[0].m[v][c], dt, rx.m[v][c]);
                 nw = helper_ab2(w, dv.m[v][c], r.ring_dv[0].m[v][c], dt, 0.0);
             } else {
-                nx = helper_euler(x, dx.m[v][c], dt, 0.0);
+                nx = helper_euler(x, dx.m[v][c], dt, rx.m[v][c]);
                 nw = helper_euler(w, dv.m[v][c], dt, 0.0);
             }
             r.pos.m[v][c] = nx;
@@ -779,6 +802,10 @@ int rods_oracle_step(void* h, uint64_t n_steps) {
     const int64_t S = (int64_t)o.smap.n_sub;
     const double dt = o.cfg.dt;
     for (uint64_t it = 0; it < n_steps; ++it) {
+        if (o.cfg.noise_mode == CRB_NOISE_TABLE && o.noise_ids && o.noise_cursor >= o.noise_steps) {
+            g_err = "noise table exhausted";
+            return CRB_ERR_STATE;
+        }
         run_forces(o);
         std::atomic<int> ok{1};
         std::atomic<uint64_t> ndiv{0};
@@ -812,7 +839,17 @@ int rods_oracle_step(void* h, uint64_t n_steps) {
         parallel_for(S, o.n_threads, [&](int64_t s) { sort_step_1(o, (uint64_t)s); });
         parallel_for(S, o.n_threads, [&](int64_t s) { sort_step_2(o, (uint64_t)s); });
         ++o.iteration;
+        ++o.noise_cursor;
     }
+    return 0;
+}
+
+int rods_oracle_set_noise(void* h, const double* z, uint64_t n_steps, uint64_t n_ids) {
+    Oracle& o = *(Oracle*)h;
+    o.noise.assign(z, z + n_steps * n_ids * (uint64_t)(o.D * o.V));
+    o.noise_steps = n_steps;
+    o.noise_ids = n_ids;
+    o.noise_cursor = 0;
     return 0;
 }
 

@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         L.rods_oracle_n_divisions.restype = C.c_uint64
         L.rods_oracle_n_divisions.argtypes = [vp]
         L.rods_oracle_step.argtypes = [vp, C.c_uint64]
+        L.rods_oracle_set_noise.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
         L.rods_oracle_forces.argtypes = [vp] * 4
         L.rods_oracle_get_agents.argtypes = [vp] * 6
         L.rods_oracle_get_params.argtypes = [vp, vp]
@@ -119,6 +120,12 @@ class RodsOracle:
     @property
     def n_divisions(self):
         return int(self.L.rods_oracle_n_divisions(self.h))
+
+    def set_noise(self, z):
+        """z[step][row][c * V + v] standard normal numbers (column-major fill of the nrows x D matrix, the order
+        nalgebra's from_distribution consumes the generator in)"""
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        self._check(self.L.rods_oracle_set_noise(self.h, _p(z), z.shape[0], z.shape[1]))
 
     def step(self, n_steps=1):
         self._check(self.L.rods_oracle_step(self.h, n_steps))

@@ -223,3 +223,88 @@ def test_domain_force_kind_mismatch_is_rejected(crb_lib):
     w = workloads.bacterial_rods(1, 1)
     with pytest.raises(SimulationError):
         RodSimulation(w.config(domain_force_kind=_abi.CRB_DOMAIN_FORCE_SPRING))
+
+
+def _with_diffusion(w, diffusion):
+    mech = w.mech_params.copy()
+    mech[:, 0] = diffusion
+    return mech
+
+
+@pytest.mark.parametrize("order", [2, 0])
+def test_random_contribution_noise_table(crb_lib, order):
+    """RodMechanics::get_random_contribution (bacterial_rods.rs:215-240) with the shared noise table: device and
+    oracle read the same standard normal numbers (column-major fill of the V x 3 matrix), also for daughters born
+    inside the run (their table row is a hash of Division(voxel, counter))."""
+    w = workloads.bacterial_rods(6, 5, rods_per_tile=6, spring_length_range=(5.6, 5.99), solver_order=order,
+                                 capacity_factor=3.0)
+    mech = _with_diffusion(w, 0.5e-6)
+    z = np.random.default_rng(11).standard_normal((60, 257, 15))   # fewer rows than rods: rows wrap modulo n_ids
+    dev = RodSimulation(w.config(noise_mode=_abi.CRB_NOISE_TABLE))
+    ora = RodsOracle(w.config(noise_mode=_abi.CRB_NOISE_TABLE), n_threads=4)
+    for sim in (dev, ora):
+        sim.set_agents(w.pos, w.vel, mech, w.inter_params)
+        sim.set_noise(z)
+    # one step from identical state: the random displacement itself is exact
+    dev.step(1)
+    ora.step(1)
+    pd, vd, po, vo = assert_same_population(dev, ora)
+    L = max(w.cfg_kwargs["domain_max"])
+    assert np.abs(pd - po).max() / L <= 1e-15
+    for k in (10, 10, 10, 10, 10, 9):
+        dev.step(k)
+        ora.step(k)
+        assert dev.n_agents == ora.n_agents
+    pd, vd, po, vo = assert_same_population(dev, ora)
+    assert dev.n_agents > w.n, "the test population must divide"
+    assert np.abs(pd - po).max() / L <= TRAJ_TOL
+    # table exhausted: the next step must fail loudly on both sides
+    with pytest.raises(SimulationError):
+        dev.step(1)
+
+
+def test_random_contribution_changes_the_trajectory_and_needs_a_noise_source(crb_lib):
+    w = workloads.bacterial_rods(2, 2)
+    mech = _with_diffusion(w, 0.5e-6)
+    plain = RodSimulation(w.config())
+    with pytest.raises(SimulationError):   # diffusion_constant != 0 with noise_mode NONE is refused, not ignored
+        plain.set_agents(w.pos, w.vel, mech, w.inter_params)
+    plain.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    noisy = RodSimulation(w.config(noise_mode=_abi.CRB_NOISE_PHILOX, rng_seed=5))
+    noisy.set_agents(w.pos, w.vel, mech, w.inter_params)
+    plain.step(5)
+    noisy.step(5)
+    assert np.abs(plain.get_agents()[0] - noisy.get_agents()[0]).max() > 1e-9
+
+
+def test_random_contribution_philox_statistics(crb_lib):
+    """device generator: free rods far apart (no pair forces, relaxed springs, no growth): after one Euler step every
+    vertex coordinate has moved by sqrt(dt) z / 4 * D with z standard normal: mean 0, variance 1, no correlation
+    between vertices or coordinates."""
+    V, D, dt = 5, 0.5e-6, 0.1
+    nx, nz = 64, 32
+    w = workloads.bacterial_rods(nx, nz, rods_per_tile=1, solver_order=0)
+    n = w.n
+    pos = np.zeros((n, V, 3))
+    tile = np.array([200e-6, 15e-6, 45e-6])
+    ix, iz = np.divmod(np.arange(n), nz)
+    pos[:, :, 0] = (ix * tile[0] + 90e-6)[:, None] + 3e-6 * np.arange(V)[None, :]
+    pos[:, :, 1] = 7.5e-6
+    pos[:, :, 2] = (iz * tile[2] + 22e-6)[:, None]
+    mech = _with_diffusion(w, D)
+    mech[:, 3] = 3e-6
+    mech[:, 5] = 0.0
+    mech[:, 7] = 0.0
+    dev = RodSimulation(w.config(noise_mode=_abi.CRB_NOISE_PHILOX, rng_seed=123))
+    dev.set_agents(pos, np.zeros_like(pos), mech, w.inter_params)
+    dev.step(1)
+    p1, _, ident, _, _ = dev.get_agents()
+    order = np.argsort(ident[:, 1])
+    zhat = (p1[order] - pos) / (np.sqrt(dt) * 0.25 * D)          # n x V x 3 standard normal numbers
+    flat = zhat.reshape(n, -1)
+    m = flat.size
+    assert abs(flat.mean()) < 5 / np.sqrt(m)
+    assert abs(flat.var() - 1.0) < 5 * np.sqrt(2.0 / m)
+    c = np.corrcoef(flat.T)
+    off = c - np.eye(c.shape[0])
+    assert np.abs(off).max() < 5 / np.sqrt(n)

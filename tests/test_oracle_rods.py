@@ -197,3 +197,47 @@ def test_domain_force_gel_pressure_and_surface_friction():
     o2 = ro.RodsOracle(w.config(), n_threads=2)
     o2.set_agents(pos, vel, w.mech_params[:3], w.inter_params[:3])
     assert np.abs(o2.forces()[0]).max() == 0.0
+
+
+def test_random_contribution_known_answer():
+    """RodMechanics::get_random_contribution (bacterial_rods.rs:215-240): dpos = M * 2^-2 * D / dt with M filled
+    column by column from Normal(0, sqrt(dt)), dvel = 0; the Euler helper (solvers.rs:303-312) adds dpos * dt.  A
+    relaxed straight rod at rest feels no force, so one step moves vertex v, coordinate c by exactly
+    ((sqrt(dt) z[c V + v]) * 0.25 * D / dt) * dt."""
+    V, D, dt = 5, 0.5 * UM, 0.1
+    w = workloads.bacterial_rods(1, 1, rods_per_tile=1, n_threads=1, solver_order=0)
+    pos = np.zeros((1, V, 3))
+    pos[0, :, 0] = 30 * UM + 3 * UM * np.arange(V)
+    pos[0, :, 1] = 7 * UM
+    pos[0, :, 2] = 20 * UM
+    mech = w.mech_params.copy()
+    mech[:, 0] = D
+    mech[:, 3] = 3 * UM   # spring_length == segment length: no spring force
+    mech[:, 5] = 0.0      # no growth
+    z = np.random.default_rng(3).standard_normal((2, 1, 3 * V))
+    o = ro.RodsOracle(w.config(noise_mode=_abi.CRB_NOISE_TABLE), n_threads=1)
+    o.set_agents(pos, np.zeros_like(pos), mech, w.inter_params)
+    o.set_noise(z)
+    o.step(1)
+    got = o.get_agents()[0][0]
+    m = (0.0 + np.sqrt(dt) * z[0, 0].reshape(3, V).T)          # column-major fill: entry c V + v -> (v, c)
+    want = (np.zeros((V, 3)) * dt + pos[0]) + ((m * 0.25 * D) / dt) * dt
+    np.testing.assert_array_equal(got, want)
+    # velocities get no random part (what is left is the rounding of the vertex spacing through the spring: 1e-21)
+    assert np.abs(o.get_agents()[1]).max() < 1e-18
+    # the table runs out after its two steps
+    o.step(1)
+    with pytest.raises(Exception):
+        o.step(1)
+
+
+def test_random_contribution_zero_diffusion_is_deterministic():
+    w = workloads.bacterial_rods(2, 2, n_threads=2)
+    a = ro.RodsOracle(w.config(noise_mode=_abi.CRB_NOISE_TABLE), n_threads=2)
+    b = ro.RodsOracle(w.config(), n_threads=2)
+    for o in (a, b):
+        o.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    a.set_noise(np.random.default_rng(1).standard_normal((5, w.n, 15)))
+    a.step(5)
+    b.step(5)
+    assert np.array_equal(a.get_agents()[0], b.get_agents()[0])
