@@ -11,7 +11,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-CRB_ABI_VERSION = 6
+CRB_ABI_VERSION = 7
 CRB_MAX_DIM = 3
 
 # crb_status
@@ -149,6 +149,7 @@ SYMBOLS = [
     ("crb_step_async", C.c_int, [_vp, C.c_uint64]),
     ("crb_sync", C.c_int, [_vp]),
     ("crb_iteration", C.c_uint64, [_vp]),
+    ("crb_set_iteration", C.c_int, [_vp, C.c_uint64]),
     ("crb_force_kernel_name", C.c_char_p, [_vp]),
     ("crb_snapshot_async", C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("crb_snapshot_wait", C.c_int, [_vp, _u64p]),

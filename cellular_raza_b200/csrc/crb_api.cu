@@ -1134,6 +1134,12 @@ void crb_destroy(crb_sim* s) {
 
 uint64_t crb_n_agents(const crb_sim* s) { return s ? s->n : 0; }
 uint64_t crb_iteration(const crb_sim* s) { return s ? s->iteration : 0; }
+int crb_set_iteration(crb_sim* s, uint64_t iteration) {
+    if (!s) return CRB_ERR_INVALID_ARG;
+    if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, "crb_set_iteration inside an open slab step");
+    s->iteration = iteration;
+    return 0;
+}
 uint64_t crb_kernel_launches(const crb_sim* s) { return s ? s->launches : 0; }
 const char* crb_force_kernel_name(const crb_sim* s) {
     if (!s) return "";

@@ -152,6 +152,10 @@ class DeviceSimulation:
     def iteration(self) -> int:
         return int(self._lib.crb_iteration(self._h))
 
+    def set_iteration(self, iteration: int):
+        """step counter of the handle (keys the device generator of CRB_NOISE_PHILOX together with seed and id)"""
+        self._check(self._lib.crb_set_iteration(self._h, int(iteration)))
+
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.crb_kernel_launches(self._h))

@@ -61,6 +61,7 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         sim.sync()
         h_p2p, n_p2p = state_hash()
         sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
+        slab.set_iteration(0)  # the Philox generator of configs[2] is keyed by (seed, id, iteration)
         sim.transport = "nccl"
         sim.step(n_check)
         sim.sync()
@@ -77,6 +78,7 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         if not protocol_check["p2p_equals_nccl_bitwise_on_every_rank"] or protocol_check["agents_total_p2p"] != n * world:
             raise RuntimeError(f"slab protocol check failed: {protocol_check}")
         sim.set_agents(w.pos, w.vel, None, None, w.species, w.extra["ids"])
+        slab.set_iteration(0)
 
     sim.halo_exchange()
     pairs = slab.count_candidate_pairs()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CRB_ABI_VERSION 6
+#define CRB_ABI_VERSION 7
 
 /* ---- status codes ------------------------------------------------------------------------- */
 typedef enum crb_status {
@@ -244,6 +244,12 @@ int crb_step_async(crb_sim* sim, uint64_t n_steps);
 int crb_sync(crb_sim* sim);
 /* number of steps taken since creation. */
 uint64_t crb_iteration(const crb_sim* sim);
+/* sets the step counter (the iteration number of the generated main loop, run_sim.rs:380-403): the device generator
+ * of CRB_NOISE_PHILOX is keyed by (rng_seed, agent id, iteration), so a host that restarts a run from a stored
+ * population — or repeats one from its initial state — puts the counter back where that population belongs.
+ * crb_set_agents does NOT touch the counter (a host that re-uploads the population every step must keep drawing
+ * fresh numbers). */
+int crb_set_iteration(crb_sim* sim, uint64_t iteration);
 
 /* ---- slab decomposition over several devices --------------------------------------
  * Replaces the Communicator / ChannelComm traffic of chili between subdomains

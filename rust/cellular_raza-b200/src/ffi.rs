@@ -3,7 +3,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const CRB_ABI_VERSION: u32 = 6;
+pub const CRB_ABI_VERSION: u32 = 7;
 
 pub const CRB_OK: c_int = 0;
 pub const CRB_ERR_CALC: c_int = -1;
@@ -101,6 +101,7 @@ extern "C" {
     pub fn crb_step_async(sim: *mut crb_sim, n_steps: u64) -> c_int;
     pub fn crb_sync(sim: *mut crb_sim) -> c_int;
     pub fn crb_iteration(sim: *const crb_sim) -> u64;
+    pub fn crb_set_iteration(sim: *mut crb_sim, iteration: u64) -> c_int;
     // storage snapshots that do not stop the stepping loop
     pub fn crb_snapshot_async(sim: *mut crb_sim, cap: u64, pos: *mut f64, vel: *mut f64, ids: *mut u64,
                               voxel: *mut u64, hist_dx: *mut f64, hist_dv: *mut f64, hist_len: *mut u32) -> c_int;

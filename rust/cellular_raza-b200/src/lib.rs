@@ -3,7 +3,7 @@
 //! hand-written sm_100a kernels behind the C ABI of `include/crb.h`.
 //!
 //! STATUS: this crate has NOT been compiled — the build image has no cargo/rustc.  It is written
-//! against `include/crb.h` (ABI 6) and mirrors `cellular_raza_b200/backend.py`, which drives the same
+//! against `include/crb.h` (ABI 7) and mirrors `cellular_raza_b200/backend.py`, which drives the same
 //! symbols through ctypes and is what `tests/` exercise.  Expect small fixes at first compile.
 //!
 //! What it replaces in the reference:

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_function(lib):
     assert len(fns) >= 45, sorted(fns)
     missing = [n for n in fns if not hasattr(lib, n)]
     assert not missing, f"declared in include/crb.h but not exported: {missing}"
-    assert lib.crb_abi_version() == 6
+    assert lib.crb_abi_version() == 7
 
 
 def test_ctypes_twin_binds_every_declared_function():
