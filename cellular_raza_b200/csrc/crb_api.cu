@@ -430,7 +430,7 @@ void plan_tile(crb_sim* s) {
             if (nchunks > 1 && (n2 + nchunks - 2) / (nchunks - 1) == chunk_len) continue;  // same length, more chunks
             const int kmax = chunk_len + 2;
             const size_t fixed2 = (size_t)(kTileQueue + 4) * nt * sizeof(unsigned short) +
-                                  (size_t)kT2Rows * (kmax + 1) * sizeof(u32) + 64 + 34 * per_cand + 1024 /* static */;
+                                  (size_t)kT2Rows * (kmax + 1) * sizeof(u32) + 64 + 34 * per_cand + 1536 /* static */;
             if (budget2 <= fixed2) continue;
             const u32 cap2 = (u32)std::min<size_t>(((budget2 - fixed2) / per_cand) / 2 * 2, 60000);
             const double ts = std::min(((double)cap2 - halo) / per_t, lanes);

@@ -50,6 +50,7 @@ struct TileLaunch {
     int kmax;       // max voxels of a window + 1 (row stride of the wst table)
     float cut2f;    // conservative FP32 cutoff^2 of the filter
     float cut2m;    // conservative cutoff^2 of the TF32 tensor-core filter (k_force_tile3)
+    u32 inv_nseg;   // ceil(2^32 / nseg): blockIdx.x / nseg == __umulhi(blockIdx.x, inv_nseg) (k_force_tile2, set by its launcher)
 };
 
 // exact data of one staged candidate: one address computation and two LDS.128 per evaluated pair
@@ -82,18 +83,20 @@ struct TileTarget {
     int calc_flag;
 };
 
-template <int D, int INTER, int NE>
-__device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
-                                          const TileCand* __restrict__ sc,
-                                          const u32 (&jj)[NE], const bool (&hh)[NE]) {
+// The exact record of candidate j is two 16-byte halves {x, y} = ra[j << SHIFT] and {z, meta | voxel << 32} =
+// rb[j << SHIFT]: SHIFT 1 with ra = sc, rb = sc + 16 B for the 32-byte TileCand records of k_force_tile /
+// k_force_tile3, SHIFT 0 for the two arrays of k_force_tile2.
+template <int D, int INTER, int NE, int SHIFT>
+__device__ __forceinline__ void tile_eval_rec(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
+                                              const double2* __restrict__ ra, const double2* __restrict__ rb,
+                                              const u32 (&jj)[NE], const bool (&hh)[NE]) {
     // straight-line code for NE candidates (coef() is branch-free) so that the dependent FP64 chains
     // interleave; an empty slot points at the target itself (z == 0) and contributes +0.
     double z[NE][D], cf[NE];
     int flag[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const double2* cp = reinterpret_cast<const double2*>(sc + jj[e]);
-        const double2 c0 = cp[0], c1 = cp[1];
+        const double2 c0 = ra[jj[e] << SHIFT], c1 = rb[jj[e] << SHIFT];
         z[e][0] = t.x[0] - c0.x;
         z[e][1] = t.x[1] - c0.y;
         if (D == 3) z[e][2] = t.x[2] - c1.x;
@@ -122,6 +125,20 @@ __device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& ow
 #pragma unroll
         for (int c = 0; c < D; ++c) t.acc[c] = fma(z[e][c], cf[e], t.acc[c]);
     }
+}
+
+template <int D, int INTER, int NE>
+__device__ __forceinline__ void tile_eval(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
+                                          const TileCand* __restrict__ sc,
+                                          const u32 (&jj)[NE], const bool (&hh)[NE]) {
+    const double2* r = reinterpret_cast<const double2*>(sc);
+    tile_eval_rec<D, INTER, NE, 1>(t, own, ext_radius, r, r + 1, jj, hh);
+}
+template <int D, int INTER, int NE>
+__device__ __forceinline__ void tile_eval_soa(TileTarget<D>& t, const Pot<INTER>& own, const double ext_radius,
+                                              const double2* __restrict__ sxyd, const double2* __restrict__ szm,
+                                              const u32 (&jj)[NE], const bool (&hh)[NE]) {
+    tile_eval_rec<D, INTER, NE, 0>(t, own, ext_radius, sxyd, szm, jj, hh);
 }
 
 // per-agent path over global memory (same arithmetic as k_force_integrate, uniform parameters)

@@ -18,10 +18,21 @@
 // the sorted state: the per-target summation order — and therefore every bit of the result — is the
 // one of k_force_tile and of the per-agent kernel.
 //
-// Staging: the exact data of a candidate is one 32-byte record {x, y, z, meta, voxel} (TileCand) filled
-// by cp.async; the FP32 filter copy is loaded as pairs and stored transposed ({x0,x1,y0,y1}, {z0,z1})
-// so that one LDS.128 + one LDS.64 feed the packed f32x2 distance test of two candidates.  Every row
-// starts at an even staged index and is followed by >= 8 sentinels (NaN: never pass the test).
+// Staging: the exact data of a candidate is two 16-byte records {x, y} and {z, meta, voxel} in two arrays
+// filled by cp.async (16-byte records spread the drain's random reads over all 32 banks; one 32-byte
+// record per candidate used only half of them: 45 % of the shared-memory wavefronts of the round-1 kernel
+// were bank conflicts); the FP32 filter copy is loaded as pairs and stored transposed ({x0,x1,y0,y1},
+// {z0,z1}) so that one LDS.128 + one LDS.64 feed the packed f32x2 distance test of two candidates.  Every
+// row starts at an even staged index and is followed by >= 8 sentinels (NaN: never pass the test).
+//
+// Round 2 (ncu source page, profiles/r2_ncu_k_force_tile2_8M.txt): 30 of the 96 instructions of the filter
+// block loop re-derived the shared-memory carve-up (T.cap from the constant bank -> four base addresses)
+// in EVERY iteration — the compiler rematerialises what it considers cheap instead of holding three
+// registers — and 211 instructions of integer division ran in every warp of every CTA before the
+// early-exit test.  The bases are now opaque 32-bit shared addresses (asm volatile: nothing to
+// rematerialise), the hot loads are ld.shared with immediate offsets, the grid is three-dimensional
+// (segment x chunk, tile row, tile plane) and the integrator inputs are prefetched instead of parked in 18
+// registers across the pair loop.
 #pragma once
 #include "crb_force_tile.cuh"
 
@@ -30,16 +41,47 @@ namespace crb {
 constexpr int kT2Rows = 16;  // staged rows (4 x 4)
 constexpr int kT2Pad = 8;    // sentinels after every staged row
 
+// second half of the exact record of a staged candidate ({x, y} is a plain double2)
+struct __align__(16) TileCandZ {
+    double z;
+    u32 meta;  // species | (z voxel & 0xff) << 8
+    u32 cv;    // local voxel index
+};
+
 __host__ __device__ inline size_t tile2_smem_bytes(u32 cap, int kmax, int threads) {
     const size_t c = cap + 34;  // cap includes the rows' sentinels; +34 filter over-read (even)
     size_t b = 0;
-    b += c * sizeof(TileCand);                                         // exact positions + meta + voxel
+    b += c * (sizeof(double2) + sizeof(TileCandZ));                    // exact positions + meta + voxel
     b += (c / 2) * sizeof(float4);                                     // {x0, x1, y0, y1} per pair
     b += (c / 2) * sizeof(float2);                                     // {z0, z1} per pair
     b += (size_t)kT2Rows * (kmax + 1) * sizeof(u32);                   // start[] of the 16 rows
     b += (size_t)(kTileQueue + 4) * threads * sizeof(unsigned short);  // per-lane FIFOs
     return b + 64;
 }
+
+// 32-bit shared-window address that the compiler cannot re-derive (see the header: it would otherwise recompute the
+// carve-up of the dynamic shared memory inside the hot loops)
+__device__ __forceinline__ u32 smem_addr_opaque(const void* p) {
+    u32 a = (u32)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ float4 lds_f4(u32 a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(u32 a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ u32 lds_u32(u32 a) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l1_t2(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int D, int INTER, bool FORCE_ONLY, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, const TileLaunch T) {
@@ -51,37 +93,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
 
-    // ---- carve shared memory -----------------------------------------------------------------------
-    const u32 capp = T.cap + 34;  // even
-    TileCand* sc = reinterpret_cast<TileCand*>(smem_raw);
-    float4* sxy = reinterpret_cast<float4*>(sc + capp);                  // [capp / 2]
-    float2* szz = reinterpret_cast<float2*>(sxy + capp / 2);             // [capp / 2]
-    u32* sst = reinterpret_cast<u32*>(szz + capp / 2);                   // [16][kmax + 1] copy of start[]
-    unsigned short* q = reinterpret_cast<unsigned short*>(sst + kT2Rows * (T.kmax + 1));
-    __shared__ u32 s_rowvox[kT2Rows];   // first voxel (local plain index) of every staged row
-    __shared__ u32 s_g0[kT2Rows];       // first global agent index staged per row
-    __shared__ u32 s_rs[kT2Rows + 1];   // staged index of the first candidate of every row (even)
-    __shared__ u32 s_rn[kT2Rows];       // candidates staged per row (without sentinels)
-    __shared__ int s_valid[kT2Rows];
-    __shared__ u32 s_tpre[5];           // first slot of every target row (multiples of 4)
-    __shared__ u32 s_tn[4];             // targets of every target row in the window
-    __shared__ u32 s_t0[4];             // global index of the first of them
-    __shared__ int s_tlast;             // a target row that holds targets (for lanes beyond the slots)
-    __shared__ int s_kc, s_za, s_zb;
-
-    // ---- which tile: 2 x 2 rows, chunk of the fastest axis, count-balanced segment of the chunk ------
-    const int ny2 = (n1 + 1) >> 1;
-    const int seg = blockIdx.x % T.nseg;
-    const int chunk = (blockIdx.x / T.nseg) % T.nchunks;
-    const int tileid = blockIdx.x / (T.nseg * T.nchunks);
-    const int Y = (tileid % ny2) * 2;
-    const int X = T.x_begin + (tileid / ny2) * 2;
+    // ---- which tile: grid = (segment x chunk, tile row, tile plane); CTAs beyond the segments a tile needs
+    // leave before anything else happens (broadcast loads) -------------------------------------------------
+    const int chunk = T.nseg > 1 ? (int)__umulhi(blockIdx.x, T.inv_nseg) : (int)blockIdx.x;  // blockIdx.x / nseg (exact: < 2^16)
+    const int seg = (int)blockIdx.x - chunk * T.nseg;
+    const int Y = (int)blockIdx.y * 2;
+    const int X = T.x_begin + (int)blockIdx.z * 2;
     const bool va1 = X + 1 < T.x_begin + T.x_count;  // second target plane exists
     const bool vb1 = Y + 1 < n1;                     // second target row exists
     const int ca = chunk * T.chunk_len;
     const int cb = min(ca + T.chunk_len, n2);
     {
-        // CTAs beyond the segments this tile needs leave before anything is staged (broadcast loads)
         u32 R = 0;
 #pragma unroll
         for (int tr = 0; tr < 4; ++tr) {
@@ -93,6 +115,30 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
         }
         if ((u32)seg * T.tseg >= R) return;  // seg >= ceil(R / tseg); uniform
     }
+
+    // ---- carve shared memory -----------------------------------------------------------------------
+    const u32 capp = T.cap + 34;  // even
+    double2* sxyd = reinterpret_cast<double2*>(smem_raw);                 // [capp] exact {x, y}
+    TileCandZ* szm = reinterpret_cast<TileCandZ*>(sxyd + capp);           // [capp] exact {z, meta, voxel}
+    float4* sxy = reinterpret_cast<float4*>(szm + capp);                 // [capp / 2]
+    float2* szz = reinterpret_cast<float2*>(sxy + capp / 2);             // [capp / 2]
+    u32* sst = reinterpret_cast<u32*>(szz + capp / 2);                   // [16][kmax + 1] copy of start[]
+    unsigned short* q = reinterpret_cast<unsigned short*>(sst + kT2Rows * (T.kmax + 1));
+    // the addresses of the hot loops, held in registers
+    const u32 a_sxy = smem_addr_opaque(sxy), a_szz = smem_addr_opaque(szz), a_sst = smem_addr_opaque(sst);
+    const u32 qa0 = smem_addr_opaque(q + tid);
+    __shared__ u32 s_rowvox[kT2Rows];   // first voxel (local plain index) of every staged row
+    __shared__ u32 s_g0[kT2Rows];       // first global agent index staged per row
+    __shared__ u32 s_rs[kT2Rows + 1];   // staged index of the first candidate of every row (even)
+    __shared__ u32 s_rn[kT2Rows];       // candidates staged per row (without sentinels)
+    __shared__ u32 s_off[kT2Rows];      // s_rs - s_g0: staged index = global index + s_off (wraps; even when unstaged)
+    __shared__ int s_valid[kT2Rows];
+    __shared__ u32 s_tpre[5];           // first slot of every target row (multiples of 4)
+    __shared__ u32 s_tn[4];             // targets of every target row in the window
+    __shared__ u32 s_t0[4];             // global index of the first of them
+    __shared__ int s_tlast;             // a target row that holds targets (for lanes beyond the slots)
+    __shared__ int s_kc, s_za, s_zb;
+
     if (tid < kT2Rows) {
         const int p = tid >> 2, qq = tid & 3;
         const int XX = X - 1 + p, YY = Y - 1 + qq;
@@ -224,6 +270,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
                 s_g0[lane] = a;
                 s_rs[lane] = incl - np;
                 s_rn[lane] = n;
+                s_off[lane] = incl - np - a;
             }
             if (lane == kT2Rows - 1) s_rs[kT2Rows] = incl;
         } else if (warp == 1) {
@@ -268,27 +315,27 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
                     if (o < n) {
                         const u32 gi = g0 + o;
                         a = __ldg(P.A.posf + gi);
-                        cp_async_8(&sc[k].x, P.A.pos[0] + gi);
-                        cp_async_8(&sc[k].y, P.A.pos[1] + gi);
-                        if (D == 3) cp_async_8(&sc[k].z, P.A.pos[2] + gi);
-                        cp_async_4(&sc[k].meta, P.A.meta + gi);
+                        cp_async_8(&sxyd[k].x, P.A.pos[0] + gi);
+                        cp_async_8(&sxyd[k].y, P.A.pos[1] + gi);
+                        if (D == 3) cp_async_8(&szm[k].z, P.A.pos[2] + gi);
+                        cp_async_4(&szm[k].meta, P.A.meta + gi);
                     } else {
-                        sc[k].meta = 0xffffu;
+                        szm[k].meta = 0xffffu;
                     }
                     if (o + 1 < n) {
                         const u32 gi = g0 + o + 1;
                         b = __ldg(P.A.posf + gi);
-                        cp_async_8(&sc[k + 1].x, P.A.pos[0] + gi);
-                        cp_async_8(&sc[k + 1].y, P.A.pos[1] + gi);
-                        if (D == 3) cp_async_8(&sc[k + 1].z, P.A.pos[2] + gi);
-                        cp_async_4(&sc[k + 1].meta, P.A.meta + gi);
+                        cp_async_8(&sxyd[k + 1].x, P.A.pos[0] + gi);
+                        cp_async_8(&sxyd[k + 1].y, P.A.pos[1] + gi);
+                        if (D == 3) cp_async_8(&szm[k + 1].z, P.A.pos[2] + gi);
+                        cp_async_4(&szm[k + 1].meta, P.A.meta + gi);
                     } else {
-                        sc[k + 1].meta = 0xffffu;
+                        szm[k + 1].meta = 0xffffu;
                     }
                     sxy[k >> 1] = make_float4(a.x, b.x, a.y, b.y);
                     szz[k >> 1] = make_float2(a.z, b.z);
-                    sc[k].cv = __float_as_uint(a.w);
-                    sc[k + 1].cv = __float_as_uint(b.w);
+                    szm[k].cv = __float_as_uint(a.w);
+                    szm[k + 1].cv = __float_as_uint(b.w);
                 }
             }
             // over-read region behind the last row
@@ -317,20 +364,29 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
             const int Xt = X + ta, Yt = Y + tb;
             const int sr0 = ta * 4 + tb;  // staged row of the (-1, -1) neighbour row
             const int src = sr0 + 5;      // staged row of the target's own row
-            // integrator inputs: issued now, consumed after the pair loop
-            AgentDyn<D> dyn;
-            if constexpr (!FORCE_ONLY) dyn = load_agent_dyn<D>(P, i);
+            // integrator inputs: only prefetched here (18 registers would otherwise be parked across the pair loop)
+            if constexpr (!FORCE_ONLY) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    if (P.mech != CRB_MECH_BROWNIAN) prefetch_l1_t2(&P.A.vel[c][i]);
+                    prefetch_l1_t2(&P.A.h1x[c][i]);
+                    prefetch_l1_t2(&P.A.h1v[c][i]);
+                }
+            }
             const u32 sj_self = s_rs[src] + (i - s_g0[src]);
-            const TileCand self = sc[sj_self];
             TileTarget<D> t;
-            t.x[0] = self.x;
-            t.x[1] = self.y;
-            if (D == 3) t.x[2] = self.z;
+            {
+                const double2 sa = sxyd[sj_self];
+                const TileCandZ sb = szm[sj_self];
+                t.x[0] = sa.x;
+                t.x[1] = sa.y;
+                if (D == 3) t.x[2] = sb.z;
+                t.my_v = sb.cv;
+                t.sp = (u8)(sb.meta & 0xffu);
+                t.zw = sb.meta >> 8;
+            }
 #pragma unroll
             for (int c = 0; c < D; ++c) t.acc[c] = 0.0;
-            t.my_v = self.cv;
-            t.sp = (u8)(self.meta & 0xffu);
-            t.zw = self.meta >> 8;
             t.calc_flag = 0;
             t.subv_lo = 0;
             t.subv_len = 0;
@@ -365,8 +421,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
             const int zlo = max(zmin - 1, wa), zhi = min(zmax + 2, wb);
 
             // per-lane FIFO of in-range candidate indices (ascending): q[k][tid]
-            unsigned short* const q0 = q + tid;
-            const u32 qa0 = (u32)__cvta_generic_to_shared(q0);
             u32 qa = qa0;
             auto drain = [&]() {
                 const u32 nq = (qa - qa0) / (2u * nthreads);
@@ -376,59 +430,66 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
                     bool hh[NE];
 #pragma unroll
                     for (int e = 0; e < NE; ++e) {
-                        const u32 ent = q0[(k + e) * nthreads];
+                        u32 ent;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ent) : "r"(qa0 + (k + e) * 2u * nthreads));
                         hh[e] = (k + e < nq) & (ent != sj_self);
                         jj[e] = hh[e] ? ent : sj_self;
                     }
-                    tile_eval<D, INTER, NE>(t, own, ext_radius, sc, jj, hh);
+                    tile_eval_soa<D, INTER, NE>(t, own, ext_radius, sxyd, reinterpret_cast<const double2*>(szm), jj, hh);
                 }
                 qa = qa0;
             };
             const u32 qfull = qa0 + 2u * (kTileQueue - 8) * nthreads;
             const float2 xf2 = make_float2(-xf, -xf), yf2 = make_float2(-yf, -yf), zf2 = make_float2(-zf, -zf);
+            // start[] entries of this sub-group's window inside row sr: a_sst + 4 (sr sstride + z - zb0)
+            const u32 a_wlo = a_sst + 4u * (u32)(zlo - zb0), a_whi = a_sst + 4u * (u32)(zhi - zb0);
+            const u32 rstride = 4u * (u32)sstride;
 
 #pragma unroll 1
-            for (int r = 0; r < 9; ++r) {
-                const int sr = sr0 + (r / 3) * 4 + (r % 3);
-                const u32 off = s_rs[sr] - s_g0[sr];  // even for a row that is not staged
-                const u32 lo = off + SS(sr, zlo), hi = off + SS(sr, zhi);
-                const u32 lo2 = lo & ~1u;  // blocks start at an even candidate (pair layout); the extra
-                                           // leading candidate belongs to voxel zlo-1 of the same row:
-                                           // rejected by the distance test or by the adjacency test
-                const u32 n = hi - lo2;
-                const u32 nmax = __reduce_max_sync(0xffffffffu, n);
-                if (nmax == 0) continue;  // warp-uniform
-                for (u32 k0 = 0; k0 < nmax; k0 += 8) {
-                    if (__any_sync(0xffffffffu, qa > qfull)) drain();
-                    // a block past the lane's range is disabled through the threshold; a block that
-                    // starts inside may over-read <= 7 entries (later voxels of the row or sentinels)
-                    const float cut = k0 < n ? T.cut2f : -1.0f;
-                    const u32 b8 = min(lo2 + k0, limit);
-                    const u32 p4 = b8 >> 1;
-                    float4 ca4[4];
-                    float2 cz2[4];
+            for (int ra = 0; ra < 3; ++ra) {
+#pragma unroll 1
+                for (int rb = 0; rb < 3; ++rb) {
+                    const int sr = sr0 + ra * 4 + rb;
+                    const u32 off = s_off[sr];  // even for a row that is not staged
+                    const u32 lo = off + lds_u32(a_wlo + (u32)sr * rstride), hi = off + lds_u32(a_whi + (u32)sr * rstride);
+                    const u32 lo2 = lo & ~1u;  // blocks start at an even candidate (pair layout); the extra
+                                               // leading candidate belongs to voxel zlo-1 of the same row:
+                                               // rejected by the distance test or by the adjacency test
+                    const u32 n = hi - lo2;
+                    const u32 nmax = __reduce_max_sync(0xffffffffu, n);
+                    if (nmax == 0) continue;  // warp-uniform
+                    for (u32 k0 = 0; k0 < nmax; k0 += 8) {
+                        if (__any_sync(0xffffffffu, qa > qfull)) drain();
+                        // a block past the lane's range is disabled through the threshold; a block that
+                        // starts inside may over-read <= 7 entries (later voxels of the row or sentinels)
+                        const float cut = k0 < n ? T.cut2f : -1.0f;
+                        const u32 b8 = min(lo2 + k0, limit);
+                        const u32 axy = a_sxy + b8 * 8u, azz = a_szz + b8 * 4u;
+                        float4 ca4[4];
+                        float2 cz2[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {  // all loads first: the queue stores below alias smem
-                        ca4[u] = sxy[p4 + u];
-                        if (D == 3) cz2[u] = szz[p4 + u];
-                    }
+                        for (int u = 0; u < 4; ++u) {  // all loads first: the queue stores below alias smem
+                            ca4[u] = lds_f4(axy + 16u * u);
+                            if (D == 3) cz2[u] = lds_f2(azz + 8u * u);
+                        }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float2 dx = __fadd2_rn(make_float2(ca4[u].x, ca4[u].y), xf2);
-                        const float2 dy = __fadd2_rn(make_float2(ca4[u].z, ca4[u].w), yf2);
-                        float2 d2 = __fmul2_rn(dx, dx);
-                        d2 = __ffma2_rn(dy, dy, d2);
-                        if (D == 3) {
-                            const float2 dz = __fadd2_rn(cz2[u], zf2);
-                            d2 = __ffma2_rn(dz, dz, d2);
-                        }
-                        if (d2.x <= cut) {
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u)) : "memory");
-                            qa += 2u * nthreads;
-                        }
-                        if (d2.y <= cut) {
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u + 1)) : "memory");
-                            qa += 2u * nthreads;
+                        for (int u = 0; u < 4; ++u) {
+                            const float2 dx = __fadd2_rn(make_float2(ca4[u].x, ca4[u].y), xf2);
+                            const float2 dy = __fadd2_rn(make_float2(ca4[u].z, ca4[u].w), yf2);
+                            float2 d2 = __fmul2_rn(dx, dx);
+                            d2 = __ffma2_rn(dy, dy, d2);
+                            if (D == 3) {
+                                const float2 dz = __fadd2_rn(cz2[u], zf2);
+                                d2 = __ffma2_rn(dz, dz, d2);
+                            }
+                            if (d2.x <= cut) {
+                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u)) : "memory");
+                                qa += 2u * nthreads;
+                            }
+                            if (d2.y <= cut) {
+                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(qa), "h"((unsigned short)(b8 + 2 * u + 1)) : "memory");
+                                qa += 2u * nthreads;
+                            }
                         }
                     }
                 }
@@ -442,7 +503,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
 #pragma unroll
                     for (int c = 0; c < D; ++c) P.force_out[(u64)c * P.cap + i] = t.acc[c];
                 } else {
-                    integrate_agent<D, true>(P, i, t.my_v, SS(src, zt), Xt, Yt, zt, t.x, t.acc, dyn);
+                    integrate_agent<D, true>(P, i, t.my_v, SS(src, zt), Xt, Yt, zt, t.x, t.acc, load_agent_dyn<D>(P, i));
                 }
             }
         }

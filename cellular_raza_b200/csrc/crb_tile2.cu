@@ -32,7 +32,14 @@ cudaError_t go(K k, const KParams& P, const TileLaunch& T, u32 grid, int threads
             have = smem;
         }
     }
-    k<<<grid, threads, smem, st>>>(P, T);
+    // grid (segments x chunks, tile rows, tile planes): no integer division by run-time values in the kernel's
+    // prologue except the segment / chunk split, which is one multiply-high by inv_nseg
+    TileLaunch U = T;
+    U.inv_nseg = (u32)((0x100000000ull + (u64)T.nseg - 1) / (u64)T.nseg);
+    const u32 gx = (u32)T.nseg * (u32)T.nchunks, gy = (u32)(P.g.ng[1] + 1) / 2;
+    const u32 gz = grid / (gx * gy);
+    if (gx >= 65536u || gy >= 65536u || gz >= 65536u) return cudaErrorInvalidConfiguration;
+    k<<<dim3(gx, gy, gz), threads, smem, st>>>(P, U);
     return cudaGetLastError();
 }
 
