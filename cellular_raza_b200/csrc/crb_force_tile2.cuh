@@ -422,9 +422,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
 
             // per-lane FIFO of in-range candidate indices (ascending): q[k][tid]
             u32 qa = qa0;
+            // (runs for whichever lanes are converged at the call: all of them at the end of the pass, only the
+            // lanes whose FIFO is nearly full inside the filter loop — a rare, divergent call instead of a vote per block)
             auto drain = [&]() {
                 const u32 nq = (qa - qa0) / (2u * nthreads);
-                const u32 nqmax = __reduce_max_sync(0xffffffffu, nq);
+                const u32 nqmax = __reduce_max_sync(__activemask(), nq);
                 for (u32 k = 0; k < nqmax; k += NE) {
                     u32 jj[NE];
                     bool hh[NE];
@@ -439,7 +441,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
                 }
                 qa = qa0;
             };
-            const u32 qfull = qa0 + 2u * (kTileQueue - 8) * nthreads;
+            u32 qfull = qa0 + 2u * (kTileQueue - 8) * nthreads;
+            asm volatile("" : "+r"(qfull));  // held in a register: one compare per block instead of add + compare
             const float2 xf2 = make_float2(-xf, -xf), yf2 = make_float2(-yf, -yf), zf2 = make_float2(-zf, -zf);
             // start[] entries of this sub-group's window inside row sr: a_sst + 4 (sr sstride + z - zb0)
             const u32 a_wlo = a_sst + 4u * (u32)(zlo - zb0), a_whi = a_sst + 4u * (u32)(zhi - zb0);
@@ -458,12 +461,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
                     const u32 n = hi - lo2;
                     const u32 nmax = __reduce_max_sync(0xffffffffu, n);
                     if (nmax == 0) continue;  // warp-uniform
-                    for (u32 k0 = 0; k0 < nmax; k0 += 8) {
-                        if (__any_sync(0xffffffffu, qa > qfull)) drain();
-                        // a block past the lane's range is disabled through the threshold; a block that
-                        // starts inside may over-read <= 7 entries (later voxels of the row or sentinels)
-                        const float cut = k0 < n ? T.cut2f : -1.0f;
-                        const u32 b8 = min(lo2 + k0, limit);
+                    // x = first candidate of the lane's current block; a lane whose own range [lo2, hi) has ended reads
+                    // the block of sentinels at `limit` (never pass) while the longest sub-group of the warp finishes
+                    const u32 xend = lo2 + nmax;
+                    for (u32 x = lo2; x < xend; x += 8) {
+                        if (qa > qfull) drain();
+                        // a block that starts inside the range may over-read <= 7 entries (later voxels of the row or
+                        // sentinels)
+                        const u32 b8 = x < hi ? x : limit;
+                        const float cut = T.cut2f;
                         const u32 axy = a_sxy + b8 * 8u, azz = a_szz + b8 * 4u;
                         float4 ca4[4];
                         float2 cz2[4];

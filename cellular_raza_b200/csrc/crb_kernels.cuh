@@ -413,7 +413,9 @@ __device__ __forceinline__ void integrate_agent(const KParams& P, const u64 i, c
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             dxv[c] = vel[c];
-            dvv[c] = __dsub_rn(__ddiv_rn(acc[c], mass), __dmul_rn(damping, vel[c]));
+            // x / 1 == x exactly: the shipped mass (cell_sorting/src/main.rs:141) skips three IEEE divisions
+            const double a_over_m = (UNIFORM && mass == 1.0) ? acc[c] : __ddiv_rn(acc[c], mass);
+            dvv[c] = __dsub_rn(a_over_m, __dmul_rn(damping, vel[c]));
         }
     } else if (brownian) {  // mechanics.rs:349-356
         const double f = __ddiv_rn(mp[0], mp[1]);
