@@ -347,6 +347,36 @@ def extra_config_legs(args, dev_id: int) -> dict:
     return out
 
 
+def pcie_copy_floor_ms(h2d_bytes: int, d2h_bytes: int, steps: int, barrier=None) -> float:
+    """What the host link alone allows for the e2e loop: per step ``h2d_bytes`` pinned host -> device and ``d2h_bytes``
+    device -> pinned host on two streams (full duplex), nothing else, averaged over ``steps``; with ``barrier`` every
+    rank of the node copies at the same time (the ranks share the host's memory and PCIe root complexes).  Reported
+    next to e2e so that the plumbing and the kernels can be told apart."""
+    import torch
+
+    hin = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    din = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device="cuda")
+    dout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def one():
+        with torch.cuda.stream(s_in):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hout.copy_(dout, non_blocking=True)
+
+    one()
+    torch.cuda.synchronize()
+    if barrier is not None:
+        barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps * 1e3
+
+
 def measure_point(args, dev_id: int) -> dict:
     """one workload on one GPU -> the JSON line as a dict"""
     import torch
@@ -418,6 +448,11 @@ def measure_point(args, dev_id: int) -> dict:
         "traffic": ncu_traffic(n, "force"), "share_of_step": force_ms / ms_stage_total,
         "algorithmic_flop_per_pair": flop_per_pair(args), "pairs_per_launch": pairs_per_launch,
         "pair_forces_per_s": pairs_per_launch / (force_avg_ms * 1e-3),
+        # `achieved` is delivered reference-equivalent work (SURVEY 8d counts the potential for EVERY candidate of the
+        # 27 voxels; the FP32 filter skips the ~85 % beyond the cutoff, whose contribution is exactly zero), not
+        # executed DFMAs: what limits the kernel is instruction issue
+        "limiter": "instruction issue (ncu, 8 M cells: issue-active 57.5 %, executed FP64 pipe 20 %, "
+                   "profiles/r2_ncu_k_force_tile2_v12_8M.txt)",
     }
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     reorder_avg_ms = reorder_ms / max(args.steps, 1)
@@ -494,10 +529,12 @@ def measure_point(args, dev_id: int) -> dict:
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
         sim_b.close()
+        floor_ms = pcie_copy_floor_ms(int(n * (24 + 24 + 1)), int(n * 48), max(e2e_steps, 5))
         e2e = {
             "value": n * e2e_steps / dt_e2e, "unit": UNIT,
             "h2d_bytes_per_step": int(n * (24 + 24 + 1)), "d2h_bytes_per_step": int(n * 48),
             "ms_per_step": dt_e2e / e2e_steps * 1e3,
+            "pcie_copy_floor_ms_per_step": floor_ms,  # the same bytes both ways, no kernels (measured in this run)
             "what": "per step: crb_set_agents_async(pinned host pos, vel, species) + crb_step_async(1) + "
                     "crb_snapshot_async(pinned host pos, vel) + crb_snapshot_wait; two handles alternate so that "
                     "upload, step and download of consecutive populations overlap",

@@ -186,8 +186,14 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         dt_e2e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
         dt_e2e = float(dt_e2e.item())
+        # the host link alone, every rank copying at the same time (same bytes per rank and step, no kernels)
+        floor_t = torch.tensor([helpers.pcie_copy_floor_ms(int(n_rank * (24 + 24 + 1 + 8)), int(n_rank * 48),
+                                                           max(e2e_steps, 5), barrier=dist.barrier)],
+                               device="cuda", dtype=torch.float64)
+        dist.all_reduce(floor_t, op=dist.ReduceOp.MAX)
         e2e = {
             "value": n * world * e2e_steps / dt_e2e, "unit": helpers.UNIT,
+            "pcie_copy_floor_ms_per_step": float(floor_t.item()),
             "h2d_bytes_per_step": int(world * n * (24 + 24 + 1 + 8)), "d2h_bytes_per_step": int(world * n * 48),
             "ms_per_step": dt_e2e / e2e_steps * 1e3, "host_memory": numa,
             "what": "per rank and step: crb_set_agents_async(pinned host pos, vel, species, ids) + slab step (halo + migration "
