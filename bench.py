@@ -529,10 +529,13 @@ def measure_point(args, dev_id: int) -> dict:
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
         sim_b.close()
-        floor_ms = pcie_copy_floor_ms(int(n * (24 + 24 + 1)), int(n * 48), max(e2e_steps, 5))
+        # bytes that cross the host link per step: positions always; velocities unless the mechanics has none
+        # (Brownian3D: the library does not read them); one species byte where the potential uses it
+        h2d = int(n * (24 + (0 if args.workload == "brownian_morse" else 24) + (1 if hs is not None else 0)))
+        floor_ms = pcie_copy_floor_ms(h2d, int(n * 48), max(e2e_steps, 5))
         e2e = {
             "value": n * e2e_steps / dt_e2e, "unit": UNIT,
-            "h2d_bytes_per_step": int(n * (24 + 24 + 1)), "d2h_bytes_per_step": int(n * 48),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n * 48),
             "ms_per_step": dt_e2e / e2e_steps * 1e3,
             "pcie_copy_floor_ms_per_step": floor_ms,  # the same bytes both ways, no kernels (measured in this run)
             "what": "per step: crb_set_agents_async(pinned host pos, vel, species) + crb_step_async(1) + "

@@ -77,6 +77,7 @@ struct crb_sim {
     // (lowest priority) while the halo travels on `stream` (highest priority)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_interior = nullptr;
+    bool kernels_only = false;  // the handle is driven through the asynchronous API: no copy-engine memsets / D2D copies
     int interior_state = 0;  // 0 none, 1 crb_slab_compute_interior done (boundary pending)
     // storage snapshots: packed on `stream` into `snap`, copied to the caller's host buffers on `stream_io`
     cudaStream_t stream_io = nullptr;
@@ -708,17 +709,25 @@ int check_latch(crb_sim* s) {
 }
 
 // host rows (agent-major, `width` doubles) -> device columns
-int upload_rows(crb_sim* s, const double* host, int width, double* const* cols, u64 n) {
+int upload_rows_copy(crb_sim* s, const double* host, int width, u64 n, u64 stage_off) {
     if (!n) return 0;
     if (width > 8) return fail(s, CRB_ERR_INVALID_ARG, "row width > 8");
-    CU(s, cudaMemcpyAsync(s->stage, host, n * width * sizeof(double), cudaMemcpyHostToDevice,
-                          s->stream));
+    CU(s, cudaMemcpyAsync(s->stage + stage_off, host, n * width * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+int upload_rows_unpack(crb_sim* s, int width, double* const* cols, u64 n, u64 stage_off) {
+    if (!n) return 0;
     double* c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = 0; k < width; ++k) c[k] = cols[k] ? cols[k] + s->G : nullptr;  // owned agents start at G
-    k_unpack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, width, c[0], c[1], c[2], c[3],
+    k_unpack_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage + stage_off, width, c[0], c[1], c[2], c[3],
                                                             c[4], c[5], c[6], c[7], n);
     s->launches++;
     return 0;
+}
+int upload_rows(crb_sim* s, const double* host, int width, double* const* cols, u64 n) {
+    int rc;
+    if ((rc = upload_rows_copy(s, host, width, n, 0))) return rc;
+    return upload_rows_unpack(s, width, cols, n, 0);
 }
 
 int download_rows(crb_sim* s, double* host, int width, const double* const* cols, u64 n) {
@@ -1198,35 +1207,73 @@ static int set_agents_impl(crb_sim* s, uint64_t n, const double* pos, const doub
         s->uniform = false;
     }
     int rc;
-    if ((rc = upload_rows(s, pos, D, s->T.pos, n))) return rc;
-    if (vel && s->cfg.mechanics_kind != CRB_MECH_BROWNIAN) {
-        if ((rc = upload_rows(s, vel, D, s->T.vel, n))) return rc;
+    const bool has_vel = vel && s->cfg.mechanics_kind != CRB_MECH_BROWNIAN;
+    if (async) {
+        // both host transfers first, then the kernels: a transfer queued behind an unpack kernel would wait for that
+        // kernel to find free SMs next to the force pass of the handle this one alternates with, and the copy
+        // engine would idle meanwhile (the staging buffer holds 8 doubles per agent: pos and vel rows side by side)
+        if ((rc = upload_rows_copy(s, pos, D, n, 0))) return rc;
+        if (has_vel && (rc = upload_rows_copy(s, vel, D, n, n * D))) return rc;
+        if (species) CU(s, cudaMemcpyAsync(s->X.species + s->G, species, n, cudaMemcpyHostToDevice, s->stream));
+        if (ids) CU(s, cudaMemcpyAsync(s->X.id + s->G, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+        if ((rc = upload_rows_unpack(s, D, s->T.pos, n, 0))) return rc;
+        if (has_vel && (rc = upload_rows_unpack(s, D, s->T.vel, n, n * D))) return rc;
     } else {
-        for (int d = 0; d < D; ++d)
-            CU(s, cudaMemsetAsync(s->T.vel[d] + s->G, 0, n * sizeof(double), s->stream));
+        if ((rc = upload_rows(s, pos, D, s->T.pos, n))) return rc;
+        if (has_vel && (rc = upload_rows(s, vel, D, s->T.vel, n))) return rc;
     }
-    for (int d = 0; d < D; ++d) {
-        CU(s, cudaMemsetAsync(s->T.h1x[d] + s->G, 0, n * sizeof(double), s->stream));
-        CU(s, cudaMemsetAsync(s->T.h1v[d] + s->G, 0, n * sizeof(double), s->stream));
-        CU(s, cudaMemsetAsync(s->T.h0x[d] + s->G, 0, n * sizeof(double), s->stream));
-        CU(s, cudaMemsetAsync(s->T.h0v[d] + s->G, 0, n * sizeof(double), s->stream));
+    if (async) {
+        // kernels only (see k_zero_cols)
+        s->kernels_only = true;
+        ZeroCols Z;
+        std::memset(&Z, 0, sizeof(Z));
+        for (int d = 0; d < D; ++d) {
+            if (!has_vel) Z.col[Z.n_cols++] = s->T.vel[d] + s->G;
+            Z.col[Z.n_cols++] = s->T.h1x[d] + s->G;
+            Z.col[Z.n_cols++] = s->T.h1v[d] + s->G;
+            Z.col[Z.n_cols++] = s->T.h0x[d] + s->G;
+            Z.col[Z.n_cols++] = s->T.h0v[d] + s->G;
+        }
+        Z.bytes_a = s->T.hlen + s->G;
+        Z.bytes_b = species ? nullptr : s->X.species + s->G;
+        if (n) {
+            k_zero_cols<<<blocks_for(n, 256), 256, 0, s->stream>>>(Z, n);
+            s->launches++;
+        }
+    } else {
+        if (!has_vel)
+            for (int d = 0; d < D; ++d)
+                CU(s, cudaMemsetAsync(s->T.vel[d] + s->G, 0, n * sizeof(double), s->stream));
+        for (int d = 0; d < D; ++d) {
+            CU(s, cudaMemsetAsync(s->T.h1x[d] + s->G, 0, n * sizeof(double), s->stream));
+            CU(s, cudaMemsetAsync(s->T.h1v[d] + s->G, 0, n * sizeof(double), s->stream));
+            CU(s, cudaMemsetAsync(s->T.h0x[d] + s->G, 0, n * sizeof(double), s->stream));
+            CU(s, cudaMemsetAsync(s->T.h0v[d] + s->G, 0, n * sizeof(double), s->stream));
+        }
+        CU(s, cudaMemsetAsync(s->T.hlen + s->G, 0, n, s->stream));
     }
-    CU(s, cudaMemsetAsync(s->T.hlen + s->G, 0, n, s->stream));
     if (!s->uniform) {
         if ((rc = upload_rows(s, mech_params, s->n_mp, s->X.mp, n))) return rc;
         if ((rc = upload_rows(s, inter_params, s->n_ip, s->X.ip, n))) return rc;
     }
-    if (species)
-        CU(s, cudaMemcpyAsync(s->X.species + s->G, species, n, cudaMemcpyHostToDevice, s->stream));
-    else
-        CU(s, cudaMemsetAsync(s->X.species + s->G, 0, n, s->stream));
-    if (ids)
-        CU(s, cudaMemcpyAsync(s->X.id + s->G, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
-    else if (n) {
+    if (!async) {
+        if (species)
+            CU(s, cudaMemcpyAsync(s->X.species + s->G, species, n, cudaMemcpyHostToDevice, s->stream));
+        else
+            CU(s, cudaMemsetAsync(s->X.species + s->G, 0, n, s->stream));
+    }
+    if (ids) {
+        if (!async) CU(s, cudaMemcpyAsync(s->X.id + s->G, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    } else if (n) {
         k_iota_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->X.id + s->G, n);
         s->launches++;
     }
-    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    if (async) {
+        k_zero_u32<<<blocks_for(s->nvox + 1, 256), 256, 0, s->stream>>>(s->count_new, s->nvox + 1, nullptr, 0, nullptr, 0);
+        s->launches++;
+    } else {
+        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    }
     s->n = n;
     s->slab_async_pending = false;  // the host-side count is authoritative again
     KParams P = make_params(s);
@@ -1598,8 +1645,22 @@ void step_mark(crb_sim* s) {
 }
 int step_compute(crb_sim* s, bool save_prev) {
     int rc;
-    if ((rc = step_prepare(s))) return rc;
-    if ((rc = step_launch(s, save_prev, PlaneRange()))) return rc;
+    if ((rc = step_prepare(s, s->kernels_only))) return rc;
+    if (s->kernels_only && s->stream2 && s->n && (s->tile_ok || s->tile2_ok || s->tile3_ok) && !s->timers_on) {
+        // pipelined host (two handles alternate on one device): the force pass runs on the handle's LOW-priority
+        // stream, so that the short unpack / ingest / pack kernels of the other handle — queued on its high-priority
+        // stream between two host transfers — are scheduled as soon as an SM has room instead of behind the ~40,000
+        // CTAs of this pass; a late pack kernel would leave the copy engines idle
+        CU(s, cudaEventRecord(s->ev_ready, s->stream));
+        CU(s, cudaStreamWaitEvent(s->stream2, s->ev_ready, 0));
+        PlaneRange pr;
+        pr.st = s->stream2;
+        if ((rc = step_launch(s, save_prev, pr))) return rc;
+        CU(s, cudaEventRecord(s->ev_interior, s->stream2));
+        CU(s, cudaStreamWaitEvent(s->stream, s->ev_interior, 0));
+    } else if ((rc = step_launch(s, save_prev, PlaneRange()))) {
+        return rc;
+    }
     step_mark(s);
     return 0;
 }
@@ -1681,6 +1742,10 @@ int crb_step_async(crb_sim* s, uint64_t n_steps) { return step_impl(s, n_steps, 
 
 static int step_impl(crb_sim* s, uint64_t n_steps, bool async) {
     if (!s) return CRB_ERR_INVALID_ARG;
+    if (async && !s->kernels_only) {
+        s->kernels_only = true;
+        graphs_invalidate(s);  // (a captured step holds a memset node)
+    }
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "crb_step before crb_set_agents");
     if (s->world > 1)
         return fail(s, CRB_ERR_STATE, "slab handle: drive the step with crb_slab_* (halo/migration exchange)");
@@ -2386,7 +2451,10 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
             else
                 pack(b_vel, D, s->X.vel);
         }
-        if (ids) CU(s, cudaMemcpyAsync(b_id, s->X.id + s->G, n * sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+        if (ids) {
+            k_copy_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>(b_id, s->X.id + s->G, n);
+            s->launches++;
+        }
         if (voxel) {
             const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
             k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key + s->G, b_vox, base, n);
@@ -2401,7 +2469,10 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
             }
             pack(which == 0 ? b_hx : b_hv, 2 * D, cols);
         }
-        CU(s, cudaMemcpyAsync(b_hl, s->X.hlen + s->G, n, cudaMemcpyDeviceToDevice, s->stream));
+        if (hist_len || hist_dx || hist_dv) {  // (crb_snapshot_wait orders the ring entries by the fill count)
+            k_copy_u8<<<blocks_for(n, 256), 256, 0, s->stream>>>(b_hl, s->X.hlen + s->G, n);
+            s->launches++;
+        }
     }
     CU(s, cudaGetLastError());
     CU(s, cudaEventRecord(s->ev_snap_packed, s->stream));
@@ -2413,7 +2484,8 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
         if (voxel) CU(s, cudaMemcpyAsync(voxel, b_vox, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream_io));
         if (hist_dx) CU(s, cudaMemcpyAsync(hist_dx, b_hx, n * 2 * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream_io));
         if (hist_dv) CU(s, cudaMemcpyAsync(hist_dv, b_hv, n * 2 * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream_io));
-        CU(s, cudaMemcpyAsync(s->snap_hlen_host, b_hl, n, cudaMemcpyDeviceToHost, s->stream_io));
+        if (hist_len || hist_dx || hist_dv)
+            CU(s, cudaMemcpyAsync(s->snap_hlen_host, b_hl, n, cudaMemcpyDeviceToHost, s->stream_io));
     }
     CU(s, cudaEventRecord(s->ev_snap_done, s->stream_io));
     s->snap_pending = true;

@@ -1269,6 +1269,31 @@ __global__ void k_zero_u32(u32* __restrict__ a, u64 n, u32* __restrict__ b, u64 
     if (i < nb) b[i] = 0u;
     if (i < nc) c[i] = 0ull;
 }
+// asynchronous API (crb_set_agents_async / crb_step_async / crb_snapshot_async): the small clears and device copies
+// of a handle are kernels, not copy-engine operations — a memset queued by one handle otherwise sits in the copy
+// engine's queue behind the multi-millisecond host transfer of the handle it alternates with, and holds up the
+// kernels that wait for it (the e2e pipeline lost ~2 ms per step to that)
+struct ZeroCols {
+    double* col[16];
+    int n_cols;
+    u8* bytes_a;  // optional byte arrays of n entries
+    u8* bytes_b;
+};
+__global__ void k_zero_cols(const ZeroCols Z, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < Z.n_cols; ++k) Z.col[k][i] = 0.0;
+    if (Z.bytes_a) Z.bytes_a[i] = 0;
+    if (Z.bytes_b) Z.bytes_b[i] = 0;
+}
+__global__ void k_copy_u8(u8* __restrict__ dst, const u8* __restrict__ src, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+__global__ void k_copy_u64(u64* __restrict__ dst, const u64* __restrict__ src, u64 n) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
 __global__ void k_set_u64(u64* a, u64 v) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *a = v;
 }

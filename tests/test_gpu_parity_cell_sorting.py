@@ -163,6 +163,26 @@ def test_c2_one_million_cells(oracle_lib, crb_lib):
     assert md == mo
 
 
+@pytest.mark.parametrize("n_threads,steps", [(1, 40), (4, 25)])
+def test_trajectory_200k_cells(oracle_lib, crb_lib, n_threads, steps):
+    """a population large enough for the 2 x 2-row tile kernel, many chili subdomains and tens of thousands of
+    migrations, followed step by step against the oracle: positions <= 1e-9 L, voxel assignment and the migration
+    set of the last step bit-exact."""
+    w = workloads.cell_sorting_scaled(200_000, n_threads=n_threads)
+    L = float(w.cfg_kwargs["domain_max"][0])
+    dev, ora = parity.make_pair(w, n_threads_oracle=8)
+    assert "tile2" in dev.force_kernel_name
+    dev.step(steps)
+    ora.step(steps)
+    perr, verr, key_diff = parity.state_errors(dev, ora, L)
+    assert perr <= 1e-9, perr
+    assert not key_diff.any()
+    md = set(zip(*[a.tolist() for a in dev.get_migrations()]))
+    mo = set(zip(*[a.tolist() for a in ora.get_migrations()]))
+    assert md == mo and len(md) > 1000
+    parity.assert_same_membership(dev, ora)
+
+
 def test_full_size_8m_properties(crb_lib):
     """BASELINE.json configs[4] per-GPU size (8 M cells, 104^3 voxels): the oracle needs minutes here, so
     the bench-size run is checked through size-independent properties — voxel keys recomputed with IEEE
