@@ -73,7 +73,7 @@ def build(force: bool = False, verbose: bool = False, extra: list[str] | None = 
         if verbose:
             print(f"==== {src.name}\n" + res.stdout + res.stderr)
     cmd = [nvcc_path(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
-           *[str(o) for _, o, _ in results]]
+           *[str(o) for _, o, _ in results], "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
