@@ -1160,6 +1160,35 @@ const char* crb_force_kernel_name(const crb_sim* s) {
     return "k_force_integrate";
 }
 
+// do all n rows of `width` doubles equal `row`?  One pass on all host cores (8 M agents are 320 MB of parameter rows;
+// the single-threaded scan was a visible part of crb_set_agents for a host that does not declare the uniform row)
+static bool rows_all_equal(const double* rows, u64 n, int width, const double* row) {
+    if (!n || !width) return true;
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned nth = n < 65536 ? 1u : hw;
+    std::vector<int> bad(nth, 0);
+    auto scan = [&](unsigned t) {
+        const u64 a = n * t / nth, b = n * (t + 1) / nth;
+        int acc = 0;
+        for (u64 i = a; i < b && !acc; i += 4096) {  // early exit per block of rows, branch-free inside
+            const u64 e = std::min(b, i + 4096);
+            for (u64 j = i; j < e; ++j)
+                for (int k = 0; k < width; ++k) acc |= rows[j * width + k] != row[k];
+        }
+        bad[t] = acc;
+    };
+    if (nth == 1) {
+        scan(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nth; ++t) th.emplace_back(scan, t);
+        for (auto& x : th) x.join();
+    }
+    for (int b : bad)
+        if (b) return false;
+    return true;
+}
+
 static int set_agents_impl(crb_sim* s, uint64_t n, const double* pos, const double* vel,
                            const double* mech_params, const double* inter_params, const uint8_t* species,
                            const uint64_t* ids, bool async) {
@@ -1192,12 +1221,7 @@ static int set_agents_impl(crb_sim* s, uint64_t n, const double* pos, const doub
         s->uniform = true;
         for (int k = 0; k < s->n_mp; ++k) s->uni.mp[k] = n ? mech_params[k] : 0.0;
         for (int k = 0; k < s->n_ip; ++k) s->uni.ip[k] = n ? inter_params[k] : 0.0;
-        for (u64 i = 1; i < n && s->uniform; ++i) {
-            for (int k = 0; k < s->n_mp; ++k)
-                if (mech_params[i * s->n_mp + k] != s->uni.mp[k]) s->uniform = false;
-            for (int k = 0; k < s->n_ip; ++k)
-                if (inter_params[i * s->n_ip + k] != s->uni.ip[k]) s->uniform = false;
-        }
+        s->uniform = rows_all_equal(mech_params, n, s->n_mp, s->uni.mp) && rows_all_equal(inter_params, n, s->n_ip, s->uni.ip);
     }
     // the uniform-parameter kernels evaluate the Morse exponential without overflow handling (exp_bounded): its
     // largest argument, potential_stiffness * (R1 + R2) at distance 0, must stay below 700; such a parameter row

@@ -118,6 +118,59 @@ def test_snapshot_async_equals_blocking_download(crb_lib):
     sim.close()
 
 
+@pytest.mark.parametrize("n_steps", [1, 7])
+def test_async_pipeline_equals_synchronous_calls(crb_lib, n_steps):
+    """crb_set_agents_async + crb_step_async + crb_snapshot_async on two alternating handles (the e2e loop of bench.py:
+    transfers first, force pass on the low-priority stream, kernels instead of copy-engine clears; n_steps = 7 also
+    replays the two-step CUDA graphs) leave exactly the bits of crb_set_agents + crb_step + crb_get_agents."""
+    import ctypes as C
+
+    from cellular_raza_b200 import workloads
+    from cellular_raza_b200.device import DeviceSimulation, _ptr
+
+    w = workloads.cell_sorting_scaled(120_000, 7.1)
+    ref = DeviceSimulation(w.config())
+    ref.set_uniform_params(w.mech_params[0], w.inter_params[0])
+    pops = [(w.pos, w.vel)]
+    want = []
+    for _ in range(4):  # every population is the result of the previous one
+        ref.set_agents(pops[-1][0], pops[-1][1], None, None, w.species)
+        ref.step(n_steps)
+        pos, vel, ids, _ = ref.get_agents()
+        o = np.argsort(ids, kind="stable")
+        want.append((pos[o], vel[o]))
+        pops.append(want[-1])
+    ref.close()
+
+    sims = [DeviceSimulation(w.config()) for _ in range(2)]
+    for s in sims:
+        s.set_uniform_params(w.mech_params[0], w.inter_params[0])
+    lib = sims[0]._lib
+    n = w.n
+    nn = C.c_uint64()
+    species = sims[0]._pinned("sp", (n,), np.uint8)
+    species[:] = w.species
+    got = []
+    for k in range(4):
+        s = sims[k % 2]
+        hin_p, hin_v = s._pinned("in_pos", (n, 3), np.float64), s._pinned("in_vel", (n, 3), np.float64)
+        hin_p[:], hin_v[:] = pops[k]
+        out_p, out_v = s._pinned("out_pos", (n, 3), np.float64), s._pinned("out_vel", (n, 3), np.float64)
+        out_i = s._pinned("out_ids", (n,), np.uint64)
+        s._check(lib.crb_set_agents_async(s._h, n, _ptr(hin_p), _ptr(hin_v), None, None, _ptr(species), None))
+        s._check(lib.crb_step_async(s._h, n_steps))
+        s._check(lib.crb_snapshot_async(s._h, n, _ptr(out_p), _ptr(out_v), _ptr(out_i), None, None, None, None))
+        s._check(lib.crb_snapshot_wait(s._h, C.byref(nn)))
+        s.sync()  # latched errors of the asynchronous calls surface here
+        assert nn.value == n
+        o = np.argsort(out_i, kind="stable")
+        got.append((out_p[o].copy(), out_v[o].copy()))
+    for (gp, gv), (wp, wv) in zip(got, want):
+        assert np.array_equal(gp, wp) and np.array_equal(gv, wv)
+    for s in sims:
+        s.close()
+
+
 def test_domain_force_spring_like_reference_test(crb_lib):
     """cellular_raza/tests/domain_force_spring.rs:76-117 through run_simulation with aspects
     [Mechanics, DomainForce]: x(t) = x0 cos(omega t) within 1e-3 at every saved iteration."""
