@@ -57,6 +57,8 @@ struct crb_sim {
     bool has_lo = false, has_hi = false;  // neighbours below / above along axis 0
     HaloLayout hl;
     MigLayout ml;
+    RodHaloLayout rhl;  // CRB_MECH_ROD slabs: hl.bytes / ml.bytes hold the sizes of these layouts
+    RodMigLayout rml;
     bool step_open = false;  // crb_slab_compute done, crb_slab_finish pending
     bool mig_counts_pending = false;  // export enqueued without reading its counts back (n_out == NULL)
     u64 mig_out[2] = {0, 0};          // agents exported in the open step (lo, hi)
@@ -907,8 +909,6 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
                         "CRB_MECH_ROD needs dim == 3 and interaction_kind == CRB_INT_MORSE (RodInteraction<MorsePotential>)");
         if (cfg->rod_n_vertices < 2 || cfg->rod_n_vertices > CRB_MAX_ROD_VERTICES)
             return fail(nullptr, CRB_ERR_INVALID_ARG, "rod_n_vertices must be in [2, 8]");
-        if (cfg->world_size != 1)
-            return fail(nullptr, CRB_ERR_INVALID_ARG, "CRB_MECH_ROD: slab decomposition is not implemented yet");
     }
     if (cfg->interaction_kind > CRB_INT_NONE)
         return fail(nullptr, CRB_ERR_INVALID_ARG, "unknown interaction_kind");
@@ -1037,6 +1037,38 @@ int crb_create(const crb_config* cfg, crb_sim** out) {
         M.off_hlen = take(M.mcap);
         M.off_sp = take(M.mcap);
         M.bytes = off;
+        if (rods) {
+            // rods travel with their own layouts (crb_rods.cuh); crb_slab_halo_bytes / crb_slab_migration_bytes
+            // report their sizes
+            const int W = 3 * (int)cfg->rod_n_vertices;
+            RodHaloLayout& RH = s->rhl;
+            std::memset(&RH, 0, sizeof(RH));
+            RH.gcap = s->G;
+            RH.plane = plane;
+            RH.W = W;
+            off = 64;
+            RH.off_rel = take((plane + 1) * sizeof(u32));
+            RH.off_pos = take(RH.gcap * W * sizeof(double));
+            RH.off_cen = take(RH.gcap * 4 * sizeof(double));
+            RH.bytes = off;
+            RodMigLayout& RM = s->rml;
+            std::memset(&RM, 0, sizeof(RM));
+            RM.mcap = s->mcap;
+            RM.W = W;
+            off = 64;
+            RM.off_dyn = take(RM.mcap * 6 * W * sizeof(double));
+            RM.off_len = take(RM.mcap * sizeof(double));
+            RM.off_growth = take(RM.mcap * sizeof(double));
+            RM.off_cen = take(RM.mcap * 4 * sizeof(double));
+            RM.off_ident = take(RM.mcap * 3 * sizeof(u64));
+            RM.off_parent = take(RM.mcap * 3 * sizeof(u64));
+            RM.off_sortkey = take(RM.mcap * sizeof(u64));
+            RM.off_gvox = take(RM.mcap * sizeof(u64));
+            RM.off_hlen = take(RM.mcap);
+            RM.bytes = off;
+            H.bytes = RH.bytes;
+            M.bytes = RM.bytes;
+        }
     }
     s->graphs_off = std::getenv("CRB_NO_GRAPH") != nullptr;
     if (const char* kc = std::getenv("CRB_FORCE_KERNEL")) {
@@ -1816,6 +1848,7 @@ int crb_slab_halo_export(crb_sim* s, void* lo_buf, void* hi_buf) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_slab_halo_export(s, lo_buf, hi_buf);
     const u64 plane = s->hl.plane;
     const u32 threads = 256;
     const u32 grid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
@@ -1843,6 +1876,7 @@ int crb_slab_halo_import(crb_sim* s, const void* lo_buf, const void* hi_buf) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_slab_halo_import(s, lo_buf, hi_buf);
     const u64 plane = s->hl.plane;
     const u32 threads = 256;
     const u32 grid = blocks_for(std::max<u64>(s->hl.gcap, plane + 1), threads);
@@ -1877,6 +1911,11 @@ int crb_slab_compute(crb_sim* s, int save_prev) {
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->aux_settable = false;
     int rc;
+    if (s->rods) {
+        if ((rc = rods_compute(s, save_prev != 0))) return rc;
+        s->step_open = true;
+        return 0;
+    }
     if ((rc = step_compute(s, save_prev != 0))) return rc;
     s->step_open = true;
     return 0;
@@ -1894,7 +1933,8 @@ int crb_slab_compute_interior(crb_sim* s, int save_prev) {
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
     if (s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_finish pending");
     if (s->interior_state) return fail(s, CRB_ERR_STATE, "crb_slab_compute_boundary pending");
-    if (s->rods) return fail(s, CRB_ERR_STATE, "rods are not slab-decomposed");
+    if (s->rods)
+        return fail(s, CRB_ERR_STATE, "rods: the force pass is not split into interior / boundary planes; use crb_slab_compute");
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->aux_settable = false;
     int rc;
@@ -1957,6 +1997,7 @@ int crb_slab_migration_export(crb_sim* s, void* lo_buf, void* hi_buf, uint64_t n
     s->mig_out[0] = s->mig_out[1] = 0;
     s->mig_counts_pending = false;
     if (s->world == 1) return 0;
+    if (s->rods) return rods_slab_migration_export(s, lo_buf, hi_buf, n_out);
     const u64 plane = s->hl.plane;
     CU(s, cudaMemsetAsync(s->scratch_u64, 0, 2 * sizeof(u64), s->stream));
     stage_begin(s, 4);
@@ -2024,6 +2065,7 @@ int crb_slab_migration_import(crb_sim* s, const void* lo_buf, const void* hi_buf
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->step_open) return fail(s, CRB_ERR_STATE, "crb_slab_compute first");
     CU(s, cudaSetDevice((int)s->cfg.device));
+    if (s->rods) return rods_slab_migration_import(s, lo_buf, hi_buf, n_in);
     u64 cnt[2] = {0, 0};
     u64 outc[2] = {0, 0};
     if (s->has_lo) {
@@ -2090,6 +2132,7 @@ int crb_slab_finish(crb_sim* s, int save_prev) {
     CU(s, cudaSetDevice((int)s->cfg.device));
     s->step_open = false;
     int rc;
+    if (s->rods) return rods_finish(s, save_prev != 0);
     if ((rc = step_finish(s, save_prev != 0))) return rc;
     plan_tile(s);
     return 0;
@@ -2212,7 +2255,9 @@ int crb_slab_step_async(crb_sim* s, uint64_t n_steps) { return slab_step_impl(s,
 static int slab_step_impl(crb_sim* s, uint64_t n_steps, bool async) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
-    if (s->rods) return fail(s, CRB_ERR_STATE, "rods are not slab-decomposed");
+    if (s->rods)
+        return fail(s, CRB_ERR_STATE, "rods: crb_slab_step is not available (division counts are read back every step); "
+                                      "use the six-phase protocol crb_slab_halo_export .. crb_slab_finish");
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, "a crb_slab_compute .. crb_slab_finish step is open");
     if (s->world > 1 && ((s->has_lo && !s->peer_arena[0]) || (s->has_hi && !s->peer_arena[1])))
         return fail(s, CRB_ERR_STATE, "crb_slab_step: connect the neighbours first (crb_slab_connect / crb_slab_connect_ipc)");

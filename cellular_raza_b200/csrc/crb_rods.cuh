@@ -40,7 +40,9 @@ struct RodState {
 struct RodParams {
     Grid g;
     RodState A, B;
-    u64 n;    // rods in A
+    u64 n;    // owned rods in A: slots [first, first + n)
+    u64 first;      // index of the first owned rod (ghost capacity G of a slab; 0 on a single device)
+    u64 src_limit;  // one past the last slot a source (owned rod, daughter, arrival) may take
     u64 cap;  // plane stride
     u32 *key, *start, *newkey, *rank_arb, *count_new;
     u64 *sortkey;
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(kRodThreads) k_rod_force(const RodParams P) {
     const int tid = threadIdx.x;
     const u64 t = (u64)blockIdx.x * kRodThreads + tid;
     const bool valid = t < P.n;
-    const u64 i = valid ? t : 0;
+    const u64 i = P.first + (valid ? t : 0);
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
     const u64 cap = P.cap;
@@ -582,8 +584,9 @@ __global__ void __launch_bounds__(kRodThreads) k_rod_force(const RodParams P) {
 // this once-per-rod code in full)
 template <int V>
 __global__ void __launch_bounds__(128, 4) k_rod_update(const RodParams P) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    const u64 i = P.first + t;
     const u64 cap = P.cap;
     double own[V][3], acc[V][3];
 #pragma unroll
@@ -606,8 +609,10 @@ __global__ void __launch_bounds__(128, 4) k_rod_update(const RodParams P) {
 // ------------------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(128) k_rod_divide(const RodParams P) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n || !P.div_flag[i]) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    const u64 i = P.first + t;
+    if (!P.div_flag[i]) return;
     const u64 cap = P.cap;
     const u32 vk = P.key[i];
     const u32 lo = P.start[vk], hi = P.start[vk + 1];
@@ -618,8 +623,8 @@ __global__ void __launch_bounds__(128) k_rod_divide(const RodParams P) {
         m += q < (u32)i ? fl : 0u;
     }
     const u32 c0 = P.id_counter[vk];
-    const u64 d = P.n + atomicAdd(P.n_div, 1u);
-    if (d >= cap) {
+    const u64 d = P.first + P.n + atomicAdd(P.n_div, 1u);
+    if (d >= P.src_limit) {
         latch_error(P.err, CRB_ERR_CAPACITY, P.A.ident[cap + i]);
         return;
     }
@@ -769,12 +774,14 @@ struct RodReorderParams {
     const u64* sortkey;
     u32* key_out;
     u64 n, cap;
+    u64 first;  // destination slots [first, first + n)
     int W;  // 3 V planes
     int save_prev;
 };
 __global__ void __launch_bounds__(256) k_rod_reorder(const RodReorderParams R) {
-    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= R.n) return;
+    const u64 tp = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tp >= R.n) return;
+    const u64 p = R.first + tp;
     const u32 i = R.tmp_idx[p];
     const u32 v = R.newkey[i];
     const u32 sb = R.start_new[v], se = R.start_new[v + 1];
@@ -844,11 +851,12 @@ __global__ void k_rod_pack_u64(u64* __restrict__ rows, const u64* __restrict__ p
     if (i >= n) return;
     for (int w = 0; w < W; ++w) rows[i * W + w] = planes[(u64)w * cap + i];
 }
-__global__ void k_rod_init_ident(RodState X, const u64* __restrict__ ids, u64 cap, u64 n) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void k_rod_init_ident(RodState X, const u64* __restrict__ ids, u64 cap, u64 n, u64 first) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u64 i = first + t;
     X.ident[i] = 1;  // Initial(n)
-    X.ident[cap + i] = ids ? ids[i] : i;
+    X.ident[cap + i] = ids ? ids[t] : t;
     X.ident[2 * cap + i] = 0;
     X.parent[i] = ~0ull;
     X.parent[cap + i] = 0;
@@ -859,8 +867,9 @@ __global__ void k_rod_init_ident(RodState X, const u64* __restrict__ ids, u64 ca
 // get_voxel_index_of_raw (bacterial_rods.rs:368-372, cartesian_cuboid_n.rs:320-337)
 template <int V>
 __global__ void k_rod_ingest(const RodParams P) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    const u64 i = P.first + t;
     const Grid& g = P.g;
     const u64 cap = P.cap;
     double mean[3];
@@ -901,8 +910,156 @@ __global__ void k_rod_ingest(const RodParams P) {
             nk = ((u32)l0 * (u32)g.ng[1] + (u32)q1) * (u32)g.ng[2] + (u32)q2;
     }
     P.newkey[i] = nk;
-    P.sortkey[i] = i;
+    P.sortkey[i] = t;
     P.rank_arb[i] = atomicAdd(&P.count_new[nk], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab exchange of rods (the PosInformation / SendCell messages of chili/update_mechanics.rs:12-61
+// between subdomains on different devices).  Same protocol as the point agents (crb_kernels.cuh): one fixed-size
+// halo buffer and one fixed-size migration buffer per face, every column a plane of `cap` entries.
+//   halo:      [n, mode | rel[plane + 1] | pos 3V planes | cen 4 planes]           (what k_rod_force reads of a candidate)
+//   migration: [n, mode | pos, vel, h1x, h1v, h0x, h0v: 6 x 3V planes | len | growth | cen 4 | ident 3 | parent 3 |
+//               sortkey | global voxel | hlen]
+// ------------------------------------------------------------------------------------------------
+struct RodHaloLayout {
+    u64 gcap, plane, bytes;
+    u64 off_rel, off_pos, off_cen;  // pos: 3V planes of gcap doubles, cen: 4 planes
+    int W;
+};
+__global__ void k_rod_halo_export(const RodState A, u64 cap, const u32* __restrict__ start, u32 v0, RodHaloLayout L,
+                                  unsigned char* __restrict__ buf, int* err) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 a = start[v0], b = start[v0 + (u32)L.plane];
+    const u64 n = b - a;
+    if (t == 0) {
+        reinterpret_cast<u64*>(buf)[0] = n;
+        reinterpret_cast<u64*>(buf)[1] = (u64)L.W;
+        if (n > L.gcap) latch_error(err, CRB_ERR_CAPACITY, n);
+    }
+    if (t <= L.plane) reinterpret_cast<u32*>(buf + L.off_rel)[t] = start[v0 + (u32)t] - a;
+    if (t < n && t < L.gcap) {
+        const u64 i = a + t;
+        double* pos = reinterpret_cast<double*>(buf + L.off_pos);
+        double* cen = reinterpret_cast<double*>(buf + L.off_cen);
+        for (int w = 0; w < L.W; ++w) pos[(u64)w * L.gcap + t] = A.pos[(u64)w * cap + i];
+        for (int w = 0; w < 4; ++w) cen[(u64)w * L.gcap + t] = A.cen[(u64)w * cap + i];
+    }
+}
+// lower ghost plane: the rods end at `edge` (= first owned slot); upper: they begin at `edge` (= first + n)
+__global__ void k_rod_halo_import(RodState A, u64 cap, u32* __restrict__ start, u32 v0, u64 edge, int lower,
+                                  RodHaloLayout L, const unsigned char* __restrict__ buf, int* err) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 n = reinterpret_cast<const u64*>(buf)[0];
+    if (n > L.gcap || reinterpret_cast<const u64*>(buf)[1] != (u64)L.W) {
+        if (t == 0) latch_error(err, n > L.gcap ? CRB_ERR_CAPACITY : CRB_ERR_STATE, n);
+        return;
+    }
+    const u64 base = lower ? edge - n : edge;
+    const u32* rel = reinterpret_cast<const u32*>(buf + L.off_rel);
+    if (t <= L.plane) start[v0 + t] = (u32)(base + rel[t]);
+    if (t < n) {
+        const u64 i = base + t;
+        const double* pos = reinterpret_cast<const double*>(buf + L.off_pos);
+        const double* cen = reinterpret_cast<const double*>(buf + L.off_cen);
+        for (int w = 0; w < L.W; ++w) A.pos[(u64)w * cap + i] = pos[(u64)w * L.gcap + t];
+        for (int w = 0; w < 4; ++w) A.cen[(u64)w * cap + i] = cen[(u64)w * L.gcap + t];
+    }
+}
+
+struct RodMigLayout {
+    u64 mcap, bytes;
+    u64 off_dyn;  // 6 arrays x W planes of mcap doubles: pos, vel, h1x, h1v, h0x, h0v
+    u64 off_len, off_growth, off_cen, off_ident, off_parent, off_sortkey, off_gvox, off_hlen;
+    int W;
+};
+struct RodMigParams {
+    RodState A, B;  // A: identifiers (pre-step slots), B: integrated state
+    u64 cap;
+    u32* newkey;
+    u64* sortkey;
+    u32 *rank_arb, *count_new;
+    u64 first, n;  // export: sources [first, first + n); import: arrivals go to [first, first + n)
+    u32 lo_end, hi_begin;
+    u64 vox_base, nvox;
+    RodMigLayout L;
+    unsigned char* buf[2];
+    u64* counter;  // [2]
+    int* err;
+};
+__global__ void k_rod_mig_export(const RodMigParams M) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        if (M.buf[0]) reinterpret_cast<u64*>(M.buf[0])[1] = (u64)M.L.W;
+        if (M.buf[1]) reinterpret_cast<u64*>(M.buf[1])[1] = (u64)M.L.W;
+    }
+    if (t >= M.n) return;
+    const u64 i = M.first + t;
+    const u32 k = M.newkey[i];
+    int side;
+    if (k < M.lo_end) side = 0;
+    else if (k >= M.hi_begin && k != CRB_KEY_GONE) side = 1;
+    else return;
+    const u64 slot = atomicAdd(&M.counter[side], 1ull);
+    M.newkey[i] = CRB_KEY_GONE;
+    const u64 cap = M.cap;
+    if (slot >= M.L.mcap) {
+        latch_error(M.err, CRB_ERR_CAPACITY, M.A.ident[cap + i]);
+        return;
+    }
+    unsigned char* buf = M.buf[side];
+    const RodMigLayout& L = M.L;
+    const u64 mc = L.mcap;
+    double* dyn = reinterpret_cast<double*>(buf + L.off_dyn);
+    const double* src[6] = {M.B.pos, M.B.vel, M.B.h1x, M.B.h1v, M.B.h0x, M.B.h0v};
+    for (int a = 0; a < 6; ++a)
+        for (int w = 0; w < L.W; ++w) dyn[((u64)a * L.W + w) * mc + slot] = src[a][(u64)w * cap + i];
+    reinterpret_cast<double*>(buf + L.off_len)[slot] = M.B.len[i];
+    reinterpret_cast<double*>(buf + L.off_growth)[slot] = M.B.growth[i];
+    for (int w = 0; w < 4; ++w) reinterpret_cast<double*>(buf + L.off_cen)[(u64)w * mc + slot] = M.B.cen[(u64)w * cap + i];
+    for (int w = 0; w < 3; ++w) {
+        reinterpret_cast<u64*>(buf + L.off_ident)[(u64)w * mc + slot] = M.A.ident[(u64)w * cap + i];
+        reinterpret_cast<u64*>(buf + L.off_parent)[(u64)w * mc + slot] = M.A.parent[(u64)w * cap + i];
+    }
+    reinterpret_cast<u64*>(buf + L.off_sortkey)[slot] = M.sortkey[i];
+    reinterpret_cast<u64*>(buf + L.off_gvox)[slot] = M.vox_base + k;
+    (buf + L.off_hlen)[slot] = M.B.hlen[i];
+}
+// arrivals of ONE face -> unsorted source slots [first, first + n) of B (identifiers into A at the same slots)
+__global__ void k_rod_mig_import(const RodMigParams M, int side) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M.n) return;
+    const unsigned char* buf = M.buf[side];
+    const u64 i = M.first + t;
+    if (reinterpret_cast<const u64*>(buf)[1] != (u64)M.L.W) {
+        if (t == 0) latch_error(M.err, CRB_ERR_STATE, reinterpret_cast<const u64*>(buf)[1]);
+        M.newkey[i] = CRB_KEY_GONE;
+        return;
+    }
+    const RodMigLayout& L = M.L;
+    const u64 mc = L.mcap, cap = M.cap;
+    const double* dyn = reinterpret_cast<const double*>(buf + L.off_dyn);
+    double* dst[6] = {M.B.pos, M.B.vel, M.B.h1x, M.B.h1v, M.B.h0x, M.B.h0v};
+    for (int a = 0; a < 6; ++a)
+        for (int w = 0; w < L.W; ++w) dst[a][(u64)w * cap + i] = dyn[((u64)a * L.W + w) * mc + t];
+    M.B.len[i] = reinterpret_cast<const double*>(buf + L.off_len)[t];
+    M.B.growth[i] = reinterpret_cast<const double*>(buf + L.off_growth)[t];
+    for (int w = 0; w < 4; ++w) M.B.cen[(u64)w * cap + i] = reinterpret_cast<const double*>(buf + L.off_cen)[(u64)w * mc + t];
+    for (int w = 0; w < 3; ++w) {
+        M.A.ident[(u64)w * cap + i] = reinterpret_cast<const u64*>(buf + L.off_ident)[(u64)w * mc + t];
+        M.A.parent[(u64)w * cap + i] = reinterpret_cast<const u64*>(buf + L.off_parent)[(u64)w * mc + t];
+    }
+    M.sortkey[i] = reinterpret_cast<const u64*>(buf + L.off_sortkey)[t];
+    M.B.hlen[i] = (buf + L.off_hlen)[t];
+    const u64 gv = reinterpret_cast<const u64*>(buf + L.off_gvox)[t];
+    if (gv < M.vox_base || gv - M.vox_base >= M.nvox) {
+        latch_error(M.err, CRB_ERR_INDEX, M.A.ident[cap + i]);
+        M.newkey[i] = CRB_KEY_GONE;
+        return;
+    }
+    const u32 nk = (u32)(gv - M.vox_base);
+    M.newkey[i] = nk;
+    M.rank_arb[i] = atomicAdd(&M.count_new[nk], 1u);
 }
 
 }  // namespace crb

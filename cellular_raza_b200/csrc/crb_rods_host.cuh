@@ -53,6 +53,8 @@ RodParams rods_params(crb_sim* s) {
     P.A = s->RX;
     P.B = s->RT;
     P.n = s->n;
+    P.first = s->G;
+    P.src_limit = s->cap_total - s->G;  // [first, src_limit): owned rods, daughters, arrivals
     P.cap = s->cap_total;
     P.key = s->key;
     P.start = s->start;
@@ -162,15 +164,17 @@ void rods_launch_ingest(crb_sim* s, const RodParams& P) {
 }
 
 // scan count_new -> start_alt, fill, reorder RT (+ RX identifiers) -> RY, swap
-int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev) {
+// n_src sources at [G, G + n_src) (owned rods, daughters, arrivals; leavers are marked CRB_KEY_GONE), n_new of
+// them remain = destination slots [G, G + n_new)
+int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev, u64 n_new) {
     const u64 nv = s->nvox;
     stage_begin(s, 1);
     if (s->n_tiles == 1) {
-        k_scan_single<<<1, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, nv, 0u);
+        k_scan_single<<<1, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, nv, (u32)s->G);
         stage_end(s, 1, 1);
     } else {
         k_scan_tiles<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->count_new, s->start_alt, s->tile_sums, nv);
-        k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv, 0u);
+        k_scan_sums<<<1, kScanThreads, 0, s->stream>>>(s->tile_sums, s->n_tiles, s->start_alt + nv, (u32)s->G);
         k_scan_add<<<s->n_tiles, kScanThreads, 0, s->stream>>>(s->start_alt, s->tile_sums, nv);
         stage_end(s, 1, 3);
     }
@@ -178,7 +182,7 @@ int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev) {
     int nl = 0;
     if (n_src) {
         k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt, s->tmp_idx,
-                                                             0, n_src);
+                                                             s->G, n_src);
         RodReorderParams R;
         std::memset(&R, 0, sizeof(R));
         R.A = s->RX;
@@ -189,11 +193,12 @@ int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev) {
         R.tmp_idx = s->tmp_idx;
         R.sortkey = s->sortkey;
         R.key_out = s->key_alt;
-        R.n = n_src;
+        R.n = n_new;
+        R.first = s->G;
         R.cap = s->cap_total;
         R.W = 3 * s->V;
         R.save_prev = save_prev ? 1 : 0;
-        k_rod_reorder<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(R);
+        if (n_new) k_rod_reorder<<<blocks_for(n_new, 256), 256, 0, s->stream>>>(R);
         nl = 2;
     }
     stage_end(s, 2, nl);
@@ -208,13 +213,13 @@ int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev) {
 int rods_upload_planes(crb_sim* s, const double* host, int W, double* planes, u64 n) {
     if (!n) return 0;
     CU(s, cudaMemcpyAsync(s->stage, host, n * W * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    k_rod_unpack<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, planes, W, s->cap_total, n);
+    k_rod_unpack<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, planes + s->G, W, s->cap_total, n);
     s->launches++;
     return 0;
 }
 int rods_download_planes(crb_sim* s, double* host, int W, const double* planes, u64 n) {
     if (!n) return 0;
-    k_rod_pack<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, planes, W, s->cap_total, n);
+    k_rod_pack<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->stage, planes + s->G, W, s->cap_total, n);
     s->launches++;
     CU(s, cudaMemcpyAsync(host, s->stage, n * W * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
@@ -226,6 +231,10 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
     const int W = 3 * s->V;
     // RodMechanics / MorsePotential fields are uniform except spring_length and growth_rate
     std::vector<double> len(n), growth(n);
+    if (s->world > 1 && !s->uniform_declared)
+        return fail(s, CRB_ERR_INVALID_ARG,
+                    "rods on a slab handle: declare the uniform RodMechanics / MorsePotential rows with "
+                    "crb_set_uniform_params on EVERY rank (a slab that starts empty has no row of its own)");
     if (s->uniform_declared && !mech_params) {
         for (u64 i = 0; i < n; ++i) {
             len[i] = s->uni.mp[RMP_LENGTH];
@@ -298,8 +307,8 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
     for (double* p : {s->RT.h1x, s->RT.h1v, s->RT.h0x, s->RT.h0v})
         CU(s, cudaMemsetAsync(p, 0, s->cap_total * W * sizeof(double), s->stream));
     CU(s, cudaMemsetAsync(s->RT.hlen, 0, s->cap_total, s->stream));
-    CU(s, cudaMemcpyAsync(s->RT.len, len.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    CU(s, cudaMemcpyAsync(s->RT.growth, growth.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(s, cudaMemcpyAsync(s->RT.len + s->G, len.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(s, cudaMemcpyAsync(s->RT.growth + s->G, growth.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     u64* d_ids = nullptr;
     if (ids && n) {
         CU(s, cudaStreamSynchronize(s->stream));
@@ -307,7 +316,7 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
         CU(s, cudaMemcpyAsync(d_ids, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
     }
     if (n) {
-        k_rod_init_ident<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->RX, d_ids, s->cap_total, n);
+        k_rod_init_ident<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->RX, d_ids, s->cap_total, n, s->G);
         s->launches++;
     }
     CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
@@ -321,7 +330,7 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
         s->have_agents = false;
         return rc;
     }
-    if ((rc = rods_sort_into_place(s, n, true))) return rc;
+    if ((rc = rods_sort_into_place(s, n, true, n))) return rc;
     k_rod_init_counters<<<blocks_for(s->nvox, 256), 256, 0, s->stream>>>(s->start, s->id_counter, s->nvox);
     s->launches++;
     CU(s, cudaStreamSynchronize(s->stream));
@@ -334,52 +343,214 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
     return 0;
 }
 
+// stage A of one step: pair forces + per-rod update + divisions for the owned rods (ghost planes must hold the
+// neighbours' boundary rods on a slab); the number of daughters is read back (the sources of the rebuild are
+// [G, G + n + n_div))
+int rods_compute(crb_sim* s, bool last) {
+    if (s->cfg.noise_mode == CRB_NOISE_TABLE && s->uni.mp[RMP_DIFF] != 0.0 && s->noise_cursor >= s->noise_steps)
+        return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
+    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+    CU(s, cudaMemsetAsync(s->n_div_dev, 0, sizeof(u32), s->stream));
+    RodParams P = rods_params(s);
+    P.save_prev = last ? 1 : 0;
+    stage_begin(s, 0);
+    if (rods_split()) {
+        int rc0;
+        if (!s->force_out && (rc0 = dalloc(s, &s->force_out, s->cap_total * 3 * s->V))) return rc0;
+        if (!s->nb_out && (rc0 = dalloc(s, &s->nb_out, s->cap_total))) return rc0;
+        P.force_out = s->force_out;
+        P.nb_out = s->nb_out;
+        rods_launch_force(s, P, true);
+        rods_launch_update(s, P);
+        stage_end(s, 0, s->n ? 2 : 0);
+    } else {
+        rods_launch_force(s, P, false);
+        stage_end(s, 0, s->n ? 1 : 0);
+    }
+    stage_begin(s, 4);
+    rods_launch_divide(s, P);
+    if (s->n)
+        k_rod_bump_counters<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(s->div_flag + s->G, s->key + s->G,
+                                                                         s->id_counter, s->n);
+    stage_end(s, 4, s->n ? 2 : 0);
+    u32 n_div = 0;
+    CU(s, cudaMemcpyAsync(&n_div, s->n_div_dev, sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    CU(s, cudaGetLastError());
+    if (s->n + n_div > s->cap + (s->world > 1 ? s->mcap : 0)) {
+        check_latch(s);
+        return fail(s, CRB_ERR_CAPACITY, "more agents than capacity after division");
+    }
+    s->last_step_n = s->n;
+    s->last_divisions = n_div;
+    s->n_src = s->n + n_div;
+    s->n_gone = 0;
+    return 0;
+}
+// stage B: cell-list rebuild over the sources of stage A (+ arrivals, - leavers on a slab)
+int rods_finish(crb_sim* s, bool last) {
+    const u64 n_new = s->n_src - s->n_gone;
+    if (n_new > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity after division / migration");
+    int rc;
+    if ((rc = rods_sort_into_place(s, s->n_src, last, n_new))) return rc;
+    s->n = n_new;
+    s->iteration++;
+    s->noise_cursor++;
+    return 0;
+}
+
 int rods_step(crb_sim* s, u64 n_steps) {
     for (u64 it = 0; it < n_steps; ++it) {
         const bool last = it + 1 == n_steps;
-        if (s->cfg.noise_mode == CRB_NOISE_TABLE && s->uni.mp[RMP_DIFF] != 0.0 && s->noise_cursor >= s->noise_steps)
-            return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
-        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
-        CU(s, cudaMemsetAsync(s->n_div_dev, 0, sizeof(u32), s->stream));
-        RodParams P = rods_params(s);
-        P.save_prev = last ? 1 : 0;
-        stage_begin(s, 0);
-        if (rods_split()) {
-            int rc0;
-            if (!s->force_out && (rc0 = dalloc(s, &s->force_out, s->cap_total * 3 * s->V))) return rc0;
-            if (!s->nb_out && (rc0 = dalloc(s, &s->nb_out, s->cap_total))) return rc0;
-            P.force_out = s->force_out;
-            P.nb_out = s->nb_out;
-            rods_launch_force(s, P, true);
-            rods_launch_update(s, P);
-            stage_end(s, 0, s->n ? 2 : 0);
-        } else {
-            rods_launch_force(s, P, false);
-            stage_end(s, 0, s->n ? 1 : 0);
-        }
-        stage_begin(s, 4);
-        rods_launch_divide(s, P);
-        if (s->n)
-            k_rod_bump_counters<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(s->div_flag, s->key, s->id_counter,
-                                                                             s->n);
-        stage_end(s, 4, s->n ? 2 : 0);
-        u32 n_div = 0;
-        CU(s, cudaMemcpyAsync(&n_div, s->n_div_dev, sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
-        CU(s, cudaStreamSynchronize(s->stream));
-        CU(s, cudaGetLastError());
-        if (s->n + n_div > s->cap) {
-            check_latch(s);
-            return fail(s, CRB_ERR_CAPACITY, "more agents than capacity after division");
-        }
-        s->last_step_n = s->n;
-        s->last_divisions = n_div;
         int rc;
-        if ((rc = rods_sort_into_place(s, s->n + n_div, last))) return rc;
-        s->n += n_div;
-        s->iteration++;
-        s->noise_cursor++;
+        if ((rc = rods_compute(s, last))) return rc;
+        if ((rc = rods_finish(s, last))) return rc;
     }
     return check_latch(s);
+}
+
+// ---- slab protocol (crb_slab_* with mechanics_kind == CRB_MECH_ROD): same six phases as the point agents ------------
+int rods_slab_halo_export(crb_sim* s, void* lo_buf, void* hi_buf) {
+    const u64 plane = s->rhl.plane;
+    const u32 grid = blocks_for(std::max<u64>(s->rhl.gcap, plane + 1), 256);
+    stage_begin(s, 3);
+    int nl = 0;
+    if (s->has_lo && lo_buf) {
+        k_rod_halo_export<<<grid, 256, 0, s->stream>>>(s->RX, s->cap_total, s->start, (u32)(s->g.own_lo * plane), s->rhl,
+                                                      (unsigned char*)lo_buf, s->err);
+        ++nl;
+    }
+    if (s->has_hi && hi_buf) {
+        k_rod_halo_export<<<grid, 256, 0, s->stream>>>(s->RX, s->cap_total, s->start, (u32)((s->g.own_hi - 1) * plane),
+                                                      s->rhl, (unsigned char*)hi_buf, s->err);
+        ++nl;
+    }
+    stage_end(s, 3, nl);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+int rods_slab_halo_import(crb_sim* s, const void* lo_buf, const void* hi_buf) {
+    const u64 plane = s->rhl.plane;
+    const u32 grid = blocks_for(std::max<u64>(s->rhl.gcap, plane + 1), 256);
+    stage_begin(s, 3);
+    int nl = 0;
+    if (s->has_lo) {
+        if (!lo_buf) return fail(s, CRB_ERR_INVALID_ARG, "lower halo buffer missing");
+        k_rod_halo_import<<<grid, 256, 0, s->stream>>>(s->RX, s->cap_total, s->start, 0u, s->G, 1, s->rhl,
+                                                      (const unsigned char*)lo_buf, s->err);
+        ++nl;
+    }
+    if (s->has_hi) {
+        if (!hi_buf) return fail(s, CRB_ERR_INVALID_ARG, "upper halo buffer missing");
+        k_rod_halo_import<<<grid, 256, 0, s->stream>>>(s->RX, s->cap_total, s->start, (u32)((s->g.L0 - 1) * plane),
+                                                      s->G + s->n, 0, s->rhl, (const unsigned char*)hi_buf, s->err);
+        ++nl;
+    }
+    stage_end(s, 3, nl);
+    CU(s, cudaGetLastError());
+    return 0;
+}
+RodMigParams rods_mig_params(crb_sim* s) {
+    RodMigParams M;
+    std::memset(&M, 0, sizeof(M));
+    const u64 plane = s->rhl.plane;
+    M.A = s->RX;
+    M.B = s->RT;
+    M.cap = s->cap_total;
+    M.newkey = s->newkey;
+    M.sortkey = s->sortkey;
+    M.rank_arb = s->rank_arb;
+    M.count_new = s->count_new;
+    M.lo_end = s->has_lo ? (u32)plane : 0u;
+    M.hi_begin = s->has_hi ? (u32)((s->g.L0 - 1) * plane) : 0xffffffffu;
+    M.vox_base = (u64)s->g.p0 * plane;
+    M.nvox = s->nvox;
+    M.L = s->rml;
+    M.counter = s->scratch_u64;
+    M.err = s->err;
+    return M;
+}
+int rods_slab_migration_export(crb_sim* s, void* lo_buf, void* hi_buf, uint64_t n_out[2]) {
+    const u64 plane = s->rhl.plane;
+    if ((s->has_lo && !lo_buf) || (s->has_hi && !hi_buf)) return fail(s, CRB_ERR_INVALID_ARG, "migration buffer missing");
+    CU(s, cudaMemsetAsync(s->scratch_u64, 0, 2 * sizeof(u64), s->stream));
+    stage_begin(s, 4);
+    int nl = 0;
+    if (s->n_src) {
+        RodMigParams M = rods_mig_params(s);
+        M.first = s->G;
+        M.n = s->n_src;  // owned rods of the step and the daughters born in it
+        M.buf[0] = (unsigned char*)lo_buf;
+        M.buf[1] = (unsigned char*)hi_buf;
+        k_rod_mig_export<<<blocks_for(s->n_src, 256), 256, 0, s->stream>>>(M);
+        ++nl;
+    }
+    // the leavers were counted in the histogram of the ghost planes: they take no slot here
+    if (s->has_lo) CU(s, cudaMemsetAsync(s->count_new, 0, plane * sizeof(u32), s->stream));
+    if (s->has_hi) CU(s, cudaMemsetAsync(s->count_new + (s->g.L0 - 1) * plane, 0, plane * sizeof(u32), s->stream));
+    if (s->has_lo) CU(s, cudaMemcpyAsync(lo_buf, s->scratch_u64, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+    if (s->has_hi) CU(s, cudaMemcpyAsync(hi_buf, s->scratch_u64 + 1, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+    stage_end(s, 4, nl);
+    CU(s, cudaGetLastError());
+    if (!n_out) {
+        s->mig_counts_pending = true;
+        return 0;
+    }
+    u64 cnt[2] = {0, 0};
+    CU(s, cudaMemcpyAsync(cnt, s->scratch_u64, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (cnt[0] > s->mcap || cnt[1] > s->mcap)
+        return fail(s, CRB_ERR_CAPACITY, "more migrating rods than migration_capacity");
+    n_out[0] = s->mig_out[0] = cnt[0];
+    n_out[1] = s->mig_out[1] = cnt[1];
+    s->n_gone = cnt[0] + cnt[1];
+    return 0;
+}
+int rods_slab_migration_import(crb_sim* s, const void* lo_buf, const void* hi_buf, uint64_t n_in[2]) {
+    u64 cnt[2] = {0, 0}, outc[2] = {0, 0};
+    if (s->has_lo) {
+        if (!lo_buf) return fail(s, CRB_ERR_INVALID_ARG, "lower migration buffer missing");
+        CU(s, cudaMemcpyAsync(&cnt[0], lo_buf, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (s->has_hi) {
+        if (!hi_buf) return fail(s, CRB_ERR_INVALID_ARG, "upper migration buffer missing");
+        CU(s, cudaMemcpyAsync(&cnt[1], hi_buf, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (s->mig_counts_pending)
+        CU(s, cudaMemcpyAsync(outc, s->scratch_u64, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (s->mig_counts_pending) {
+        s->mig_counts_pending = false;
+        if (outc[0] > s->mcap || outc[1] > s->mcap)
+            return fail(s, CRB_ERR_CAPACITY, "more migrating rods than migration_capacity");
+        s->mig_out[0] = outc[0];
+        s->mig_out[1] = outc[1];
+        s->n_gone = outc[0] + outc[1];
+    }
+    if (cnt[0] > s->mcap || cnt[1] > s->mcap)
+        return fail(s, CRB_ERR_CAPACITY, "more arriving rods than migration_capacity");
+    if (s->G + s->n_src + cnt[0] + cnt[1] > s->cap_total - s->G)
+        return fail(s, CRB_ERR_CAPACITY, "more rods than capacity");
+    stage_begin(s, 4);
+    int nl = 0;
+    for (int side = 0; side < 2; ++side) {
+        if (!cnt[side]) continue;
+        RodMigParams M = rods_mig_params(s);
+        M.first = s->G + s->n_src;
+        M.n = cnt[side];
+        M.buf[0] = (unsigned char*)lo_buf;
+        M.buf[1] = (unsigned char*)hi_buf;
+        k_rod_mig_import<<<blocks_for(cnt[side], 256), 256, 0, s->stream>>>(M, side);
+        ++nl;
+        s->n_src += cnt[side];
+    }
+    stage_end(s, 4, nl);
+    CU(s, cudaGetLastError());
+    if (n_in) {
+        n_in[0] = cnt[0];
+        n_in[1] = cnt[1];
+    }
+    return 0;
 }
 
 int rods_get_agents(crb_sim* s, u64 cap, double* pos, double* vel, u64* ids, u64* voxel) {
@@ -389,10 +560,10 @@ int rods_get_agents(crb_sim* s, u64 cap, double* pos, double* vel, u64* ids, u64
     if (pos && (rc = rods_download_planes(s, pos, W, s->RX.pos, n))) return rc;
     if (vel && (rc = rods_download_planes(s, vel, W, s->RX.vel, n))) return rc;
     if (ids)
-        CU(s, cudaMemcpyAsync(ids, s->RX.ident + s->cap_total, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaMemcpyAsync(ids, s->RX.ident + s->cap_total + s->G, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     if (voxel && n) {
         const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
-        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key, (u64*)s->stage, base, n);
+        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key + s->G, (u64*)s->stage, base, n);
         s->launches++;
         CU(s, cudaMemcpyAsync(voxel, s->stage, n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     }
@@ -406,7 +577,7 @@ int rods_get_identifiers(crb_sim* s, u64 cap, u64* ident, u64* parent) {
     for (int which = 0; which < 2; ++which) {
         u64* out = which == 0 ? ident : parent;
         if (!out) continue;
-        k_rod_pack_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>((u64*)s->stage, which == 0 ? s->RX.ident : s->RX.parent,
+        k_rod_pack_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>((u64*)s->stage, (which == 0 ? s->RX.ident : s->RX.parent) + s->G,
                                                                  3, s->cap_total, n);
         s->launches++;
         CU(s, cudaMemcpyAsync(out, s->stage, n * 3 * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
@@ -419,8 +590,8 @@ int rods_get_params(crb_sim* s, u64 cap, double* mech_params, double* inter_para
     const u64 n = s->n;
     if (mech_params) {
         std::vector<double> len(n), growth(n);
-        CU(s, cudaMemcpyAsync(len.data(), s->RX.len, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-        CU(s, cudaMemcpyAsync(growth.data(), s->RX.growth, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaMemcpyAsync(len.data(), s->RX.len + s->G, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaMemcpyAsync(growth.data(), s->RX.growth + s->G, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
         CU(s, cudaStreamSynchronize(s->stream));
         for (u64 i = 0; i < n; ++i) {
             for (int k = 0; k < 8; ++k) mech_params[i * 8 + k] = s->uni.mp[k];
@@ -440,7 +611,7 @@ int rods_get_aux(crb_sim* s, u64 cap, double* hist_dx, double* hist_dv, uint32_t
     const u64 n = s->n;
     const int W = 3 * s->V;
     std::vector<u8> hl(n);
-    CU(s, cudaMemcpyAsync(hl.data(), s->RX.hlen, n, cudaMemcpyDeviceToHost, s->stream));
+    CU(s, cudaMemcpyAsync(hl.data(), s->RX.hlen + s->G, n, cudaMemcpyDeviceToHost, s->stream));
     CU(s, cudaStreamSynchronize(s->stream));
     std::vector<double> older(n * W), newest(n * W);
     int rc;
@@ -479,7 +650,7 @@ int rods_debug_forces(crb_sim* s, double* force, u64* counts) {
     CU(s, cudaGetLastError());
     if (force && (rc = rods_download_planes(s, force, 3 * s->V, s->force_out, s->n))) return rc;
     if (counts)
-        CU(s, cudaMemcpyAsync(counts, s->nb_out, s->n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaMemcpyAsync(counts, s->nb_out + s->G, s->n * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     return check_latch(s);
 }
 

@@ -359,6 +359,84 @@ class LocalSlabGroup:
         return sum(rk.kernel_launches for rk in self.ranks)
 
 
+class RodSlabRank(SlabRank):
+    """One slab of bacterial rods (``mechanics_kind == CRB_MECH_ROD``): the slab protocol of :class:`SlabRank`
+    with the rod-shaped setters / getters of :class:`cellular_raza_b200.rods.RodSimulation`."""
+
+    def __init__(self, cfg: _abi.CrbConfig, rank: int, world: int, device: int = 0, **caps):
+        if int(cfg.mechanics_kind) != _abi.CRB_MECH_ROD:
+            raise ValueError("RodSlabRank needs mechanics_kind == CRB_MECH_ROD")
+        super().__init__(cfg, rank, world, device, **caps)
+        self.V = int(cfg.rod_n_vertices)
+
+
+def _rod_methods():
+    # the rod-shaped accessors are plain functions of (self._lib, self._h, self.V, self.dim): shared, not copied
+    from .rods import RodSimulation
+
+    for name in ("set_agents", "get_agents", "get_params", "get_aux", "set_noise", "debug_forces",
+                 "debug_neighbor_counts"):
+        setattr(RodSlabRank, name, getattr(RodSimulation, name))
+    RodSlabRank.n_divisions = RodSimulation.n_divisions
+
+
+_rod_methods()
+
+
+class LocalRodSlabGroup(LocalSlabGroup):
+    """``world`` slabs of rods driven by one process through the six-phase protocol (halo: the vertex positions and
+    bounding spheres of the boundary planes; migration: complete rods incl. identifiers and AuxStorage; divisions
+    happen on the slab that owns the mother's voxel, as ``Voxel::id_counter`` demands).  Gathered views come back
+    in rank order = ascending global voxel, chili in-voxel order: the order of a single handle."""
+
+    def __init__(self, make_cfg, world: int, devices: Sequence[int] | None = None, **caps):
+        devices = list(devices) if devices is not None else [0] * world
+        self.world = world
+        self.overlap = False  # (the rod force pass is not split into interior / boundary planes)
+        self.transport = "copy"
+        self.ranks = [RodSlabRank(make_cfg(), r, world, devices[r], **caps) for r in range(world)]
+        self.cfg = self.ranks[0].cfg
+        self.dim = self.ranks[0].dim
+        self.V = self.ranks[0].V
+
+    def set_agents(self, pos, vel, mech_params, inter_params, ids=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        n = pos.shape[0]
+        pos = pos.reshape(n, self.V, 3)
+        # SortCells::get_voxel_index_of of CartesianCuboidRods: mean of the vertices (bacterial_rods.rs:368-372); the
+        # sum runs over the vertices in order, like nalgebra's row_sum and like the device
+        mean0 = np.zeros(n)
+        for v in range(self.V):
+            mean0 = mean0 + pos[:, v, 0]
+        mean0 = mean0 / float(self.V)
+        owner = rank_of_position(mean0, self.cfg.domain_min[0], self.cfg.dx[0], int(self.cfg.n_voxels[0]), self.world)
+        ids = np.arange(n, dtype=np.uint64) if ids is None else np.asarray(ids, dtype=np.uint64)
+        rk0 = self.ranks[0]
+        mp = np.ascontiguousarray(np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, rk0.n_mech)))
+        ip = np.ascontiguousarray(np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, rk0.n_inter)))
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64).reshape(n, self.V, 3)
+        for r, rk in enumerate(self.ranks):
+            m = owner == r
+            # every rank declares the uniform rows (spring_length and growth_rate are per rod and come with the rows)
+            rk.set_uniform_params(mp[0] if n else None, ip[0] if n else None)
+            rk.set_agents(pos[m], None if vel is None else vel[m], mp[m], ip[m], ids=ids[m])
+
+    def get_agents(self):
+        parts = [rk.get_agents() for rk in self.ranks]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+
+    def get_params(self):
+        return np.concatenate([rk.get_params() for rk in self.ranks])
+
+    def debug_neighbor_counts(self):
+        self.halo_exchange()
+        return np.concatenate([rk.debug_neighbor_counts() for rk in self.ranks])
+
+    @property
+    def n_divisions(self) -> int:
+        return sum(rk.n_divisions for rk in self.ranks)
+
+
 class SlabSimulation:
     """One slab per process (``torch.distributed`` must be initialised with the nccl backend); halo and
     migration buffers travel with ncclSend/ncclRecv over NVLink."""
