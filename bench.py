@@ -53,7 +53,7 @@ def parse_args():
                     help="cpu_baseline: CPU work of the bounded sample (steps chosen from one probe step)")
     ap.add_argument("--workload", default="cell_sorting", choices=["cell_sorting", "brownian_morse", "bacterial_rods", "cell_sorting_as_shipped"],
                     help="cell_sorting = the headline (BASELINE.json configs[1]/[4]); brownian_morse = configs[2] "
-                         "(N > 1: ONE cube of cells-per-gpu x N agents cut into slabs); bacterial_rods = configs[3] (1 GPU); "
+                         "(N > 1: ONE cube of cells-per-gpu x N agents cut into slabs); bacterial_rods = configs[3] (N > 1: slabs, weak scaling); "
                          "cell_sorting_as_shipped = configs[0] (1,600 cells, latency-bound, 1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -299,10 +299,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     if args.gpus > 1:
-        if args.workload in ("bacterial_rods", "cell_sorting_as_shipped"):
-            raise SystemExit(f"--workload {args.workload} is a single-GPU line (rods are not slab-decomposed; "
-                             "1,600 cells do not fill one GPU): run it with --gpus 1")
+        if args.workload == "cell_sorting_as_shipped":
+            raise SystemExit("--workload cell_sorting_as_shipped is a single-GPU line (1,600 cells do not fill one GPU): "
+                             "run it with --gpus 1")
         from cellular_raza_b200 import multi_gpu_bench
+
+        if args.workload == "bacterial_rods":
+            return multi_gpu_bench.run_rods(args, rank, world, local_rank, sys.modules[__name__])
 
         return multi_gpu_bench.run(args, rank, world, local_rank, sys.modules[__name__])
 

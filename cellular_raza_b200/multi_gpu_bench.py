@@ -247,3 +247,103 @@ def run(args, rank: int, world: int, local_rank: int, helpers):
         print(json.dumps(line), flush=True)
     sim.close()
     dist.destroy_process_group()
+
+
+def run_rods(args, rank: int, world: int, local_rank: int, helpers):
+    """BASELINE.json configs[3] over slabs: every rank owns ``cells-per-gpu`` rods of a domain ``world`` times longer
+    along axis 0 (weak scaling); six-phase protocol over ncclSend/ncclRecv (halo = vertex positions of the boundary
+    planes, migration = complete rods), divisions inside the timed region.  agent-steps = steps x mean of the global
+    rod count before / after."""
+    import torch
+    import torch.distributed as dist
+
+    from . import workloads
+    from .device import measure_fp64_peak
+    from .slabs import SlabSimulation
+
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+    w = workloads.bacterial_rods_slab(args.cells_per_gpu, rank, world, n_threads=args.n_threads_ref)
+    cfg = w.config(capacity=int(w.n * 1.5) + 4096, device=local_rank)
+    sim = SlabSimulation(cfg, device=local_rank)
+    sim.set_agents(w.pos, w.vel, w.mech_params, w.inter_params, ids=w.extra["ids"])
+    slab = sim.slab
+    stream = slab.torch_stream
+
+    def total(x):
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    sim.halo_exchange()
+    pairs0 = slab.count_candidate_pairs()
+    sim.step(max(args.warmup, 3))
+    sim.sync()
+    fp64_peak, _ = measure_fp64_peak(local_rank)
+    sampler = helpers.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    slab.enable_timers(True)
+    slab.reset_timers()
+    l0 = slab.kernel_launches
+    n_before = total(slab.n_agents)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.step(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    launches = slab.kernel_launches - l0
+    force_ms, _ = slab.stage_time_ms(0)
+    scan_ms, _ = slab.stage_time_ms(1)
+    reorder_ms, _ = slab.stage_time_ms(2)
+    halo_ms, _ = slab.stage_time_ms(3)
+    mig_ms, _ = slab.stage_time_ms(4)
+    slab.enable_timers(False)
+    clocks = sampler.stop() if rank == 0 else None
+    n_after = total(slab.n_agents)
+    sim.halo_exchange()
+    pairs = total(0.5 * (pairs0 + slab.count_candidate_pairs()))
+    fm = torch.tensor([force_ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(fm, op=dist.ReduceOp.MAX)
+    value = 0.5 * (n_before + n_after) * args.steps / (ms_total * 1e-3)
+    if rank == 0:
+        force_avg_ms = float(fm.item()) / max(args.steps, 1)
+        achieved_tf = pairs / world * helpers.ROD_FLOP_PER_PAIR / (force_avg_ms * 1e-3) / 1e12
+        line = {
+            "metric": helpers.METRIC, "value": value, "unit": helpers.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "bacterial_rods (BASELINE.json configs[3]) over slabs", "rods_per_gpu_initial": w.n,
+                       "rods_before": n_before, "rods_after": n_after, "vertices": 5,
+                       "aspects": "Mechanics, Interaction, Cycle, NeighborSensing", "dt_min": 0.1,
+                       "decomposition": f"slab{world}", "halo_bytes_per_face": slab.halo_bytes,
+                       "migration_bytes_per_face": slab.mig_bytes,
+                       "exchange": "six-phase protocol, ncclSend/ncclRecv (torch.distributed.batch_isend_irecv); the rod "
+                                   "force pass is not split into interior / boundary planes; two host synchronisations "
+                                   "per step (division count, arrival counts)",
+                       "l2_policy": "working set larger than L2 (three state copies x ~1 KB per rod)"},
+            "roofline": {"kernel": "k_rod_force + k_rod_update (per GPU, slowest rank)", "bound": "fp64",
+                         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                         "peak_source": "DFMA micro-kernel measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "traffic": None, "share_of_step": float(fm.item()) / ms_total,
+                         "algorithmic_flop_per_pair": helpers.ROD_FLOP_PER_PAIR, "pairs_per_launch": pairs / world},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches) * world, "clocks": clocks,
+            "stage_ms_per_step": {"force_update": force_ms / args.steps, "scan": scan_ms / args.steps,
+                                  "reorder": reorder_ms / args.steps, "halo_pack_unpack": halo_ms / args.steps,
+                                  "divide_migration": mig_ms / args.steps},
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    dist.destroy_process_group()

@@ -456,7 +456,13 @@ class SlabSimulation:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         device = torch.cuda.current_device() if device is None else device
-        self.slab = SlabRank(cfg, self.rank, self.world, device, **caps)
+        self.rods = int(cfg.mechanics_kind) == _abi.CRB_MECH_ROD
+        if self.rods:
+            # rods: six-phase protocol only (division counts are read back every step; the force pass is not split)
+            self.overlap, self.transport, transport = False, "nccl", "nccl"
+            self.slab = RodSlabRank(cfg, self.rank, self.world, device, **caps)
+        else:
+            self.slab = SlabRank(cfg, self.rank, self.world, device, **caps)
         # the exchange buffers have a fixed size derived from the capacities: a rank with another size
         # would leave its neighbour waiting in ncclRecv forever, so compare before the first exchange
         mine = torch.tensor([self.slab.halo_bytes, self.slab.mig_bytes], dtype=torch.int64,
@@ -488,6 +494,20 @@ class SlabSimulation:
         """``pos`` … are THIS rank's agents (axis-0 coordinate inside the slab).  When parameter arrays are given,
         whether all agents of ALL ranks share one row is agreed on with one all_gather: every rank then declares
         that row (or none does) — a rank never decides from its own subset (an empty slab has no row at all)."""
+        if self.rods:
+            # rods: uniform rows except spring_length / growth_rate, declared on every rank (row 0 of the first rank
+            # that holds a rod); the per-rod rows travel with set_agents
+            n = len(pos)
+            mp = np.ascontiguousarray(np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, self.slab.n_mech)))
+            ip = np.ascontiguousarray(np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, self.slab.n_inter)))
+            every = [None] * self.world
+            self.dist.all_gather_object(every, (mp[0].tolist(), ip[0].tolist()) if n else None, group=self.group)
+            rows = [e for e in every if e is not None]
+            if not rows:
+                raise ValueError("no rank holds a rod")
+            self.slab.set_uniform_params(np.array(rows[0][0]), np.array(rows[0][1]))
+            self.slab.set_agents(pos, vel, mp, ip, ids=ids)
+            return
         if mech_params is not None and inter_params is not None and not self._declared:
             n = len(pos)
             mp = np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, self.slab.n_mech))

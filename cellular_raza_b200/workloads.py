@@ -273,6 +273,8 @@ def bacterial_rods(
     pair_weight_mode: int = _abi.CRB_WEIGHT_CHILI,
     solver_order: int = 2,
     capacity_factor: float = 2.0,
+    tile_x0: int = 0,
+    n_tiles_x_total: int | None = None,
 ) -> Workload:
     """cellular_raza-examples/bacterial_rods as shipped (src/main.rs:111-212), tiled: every tile is the
     shipped domain (200 x 15 x 45 um, [8, 1, 2] voxels) holding ``rods_per_tile`` rods placed by the
@@ -289,7 +291,9 @@ def bacterial_rods(
     domain_size = 50.0 * um
     tile = np.array([4.0 * domain_size, delta_x, 3.0 * delta_x])
     n = n_tiles_x * n_tiles_z * rods_per_tile
-    tx = np.repeat(np.arange(n_tiles_x), n_tiles_z * rods_per_tile)
+    # (slabs: only the tiles [tile_x0, tile_x0 + n_tiles_x) of a domain n_tiles_x_total tiles long are populated)
+    n_tot_x = n_tiles_x if n_tiles_x_total is None else n_tiles_x_total
+    tx = np.repeat(np.arange(n_tiles_x), n_tiles_z * rods_per_tile) + tile_x0
     tz = np.tile(np.repeat(np.arange(n_tiles_z), rods_per_tile), n_tiles_x)
     pos = np.zeros((n, V, 3))
     pos[:, 0, 0] = rng.uniform(delta_x, 2.0 * delta_x, n) + tx * tile[0]
@@ -309,7 +313,7 @@ def bacterial_rods(
             pos[todo, i, 2] = pos[todo, i - 1, 2]
         y, x = pos[todo, :, 1], pos[todo, :, 0]
         bad = ((y.min(axis=1) < margin) | (y.max(axis=1) > tile[1] - margin) | (x.min(axis=1) < margin)
-               | (x.max(axis=1) > tile[0] * n_tiles_x - margin))
+               | (x.max(axis=1) > tile[0] * n_tot_x - margin))
         todo = todo[bad]
     spring_length = rng.uniform(spring_length_range[0], spring_length_range[1], n) * um
     growth_base = 0.1 * um / MINUTE
@@ -320,8 +324,8 @@ def bacterial_rods(
     mech[:, 3] = spring_length
     inter = np.tile([3.0 * um, 0.5 / um, 5.0 * um, 0.1 * um**2 / MINUTE**2], (n, 1))
     mn = [0.0, 0.0, 0.0]
-    mx = [tile[0] * n_tiles_x, tile[1], tile[2] * n_tiles_z]
-    nv = np.array([8 * n_tiles_x, 1, 2 * n_tiles_z], dtype=np.uint64)
+    mx = [tile[0] * n_tot_x, tile[1], tile[2] * n_tiles_z]
+    nv = np.array([8 * n_tot_x, 1, 2 * n_tiles_z], dtype=np.uint64)
     dx = (np.asarray(mx) - np.asarray(mn)) / nv.astype(np.float64)  # from_boundaries_and_n_voxels
     cfg = dict(
         dim=3,
@@ -340,3 +344,15 @@ def bacterial_rods(
         inter_params=inter,
         species=None,
     )
+
+
+def bacterial_rods_slab(rods_per_rank: int, rank: int, world: int, *, rods_per_tile: int = 5, seed: int = 5,
+                        n_threads: int = 8, spring_length_range=(4.0, 6.0)) -> Workload:
+    """Weak-scaling rod population (BASELINE.json configs[3] per GPU): the domain of :func:`bacterial_rods` at the
+    shipped rod density, ``world`` times longer along x; only THIS rank's tiles are generated (independent PCG64
+    stream per rank), ids are globally unique.  ``cfg_kwargs`` describe the GLOBAL domain."""
+    side = max(int(round((rods_per_rank / rods_per_tile) ** 0.5)), 1)
+    w = bacterial_rods(side, side, rods_per_tile=rods_per_tile, seed=[seed, rank], n_threads=n_threads,
+                       spring_length_range=spring_length_range, tile_x0=rank * side, n_tiles_x_total=world * side)
+    w.extra["ids"] = np.arange(w.n, dtype=np.uint64) + np.uint64(rank) * np.uint64(w.n)
+    return w

@@ -64,7 +64,10 @@ typedef enum crb_mechanics_kind {
                                     dim 3 and 2 <= rod_n_vertices <= 8; the step then runs aspects
                                     [Mechanics, Interaction, Cycle, NeighborSensing] (main.rs:202-210).
                                     spring_length and growth_rate are per-agent state, the other
-                                    entries must be equal for all agents. */
+                                    entries must be equal for all agents.  Slabs (world_size > 1): the six-phase
+                                    protocol crb_slab_halo_export .. crb_slab_finish with crb_slab_compute (no
+                                    interior / boundary split, no crb_slab_step); the uniform rows must be declared
+                                    with crb_set_uniform_params on every rank. */
 } crb_mechanics_kind;
 
 /* Interaction kinds and their per-agent parameter rows (inter_params[i*n_inter + k]).
