@@ -802,27 +802,24 @@ struct ReorderParams {
     u64 nvox_dev;  // != 0: the number of destinations is start_new[nvox_dev] - first (device-side counts)
 };
 
-__global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
+// Two groups of loads (positions + velocities + scalars, then the increment history) instead of one: at most nine
+// doubles are in flight per thread, which lets the kernel fit 40 registers without spills = 48 resident warps per SM
+// instead of 32.  k_reorder is latency bound — occupancy is what buys bandwidth: 0.443 -> 0.407 ms at 8 M cells,
+// 0.0657 -> 0.0594 ms at 1 M (one box, round 2).  Capping the one-group form at 48 / 40 registers spilled and lost
+// (0.53 / 0.56 ms); four groups at 32 registers spill as well.
+__global__ void __launch_bounds__(256, 6) k_reorder(const ReorderParams R) {
     const u64 tp = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u64 n_dst = R.nvox_dev ? (u64)__ldg(&R.start_new[R.nvox_dev]) - R.first : R.n;
     if (tp >= n_dst) return;
     const u64 p = R.first + tp;
     const u32 i = R.tmp_idx[p];
-    // ---- every load of the agent's state is issued BEFORE the rank loop and before any store: the
-    // kernel is latency bound (one long-scoreboard stall per load otherwise), so the bytes in flight per
-    // thread decide the bandwidth (12-18 independent 8-byte loads instead of one at a time)
-    double bp[3], bv[3], bx[3], bw[3], b0x[3], b0v[3];
+    // ---- group 1: issued BEFORE the rank loop and before any store (one long-scoreboard stall for all of them)
+    double bp[3], bv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (c < R.D) {
             bp[c] = __ldg(&R.B.pos[c][i]);
             bv[c] = __ldg(&R.B.vel[c][i]);
-            bx[c] = __ldg(&R.B.h1x[c][i]);
-            bw[c] = __ldg(&R.B.h1v[c][i]);
-            if (R.save_prev) {
-                b0x[c] = __ldg(&R.B.h0x[c][i]);
-                b0v[c] = __ldg(&R.B.h0v[c][i]);
-            }
         }
     }
     const u8 hl = __ldg(&R.B.hlen[i]);
@@ -835,6 +832,15 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
     u32 rank = 0;
     for (u32 q = sb; q < se; ++q) rank += (__ldg(&R.sortkey[__ldg(&R.tmp_idx[q])]) < my) ? 1u : 0u;
     const u64 d = (u64)sb + rank;
+    // ---- group 2: the increment history, in flight while group 1 is stored
+    double bx[3], bw[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c < R.D) {
+            bx[c] = __ldg(&R.B.h1x[c][i]);
+            bw[c] = __ldg(&R.B.h1v[c][i]);
+        }
+    }
     R.key_out[d] = v;
     if (R.slot_of_src) R.slot_of_src[i] = (u32)d;
 #pragma unroll
@@ -842,12 +848,6 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
         if (c < R.D) {
             R.Y.pos[c][d] = bp[c];
             R.Y.vel[c][d] = bv[c];
-            R.Y.h1x[c][d] = bx[c];
-            R.Y.h1v[c][d] = bw[c];
-            if (R.save_prev) {
-                R.Y.h0x[c][d] = b0x[c];
-                R.Y.h0v[c][d] = b0v[c];
-            }
         }
     }
     {
@@ -862,6 +862,22 @@ __global__ void __launch_bounds__(256) k_reorder(const ReorderParams R) {
     R.Y.hlen[d] = hl;
     R.Y.id[d] = id;
     if (R.has_species) R.Y.species[d] = sp;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c < R.D) {
+            R.Y.h1x[c][d] = bx[c];
+            R.Y.h1v[c][d] = bw[c];
+        }
+    }
+    if (R.save_prev) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c < R.D) {
+                R.Y.h0x[c][d] = __ldg(&R.B.h0x[c][i]);
+                R.Y.h0v[c][d] = __ldg(&R.B.h0v[c][i]);
+            }
+        }
+    }
     for (int k = 0; k < R.n_mp; ++k) R.Y.mp[k][d] = R.A.mp[k][i];
     for (int k = 0; k < R.n_ip; ++k) R.Y.ip[k][d] = R.A.ip[k][i];
 }

@@ -778,7 +778,11 @@ struct RodReorderParams {
     int W;  // 3 V planes
     int save_prev;
 };
-__global__ void __launch_bounds__(256) k_rod_reorder(const RodReorderParams R) {
+// latency bound like k_reorder: occupancy buys bandwidth.  Groups of 4 planes x 4 arrays (16 loads in flight) at
+// (256, 4) = 64 registers without spills: 0.58 -> 0.45 ms at 2 M rods against the unbounded 118-register build with
+// groups of 6 (groups of 6 at (256, 3): 0.49 ms; groups of 3 at (256, 5): 0.46 ms, spills) — one box, round 2
+constexpr int kRodReorderGroup = 4;
+__global__ void __launch_bounds__(256, 4) k_rod_reorder(const RodReorderParams R) {
     const u64 tp = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (tp >= R.n) return;
     const u64 p = R.first + tp;
@@ -790,12 +794,12 @@ __global__ void __launch_bounds__(256) k_rod_reorder(const RodReorderParams R) {
     for (u32 q = sb; q < se; ++q) rank += (R.sortkey[R.tmp_idx[q]] < my) ? 1u : 0u;
     const u64 d = (u64)sb + rank;
     R.key_out[d] = v;
-    // latency-bound gather: groups of 6 planes x 4 arrays = 24 independent loads in flight per thread
+    // latency-bound gather: groups of kRodReorderGroup planes x 4 arrays of independent loads in flight per thread
     // before the first store (one long-scoreboard stall per group instead of one per load)
-    for (int w0 = 0; w0 < R.W; w0 += 6) {
-        double a[6], b[6], c[6], e[6];
+    for (int w0 = 0; w0 < R.W; w0 += kRodReorderGroup) {
+        double a[kRodReorderGroup], b[kRodReorderGroup], c[kRodReorderGroup], e[kRodReorderGroup];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < kRodReorderGroup; ++k) {
             if (w0 + k < R.W) {
                 const u64 oi = (u64)(w0 + k) * R.cap + i;
                 a[k] = __ldg(&R.B.pos[oi]);
@@ -805,7 +809,7 @@ __global__ void __launch_bounds__(256) k_rod_reorder(const RodReorderParams R) {
             }
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < kRodReorderGroup; ++k) {
             if (w0 + k < R.W) {
                 const u64 od = (u64)(w0 + k) * R.cap + d;
                 R.Y.pos[od] = a[k];
