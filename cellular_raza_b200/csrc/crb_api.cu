@@ -142,6 +142,7 @@ struct crb_sim {
     u8* div_flag = nullptr;
     u32* id_counter = nullptr;
     u32* n_div_dev = nullptr;
+    u32* div_list = nullptr;  // rods: slots with a pending Division event in this step
     u64* nb_out = nullptr;
     u64 last_divisions = 0;
     std::vector<void*> allocs;

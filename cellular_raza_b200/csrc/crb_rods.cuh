@@ -48,7 +48,8 @@ struct RodParams {
     u64 *sortkey;
     u8 *div_flag;     // [cap] Division event pending for source slot i
     u32 *id_counter;  // Voxel::id_counter per local voxel
-    u32 *n_div;       // device counter: daughters created this step
+    u32 *n_div;       // device counters: [0] daughters created this step, [1] entries of div_list
+    u32 *div_list;    // slots of the rods with a pending Division event (written by the epilogue, any order)
     double *force_out;
     u64 *nb_out;
     int *err;
@@ -355,6 +356,7 @@ __device__ __forceinline__ void rod_epilogue(const RodParams& P, const u64 i, do
     const bool divide = len > P.threshold;
     P.div_flag[i] = divide ? 1 : 0;
     if (divide) {
+        P.div_list[atomicAdd(P.n_div + 1, 1u)] = (u32)i;
         // completed by k_rod_divide (geometry changes before boundary and voxel key)
 #pragma unroll
         for (int v = 0; v < V; ++v)
@@ -608,11 +610,16 @@ __global__ void __launch_bounds__(128, 4) k_rod_update(const RodParams P) {
 // behind all cells of v in mother order; the daughter starts with a fresh AuxStorage.
 // ------------------------------------------------------------------------------------------------
 template <int V>
+__device__ __forceinline__ void rod_divide_one(const RodParams& P, const u64 i);
+template <int V>
 __global__ void __launch_bounds__(128) k_rod_divide(const RodParams P) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n) return;
-    const u64 i = P.first + t;
-    if (!P.div_flag[i]) return;
+    // one thread per entry of the division list (a few per mille of the rods divide in a step: a thread per rod
+    // spent 0.09 ms at 2 M rods on reading flags with the 254 registers of this kernel)
+    const u32 nl = P.n_div[1];
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < nl; e += gridDim.x * blockDim.x) rod_divide_one<V>(P, P.div_list[e]);
+}
+template <int V>
+__device__ __forceinline__ void rod_divide_one(const RodParams& P, const u64 i) {
     const u64 cap = P.cap;
     const u32 vk = P.key[i];
     const u32 lo = P.start[vk], hi = P.start[vk + 1];
@@ -753,10 +760,11 @@ __global__ void __launch_bounds__(128) k_rod_divide(const RodParams P) {
 }
 
 // Voxel::id_counter += 2 per division (one for the mother, one for the daughter)
-__global__ void k_rod_bump_counters(const u8* __restrict__ div_flag, const u32* __restrict__ key,
-                                    u32* __restrict__ id_counter, u64 n) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && div_flag[i]) atomicAdd(&id_counter[key[i]], 2u);
+__global__ void k_rod_bump_counters(const u32* __restrict__ div_list, const u32* __restrict__ n_div,
+                                    const u32* __restrict__ key, u32* __restrict__ id_counter) {
+    const u32 nl = n_div[1];
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < nl; e += gridDim.x * blockDim.x)
+        atomicAdd(&id_counter[key[div_list[e]]], 2u);
 }
 
 // insert_initial_cells (chili/datastructures.rs:278-299): voxel.id_counter = number of initial cells

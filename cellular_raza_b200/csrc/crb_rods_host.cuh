@@ -31,7 +31,7 @@ int rods_alloc(crb_sim* s) {
     if ((rc = rods_alloc_state(s, s->RY, true, true))) return rc;
     if ((rc = rods_alloc_state(s, s->RT, true, false))) return rc;
     if ((rc = dalloc(s, &s->div_flag, s->cap_total)) || (rc = dalloc(s, &s->id_counter, s->nvox + 1)) ||
-        (rc = dalloc(s, &s->n_div_dev, 4)))
+        (rc = dalloc(s, &s->n_div_dev, 4)) || (rc = dalloc(s, &s->div_list, s->cap_total)))
         return rc;
     CU(s, cudaMemsetAsync(s->div_flag, 0, s->cap_total, s->stream));
     CU(s, cudaMemsetAsync(s->id_counter, 0, (s->nvox + 1) * sizeof(u32), s->stream));
@@ -65,6 +65,7 @@ RodParams rods_params(crb_sim* s) {
     P.div_flag = s->div_flag;
     P.id_counter = s->id_counter;
     P.n_div = s->n_div_dev;
+    P.div_list = s->div_list;
     P.force_out = s->force_out;
     P.nb_out = s->nb_out;
     P.err = s->err;
@@ -118,8 +119,8 @@ void rods_launch_update_v(crb_sim* s, const RodParams& P) {
 }
 template <int V>
 void rods_launch_divide_v(crb_sim* s, const RodParams& P) {
-    const u32 grid = blocks_for(P.n, 128);
-    if (grid) k_rod_divide<V><<<grid, 128, 0, s->stream>>>(P);
+    // a fixed grid that strides over the division list (its length lives on the device)
+    if (P.n) k_rod_divide<V><<<148 * 2, 128, 0, s->stream>>>(P);
 }
 template <int V>
 void rods_launch_ingest_v(crb_sim* s, const RodParams& P) {
@@ -350,7 +351,7 @@ int rods_compute(crb_sim* s, bool last) {
     if (s->cfg.noise_mode == CRB_NOISE_TABLE && s->uni.mp[RMP_DIFF] != 0.0 && s->noise_cursor >= s->noise_steps)
         return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
     CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
-    CU(s, cudaMemsetAsync(s->n_div_dev, 0, sizeof(u32), s->stream));
+    CU(s, cudaMemsetAsync(s->n_div_dev, 0, 2 * sizeof(u32), s->stream));
     RodParams P = rods_params(s);
     P.save_prev = last ? 1 : 0;
     stage_begin(s, 0);
@@ -370,8 +371,7 @@ int rods_compute(crb_sim* s, bool last) {
     stage_begin(s, 4);
     rods_launch_divide(s, P);
     if (s->n)
-        k_rod_bump_counters<<<blocks_for(s->n, 256), 256, 0, s->stream>>>(s->div_flag + s->G, s->key + s->G,
-                                                                         s->id_counter, s->n);
+        k_rod_bump_counters<<<148, 256, 0, s->stream>>>(s->div_list, s->n_div_dev, s->key, s->id_counter);
     stage_end(s, 4, s->n ? 2 : 0);
     u32 n_div = 0;
     CU(s, cudaMemcpyAsync(&n_div, s->n_div_dev, sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
