@@ -440,7 +440,7 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
     agents = list(agents)
     if agents and isinstance(agents[0], RodAgent):
         return _run_rods(domain, agents, settings, aspects, mechanics_solver_order=mechanics_solver_order,
-                         pair_weight_mode=pair_weight_mode, device=device, capacity=capacity)
+                         pair_weight_mode=pair_weight_mode, device=device, capacity=capacity, devices=devices)
     unsupported = set(aspects) - {"Mechanics", "Interaction", "DomainForce"}
     if unsupported or "Mechanics" not in aspects:
         raise SimulationError(_abi.CRB_ERR_INVALID_ARG, f"aspects {sorted(unsupported)} are outside the hot path (SURVEY.md §8)")
@@ -746,7 +746,8 @@ def _matrix_json(m: np.ndarray):
 
 
 def _run_rods(domain, agents: Sequence[RodAgent], settings: Settings, aspects, *, mechanics_solver_order: int,
-              pair_weight_mode: int, device: int, capacity: int | None = None) -> StorageAccess:
+              pair_weight_mode: int, device: int, capacity: int | None = None,
+              devices: Sequence[int] | None = None) -> StorageAccess:
     """``run_simulation!(domain, agents, settings, aspects: [Mechanics, Interaction, Cycle, NeighborSensing],
     zero_force_default: |c| MatrixXx3::zeros(nrows))`` of examples/bacterial_rods/src/main.rs:202-210.
     The rod count changes when rods divide (``CycleEvent::Division``), identifiers follow
@@ -792,7 +793,16 @@ def _run_rods(domain, agents: Sequence[RodAgent], settings: Settings, aspects, *
     def rod_sub_of(vox):
         return np.searchsorted(_firsts, np.asarray(vox, dtype=np.int64), side="right") - 1
 
-    sim = RodSimulation(cfg)
+    if devices is not None and len(devices) > 1:
+        # one slab of voxel planes per listed GPU, driven by this host thread; the gathered views come back in the
+        # order of the single-device run (rank order = ascending voxel), so the snapshots are the same bit for bit
+        import copy
+
+        from .slabs import LocalRodSlabGroup
+
+        sim = LocalRodSlabGroup(lambda: copy.copy(cfg), len(devices), devices=list(devices))
+    else:
+        sim = RodSimulation(cfg)
     try:
         sim.set_agents(pos, vel, mp, ip)
         sb = settings.storage

@@ -282,3 +282,40 @@ def test_run_simulation_over_slabs_equals_single_device(crb_lib):
             assert np.array_equal(c["pos"], d["pos"]) and np.array_equal(c["vel"], d["vel"])
             assert c["voxel"] == d["voxel"]
             assert np.array_equal(c["aux"]["positions"], d["aux"]["positions"])
+
+
+def test_bacterial_rods_over_slabs_through_run_simulation(crb_lib):
+    """run_simulation(..., devices=[0, 0, 0]) for rod agents: three slabs of voxel planes driven by one host thread
+    (LocalRodSlabGroup) store the snapshots of the single-device run bit for bit — identifiers incl.
+    Division(voxel, counter), parents, positions, voxels."""
+    from cellular_raza_b200 import workloads
+
+    w = workloads.bacterial_rods(3, 2, rods_per_tile=6, spring_length_range=(5.5, 5.99))
+    pos = w.pos.copy()
+    pos[:, :, 0] += 180e-6  # rod clusters next to the slab faces x = 200 um and 400 um (24 planes, 3 slabs)
+    keep = pos[:, :, 0].max(axis=1) < w.cfg_kwargs["domain_max"][0] - 1e-6
+    agents = []
+    for k in np.nonzero(keep)[0]:
+        mp, ip = w.mech_params[k], w.inter_params[k]
+        mech = cr.RodMechanics(pos[k].tolist(), w.vel[k].tolist(), mp[0], mp[1], mp[2], mp[3], mp[4])
+        agents.append(cr.RodAgent(mech, cr.RodInteraction(cr.MorsePotential(ip[0], ip[1], ip[2], ip[3])),
+                                  growth_rate=mp[5], spring_length_threshold=mp[6], growth_base_rate=mp[7]))
+    kw = w.cfg_kwargs
+    domain = cr.CartesianCuboidRods(cr.CartesianCuboid.from_boundaries_and_n_voxels(
+        kw["domain_min"], kw["domain_max"], [int(x) for x in kw["n_voxels"]]))
+
+    def run(devices):
+        settings = cr.Settings(8, cr.FixedStepsize.from_partial_save_steps(0.0, kw["dt"], 90, 30),
+                               cr.StorageBuilder(priority=["Memory"]))
+        return cr.run_simulation(domain, agents, settings, devices=devices,
+                                 aspects=["Mechanics", "Interaction", "Cycle", "NeighborSensing"])
+
+    one, three = run(None), run([0, 0, 0])
+    assert one.cells.get_all_iterations() == three.cells.get_all_iterations() == [0, 30, 60, 90]
+    for it in (30, 60, 90):
+        a, b = one.cells.memory[it], three.cells.memory[it]
+        assert list(a) == list(b)  # same identifiers in the same save order
+        for key in a:
+            assert np.array_equal(a[key]["pos"], b[key]["pos"]) and a[key]["voxel"] == b[key]["voxel"]
+            assert a[key]["parent"] == b[key]["parent"]
+    assert len(one.cells.memory[90]) > len(agents)  # rods divided
