@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_force_tile2(const KParams P, c
     constexpr int nthreads = NT;  // launch contract: blockDim.x == NT (128: 4 CTAs/SM, 256: 2 CTAs/SM)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = nthreads >> 5;
-    constexpr int NE = 4;  // candidates evaluated per drain iteration and lane
+    // candidates evaluated per drain iteration and lane (interleaved FP64 chains).  Same-box sweep, round 2: 2 / 3 / 4
+    // are within 0.2 % of each other for the species potential; Morse (a longer chain per pair, 128 registers) is
+    // 1.8 % faster with 3
+    constexpr int NE = INTER == CRB_INT_MORSE ? 3 : 4;
     const Grid& g = P.g;
     const int n1 = g.ng[1], n2 = g.ng[2];
 
