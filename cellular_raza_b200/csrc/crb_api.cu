@@ -630,7 +630,7 @@ int sort_into_place(crb_sim* s, u64 n_src, u64 n_new, bool save_prev, bool inges
     stage_begin(s, 2);
     int nl = 0;
     if (n_src) {
-        k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt,
+        k_fill<<<blocks_for(n_src, 256 * kFillPerThread), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt,
                                                              s->tmp_idx, s->G, n_src, dev_counts ? s->cnt + 1 : nullptr);
         ++nl;
     }

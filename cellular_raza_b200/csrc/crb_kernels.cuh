@@ -771,16 +771,29 @@ __global__ void __launch_bounds__(kScanThreads)
 // ------------------------------------------------------------------------------------------------
 // n_dev != nullptr: the number of sources is read from device memory (crb_slab_step: the host never learns the
 // counts between steps; the grid is sized by the capacity)
-__global__ void k_fill(const u32* __restrict__ newkey, const u32* __restrict__ rank_arb,
-                       const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 first, u64 n,
-                       const u64* __restrict__ n_dev = nullptr) {
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+// Four sources per thread (one per 256-thread stripe of the CTA's 1,024: every access stays coalesced): eight
+// independent loads, then four gathers of start_new[], then four stores — the pass is a chain of three dependent
+// memory operations per source and nothing else, so the loads in flight per thread decide its speed (one source per
+// thread: 0.040 ms at 8 M cells, a tenth of the rebuild).
+constexpr int kFillPerThread = 4;
+__global__ void __launch_bounds__(256) k_fill(const u32* __restrict__ newkey, const u32* __restrict__ rank_arb,
+                                              const u32* __restrict__ start_new, u32* __restrict__ tmp_idx, u64 first, u64 n,
+                                              const u64* __restrict__ n_dev = nullptr) {
     if (n_dev) n = *n_dev;
-    if (t >= n) return;
-    const u64 i = first + t;
-    const u32 k = newkey[i];
-    if (k == CRB_KEY_GONE) return;  // migrated to a neighbouring slab
-    tmp_idx[start_new[k] + rank_arb[i]] = (u32)i;
+    const u64 t0 = (u64)blockIdx.x * (256 * kFillPerThread) + threadIdx.x;
+    u32 k[kFillPerThread], r[kFillPerThread];
+#pragma unroll
+    for (int j = 0; j < kFillPerThread; ++j) {
+        const u64 t = t0 + (u64)j * 256;
+        k[j] = t < n ? __ldg(&newkey[first + t]) : CRB_KEY_GONE;
+        r[j] = t < n ? __ldg(&rank_arb[first + t]) : 0u;
+    }
+    u32 sb[kFillPerThread];
+#pragma unroll
+    for (int j = 0; j < kFillPerThread; ++j) sb[j] = k[j] != CRB_KEY_GONE ? __ldg(&start_new[k[j]]) : 0u;  // GONE: migrated away
+#pragma unroll
+    for (int j = 0; j < kFillPerThread; ++j)
+        if (k[j] != CRB_KEY_GONE) tmp_idx[sb[j] + r[j]] = (u32)(first + t0 + (u64)j * 256);
 }
 
 struct ReorderParams {

@@ -182,7 +182,7 @@ int rods_sort_into_place(crb_sim* s, u64 n_src, bool save_prev, u64 n_new) {
     stage_begin(s, 2);
     int nl = 0;
     if (n_src) {
-        k_fill<<<blocks_for(n_src, 256), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt, s->tmp_idx,
+        k_fill<<<blocks_for(n_src, 256 * kFillPerThread), 256, 0, s->stream>>>(s->newkey, s->rank_arb, s->start_alt, s->tmp_idx,
                                                              s->G, n_src);
         RodReorderParams R;
         std::memset(&R, 0, sizeof(R));
