@@ -80,3 +80,30 @@ def test_neighbor_exchange_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def test_rod_slab_workload_lies_in_its_own_planes():
+    """bacterial_rods_slab (bench.py --gpus N --workload bacterial_rods): every rank generates the rods of its own
+    slab of the N-times-longer domain, ids are globally unique, and the owner computed from the mean of the vertices
+    (SortCells::get_voxel_index_of of CartesianCuboidRods) is the generating rank"""
+    from cellular_raza_b200 import workloads
+    from cellular_raza_b200.slabs import rank_of_position, slab_planes
+
+    world = 4
+    parts = [workloads.bacterial_rods_slab(2000, r, world) for r in range(world)]
+    nv = parts[0].cfg_kwargs["n_voxels"]
+    assert all((p.cfg_kwargs["n_voxels"] == nv).all() for p in parts)  # the GLOBAL domain on every rank
+    ids = np.concatenate([p.extra["ids"] for p in parts])
+    assert len(np.unique(ids)) == len(ids)
+    planes = slab_planes(int(nv[0]), world)
+    dx0 = parts[0].cfg_kwargs["dx"][0]
+    for r, p in enumerate(parts):
+        V = p.pos.shape[1]
+        mean0 = sum(p.pos[:, v, 0] for v in range(V)) / float(V)
+        owner = rank_of_position(mean0, 0.0, dx0, int(nv[0]), world)
+        assert (owner == r).all()
+        first, count = planes[r]
+        assert mean0.min() >= first * dx0 and mean0.max() < (first + count) * dx0
+    # one rank of one is the plain workload
+    a, b = workloads.bacterial_rods_slab(500, 0, 1), workloads.bacterial_rods(10, 10, seed=[5, 0], spring_length_range=(4.0, 6.0))
+    assert np.array_equal(a.pos, b.pos)
