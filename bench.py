@@ -322,8 +322,8 @@ def run_b200(args):
 EXTRA_LEGS = (
     # key, workload, cells, steps, warmup, e2e steps
     ("configs[0] cell_sorting as shipped (1,600 cells)", "cell_sorting_as_shipped", 1600, 2000, 50, 20),
-    ("configs[1] cell_sorting 1 M cells", "cell_sorting", 1_000_000, 20, 5, 5),
-    ("configs[2] Brownian3D + Morse 8 M cells (1 GPU)", "brownian_morse", 8_000_000, 8, 3, 3),
+    ("configs[1] cell_sorting 1 M cells", "cell_sorting", 1_000_000, 20, 5, 12),
+    ("configs[2] Brownian3D + Morse 8 M cells (1 GPU)", "brownian_morse", 8_000_000, 8, 3, 8),
     ("configs[3] bacterial_rods 2 M rods", "bacterial_rods", 2_000_000, 8, 3, 3),
 )
 

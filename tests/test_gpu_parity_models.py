@@ -229,3 +229,28 @@ def test_no_interaction_aspect(oracle_lib, crb_lib):
     assert perr <= 1e-13 and verr <= 1e-13 and not key_diff.any()
     dev.close()
     ora.close()
+
+
+def test_set_iteration_rewinds_the_device_generator(crb_lib):
+    """CRB_NOISE_PHILOX is keyed by (rng_seed, agent id, iteration): crb_set_agents keeps the step counter (a host that
+    re-uploads its population every step must keep drawing fresh numbers), crb_set_iteration puts it back — the same
+    population from the same counter repeats its trajectory bit for bit, from another counter it does not."""
+    w = workloads.brownian_morse(20_000, 12.0 * 13, noise_mode=_abi.CRB_NOISE_PHILOX)
+    sim = DeviceSimulation(w.config(rng_seed=11))
+    sim.set_uniform_params(w.mech_params[0], w.inter_params[0])
+
+    def run(start_iteration=None):
+        sim.set_agents(w.pos, w.vel, None, None, w.species)
+        if start_iteration is not None:
+            sim.set_iteration(start_iteration)
+        it0 = sim.iteration
+        sim.step(6)
+        pos, _, ids, _ = sim.get_agents()
+        return it0, pos[np.argsort(ids)]
+
+    it_a, a = run(0)
+    it_b, b = run()          # the counter went on: other numbers
+    it_c, c = run(0)         # rewound: the first run again
+    assert (it_a, it_b, it_c) == (0, 6, 0)
+    assert np.array_equal(a, c) and not np.array_equal(a, b)
+    sim.close()
