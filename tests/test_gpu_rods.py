@@ -308,3 +308,47 @@ def test_random_contribution_philox_statistics(crb_lib):
     c = np.corrcoef(flat.T)
     off = c - np.eye(c.shape[0])
     assert np.abs(off).max() < 5 / np.sqrt(n)
+
+
+@pytest.mark.parametrize("n_threads", [1, 4])
+def test_device_equals_the_independent_transcription(crb_lib, n_threads):
+    """the device against tests/ref_transcript_rods.py (a literal Python transcription of the Rust that never reads
+    oracle/), without the oracle in the loop: forces <= 1e-12, neighbour counts exact, three steps with growth"""
+    import ref_transcript as R
+    import ref_transcript_rods as T
+
+    V = 5
+    w = workloads.bacterial_rods(2, 2, rods_per_tile=7, n_threads=n_threads, spring_length_range=(2.0, 3.5))
+    kw = w.cfg_kwargs
+    cub = R.CartesianCuboid.from_boundaries_and_n_voxels(list(kw["domain_min"]), list(kw["domain_max"]), [int(x) for x in kw["n_voxels"]])
+    t = T.RodsTranscript(cub, V, n_threads, kw["dt"], 2)
+    cells, states = [], {}
+    for k in range(w.n):
+        mp, ip = w.mech_params[k], w.inter_params[k]
+        m = T.RodMechanics(T.flat(w.pos[k].tolist()), T.flat(w.vel[k].tolist()), mp[0], mp[1], mp[2], mp[3], mp[4], V)
+        cells.append(R.Cell(k, m, T.RodInteraction(R.MorsePotential(*ip), V)))
+        states[k] = T.RodCellState(mp[5], mp[6], mp[7])
+    t.set_cells(cells)
+    dev = RodSimulation(w.config())
+    dev.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    keys = dev.get_agents()[2][:, 1].astype(int)
+    fd, nbd = dev.debug_forces(), dev.debug_neighbor_counts()
+    ft, nbt = t.forces(), t.neighbor_counts()
+    assert nbd.sum() > 50
+    for row, k in enumerate(keys):
+        f_t, abs_sum = ft[k]
+        f_t = np.array(f_t).reshape(V, 3)
+        assert np.abs(fd[row] - f_t).max() / max(np.abs(f_t).max(), abs_sum, 1e-300) <= FORCE_TOL
+        assert int(nbd[row]) == nbt[k]
+    L = max(kw["domain_max"])
+    for _ in range(3):
+        dev.step(1)
+        t.step(states=states)
+    pd, vd, ident, _, vox = dev.get_agents()
+    mp = dev.get_params()
+    got = {c.key: (c, p) for p, c, _ in t.cells_in_order()}
+    for row, k in enumerate(ident[:, 1].astype(int)):
+        c, plain = got[k]
+        assert np.abs(pd[row].reshape(-1) - np.array(c.mech.pos)).max() / L <= TRAJ_TOL
+        assert int(vox[row]) == plain
+        assert mp[row, 5] == states[k].growth_rate
