@@ -633,9 +633,13 @@ def run_rods(args, dev_id: int):
     }
 
     # ---- e2e: host buffers in, host buffers out, every step (the rod count is pinned by re-uploading the
-    # same n rods; positions/velocities of the previous step's first n rods are fed back) ---------------
+    # same n rods every step).  Two handles alternate; a rod step always synchronises (the division count is read
+    # back), so the upload of population k + 1 is queued on the OTHER handle before the step of population k is
+    # called: the host link carries upload k + 1 and download k - 1 while the device steps population k. ----------
     e2e = None
     if not args.no_e2e:
+        import ctypes
+
         nn = w.n
         V = 5
         hp = torch.from_numpy(np.ascontiguousarray(w.pos)).pin_memory()
@@ -643,26 +647,61 @@ def run_rods(args, dev_id: int):
         hm = torch.from_numpy(np.ascontiguousarray(w.mech_params)).pin_memory()
         hi = torch.from_numpy(np.ascontiguousarray(w.inter_params)).pin_memory()
         cap_out = int(nn * 1.2) + 16
-        op = torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()
-        ov = torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()
-        lib, h = sim._lib, sim._h
+        lib = sim._lib
+        sim2 = RodSimulation(w.config(device=dev_id))
+        hs = [sim._h, sim2._h]
+        outs = [(torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory(),
+                 torch.empty((cap_out, V, 3), dtype=torch.float64).pin_memory()) for _ in range(2)]
         e2e_steps = getattr(args, "e2e_steps", None) or args.steps
-        for k in range(2 + e2e_steps):
-            if k == 2:
+        warm = 2
+        total = warm + e2e_steps
+
+        def chk(rc, h):
+            if rc:
+                raise RuntimeError((lib.crb_last_error(h) or b"").decode())
+
+        def upload(k):
+            h = hs[k % 2]
+            chk(lib.crb_set_agents_async(h, nn, hp.data_ptr(), hv.data_ptr(), hm.data_ptr(), hi.data_ptr(), None, None), h)
+
+        upload(0)
+        pending = [False, False]
+        n_out = ctypes.c_uint64()
+        for k in range(total):
+            if k == warm:
+                for j in range(2):
+                    if pending[j]:
+                        chk(lib.crb_snapshot_wait(hs[j], ctypes.byref(n_out)), hs[j])
+                        pending[j] = False
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-            rc = lib.crb_set_agents(h, nn, hp.data_ptr(), hv.data_ptr(), hm.data_ptr(), hi.data_ptr(), None, None)
-            rc = rc or lib.crb_step(h, 1)
-            rc = rc or lib.crb_get_agents(h, cap_out, op.data_ptr(), ov.data_ptr(), None, None)
-            if rc:
-                raise RuntimeError(lib.crb_last_error(h))
+            j = k % 2
+            h = hs[j]
+            if k + 1 < total:
+                upload(k + 1)  # (its previous download reads the packed snapshot buffer, not the state)
+            chk(lib.crb_step(h, 1), h)
+            if pending[1 - j]:
+                chk(lib.crb_snapshot_wait(hs[1 - j], ctypes.byref(n_out)), hs[1 - j])
+                pending[1 - j] = False
+            chk(lib.crb_snapshot_async(h, cap_out, outs[j][0].data_ptr(), outs[j][1].data_ptr(), None, None, None, None, None), h)
+            pending[j] = True
+        for j in range(2):
+            if pending[j]:
+                chk(lib.crb_snapshot_wait(hs[j], ctypes.byref(n_out)), hs[j])
         torch.cuda.synchronize()
         dt_e2e = time.perf_counter() - t0
+        sim2.close()
+        h2d = int(nn * (2 * V * 24 + 8 * 8 + 4 * 8))
+        d2h = int(int(n_out.value) * 2 * V * 24)
+        floor_ms = pcie_copy_floor_ms(h2d, d2h, max(e2e_steps, 5))
         e2e = {
             "value": nn * e2e_steps / dt_e2e, "unit": UNIT,
-            "h2d_bytes_per_step": int(nn * (2 * V * 24 + 8 * 8 + 4 * 8)), "d2h_bytes_per_step": int(nn * 2 * V * 24),
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": dt_e2e / e2e_steps * 1e3,
-            "what": "crb_set_agents(pinned host pos, vel, mech, inter rows) + crb_step(1) + crb_get_agents(host pos, vel) per step",
+            "pcie_copy_floor_ms_per_step": floor_ms,
+            "what": "per step: crb_set_agents_async(pinned host pos, vel, mech, inter rows; rows checked on the device) + "
+                    "crb_step(1) + crb_snapshot_async(pinned host pos, vel) + crb_snapshot_wait; two handles alternate, "
+                    "the next upload is queued before the (synchronising) rod step",
         }
 
     cpu = None

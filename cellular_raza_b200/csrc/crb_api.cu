@@ -101,6 +101,7 @@ struct crb_sim {
     u32* tile_sums = nullptr;
     u32 n_tiles = 0;
     double* stage = nullptr;  // cap * 8 doubles staging for agent-major host rows
+    double* rod_up = nullptr;  // rods, crb_set_agents_async: pos, vel, parameter rows and ids of one upload side by side
     double* force_out = nullptr;
     double* noise = nullptr;
     u64 noise_steps = 0, noise_ids = 0, noise_cursor = 0;
@@ -679,7 +680,13 @@ void graphs_invalidate(crb_sim* s) {
 }
 
 int check_latch(crb_sim* s) {
-    CU(s, cudaMemcpyAsync(s->err_host, s->err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (s->kernels_only && s->rods) {
+        // pipelined rod handle: the latch travels by a store into the page-locked words instead of a copy-engine
+        // transfer (which would queue behind the snapshot download of the handle this one alternates with)
+        k_rod_report<<<1, 32, 0, s->stream>>>(nullptr, s->err, nullptr, s->err_host);
+    } else {
+        CU(s, cudaMemcpyAsync(s->err_host, s->err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    }
     CU(s, cudaStreamSynchronize(s->stream));
     if (s->err_host[1]) {
         const int code = s->err_host[0];
@@ -706,6 +713,10 @@ int check_latch(crb_sim* s) {
                 return fail(s, code, "slab exchange: the neighbouring slab uses another parameter mode (uniform row vs "
                                      "per-agent columns, or a different uniform row): declare the same row with "
                                      "crb_set_uniform_params on every rank, or on none");
+            case CRB_ERR_INVALID_ARG:
+                return fail(s, code, "rods: all RodMechanics parameters except spring_length and growth_rate, and all "
+                                     "interaction parameters, must be uniform (row " + std::to_string(id) +
+                                         " of the rows given to crb_set_agents_async differs from row 0)");
             default: return fail(s, code, "device error " + std::to_string(code));
         }
     }
@@ -1227,11 +1238,12 @@ static int set_agents_impl(crb_sim* s, uint64_t n, const double* pos, const doub
                            const uint64_t* ids, bool async) {
     if (!s) return CRB_ERR_INVALID_ARG;
     graphs_invalidate(s);
-    if (async && s->rods) return fail(s, CRB_ERR_STATE, "crb_set_agents_async: not available for CRB_MECH_ROD");
     if (n > s->cap) return fail(s, CRB_ERR_CAPACITY, "more agents than capacity");
     if (n && !pos) return fail(s, CRB_ERR_INVALID_ARG, "pos is required");
     CU(s, cudaSetDevice((int)s->cfg.device));
-    if (s->rods) return rods_set_agents(s, n, pos, vel, mech_params, inter_params, (const u64*)ids);
+    if (s->rods)
+        return async ? rods_set_agents_async(s, n, pos, vel, mech_params, inter_params, (const u64*)ids)
+                     : rods_set_agents(s, n, pos, vel, mech_params, inter_params, (const u64*)ids);
     const int D = s->D;
     // uniform-parameter fast path: all agents share one parameter row
     if (s->uniform_declared) {
@@ -2476,7 +2488,8 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
                        double* hist_dx, double* hist_dv, uint32_t* hist_len) {
     if (!s) return CRB_ERR_INVALID_ARG;
     if (!s->have_agents) return fail(s, CRB_ERR_STATE, "no agents");
-    if (s->rods) return fail(s, CRB_ERR_STATE, "rods: use crb_get_agents / crb_get_aux");
+    if (s->rods && (hist_dx || hist_dv || hist_len))
+        return fail(s, CRB_ERR_INVALID_ARG, "rods: the ring buffers are read with crb_get_aux");
     if (s->step_open || s->interior_state) return fail(s, CRB_ERR_STATE, "snapshot inside an open slab step");
     if (cap < s->n) return fail(s, CRB_ERR_CAPACITY, "output buffers too small");
     CU(s, cudaSetDevice((int)s->cfg.device));
@@ -2488,7 +2501,7 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
         CU(s, cudaEventCreateWithFlags(&s->ev_snap_done, cudaEventDisableTiming));
     }
     const u64 n = s->n;
-    const int D = s->D;
+    const int D = s->rods ? 3 * s->V : s->D;  // doubles per position row (rods: V vertices x 3)
     const u64 per = (u64)(2 * D + 2 + 4 * D + 1);  // doubles per agent: pos, vel, id, voxel, hx, hv, hlen (padded)
     if (s->snap_cap < s->cap) {
         if (s->snap) cudaFree(s->snap);
@@ -2514,7 +2527,9 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
                                                               c[6], c[7], n);
         s->launches++;
     };
-    if (n) {
+    if (s->rods) {
+        if ((rc = rods_snapshot_pack(s, b_pos, b_vel, b_id, b_vox, pos, vel, ids, voxel))) return rc;
+    } else if (n) {
         if (pos) pack(b_pos, D, s->X.pos);
         if (vel) {
             if (s->cfg.mechanics_kind == CRB_MECH_BROWNIAN)

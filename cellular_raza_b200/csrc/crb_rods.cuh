@@ -871,6 +871,59 @@ __global__ void k_rod_pack_u64(u64* __restrict__ rows, const u64* __restrict__ p
     if (i >= n) return;
     for (int w = 0; w < W; ++w) rows[i * W + w] = planes[(u64)w * cap + i];
 }
+// crb_set_agents_async: the check of the parameter rows (every RodMechanics / MorsePotential field except
+// spring_length and growth_rate is one value for all rods) and the extraction of the two per-rod columns happen on
+// the device, from the rows as they were uploaded; a mismatch is latched like any other device-side error
+struct RodUniformRow {
+    double mp[8], ip[4];
+};
+__global__ void k_rod_param_rows(const double* __restrict__ mech_rows, const double* __restrict__ inter_rows,
+                                 const RodUniformRow U, double* __restrict__ len, double* __restrict__ growth,
+                                 u64 n, int* err) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool bad = false;
+    double l = U.mp[3], g = U.mp[5];
+    if (mech_rows) {
+        const double* r = mech_rows + i * 8;
+        bad = (r[0] != U.mp[0]) | (r[1] != U.mp[1]) | (r[2] != U.mp[2]) | (r[4] != U.mp[4]) | (r[6] != U.mp[6]) |
+              (r[7] != U.mp[7]);
+        l = r[3];
+        g = r[5];
+    }
+    if (inter_rows) {
+        const double* r = inter_rows + i * 4;
+        bad |= (r[0] != U.ip[0]) | (r[1] != U.ip[1]) | (r[2] != U.ip[2]) | (r[3] != U.ip[3]);
+    }
+    len[i] = l;
+    growth[i] = g;
+    if (bad) latch_error(err, CRB_ERR_INVALID_ARG, i);
+}
+// clears as a kernel (see k_zero_cols: a copy-engine memset of a pipelined handle queues behind the host transfer of
+// the handle it alternates with)
+struct RodZeroRanges {
+    double* p[8];
+    u64 count[8];
+    u8* b[2];
+    u64 nb[2];
+    int n;
+};
+__global__ void k_rod_zero(const RodZeroRanges Z) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < Z.n; ++k)
+        for (u64 i = t0; i < Z.count[k]; i += stride) Z.p[k][i] = 0.0;
+    for (int k = 0; k < 2; ++k)
+        for (u64 i = t0; i < Z.nb[k]; i += stride) Z.b[k][i] = 0;
+}
+// the division count and / or the error latch into page-locked host words (device-accessible under unified
+// addressing), read by the host after the stream synchronises
+__global__ void k_rod_report(const u32* __restrict__ n_div, const int* __restrict__ err, u64* host_count, int* host_err) {
+    const int t = threadIdx.x;
+    if (host_count && t == 0) host_count[0] = n_div[0];
+    if (host_err && t < 4) host_err[t] = err[t];
+    __threadfence_system();
+}
 __global__ void k_rod_init_ident(RodState X, const u64* __restrict__ ids, u64 cap, u64 n, u64 first) {
     const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;

@@ -344,14 +344,134 @@ int rods_set_agents(crb_sim* s, u64 n, const double* pos, const double* vel, con
     return 0;
 }
 
+// crb_set_agents_async for rods: everything is queued on the handle's stream and nothing waits for the device.  All
+// host transfers go first (into one arena: positions, velocities, parameter rows, ids side by side), then the kernels
+// (a transfer queued behind a kernel would wait for that kernel to find free SMs next to the step of the handle this
+// one alternates with); clears are kernels; the parameter rows are checked on the device (k_rod_param_rows); an
+// ingestion error stays latched until the next synchronising call (crb_step of a rod handle always is one).
+int rods_set_agents_async(crb_sim* s, u64 n, const double* pos, const double* vel, const double* mech_params,
+                          const double* inter_params, const u64* ids) {
+    const int W = 3 * s->V;
+    if (s->world > 1) return fail(s, CRB_ERR_STATE, "crb_set_agents_async: not available for rods on a slab handle");
+    if (!mech_params && !s->uniform_declared)
+        return fail(s, CRB_ERR_INVALID_ARG, "mech_params and inter_params are required (or crb_set_uniform_params)");
+    if (n && mech_params) {
+        if (!inter_params && !s->uniform_declared)
+            return fail(s, CRB_ERR_INVALID_ARG, "mech_params and inter_params are required");
+        for (int k = 0; k < 8; ++k) s->uni.mp[k] = mech_params[k];  // (page-locked host memory: readable here)
+        if (inter_params)
+            for (int k = 0; k < 4; ++k) s->uni.ip[k] = inter_params[k];
+    }
+    if (n && !(s->uni.ip[1] * (s->uni.ip[0] + s->uni.ip[0]) < 700.0))
+        return fail(s, CRB_ERR_CALC, "CalcError: MorsePotential potential_stiffness * 2 radius >= 700 overflows exp in f64");
+    if (s->uni.mp[RMP_DIFF] != 0.0 && s->cfg.noise_mode == CRB_NOISE_NONE)
+        return fail(s, CRB_ERR_INVALID_ARG,
+                    "rods: diffusion_constant != 0 needs noise_mode CRB_NOISE_TABLE or CRB_NOISE_PHILOX "
+                    "(RodMechanics::get_random_contribution, bacterial_rods.rs:215-240)");
+    s->uniform = true;
+    s->kernels_only = true;
+    int rc;
+    const u64 per = (u64)(2 * W + 8 + 4 + 1);
+    if (!s->rod_up && (rc = dalloc(s, &s->rod_up, s->cap * per))) return rc;
+    double* u_pos = s->rod_up;
+    double* u_vel = u_pos + n * W;
+    double* u_mp = u_vel + n * W;
+    double* u_ip = u_mp + n * 8;
+    u64* u_id = (u64*)(u_ip + n * 4);
+    if (n) {
+        CU(s, cudaMemcpyAsync(u_pos, pos, n * W * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (vel) CU(s, cudaMemcpyAsync(u_vel, vel, n * W * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (mech_params) CU(s, cudaMemcpyAsync(u_mp, mech_params, n * 8 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (mech_params && inter_params)
+            CU(s, cudaMemcpyAsync(u_ip, inter_params, n * 4 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (ids) CU(s, cudaMemcpyAsync(u_id, ids, n * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    }
+    RodZeroRanges Z;
+    std::memset(&Z, 0, sizeof(Z));
+    for (double* p : {s->RT.h1x, s->RT.h1v, s->RT.h0x, s->RT.h0v}) {
+        Z.p[Z.n] = p;
+        Z.count[Z.n++] = s->cap_total * W;
+    }
+    if (!vel) {
+        Z.p[Z.n] = s->RT.vel;
+        Z.count[Z.n++] = s->cap_total * W;
+    }
+    Z.b[0] = s->RT.hlen;
+    Z.nb[0] = s->cap_total;
+    Z.b[1] = s->div_flag;
+    Z.nb[1] = s->cap_total;
+    k_rod_zero<<<148 * 8, 256, 0, s->stream>>>(Z);
+    k_zero_u32<<<blocks_for(s->nvox + 1, 256), 256, 0, s->stream>>>(s->count_new, s->nvox + 1, nullptr, 0, nullptr, 0);
+    s->launches += 2;
+    if (n) {
+        k_rod_unpack<<<blocks_for(n, 256), 256, 0, s->stream>>>(u_pos, s->RT.pos + s->G, W, s->cap_total, n);
+        if (vel) k_rod_unpack<<<blocks_for(n, 256), 256, 0, s->stream>>>(u_vel, s->RT.vel + s->G, W, s->cap_total, n);
+        RodUniformRow U;
+        for (int k = 0; k < 8; ++k) U.mp[k] = s->uni.mp[k];
+        for (int k = 0; k < 4; ++k) U.ip[k] = s->uni.ip[k];
+        k_rod_param_rows<<<blocks_for(n, 256), 256, 0, s->stream>>>(mech_params ? u_mp : nullptr,
+                                                                   mech_params && inter_params ? u_ip : nullptr, U,
+                                                                   s->RT.len + s->G, s->RT.growth + s->G, n, s->err);
+        k_rod_init_ident<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->RX, ids ? u_id : nullptr, s->cap_total, n, s->G);
+        s->launches += vel ? 4 : 3;
+    }
+    s->n = n;
+    RodParams P = rods_params(s);
+    rods_launch_ingest(s, P);
+    s->launches += n ? 1 : 0;
+    if ((rc = rods_sort_into_place(s, n, true, n))) return rc;
+    k_rod_init_counters<<<blocks_for(s->nvox, 256), 256, 0, s->stream>>>(s->start, s->id_counter, s->nvox);
+    s->launches++;
+    CU(s, cudaGetLastError());
+    s->have_agents = true;
+    s->aux_settable = false;
+    s->last_step_n = 0;
+    s->last_divisions = 0;
+    s->noise_cursor = 0;
+    return 0;
+}
+
+// crb_snapshot_async for rods: positions and velocities as agent-major V x 3 rows (the layout of crb_get_agents), the
+// number of the identifier, the voxel; packed on the handle's stream, copied on the side stream
+int rods_snapshot_pack(crb_sim* s, double* b_pos, double* b_vel, u64* b_id, u64* b_vox, bool pos, bool vel, bool ids,
+                       bool voxel) {
+    const u64 n = s->n;
+    const int W = 3 * s->V;
+    if (!n) return 0;
+    if (pos) {
+        k_rod_pack<<<blocks_for(n, 256), 256, 0, s->stream>>>(b_pos, s->RX.pos + s->G, W, s->cap_total, n);
+        s->launches++;
+    }
+    if (vel) {
+        k_rod_pack<<<blocks_for(n, 256), 256, 0, s->stream>>>(b_vel, s->RX.vel + s->G, W, s->cap_total, n);
+        s->launches++;
+    }
+    if (ids) {
+        k_copy_u64<<<blocks_for(n, 256), 256, 0, s->stream>>>(b_id, s->RX.ident + s->cap_total + s->G, n);
+        s->launches++;
+    }
+    if (voxel) {
+        const u64 base = (u64)s->g.p0 * s->g.ng[1] * s->g.ng[2];
+        k_global_keys<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->key + s->G, b_vox, base, n);
+        s->launches++;
+    }
+    CU(s, cudaGetLastError());
+    return 0;
+}
+
 // stage A of one step: pair forces + per-rod update + divisions for the owned rods (ghost planes must hold the
 // neighbours' boundary rods on a slab); the number of daughters is read back (the sources of the rebuild are
 // [G, G + n + n_div))
 int rods_compute(crb_sim* s, bool last) {
     if (s->cfg.noise_mode == CRB_NOISE_TABLE && s->uni.mp[RMP_DIFF] != 0.0 && s->noise_cursor >= s->noise_steps)
         return fail(s, CRB_ERR_STATE, "noise table exhausted: call crb_set_noise");
-    CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
-    CU(s, cudaMemsetAsync(s->n_div_dev, 0, 2 * sizeof(u32), s->stream));
+    if (s->kernels_only) {
+        k_zero_u32<<<blocks_for(s->nvox + 1, 256), 256, 0, s->stream>>>(s->count_new, s->nvox + 1, s->n_div_dev, 2, nullptr, 0);
+        s->launches++;
+    } else {
+        CU(s, cudaMemsetAsync(s->count_new, 0, (s->nvox + 1) * sizeof(u32), s->stream));
+        CU(s, cudaMemsetAsync(s->n_div_dev, 0, 2 * sizeof(u32), s->stream));
+    }
     RodParams P = rods_params(s);
     P.save_prev = last ? 1 : 0;
     stage_begin(s, 0);
@@ -374,8 +494,15 @@ int rods_compute(crb_sim* s, bool last) {
         k_rod_bump_counters<<<148, 256, 0, s->stream>>>(s->div_list, s->n_div_dev, s->key, s->id_counter);
     stage_end(s, 4, s->n ? 2 : 0);
     u32 n_div = 0;
-    CU(s, cudaMemcpyAsync(&n_div, s->n_div_dev, sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
-    CU(s, cudaStreamSynchronize(s->stream));
+    if (s->kernels_only) {  // (see check_latch)
+        k_rod_report<<<1, 32, 0, s->stream>>>(s->n_div_dev, nullptr, s->cnt_host + 4, nullptr);
+        s->launches++;
+        CU(s, cudaStreamSynchronize(s->stream));
+        n_div = (u32)s->cnt_host[4];
+    } else {
+        CU(s, cudaMemcpyAsync(&n_div, s->n_div_dev, sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaStreamSynchronize(s->stream));
+    }
     CU(s, cudaGetLastError());
     if (s->n + n_div > s->cap + (s->world > 1 ? s->mcap : 0)) {
         check_latch(s);

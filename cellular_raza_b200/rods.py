@@ -42,6 +42,39 @@ class RodSimulation(DeviceSimulation):
         ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
         self._check(self._lib.crb_set_agents(self._h, n, _ptr(pos), _ptr(vel), _ptr(mp), _ptr(ip), None, _ptr(ids)))
 
+    def set_agents_async(self, pos, vel, mech_params, inter_params, ids=None):
+        """``crb_set_agents_async``: the rows are staged in page-locked buffers of this handle and only queued; the
+        parameter rows are checked on the device and a mismatch is reported by the next ``step``."""
+        pos = np.asarray(pos, dtype=np.float64)
+        n = pos.shape[0]
+        bufs = {"pos": self._pinned("a_pos", (n, self.V, self.dim), np.float64),
+                "mp": self._pinned("a_mp", (n, self.n_mech), np.float64),
+                "ip": self._pinned("a_ip", (n, self.n_inter), np.float64)}
+        bufs["pos"][:] = pos.reshape(n, self.V, self.dim)
+        bufs["mp"][:] = np.broadcast_to(np.asarray(mech_params, dtype=np.float64), (n, self.n_mech))
+        bufs["ip"][:] = np.broadcast_to(np.asarray(inter_params, dtype=np.float64), (n, self.n_inter))
+        if vel is not None:
+            bufs["vel"] = self._pinned("a_vel", (n, self.V, self.dim), np.float64)
+            bufs["vel"][:] = np.asarray(vel, dtype=np.float64).reshape(n, self.V, self.dim)
+        if ids is not None:
+            bufs["ids"] = self._pinned("a_ids", (n,), np.uint64)
+            bufs["ids"][:] = ids
+        p = lambda k: _ptr(bufs[k]) if k in bufs else None
+        self._check(self._lib.crb_set_agents_async(self._h, n, p("pos"), p("vel"), p("mp"), p("ip"), None, p("ids")))
+
+    def snapshot_async(self, aux: bool = False):
+        """``crb_snapshot_async`` for rods: positions, velocities, identifier numbers, voxels (the ring buffers of a rod
+        are read with :meth:`get_aux`).  Returns a token for :meth:`snapshot_wait`."""
+        if aux:
+            raise ValueError("rods: the ring buffers are not part of a snapshot (get_aux)")
+        n = self.n_agents
+        bufs = {"pos": self._pinned("pos", (n, self.V, self.dim), np.float64),
+                "vel": self._pinned("vel", (n, self.V, self.dim), np.float64),
+                "ids": self._pinned("ids", (n,), np.uint64), "vox": self._pinned("vox", (n,), np.uint64)}
+        self._check(self._lib.crb_snapshot_async(self._h, n, _ptr(bufs["pos"]), _ptr(bufs["vel"]), _ptr(bufs["ids"]),
+                                                 _ptr(bufs["vox"]), None, None, None))
+        return bufs
+
     def get_agents(self):
         """-> (pos[n,V,3], vel[n,V,3], ident[n,3], parent[n,3], voxel[n]) in device order."""
         n = self.n_agents

@@ -191,7 +191,12 @@ int crb_set_agents(crb_sim* sim, uint64_t n, const double* pos, const double* ve
  * queued on the handle's stream.  The host buffers must be page-locked (crb_host_alloc) and stay untouched until the
  * next synchronising call on the handle (crb_sync, crb_step, crb_get_*, crb_snapshot_wait).  Ingestion errors
  * (BoundaryError / IndexError of an agent outside the domain) are latched on the device and returned by crb_sync /
- * crb_step.  crb_set_aux cannot follow this form.  Point agents only. */
+ * crb_step.  crb_set_aux cannot follow this form.
+ * Rods (CRB_MECH_ROD, single-device handles): the parameter rows are uploaded as given and checked ON THE DEVICE (every
+ * RodMechanics / MorsePotential field except spring_length and growth_rate must equal row 0); a row that differs is
+ * latched as CRB_ERR_INVALID_ARG and returned by the next crb_step.  From then on the handle's clears, its division
+ * count and its error latch travel as kernels / stores into page-locked words, never as copy-engine operations that
+ * would queue behind the transfers of the handle it alternates with. */
 int crb_set_agents_async(crb_sim* sim, uint64_t n, const double* pos, const double* vel,
                          const double* mech_params, const double* inter_params,
                          const uint8_t* species, const uint64_t* ids);
@@ -339,7 +344,10 @@ int crb_slab_step_async(crb_sim* sim, uint64_t n_steps);
  * handle's stream and starts the device-to-host copies on a side stream; it returns at once and
  * crb_step may be called while the copies run.  The host buffers (pinned memory from crb_host_alloc
  * for a truly asynchronous copy) belong to the library until crb_snapshot_wait returns; one snapshot
- * is in flight at a time (a second call waits for the first). */
+ * is in flight at a time (a second call waits for the first).
+ * Rods: pos / vel are the V x 3 rows of crb_get_agents, ids the number of the identifier (crb_get_identifiers has the
+ * triples), voxel as for point agents; the ring buffers are not part of a rod snapshot (hist_* must be NULL:
+ * CRB_ERR_INVALID_ARG otherwise; crb_get_aux reads them). */
 int crb_snapshot_async(crb_sim* sim, uint64_t cap, double* pos, double* vel, uint64_t* ids,
                        uint64_t* voxel, double* hist_dx, double* hist_dv, uint32_t* hist_len);
 int crb_snapshot_wait(crb_sim* sim, uint64_t* n_agents);

@@ -352,3 +352,66 @@ def test_device_equals_the_independent_transcription(crb_lib, n_threads):
         assert np.abs(pd[row].reshape(-1) - np.array(c.mech.pos)).max() / L <= TRAJ_TOL
         assert int(vox[row]) == plain
         assert mp[row, 5] == states[k].growth_rate
+
+
+def test_rods_async_pipeline_equals_synchronous_calls(crb_lib):
+    """crb_set_agents_async + crb_step + crb_snapshot_async for CRB_MECH_ROD on two alternating handles (the rods e2e
+    loop of bench.py: the next upload is queued before the step of the current handle; parameter rows checked on the
+    device; clears and the division count as kernels) leave exactly the bits of crb_set_agents + crb_step +
+    crb_get_agents — with rods that divide, so that the agent count changes between upload and snapshot."""
+    import ctypes as C
+
+    from cellular_raza_b200.device import _ptr
+
+    w = workloads.bacterial_rods(4, 4, rods_per_tile=6, spring_length_range=(5.9, 5.99))
+    n, V = w.n, 5
+    n_steps = 6
+    ref = RodSimulation(w.config())
+    want = []
+    pops = [(w.pos + k * 1e-9, w.vel) for k in range(4)]  # four populations that differ in every coordinate
+    for k in range(4):
+        ref.set_agents(pops[k][0], pops[k][1], w.mech_params, w.inter_params)
+        ref.step(n_steps)
+        pos, vel, ident, _, vox = ref.get_agents()
+        want.append((pos, vel, ident[:, 1].copy(), vox))
+    assert any(len(x[0]) > n for x in want), "the test needs divisions"
+    ref.close()
+
+    sims = [RodSimulation(w.config()) for _ in range(2)]
+    lib = sims[0]._lib
+    cap = 2 * n
+    nn = C.c_uint64()
+    hm = sims[0]._pinned("mp", (n, 8), np.float64)
+    hi = sims[0]._pinned("ip", (n, 4), np.float64)
+    hm[:], hi[:] = w.mech_params, w.inter_params
+    bufs = []
+    for s in sims:
+        bufs.append(dict(in_p=s._pinned("in_pos", (n, V, 3), np.float64), in_v=s._pinned("in_vel", (n, V, 3), np.float64),
+                         out_p=s._pinned("out_pos", (cap, V, 3), np.float64), out_v=s._pinned("out_vel", (cap, V, 3), np.float64),
+                         out_i=s._pinned("out_ids", (cap,), np.uint64), out_x=s._pinned("out_vox", (cap,), np.uint64)))
+    got = []
+    for k in range(4):
+        s, b = sims[k % 2], bufs[k % 2]
+        b["in_p"][:], b["in_v"][:] = pops[k]
+        s._check(lib.crb_set_agents_async(s._h, n, _ptr(b["in_p"]), _ptr(b["in_v"]), _ptr(hm), _ptr(hi), None, None))
+        s._check(lib.crb_step_async(s._h, n_steps))
+        s._check(lib.crb_snapshot_async(s._h, cap, _ptr(b["out_p"]), _ptr(b["out_v"]), _ptr(b["out_i"]), _ptr(b["out_x"]),
+                                        None, None, None))
+        s._check(lib.crb_snapshot_wait(s._h, C.byref(nn)))
+        m = int(nn.value)
+        assert m == s.n_agents
+        got.append((b["out_p"][:m].copy(), b["out_v"][:m].copy(), b["out_i"][:m].copy(), b["out_x"][:m].copy()))
+    for g, x in zip(got, want):
+        for a, c in zip(g, x):
+            assert np.array_equal(a, c)
+    # the ring buffers of a rod are not part of a snapshot
+    s = sims[0]
+    assert lib.crb_snapshot_async(s._h, cap, None, None, None, None, _ptr(bufs[0]["out_p"]), None, None) != 0
+    # a parameter row that differs (not spring_length / growth_rate) is found on the device and reported by the
+    # next synchronising call
+    hm[n // 2, 4] *= 2.0
+    s._check(lib.crb_set_agents_async(s._h, n, _ptr(bufs[0]["in_p"]), _ptr(bufs[0]["in_v"]), _ptr(hm), _ptr(hi), None, None))
+    with pytest.raises(Exception, match="uniform"):
+        s.step(1)
+    for s in sims:
+        s.close()
