@@ -2502,7 +2502,8 @@ int crb_snapshot_async(crb_sim* s, uint64_t cap, double* pos, double* vel, uint6
     }
     const u64 n = s->n;
     const int D = s->rods ? 3 * s->V : s->D;  // doubles per position row (rods: V vertices x 3)
-    const u64 per = (u64)(2 * D + 2 + 4 * D + 1);  // doubles per agent: pos, vel, id, voxel, hx, hv, hlen (padded)
+    // doubles per agent: pos, vel, id, voxel, hx, hv, hlen (padded); a rod snapshot carries no ring buffers
+    const u64 per = s->rods ? (u64)(2 * D + 2) : (u64)(2 * D + 2 + 4 * D + 1);
     if (s->snap_cap < s->cap) {
         if (s->snap) cudaFree(s->snap);
         if (s->snap_hlen_host) cudaFreeHost(s->snap_hlen_host);
