@@ -415,3 +415,22 @@ def test_rods_async_pipeline_equals_synchronous_calls(crb_lib):
         s.step(1)
     for s in sims:
         s.close()
+
+
+def test_rod_wrapper_async_calls(crb_lib):
+    """RodSimulation.set_agents_async / snapshot_async / snapshot_wait (the object wrappers over the calls of the test
+    above) against the synchronous wrappers"""
+    w = workloads.bacterial_rods(4, 4, rods_per_tile=6, spring_length_range=(5.9, 5.99))
+    a, b = RodSimulation(w.config()), RodSimulation(w.config())
+    a.set_agents(w.pos, w.vel, w.mech_params, w.inter_params)
+    b.set_agents_async(w.pos, w.vel, w.mech_params, w.inter_params)
+    a.step(8)
+    b.step(8)
+    pos, vel, ident, _, vox = a.get_agents()
+    sp, sv, si, sx = b.snapshot_wait(b.snapshot_async())
+    assert len(pos) > w.n
+    assert np.array_equal(sp, pos) and np.array_equal(sv, vel) and np.array_equal(si, ident[:, 1]) and np.array_equal(sx, vox)
+    with pytest.raises(ValueError):
+        b.snapshot_async(aux=True)
+    a.close()
+    b.close()
