@@ -174,3 +174,51 @@ def test_geometry_pins_of_the_reference():
     subs = d.create_subdomains(4)
     assert len(subs) == 4 and sum(len(v) for _, v in subs) == 125
     assert d.get_all_voxel_indices()[:3] == [(0, 0, 0), (0, 0, 1), (0, 0, 2)]
+
+
+# ---- randomised sweep: every potential, oracle (C++) against the transcript (Python) ------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_pair_forces_of_every_potential_random_sweep(oracle_lib, dim):
+    """2,000 random pairs per potential and dimension — distances from deep inside the clamp region to beyond the
+    cutoff, equal and different species, both sign conventions of the species potential — through
+    ``oracle_pair_force`` and through the transcript: the two restatements agree to 1e-13 of the pair force on both
+    agents (pow / exp of libm on both sides)."""
+    from oracle.chili_oracle import pair_force
+
+    rng = np.random.default_rng(20 + dim)
+    worst = 0.0
+    for _ in range(2000):
+        d = rng.standard_normal(dim)
+        d /= np.linalg.norm(d)
+        own = rng.uniform(-50.0, 50.0, dim)
+        cases = []
+        # species potential (cell_sorting/src/main.rs:43-97 and the benchmark copy)
+        rad, rad_ext = rng.uniform(3.0, 8.0, 2)
+        strength, rel = rng.uniform(0.5, 3.0), rng.uniform(1.1, 2.0)
+        so, se = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        r = rng.choice([rng.uniform(1e-3, 0.4 * rad), rng.uniform(0.4 * rad, rel * (rad + rad_ext)),
+                        rng.uniform(rel * (rad + rad_ext), 3.0 * rel * (rad + rad_ext))])
+        for kind, bench in ((0, False), (1, True)):
+            cases.append((kind, r, [rad, strength, rel], so, rad_ext, se,
+                          R.CellSpecificInteraction(so, rad, strength, rel, bench=bench), (rad_ext, se)))
+        # Morse (interaction.rs:151-260)
+        mr, ms, mc, mst = rng.uniform(1.0, 4.0), rng.uniform(0.1, 1.0), rng.uniform(8.0, 14.0), rng.uniform(0.01, 1.0)
+        cases.append((2, rng.uniform(0.05, 16.0), [mr, ms, mc, mst], 0, rad_ext, 0, R.MorsePotential(mr, ms, mc, mst), rad_ext))
+        # BoundLennardJones (interaction.rs:112-145)
+        le, lsg, lb, lc = rng.uniform(0.1, 2.0), rng.uniform(1.0, 4.0), rng.uniform(1.0, 20.0), rng.uniform(6.0, 12.0)
+        cases.append((3, rng.uniform(0.3, 14.0), [le, lsg, lb, lc], 0, 0.0, 0, R.BoundLennardJones(le, lsg, lb, lc), None))
+        # Mie (interaction.rs:330-389)
+        en = rng.uniform(3.0, 12.0)
+        em = rng.uniform(1.0, en - 0.5)
+        ir, ist, ib, ic = rng.uniform(1.0, 4.0), rng.uniform(0.05, 1.0), rng.uniform(1.0, 20.0), rng.uniform(6.0, 14.0)
+        cases.append((4, rng.uniform(0.3, 16.0), [ir, ist, ib, ic, en, em], 0, rad_ext, 0,
+                      R.MiePotential(ir, ist, ib, ic, en, em), rad_ext))
+        for kind, dist, params, s_own, ext_radius, s_ext, model, ext_info in cases:
+            ext = own - dist * d
+            fo, fe = pair_force(kind, own, ext, params, s_own, ext_radius, s_ext)
+            to, te = model.calculate_force_between(list(own), None, list(ext), None, ext_info)
+            to, te = np.array(to), np.array(te)
+            scale = max(np.abs(to).max(), np.abs(te).max(), 1e-300)
+            worst = max(worst, np.abs(fo - to).max() / scale, np.abs(fe - te).max() / scale)
+            assert (to == 0.0).all() == (fo == 0.0).all()  # the cutoff decides the same way on both sides
+    assert worst <= 1e-13, worst
