@@ -222,3 +222,62 @@ def test_pair_forces_of_every_potential_random_sweep(oracle_lib, dim):
             worst = max(worst, np.abs(fo - to).max() / scale, np.abs(fe - te).max() / scale)
             assert (to == 0.0).all() == (fo == 0.0).all()  # the cutoff decides the same way on both sides
     assert worst <= 1e-13, worst
+
+
+def test_geometry_random_sweep_oracle_against_transcript(oracle_lib):
+    """random cuboids in 1 - 3 dimensions with 1 - 6 subdomains: voxel index of random positions (faces, the lower
+    and upper corner, outside, NaN; per-step and setup variants), neighbour lists (ascending plain index) and the
+    subdomain of every voxel — C++ oracle == transcript, exactly."""
+    from cellular_raza_b200 import _abi
+    from cellular_raza_b200.device import make_config
+
+    rng = np.random.default_rng(77)
+    ran = 0
+    for trial in range(60):
+        dim = int(rng.integers(1, 4))
+        nv = [int(x) for x in rng.integers(1, 7, dim)]
+        mn = [float(x) for x in rng.uniform(-20.0, 5.0, dim)]
+        mx = [mn[i] + float(rng.uniform(3.0, 40.0)) for i in range(dim)]
+        n_threads = int(rng.integers(1, 7))
+        n_vox = int(np.prod(nv))
+        if R.get_decomp_res(n_vox, n_threads) is None:
+            continue
+        dom = R.CartesianCuboid.from_boundaries_and_n_voxels(mn, mx, nv)
+        cfg = make_config(dim=dim, mechanics_kind=_abi.CRB_MECH_NEWTON_DAMPED, interaction_kind=_abi.CRB_INT_MORSE,
+                          domain_min=mn, domain_max=mx, n_voxels=np.array(nv, dtype=np.uint64), dx=dom.dx, dt=0.1,
+                          capacity=16, ref_n_subdomains=n_threads)
+        ora = ChiliOracle(cfg)
+        try:
+            strides = [int(np.prod(nv[i + 1:])) for i in range(dim)]
+            plain = lambda idx: sum(int(a) * s for a, s in zip(idx, strides))
+            # subdomain of every voxel (create_subdomains: contiguous chunks of the enumeration)
+            sub_t = {}
+            for k, (_key, voxels) in enumerate(dom.create_subdomains(n_threads)):
+                for v in voxels:
+                    sub_t[plain(v)] = k
+            subs_o = [ora.sub_of(p) for p in range(n_vox)]
+            # (chunk keys are consecutive from 0, so the k-th group is subdomain k)
+            assert subs_o == [sub_t[p] for p in range(n_vox)]
+            # neighbours
+            for idx in dom.get_all_voxel_indices():
+                want = sorted(plain(q) for q in dom.get_neighbor_voxel_indices(idx))
+                assert list(ora.neighbors(plain(idx))) == want
+            # voxel index of positions
+            pts = [list(rng.uniform(np.array(mn) - 1.0, np.array(mx) + 1.0)) for _ in range(30)]
+            pts += [list(mn), list(mx), [np.nextafter(a, -np.inf) for a in mn], [np.nextafter(a, np.inf) for a in mn],
+                    [mn[i] + dom.dx[i] * float(rng.integers(0, nv[i] + 1)) for i in range(dim)], [float("nan")] * dim]
+            for p in pts:
+                for setup in (False, True):
+                    try:
+                        want = (dom.get_voxel_index_of_raw if setup else dom.get_index_of)(p)
+                    except R.BoundaryError:
+                        want = None
+                    got = ora.voxel_index(p, setup_variant=setup)
+                    if want is None:
+                        assert got is None, (p, setup, got)
+                    else:
+                        assert got is not None and tuple(int(x) for x in got) == want, (p, setup, got, want)
+        finally:
+            ora.close()
+        ran += 1
+    assert ran >= 40
