@@ -281,3 +281,54 @@ def test_geometry_random_sweep_oracle_against_transcript(oracle_lib):
             ora.close()
         ran += 1
     assert ran >= 40
+
+
+def _make_ref_derived():
+    import importlib.util
+    import sys
+    from pathlib import Path
+
+    if "make_ref_derived" in sys.modules:
+        return sys.modules["make_ref_derived"]
+    spec = importlib.util.spec_from_file_location("make_ref_derived", Path(__file__).resolve().parents[1] / "tools" / "make_ref_derived.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["make_ref_derived"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_chili_steps_oracle_against_transcript(oracle_lib, seed):
+    """whole steps of randomly drawn cases, built in memory by the fixture generator (nothing is written): dimension
+    2 / 3, every mechanics and potential, 1 - 5 emulated subdomains, solver orders 0 / 1 / 2, heterogeneous
+    parameters, noise tables — forces, trajectories, voxel keys, save order, ring fill and migration sets of the C++
+    oracle against the transcript"""
+    import random
+
+    mod = _make_ref_derived()
+    rng = random.Random(1000 + seed)
+    dim = rng.choice([2, 3])
+    inter = rng.choice([
+        {"kind": "cell_sorting", "radius": 6.0, "strength": 2.0, "range": 1.5},
+        {"kind": "cell_sorting_bench", "radius": 6.0, "strength": 2.0, "range": 1.5},
+        {"kind": "morse", "radius": 3.0, "stiffness": 0.5, "cutoff": 12.0, "strength": 0.5},
+        {"kind": "bound_lj", "epsilon": 0.5, "sigma": 3.0, "bound": 4.0, "cutoff": 10.0},
+        {"kind": "mie", "radius": 2.0, "strength": 0.3, "bound": 5.0, "cutoff": 10.0, "en": 4.0, "em": 2.0}])
+    edge = {"cell_sorting": 18.0, "cell_sorting_bench": 18.0, "morse": 12.0, "bound_lj": 10.0, "mie": 10.0}[inter["kind"]]
+    mech = rng.choice([{"kind": "newton", "damping": 1.2, "mass": 1.1},
+                       {"kind": "brownian", "diffusion": 0.3, "kt": 0.3},
+                       {"kind": "langevin", "mass": 1.5, "damping": 0.7, "kt": 0.4}])
+    nv = [rng.randint(2, 4) for _ in range(dim)]
+    mx = [edge * n + rng.uniform(0.0, 0.9 * edge) for n in nv]  # (from_boundaries_and_interaction_range floors)
+    noise = mech["kind"] != "newton"
+    dt = {"cell_sorting": 0.1, "cell_sorting_bench": 0.1, "morse": 0.02, "bound_lj": 0.005, "mie": 0.005}[inter["kind"]]
+    fix = mod.build(f"random_{seed}", dim=dim, mn=[0.0] * dim, mx=mx, interaction_range=edge,
+                    n_threads=rng.randint(1, 5), dt=dt, order=rng.choice([0, 1, 2]), mech=mech, inter=inter,
+                    n_agents=rng.randint(50, 90), seed=seed, steps=[1, 2, 4], vel_scale=rng.choice([0.0, 5.0, 20.0]),
+                    noise=noise, hetero=rng.random() < 0.5, write=False)
+    ora = ChiliOracle(ref_derived.config(fix))
+    try:
+        ferr, serr = ref_derived.check(ora, fix)
+    finally:
+        ora.close()
+    assert ferr <= 1e-12 and serr <= 1e-11

@@ -49,7 +49,7 @@ def crafted_pairs_3d(cutoff, r_clamp):
 
 
 def build(name, *, dim, mn, mx, interaction_range=None, n_voxels=None, n_threads, dt, order, mech, inter, n_agents,
-          seed, steps, vel_scale=0.0, crafted=None, noise=False, hetero=False, crafted_vel=None):
+          seed, steps, vel_scale=0.0, crafted=None, noise=False, hetero=False, crafted_vel=None, write=True):
     rng = random.Random(seed)
     if interaction_range is not None:
         dom = R.CartesianCuboid.from_boundaries_and_interaction_range(mn, mx, interaction_range)
@@ -127,6 +127,8 @@ def build(name, *, dim, mn, mx, interaction_range=None, n_voxels=None, n_threads
             out["checkpoints"].append({"step": k + 1, "pos": P, "vel": V, "voxel": vox, "save_order": order_keys,
                                        "hist_len": hist_len,
                                        "migrations": sorted(map(list, t.last_migrations))})
+    if not write:  # (tests/test_ref_transcript.py builds random cases in memory)
+        return out
     OUT.mkdir(exist_ok=True)
     path = OUT / f"ref_derived_{name}.json"
     path.write_text(json.dumps(out))
