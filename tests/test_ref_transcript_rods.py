@@ -158,3 +158,35 @@ def test_random_contribution_of_the_step():
     got = {c.key: c for _, c, _ in t.cells_in_order()}
     for row, k in enumerate(keys):
         assert np.abs(pos[row].reshape(-1) - np.array(got[k].mech.pos)).max() / L <= 1e-12
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_rod_populations(seed):
+    """randomly drawn rod populations (seed of the generator, 1 - 3 tiles per axis, 4 - 9 rods per tile, 1 - 6 emulated
+    subdomains, solver orders 0 / 1 / 2): forces, neighbour counts and two growing steps, oracle == transcript"""
+    rng = np.random.default_rng(500 + seed)
+    n_threads, order = int(rng.integers(1, 7)), int(rng.integers(0, 3))
+    w = workloads.bacterial_rods(int(rng.integers(1, 4)), int(rng.integers(1, 4)), rods_per_tile=int(rng.integers(4, 10)),
+                                 seed=600 + seed, n_threads=n_threads, solver_order=order, spring_length_range=(2.0, 3.5))
+    mech = w.mech_params.copy()
+    o = ro.RodsOracle(w.config(), n_threads=2)
+    o.set_agents(w.pos, w.vel, mech, w.inter_params)
+    t, states = _transcript(w, mech, n_threads, order)
+    fo, ab, nbo = o.forces()
+    keys, *_ = _oracle_by_key(o)
+    ft, nbt = t.forces(), t.neighbor_counts()
+    for row, k in enumerate(keys):
+        f_t, abs_sum = ft[k]
+        f_t = np.array(f_t).reshape(V, 3)
+        assert np.abs(fo[row] - f_t).max() / max(np.abs(f_t).max(), abs_sum, 1e-300) <= 1e-12
+        assert int(nbo[row]) == nbt[k]
+    L = max(w.cfg_kwargs["domain_max"])
+    for _ in range(2):
+        o.step(1)
+        t.step(states=states)
+    keys, pos, vel, vox = _oracle_by_key(o)
+    got = {c.key: (c, p) for p, c, _ in t.cells_in_order()}
+    for row, k in enumerate(keys):
+        c, plain = got[k]
+        assert np.abs(pos[row].reshape(-1) - np.array(c.mech.pos)).max() / L <= 1e-12
+        assert int(vox[row]) == plain
