@@ -722,7 +722,7 @@ def run_rods(args, dev_id: int):
         "gpu_launches": launches, "clocks": clocks,
         "stage_ms_per_step": {"force_integrate": force_ms / args.steps, "divide": divide_ms / args.steps,
                               "scan": scan_ms / args.steps, "reorder": reorder_ms / args.steps},
-        "note": "not the headline workload: k_rod_force is a per-rod kernel, not yet warp-cooperative (DESIGN.md §9)",
+        "note": "not the headline workload: k_rod_force is a per-rod kernel bound by the FP64 pipe (69 % under ncu; DESIGN.md §9)",
     }
     sim.close()
     return line
