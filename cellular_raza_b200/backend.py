@@ -364,20 +364,57 @@ class StorageManager:
             its |= {int(p.name) for p in self.json_dir.iterdir() if p.is_dir()}
         return sorted(its)
 
+    @staticmethod
+    def _key(identifier) -> tuple:
+        """serde form of a ``CellIdentifier`` (``{"Initial": n}`` / ``{"Division": [voxel, counter]}``, cell.rs:18-25)
+        or a tuple -> the tuple the Memory storage uses: ("Initial", n) / ("Division", voxel, counter)"""
+        if isinstance(identifier, dict):
+            (kind, val), = identifier.items()
+            return (kind, *val) if isinstance(val, (list, tuple)) else (kind, val)
+        return tuple(identifier) if isinstance(identifier, (list, tuple)) else identifier
+
     def load_all_elements_at_iteration(self, iteration: int) -> dict:
-        """-> {identifier tuple: {"pos", "vel", "id", "voxel", "aux"}}"""
+        """-> {identifier tuple: {"pos", "vel", "id", "voxel", "aux"}} (:937-944)"""
         if iteration in self.memory:
             return self.memory[iteration]
         out = {}
+        if self.json_dir is None:
+            return out
         for f in sorted((self.json_dir / f"{iteration:020d}").glob("batch_*.json")):
             for e in json.loads(f.read_text())["data"]:
                 cell, aux = e["element"]
-                ident = tuple(e["identifier"].items())[0]
-                out[ident] = {"cell": cell["cell"], "aux": aux}
+                out[self._key(e["identifier"])] = {"cell": cell["cell"], "aux": aux}
         return out
 
     def load_all_elements(self) -> dict[int, dict]:
+        """:951-964 (a BTreeMap: ascending iterations)"""
         return {it: self.load_all_elements_at_iteration(it) for it in self.get_all_iterations()}
+
+    def load_single_element(self, iteration: int, identifier):
+        """:863-871: the element, or None when the identifier is not stored at that iteration"""
+        return self.load_all_elements_at_iteration(iteration).get(self._key(identifier))
+
+    def load_element_history(self, identifier) -> dict[int, dict]:
+        """:899-931: every occurrence of the element in ascending iterations; like the reference, gathering stops at
+        the first iteration that no longer holds the identifier once it has been seen (an element lives over one
+        uninterrupted span)"""
+        out, started = {}, False
+        for it in self.get_all_iterations():
+            e = self.load_single_element(it, identifier)
+            if e is not None:
+                started = True
+                out[it] = e
+            elif started:
+                break
+        return out
+
+    def load_all_element_histories(self) -> dict[tuple, dict[int, dict]]:
+        """:969-994: identifier -> {iteration: element}"""
+        out: dict[tuple, dict[int, dict]] = {}
+        for it, elements in self.load_all_elements().items():
+            for ident, e in elements.items():
+                out.setdefault(ident, {})[it] = e
+        return out
 
 
 @dataclass

@@ -112,3 +112,42 @@ def test_f32_building_blocks_are_refused_with_a_message(name, twin):
         getattr(cr, name)([0.0, 0.0, 0.0], [0.0, 0.0, 0.0], 1.0, 1.0)
     assert e.value.code == _abi.CRB_ERR_INVALID_ARG
     assert twin in str(e.value) and "f64" in str(e.value)
+
+
+def test_storage_read_side_like_storage_interface_load(tmp_path):
+    """StorageInterfaceLoad (cellular_raza-core/src/storage/concepts.rs:863-994): single element, element history
+    (one uninterrupted span, as the reference's doc example :880-898), all histories — from memory and from the
+    SerdeJson layout (iteration directories of batch files), with Initial and Division identifiers"""
+    import json
+
+    states = {0: ["E1", "E2", "E3"], 1: ["E1", "E2", "E3", "E4"], 2: ["E1", "E2", "E3", "E4"], 3: ["E1", "E2", "E4"],
+              4: ["E2", "E4"], 5: ["E2", "E4", "E5"], 6: ["E4", "E5"]}
+    ident = {"E1": ("Initial", 1), "E2": ("Initial", 2), "E3": ("Initial", 3), "E4": ("Division", 7, 1), "E5": ("Division", 7, 2)}
+    mem = cr.StorageManager(None)
+    disk = cr.StorageManager(tmp_path / "cells" / "json")
+    for it, names in states.items():
+        mem.memory[it] = {ident[n]: {"pos": [float(it)], "name": n} for n in names}
+        d = disk.json_dir / f"{it:020d}"
+        d.mkdir(parents=True)
+        data = [{"identifier": cr._ident_json(ident[n]),
+                 "element": [{"identifier": cr._ident_json(ident[n]), "parent": None, "cell": {"name": n, "it": it}}, {"mechanics": {}}]}
+                for n in names]
+        (d / f"batch_{0:020d}_{0:020d}.json").write_text(json.dumps({"data": data[:2]}))
+        (d / f"batch_{1:020d}_{0:020d}.json").write_text(json.dumps({"data": data[2:]}))
+    for sm in (mem, disk):
+        assert sm.get_all_iterations() == list(range(7))
+        assert sorted(sm.load_all_elements_at_iteration(3)) == sorted(ident[n] for n in states[3])
+        assert sm.load_single_element(0, ("Division", 7, 1)) is None
+        assert sm.load_single_element(1, {"Division": [7, 1]}) is not None
+        assert sorted(sm.load_element_history(("Initial", 1))) == [0, 1, 2, 3]
+        assert sorted(sm.load_element_history({"Division": [7, 2]})) == [5, 6]
+        assert sorted(sm.load_element_history(("Initial", 3))) == [0, 1, 2]
+        hist = sm.load_all_element_histories()
+        assert {k: sorted(v) for k, v in hist.items()} == {
+            ident[n]: [it for it, names in states.items() if n in names] for n in ident}
+        assert list(sm.load_all_elements()) == list(range(7))
+    assert disk.load_single_element(5, ("Division", 7, 2))["cell"] == {"name": "E5", "it": 5}
+    # an identifier that re-appears after a gap: the reference stops at the gap (:880-898 "invalid state")
+    mem.memory[8] = {("Initial", 1): {"pos": [8.0]}}
+    assert sorted(mem.load_element_history(("Initial", 1))) == [0, 1, 2, 3]
+    assert cr.StorageManager(None).load_all_elements_at_iteration(0) == {}
