@@ -20,9 +20,9 @@ The Rust host crate a maintainer would add does exactly the same through the sam
 from __future__ import annotations
 
 import json
-import threading
 import math
 import os
+import threading
 import time as _time
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -306,6 +306,14 @@ class SpringDomainForce:
 
 
 # ---- time (cellular_raza-core/src/time.rs) ---------------------------------------------------------
+def _round_to_usize(x: float) -> int:
+    """``F::round`` (half AWAY from zero, unlike Python's ``round``) followed by ``to_usize`` (time.rs:203-219)"""
+    r = math.floor(abs(x) + 0.5)
+    if x < 0.0 and r > 0:
+        raise ValueError("An error in casting of float type to usize occurred")
+    return int(r)
+
+
 @dataclass
 class FixedStepsize:
     t0: float
@@ -321,8 +329,19 @@ class FixedStepsize:
             raise ValueError("No savepoints specified. Simulation will not save any results.")
         if any(t0 > p for p in pts):
             raise ValueError("Invalid time configuration! Evaluation time point is before starting time point.")
-        its = [int(round((p - t0) / dt)) for p in pts]
+        its = [_round_to_usize((p - t0) / dt) for p in pts]
         return cls(t0, dt, its, its[-1])
+
+    @classmethod
+    def from_partial_save_freq(cls, t0: float, dt: float, t_max: float, save_freq: int) -> "FixedStepsize":
+        """:135-168 as written: ``maximum_iterations = round((t_max - t0) / dt)`` and one PartialSave event at every
+        iteration n of ``(0..maximum_iterations).step_by(save_freq)`` — the end point itself is NOT a save event
+        (exclusive range), so the run ends ``maximum_iterations`` iterations in without storing its last state unless
+        ``maximum_iterations - 1`` is a multiple of ``save_freq``."""
+        if save_freq <= 0:
+            raise ValueError("save_freq must be positive")  # (step_by(0) panics)
+        mx = _round_to_usize((t_max - t0) / dt)
+        return cls(t0, dt, list(range(0, mx, save_freq)), mx)
 
     @classmethod
     def from_partial_save_steps(cls, t0: float, dt: float, n_steps: int, save_interval: int) -> "FixedStepsize":
@@ -563,8 +582,9 @@ def run_simulation(domain: CartesianCuboid, agents: Sequence[Agent], settings: S
             pending = (iteration, sim.snapshot_async(aux=True))
             _store_subdomains(subdomains, iteration, sb, agent_rows["subdomains"])  # save_subdomains (run_sim.rs:322-325)
 
-        if save_its and save_its[0] == 0:  # save_initial (time.rs:243-255)
-            save(0)
+        # save_initial (time.rs:269-280, run_sim.rs:375-378): current_time == t0 when the loop starts, so the
+        # initial state is ALWAYS stored, whether or not t0 is among the save points
+        save(0)
         it = 0
         for target in [s for s in save_its if s > 0]:
             sim.step(target - it)  # replaces (target - it) iterations of run_sim.rs:380-403
@@ -615,8 +635,7 @@ def _run_slabs(cfg, devices, agents, settings: Settings, pos, vel, mp, ip, sp, n
             _store(state, (mp[k], ip[k], sp[k]), cells, iteration, sb, names)
             _store_subdomains(subdomains, iteration, sb, names["subdomains"])
 
-        if save_its and save_its[0] == 0:
-            save(0)
+        save(0)  # save_initial: always (time.rs:269-280, run_sim.rs:375-378)
         it = 0
         for target in [x for x in save_its if x > 0]:
             grp.step(target - it)
@@ -902,8 +921,7 @@ def _run_rods(domain, agents: Sequence[RodAgent], settings: Settings, aspects, *
                               # create_subdomains hands surface_friction to the distance field (:406)
                               "surface_friction_distance": float(gel.surface_friction)}) if gel is not None else None))
 
-        if save_its and save_its[0] == 0:
-            save(0)
+        save(0)  # save_initial: always (time.rs:269-280, run_sim.rs:375-378)
         it = 0
         for target in [x for x in save_its if x > 0]:
             sim.step(target - it)

@@ -436,11 +436,10 @@ where
     let mut time_stepper = settings.time.clone();
     let mut snap = Snapshot::<D>::default();
     let mut steps_since_save = 0u64;
-    while let Some(next) = time_stepper.advance()? {
-        steps_since_save += 1;
-        if let Some(TimeEvent::PartialSave) = next.event {
-            runner.step(steps_since_save)?; // replaces that many iterations of run_sim.rs:380-403
-            steps_since_save = 0;
+    // save_cells + save_subdomains of one PartialSave event (chili/datastructures.rs:347-396)
+    macro_rules! store_snapshot {
+        ($iteration:expr) => {{
+            let iteration: u64 = $iteration;
             runner.snapshot_async(&mut snap)?;
             runner.snapshot_wait()?;
             let batch = (0..snap.ids.len()).map(|k| {
@@ -449,10 +448,22 @@ where
                 c.set_state(&snap.pos[k], &snap.vel[k]);
                 (id, (CellBox::new(id, None, c), snap.aux(k)))
             });
-            storage_cells.store_batch_elements(next.iteration as u64, batch.collect::<Vec<_>>().iter().map(|(i, e)| (i, e)))?;
+            storage_cells.store_batch_elements(iteration, batch.collect::<Vec<_>>().iter().map(|(i, e)| (i, e)))?;
             for (index, subdomain, _) in subdomains.iter() {
-                storage_subdomains.store_single_element(next.iteration as u64, index, subdomain)?;
+                storage_subdomains.store_single_element(iteration, index, subdomain)?;
             }
+        }};
+    }
+    // run_sim.rs:375-378: the stepper is at t0 when the loop starts, so the initial state is always stored
+    if let Some(first) = time_stepper.save_initial() {
+        store_snapshot!(first.iteration as u64);
+    }
+    while let Some(next) = time_stepper.advance()? {
+        steps_since_save += 1;
+        if let Some(TimeEvent::PartialSave) = next.event {
+            runner.step(steps_since_save)?; // replaces that many iterations of run_sim.rs:380-403
+            steps_since_save = 0;
+            store_snapshot!(next.iteration as u64);
         }
     }
     if steps_since_save > 0 {

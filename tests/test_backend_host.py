@@ -27,6 +27,13 @@ def test_fixed_stepsize_event_schedule():
     assert t.save_iterations[1] == 20 and t.maximum_iterations == 200
     t = cr.FixedStepsize.from_partial_save_points(1.0, 0.2, [3.0, 5.0, 11.0, 20.0])
     assert t.save_iterations == [10, 20, 50, 95]
+    # F::round is half away from zero (Python's round is half to even): (2.25 - 1.0) / 0.5 = 2.5 -> iteration 3
+    assert cr.FixedStepsize.from_partial_save_points(1.0, 0.5, [2.25]).save_iterations == [3]
+    # from_partial_save_freq as written (time.rs:135-168): events at (0..max).step_by(freq), end point exclusive
+    t = cr.FixedStepsize.from_partial_save_freq(0.0, 0.1, 10.0, 25)
+    assert t.maximum_iterations == 100 and t.save_iterations == [0, 25, 50, 75]
+    t = cr.FixedStepsize.from_partial_save_freq(0.0, 0.1, 10.1, 25)
+    assert t.maximum_iterations == 101 and t.save_iterations == [0, 25, 50, 75, 100]
     with pytest.raises(ValueError):
         cr.FixedStepsize.from_partial_save_points(1.0, 0.2, [0.5])
     with pytest.raises(ValueError):
