@@ -324,7 +324,7 @@ EXTRA_LEGS = (
     ("configs[0] cell_sorting as shipped (1,600 cells)", "cell_sorting_as_shipped", 1600, 2000, 50, 20),
     ("configs[1] cell_sorting 1 M cells", "cell_sorting", 1_000_000, 20, 5, 12),
     ("configs[2] Brownian3D + Morse 8 M cells (1 GPU)", "brownian_morse", 8_000_000, 8, 3, 8),
-    ("configs[3] bacterial_rods 2 M rods", "bacterial_rods", 2_000_000, 8, 3, 3),
+    ("configs[3] bacterial_rods 2 M rods", "bacterial_rods", 2_000_000, 8, 3, 8),
 )
 
 
