@@ -194,7 +194,8 @@ int crb_set_agents(crb_sim* sim, uint64_t n, const double* pos, const double* ve
  * crb_step.  crb_set_aux cannot follow this form.
  * Rods (CRB_MECH_ROD, single-device handles): the parameter rows are uploaded as given and checked ON THE DEVICE (every
  * RodMechanics / MorsePotential field except spring_length and growth_rate must equal row 0); a row that differs is
- * latched as CRB_ERR_INVALID_ARG and returned by the next crb_step.  From then on the handle's clears, its division
+ * latched as CRB_ERR_INVALID_ARG and returned by the next crb_step (the uploaded population is not usable after that
+ * error: upload again).  From then on the handle's clears, its division
  * count and its error latch travel as kernels / stores into page-locked words, never as copy-engine operations that
  * would queue behind the transfers of the handle it alternates with. */
 int crb_set_agents_async(crb_sim* sim, uint64_t n, const double* pos, const double* vel,
